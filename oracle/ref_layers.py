@@ -1,0 +1,181 @@
+"""TEST INFRASTRUCTURE ONLY - the CPU oracle for the layer half of the path.
+
+A torch-CPU restatement of the reference's TensorFlow-1.x layer functions, op for
+op in the reference's order (so float32 rounding matches the reference run through
+oracle/tf_shim.py), each citing the /root/reference file:line it follows.  torch
+autograd plays the role of TF autodiff (train.py:72).  Works in float32 or float64
+depending on the input dtype.
+
+Parity pinned: tests/test_oracle_golden.py checks every function here against golden
+vectors produced by running the unmodified reference (oracle/make_golden.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.
+"""
+import numpy as np
+import torch
+
+
+def _t(x):
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(x))
+    return x
+
+
+def _segment_mean(h, ids, num_segs):
+    """tf.unsorted_segment_mean: sum / max(count,1); empty segments give 0."""
+    ids = _t(ids).long()
+    s = torch.zeros((num_segs,) + tuple(h.shape[1:]), dtype=h.dtype).index_add(0, ids, h)
+    cnt = torch.zeros(num_segs, dtype=h.dtype).index_add(0, ids, torch.ones(ids.shape[0], dtype=h.dtype))
+    return s / cnt.clamp(min=1).reshape(-1, 1)
+
+
+# ------------------------------------------------------------------ input features
+def include_node_features(X_in_edges, X_in_nodes, COO_feats, redshift=None):
+    """graph.py:245-275"""
+    row_idx = _t(COO_feats[0]).long()
+    col_idx = _t(COO_feats[1]).long()
+    node_rows = X_in_nodes[row_idx]
+    node_cols = X_in_nodes[col_idx]
+    X_in = torch.cat([X_in_edges, node_rows, node_cols], dim=1)
+    if redshift is not None:
+        X_in = torch.cat([X_in, redshift], dim=1)
+    return X_in
+
+
+def get_input_features_shift_inv_ZA(init_pos, ZA_displacement, coo, diag, dims):
+    """graph.py:289-343"""
+    b, N, M = dims
+    flattened_pos = init_pos.reshape(-1, 3)
+    cols = _t(coo[1]).long()
+    edges = flattened_pos[cols].reshape(b, N, M, 3)
+    edges = edges - init_pos.unsqueeze(2)
+    flattened_za_disp = ZA_displacement.reshape(-1, 3)
+    diagonal_za = torch.zeros((b * N * M, 3), dtype=init_pos.dtype).index_add(
+        0, _t(diag).long(), flattened_za_disp)
+    return edges.reshape(-1, 3) + diagonal_za
+
+
+def get_input_features_shift_inv(X_in, coo, dims):
+    """graph.py:346-364 (raw differences - no minimum-image wrap)"""
+    b, N, M = dims
+    X = X_in.reshape(-1, 6)
+    edges = X[..., :3]
+    nodes = X[..., 3:]
+    cols = _t(coo[1]).long()
+    edges = edges[cols].reshape(b, N, M, 3)
+    edges = edges - X_in[..., :3].unsqueeze(2)
+    return edges.reshape(-1, 3), nodes
+
+
+# ------------------------------------------------------------------ graph layer
+def shift_inv_conv(h, pool_idx, num_segs, broadcast):
+    """graph.py:367-391"""
+    pooled = _segment_mean(h, pool_idx, num_segs)
+    if broadcast:
+        pooled = pooled[_t(pool_idx).long()]
+    return pooled
+
+
+def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
+    """graph.py:394-456"""
+    b, N = bN
+    row_idx, col_idx, cube_idx = COO_feats[0], COO_feats[1], COO_feats[2]
+    weights, B = layer_vars
+    W1, W2, W3, W4 = weights
+
+    def _pool(H, idx, broadcast=True):
+        return shift_inv_conv(H, idx, b * N, broadcast)
+
+    H1 = H_in @ W1
+    H2 = _pool(H_in, col_idx) @ W2
+    H3 = _pool(H_in, row_idx) @ W3
+    H4 = _pool(H_in, cube_idx) @ W4
+    H_out = (H1 + H2 + H3 + H4) + B
+    if is_last:
+        H_out = _pool(H_out, row_idx, broadcast=False).reshape(b, N, -1)
+    return H_out
+
+
+def network_func_shift_inv_za(edges, coo, num_layers, dims, activation, model_vars):
+    """graph.py:463-476"""
+    H = activation(shift_inv_layer(edges, coo, dims, model_vars.get_layer_vars(0)))
+    for layer_idx in range(1, num_layers):
+        is_last = layer_idx == num_layers - 1
+        H = shift_inv_layer(H, coo, dims, model_vars.get_layer_vars(layer_idx), is_last=is_last)
+        if not is_last:
+            H = activation(H)
+    return H
+
+
+def model_func_shift_inv_za(init_pos, COO_feats, ZA_displacement, ZA_diagonal, model_vars, dims,
+                            activation=torch.relu):
+    """graph.py:479-515"""
+    num_layers = len(model_vars.channels) - 1
+    edges = get_input_features_shift_inv_ZA(init_pos, ZA_displacement, COO_feats, ZA_diagonal, dims)
+    return network_func_shift_inv_za(edges, COO_feats, num_layers, dims[:-1], activation, model_vars)
+
+
+# ------------------------------------------------------------------ set layer
+def set_layer(h_in, layer_vars):
+    """nn.py:10-28 (only W[0] of the layer's weights is used, nn.py:22)"""
+    W, B = layer_vars
+    W = W[0]
+    h_mu = h_in.mean(dim=1, keepdim=True)
+    h = h_in - h_mu
+    return torch.einsum('bnk,kq->bnq', h, W) + B
+
+
+def network_func_set(X_in, model_vars):
+    """nn.py:31-67"""
+    num_layers = model_vars.num_layers
+    activation = model_vars.activation
+    H = activation(set_layer(X_in, model_vars.get_layer_vars(0)))
+    for layer_idx in range(1, num_layers):
+        H = set_layer(H, model_vars.get_layer_vars(layer_idx))
+        if not layer_idx >= num_layers - 1:
+            H = activation(H)
+    return H
+
+
+def model_func_set(X_in, model_vars):
+    """nn.py:70-97"""
+    return network_func_set(X_in, model_vars)
+
+
+# ------------------------------------------------------------------ readout / losses
+def get_readout(h_out):
+    """nn.py:107-119"""
+    M = h_out.shape[-1]
+    c = h_out[..., :3]
+    gt_one = (torch.sign(c - 1) + 1) / 2
+    ls_zero = -(torch.sign(c) - 1) / 2
+    rest = 1 - gt_one - ls_zero
+    readout = rest * c + gt_one * (c - 1) + ls_zero * (1 + c)
+    if M > 3:
+        readout = torch.cat([readout, h_out[..., 3:]], dim=-1)
+    return readout
+
+
+def periodic_boundary_dist(readout_full, x_truth):
+    """nn.py:123-134"""
+    readout = readout_full[..., :3]
+    t = x_truth[..., :3]
+    d1 = (readout - t) ** 2
+    d2 = (readout - (1 + t)) ** 2
+    d3 = ((1 + readout) - t) ** 2
+    return torch.minimum(torch.minimum(d1, d2), d3)
+
+
+def pbc_loss(x_pred, x_truth, scale_error=True):
+    """nn.py:137-148"""
+    error = periodic_boundary_dist(x_pred, x_truth).sum(dim=-1).mean()
+    if scale_error:
+        error = error * 1e5
+    return error
+
+
+def loss_ZA(predicted_error, true_error):
+    """nn.py:151-166"""
+    d = predicted_error - true_error
+    return (d * d).sum(dim=-1).mean()
