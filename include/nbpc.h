@@ -1,0 +1,183 @@
+/* nbpc.h - C ABI of libnbpc.so: the B200 (sm_100a) replacement for the data-parallel hot path
+ * of evdcush/N-Body_PointCloudEvolution (periodic-box kNN graph construction + set/graph layer
+ * forward/backward).
+ *
+ * The reference is 100% Python and has NO FFI layer; its boundary for this path is the set of
+ * Python call signatures in /root/reference/graph.py and nn.py.  Each entry point below names
+ * the reference function(s) (file:line) whose work it replaces.  The Python package
+ * `n-body_pointcloudevolution_b200` re-exports the reference's function names on top of these
+ * symbols (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C linkage, plain pointers and sizes; no allocation, no host synchronisation and no
+ *     stream creation inside the library.  All pointers are DEVICE pointers owned by the caller
+ *     (contiguous, row-major, 16-byte aligned unless a stride argument says otherwise);
+ *     `stream` is a cudaStream_t passed as void*.
+ *   - every call returns NBPC_OK (0) or a negative NBPC_E* code; nbpc_last_error_string() gives
+ *     the thread-local message of the last failure.
+ *   - workspaces: ask nbpc_*_workspace_bytes() first, pass a buffer at least that large.
+ *   - the library refuses to run (NBPC_EARCH) on anything but compute capability 10.0.
+ *   - c = B*N*M edges, stored row-major by (sample, particle, neighbour slot): edge e belongs to
+ *     row node e / M.  Node ids in `col`/COO are global (sample*N + particle).
+ */
+#ifndef NBPC_H_
+#define NBPC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBPC_OK 0
+#define NBPC_EINVAL (-1)     /* bad argument */
+#define NBPC_EARCH (-2)      /* device is not sm_100 */
+#define NBPC_ELAUNCH (-3)    /* CUDA launch / runtime error */
+#define NBPC_EWORKSPACE (-4) /* workspace too small */
+
+#define NBPC_ORDER_DISTANCE 0 /* ascending (d2, index): raw sklearn / get_pbc_kneighbors_csr order */
+#define NBPC_ORDER_INDEX 1    /* ascending column index: get_kneighbor_list order (scipy astype) */
+
+#define NBPC_KNN_MAX_K 64
+
+/* ---------------------------------------------------------------- library */
+int nbpc_version(void);
+const char *nbpc_last_error_string(void);
+/* NBPC_OK if the current CUDA device is compute capability 10.0, else NBPC_EARCH. */
+int nbpc_device_check(void);
+
+/* ---------------------------------------------------------------- kNN graph
+ * Replaces graph.get_kneighbor_list (graph.py:704-713; periodic=0) and
+ * graph.get_pbc_kneighbors_csr + pad_cube_boundaries + get_pcube_csr (graph.py:801-917; periodic=1).
+ *
+ * xyz: float32 positions, element (b,n,d) at xyz[b*stride_b + n*stride_n + d], d in 0..2.
+ * periodic=1: unit box; a particle has an image shifted by -1 (+1) along an axis iff
+ *   x >= (float)(1-thr)  (x <= (float)thr), exactly the padded cloud of graph.py:842; images are
+ *   formed as (double)x + shift and distances are float64, d2 = ((dx*dx)+(dy*dy))+(dz*dz) with
+ *   separately rounded multiplies and adds (scikit-learn's rdist arithmetic).
+ * include_self=0 drops the un-shifted query particle itself (sklearn queries k+1 and removes it).
+ * Ties (exactly equal d2) are broken by ascending particle index - a documented total order;
+ *   sklearn's own tie order is KD-tree traversal order and is not reproducible.
+ * idx_out: int32 (B,N,k) neighbour indices LOCAL to the sample (image indices mapped back to the
+ *   original particle, graph.py:888-893).  d2_out: optional float64 (B,N,k), always in
+ *   distance order (NULL to skip).
+ * Requires 1 <= k <= NBPC_KNN_MAX_K and k <= N - (include_self ? 0 : 1). */
+size_t nbpc_knn_workspace_bytes(int B, int N, int k, int periodic);
+int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N, int k,
+             int periodic, double boundary_threshold, int include_self, int order,
+             int32_t *idx_out, double *d2_out, void *workspace, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- adjacency
+ * Replaces graph.to_coo_batch_ZA_diag / to_coo_batch / get_indices_from_list_CSR
+ * (graph.py:593-697) and adds the CSR transpose used by every layer's col-pool and by backward.
+ *
+ * idx: int32 (B,N,M) local neighbour indices (output of nbpc_knn).
+ * coo_out: int32 (3,c): [row + iN, col + iN, i]  (graph.py:643-652).
+ * diag_out: int64 (B*N): flat edge position of the FIRST self edge (row == col) of each row, or
+ *   -1 if the row has none (graph.py:655-656 for include_self graphs).
+ * csrT_ptr int32 (B*N+1), csrT_edge int32 (c): in-edges of every node, edge ids ascending inside
+ *   a node (=> deterministic summation order).
+ * status: int32[2] device: [0] rows whose number of self edges != 1, [1] indices out of [0,N). */
+size_t nbpc_adjacency_workspace_bytes(int B, int N, int M);
+int nbpc_adjacency(const int32_t *idx, int B, int N, int M, int32_t *coo_out, int64_t *diag_out,
+                   int32_t *csrT_ptr, int32_t *csrT_edge, int32_t *status, void *workspace,
+                   size_t ws_bytes, void *stream);
+
+/* Generic: members of every segment, ascending, for arbitrary int32 ids in [0,num_segs)
+ * (what tf.unsorted_segment_mean needs to be deterministic).  status: int32[1] = ids out of range. */
+size_t nbpc_segment_csr_workspace_bytes(int64_t n_items, int num_segs);
+int nbpc_segment_csr(const int32_t *ids, int64_t n_items, int num_segs, int32_t *seg_ptr,
+                     int32_t *seg_members, int32_t *status, void *workspace, size_t ws_bytes,
+                     void *stream);
+
+/* ---------------------------------------------------------------- edge input features
+ * graph.get_input_features_shift_inv_ZA (graph.py:289-343):
+ *   edges[e] = pos[col[e]] - pos[e / M];  edges[diag[n]] += za[n]  for n < n_diag (diag[n] < 0 skipped).
+ * pos/za: (BN, 3) with leading dimension ld_pos / ld_za (floats). */
+int nbpc_edge_features_za(const float *pos, int ld_pos, const float *za, int ld_za,
+                          const int32_t *col, const int64_t *diag, int64_t n_diag, int BN, int M,
+                          float *edges_out, void *stream);
+/* graph.get_input_features_shift_inv (graph.py:346-364): raw differences of X[:, :3] (za NULL) -
+ * same kernel, exported under its own name. */
+int nbpc_edge_features(const float *pos, int ld_pos, const int32_t *col, int BN, int M,
+                       float *edges_out, void *stream);
+/* graph.include_node_features (graph.py:245-275):
+ *   out[e] = [edges[e] (E), nodes[e / M] (F), nodes[col[e]] (F), redshift[e] (R = 0 or 1)]. */
+int nbpc_include_node_features(const float *edges, int E, const float *nodes, int ld_nodes, int F,
+                               const int32_t *col, const float *redshift, int BN, int M, float *out,
+                               void *stream);
+
+/* ---------------------------------------------------------------- pooling primitive
+ * graph.shift_inv_conv (graph.py:367-391) = tf.unsorted_segment_mean (+ tf.gather_nd).
+ * nbpc_segment_reduce: out[s] = sum_{e in seg s} h[e] (/ max(count,1) if mean), members ascending.
+ * nbpc_gather_rows:    out[i] = src[ids[i]] (* 1/max(count(ids[i]),1) if seg_ptr given). */
+int nbpc_segment_reduce(const float *h, int k, const int32_t *seg_ptr, const int32_t *seg_members,
+                        int num_segs, int mean, float *out, void *stream);
+int nbpc_gather_rows(const float *src, int k, const int32_t *ids, int64_t n_ids,
+                     const int32_t *seg_ptr, float *out, void *stream);
+
+/* ---------------------------------------------------------------- shift-invariant graph layer
+ * graph.shift_inv_layer (graph.py:394-456):
+ *   Z = H W1 + pool_col(H) W2 + pool_row(H) W3 + pool_cube(H) W4 + B        (c, q)
+ *   is_last: out = row-mean(Z) (BN, q);  relu: out = max(Z, 0) (the activation the network
+ *   functions apply between layers, graph.py:466, 474-475).
+ * W: float32 (4, k, q) = [W1, W2, W3, W4]; bias (q).
+ * Saved for backward (caller-allocated): P_col (BN,k), P_row (BN,k), P_cube (B,k).
+ * Backward returns dH_in (c,k; NULL to skip - first layer), dW (4,k,q), dB (q); all sums run in
+ * a fixed order (CSR transpose + two-level trees; no float atomics) => bit-reproducible. */
+size_t nbpc_graph_layer_workspace_bytes(int B, int N, int M, int k, int q);
+int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *csrT_ptr,
+                         const int32_t *csrT_edge, int B, int N, int M, int k, int q,
+                         const float *W, const float *bias, int is_last, int relu, float *H_out,
+                         float *P_col, float *P_row, float *P_cube, void *workspace,
+                         size_t ws_bytes, void *stream);
+int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
+                         const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge,
+                         int B, int N, int M, int k, int q, const float *W, const float *P_col,
+                         const float *P_row, const float *P_cube, int is_last, int relu,
+                         float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes,
+                         void *stream);
+
+/* ---------------------------------------------------------------- set layer
+ * nn.set_layer (nn.py:10-28): out = (H - mean_N H) W + B on (B,N,k) -> (B,N,q); relu optional
+ * (nn.py:59, 65-66).  mu (B,k) is saved for backward. */
+size_t nbpc_set_layer_workspace_bytes(int B, int N, int k, int q);
+int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const float *W,
+                       const float *bias, int relu, float *H_out, float *mu, void *workspace,
+                       size_t ws_bytes, void *stream);
+int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const float *mu,
+                       int B, int N, int k, int q, const float *W, int relu, float *dH_in,
+                       float *dW, float *dB, void *workspace, size_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------- readout / losses
+ * nn.loss_ZA (nn.py:151-166): loss = mean_rows(sum_3 (pred - truth)^2); rows = B*N.
+ * nn.pbc_loss / periodic_boundary_dist (nn.py:123-148): per-axis min over {d, d-1, d+1} images,
+ *   optionally * 1e5.  nn.get_readout (nn.py:107-119): wrap the first 3 channels into [0,1).
+ * pred/truth have leading dimensions (floats) ld_pred / ld_truth >= 3; only columns 0..2 are read.
+ * *_bwd: dpred[:, :3] = dloss * d loss / d pred (dloss is a DEVICE scalar). */
+size_t nbpc_loss_workspace_bytes(int64_t rows);
+int nbpc_loss_za_fwd(const float *pred, int ld_pred, const float *truth, int ld_truth, int64_t rows,
+                     float *loss_out, void *workspace, size_t ws_bytes, void *stream);
+int nbpc_loss_za_bwd(const float *pred, int ld_pred, const float *truth, int ld_truth, int64_t rows,
+                     const float *dloss, float *dpred, int ld_dpred, void *stream);
+int nbpc_pbc_loss_fwd(const float *pred, int ld_pred, const float *truth, int ld_truth, int64_t rows,
+                      int scale_error, float *loss_out, void *workspace, size_t ws_bytes,
+                      void *stream);
+int nbpc_pbc_loss_bwd(const float *pred, int ld_pred, const float *truth, int ld_truth, int64_t rows,
+                      int scale_error, const float *dloss, float *dpred, int ld_dpred, void *stream);
+int nbpc_periodic_boundary_dist(const float *pred, int ld_pred, const float *truth, int ld_truth,
+                                int64_t rows, float *dist_out, void *stream);
+int nbpc_readout(const float *h, int64_t rows, int C, float *out, void *stream);
+
+/* ---------------------------------------------------------------- optimiser
+ * tf.train.AdamOptimizer as used by train.py:70 (TF "epsilon-hat" form):
+ *   lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  m,v updates;  p -= lr_t * m / (sqrt(v) + eps).
+ * grad_scale multiplies the gradient first (1/world_size after a sum all-reduce). */
+int nbpc_adam_tf(float *param, const float *grad, float *m, float *v, int64_t n, float lr,
+                 float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBPC_H_ */

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI in include/nbpc.h (libnbpc.so, sm_100a).
+
+The product path has NO fallback: if libnbpc.so is missing, or a call returns a
+non-zero status (no GPU, not an sm_100 device, bad argument, launch error), a
+RuntimeError is raised with the library's own message.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnbpc.so")
+
+NBPC_OK = 0
+ORDER_DISTANCE = 0
+ORDER_INDEX = 1
+KNN_MAX_K = 64
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_i64 = ctypes.c_int64
+_sz = ctypes.c_size_t
+_f = ctypes.c_float
+_d = ctypes.c_double
+
+# name -> (restype, argtypes); one entry per symbol declared in include/nbpc.h
+SIGNATURES = {
+    "nbpc_version": (_i, []),
+    "nbpc_last_error_string": (ctypes.c_char_p, []),
+    "nbpc_device_check": (_i, []),
+    "nbpc_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "nbpc_knn": (_i, [_p, _i64, _i64, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _sz, _p]),
+    "nbpc_adjacency_workspace_bytes": (_sz, [_i, _i, _i]),
+    "nbpc_adjacency": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_segment_csr_workspace_bytes": (_sz, [_i64, _i]),
+    "nbpc_segment_csr": (_i, [_p, _i64, _i, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_edge_features_za": (_i, [_p, _i, _p, _i, _p, _p, _i64, _i, _i, _p, _p]),
+    "nbpc_edge_features": (_i, [_p, _i, _p, _i, _i, _p, _p]),
+    "nbpc_include_node_features": (_i, [_p, _i, _p, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "nbpc_segment_reduce": (_i, [_p, _i, _p, _p, _i, _i, _p, _p]),
+    "nbpc_gather_rows": (_i, [_p, _i, _p, _i64, _p, _p, _p]),
+    "nbpc_graph_layer_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "nbpc_graph_layer_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_graph_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i,
+                                  _p, _p, _p, _p, _sz, _p]),
+    "nbpc_set_layer_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "nbpc_set_layer_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
+    "nbpc_set_layer_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_loss_workspace_bytes": (_sz, [_i64]),
+    "nbpc_loss_za_fwd": (_i, [_p, _i, _p, _i, _i64, _p, _p, _sz, _p]),
+    "nbpc_loss_za_bwd": (_i, [_p, _i, _p, _i, _i64, _p, _p, _i, _p]),
+    "nbpc_pbc_loss_fwd": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _sz, _p]),
+    "nbpc_pbc_loss_bwd": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _i, _p]),
+    "nbpc_periodic_boundary_dist": (_i, [_p, _i, _p, _i, _i64, _p, _p]),
+    "nbpc_readout": (_i, [_p, _i64, _i, _p, _p]),
+    "nbpc_adam_tf": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _i64, _f, _p]),
+}
+
+
+def bind(cdll):
+    """Attach restype/argtypes for every declared symbol; raises AttributeError if one is missing."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(cdll, name)
+        fn.restype = res
+        fn.argtypes = args
+    return cdll
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C n-body_pointcloudevolution_b200/csrc`). There is no CPU fallback.")
+        _lib = bind(ctypes.CDLL(LIB_PATH))
+    return _lib
+
+
+def last_error():
+    return load().nbpc_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != NBPC_OK:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")

@@ -1,0 +1,403 @@
+// graph_layer.cu - edge input features (graph.py:245-364), the pooling primitive
+// (graph.py:367-391) and the shift-invariant graph layer forward/backward (graph.py:394-456).
+//
+// Layout: edge tensors are (c, channels) row-major with c = B*N*M and edge e owned by row node
+// e / M (CSR order of the kNN graph); node tensors are (B*N, channels).
+//
+// Forward, restructured so that the three pooled terms are projected at NODE level and only one
+// small GEMM runs at edge level (same math as graph.py:437-453, different association):
+//   P_row[i] = mean_m H[iM+m]            P_col[j] = mean_{e: col[e]=j} H[e]  (CSR transpose, fixed order)
+//   P_cube[s] = mean_i P_row[i]
+//   Q_col = P_col W2                     Q_row = P_row W3 + (P_cube W4 + B)
+//   Z[e] = H[e] W1 + Q_col[col[e]] + Q_row[e/M]
+// Backward mirrors it (see nbpc_graph_layer_bwd); every reduction has a fixed order.
+//
+// This file holds the barrier-free baseline kernels (one thread per output element).  They are the
+// correctness anchor for the tiled / tensor-core kernels and also compile under NBPC_HOST_EMU.
+#include "nbpc_common.cuh"
+#include "reduce.cuh"
+
+// ------------------------------------------------------------------ input features
+__global__ void edge_features_kernel(const float *__restrict__ pos, int ld, const int32_t *__restrict__ col,
+                                     int64_t c, int M, float *__restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= c) return;
+    const int64_t r = e / M, j = col[e];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) out[e * 3 + d] = __ldg(&pos[j * ld + d]) - __ldg(&pos[r * ld + d]);
+}
+
+__global__ void edge_add_diag_kernel(const float *__restrict__ za, int ld, const int64_t *__restrict__ diag,
+                                     int64_t n_diag, int64_t c, float *__restrict__ out) {
+    int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_diag) return;
+    const int64_t e = diag[n];
+    if (e < 0 || e >= c) return;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) out[e * 3 + d] += za[n * ld + d];
+}
+
+__global__ void include_node_features_kernel(const float *__restrict__ edges, int E, const float *__restrict__ nodes,
+                                             int ld, int F, const int32_t *__restrict__ col,
+                                             const float *__restrict__ redshift, int64_t c, int M,
+                                             float *__restrict__ out) {
+    const int Wd = E + 2 * F + (redshift ? 1 : 0);
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c * Wd) return;
+    const int64_t e = t / Wd;
+    const int ch = (int)(t % Wd);
+    float v;
+    if (ch < E) v = edges[e * E + ch];
+    else if (ch < E + F) v = __ldg(&nodes[(e / M) * ld + (ch - E)]);
+    else if (ch < E + 2 * F) v = __ldg(&nodes[(int64_t)col[e] * ld + (ch - E - F)]);
+    else v = redshift[e];
+    out[t] = v;
+}
+
+// ------------------------------------------------------------------ pooling primitive
+__global__ void segment_reduce_kernel(const float *__restrict__ h, int k, const int32_t *__restrict__ seg_ptr,
+                                      const int32_t *__restrict__ members, int num_segs, int mean,
+                                      float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)num_segs * k) return;
+    const int s = (int)(t / k), ch = (int)(t % k);
+    const int b = seg_ptr[s], e = seg_ptr[s + 1];
+    float acc = 0.f;
+    for (int p = b; p < e; ++p) acc += h[(int64_t)members[p] * k + ch];
+    if (mean) acc = acc / (float)nbpc_max(e - b, 1);
+    out[t] = acc;
+}
+
+__global__ void gather_rows_kernel(const float *__restrict__ src, int k, const int32_t *__restrict__ ids,
+                                   int64_t n, const int32_t *__restrict__ seg_ptr, float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * k) return;
+    const int64_t i = t / k;
+    const int ch = (int)(t % k);
+    const int id = ids[i];
+    float v = __ldg(&src[(int64_t)id * k + ch]);
+    if (seg_ptr) v = v / (float)nbpc_max(seg_ptr[id + 1] - seg_ptr[id], 1);
+    out[t] = v;
+}
+
+// ------------------------------------------------------------------ graph layer forward
+__global__ void gl_pool_kernel(const float *__restrict__ H, int k, int M, int BN,
+                               const int32_t *__restrict__ csrT_ptr, const int32_t *__restrict__ csrT_edge,
+                               float *__restrict__ P_row, float *__restrict__ P_col) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * k) return;
+    const int node = (int)(t / k), ch = (int)(t % k);
+    float rs = 0.f;
+    const float *hr = H + (int64_t)node * M * k + ch;
+    for (int m = 0; m < M; ++m) rs += hr[(int64_t)m * k];
+    P_row[t] = rs / (float)M;
+    const int b = csrT_ptr[node], e = csrT_ptr[node + 1];
+    float cs = 0.f;
+    for (int p = b; p < e; ++p) cs += H[(int64_t)csrT_edge[p] * k + ch];
+    P_col[t] = cs / (float)nbpc_max(e - b, 1);
+}
+
+__global__ void gl_node_project_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
+                                       const float *__restrict__ P_cube, const float *__restrict__ W,
+                                       const float *__restrict__ bias, int BN, int N, int k, int q,
+                                       float *__restrict__ Q_col, float *__restrict__ Q_row) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * q) return;
+    const int node = (int)(t / q), qo = (int)(t % q);
+    const int s = node / N;
+    const float *W2 = W + (int64_t)k * q, *W3 = W + 2 * (int64_t)k * q, *W4 = W + 3 * (int64_t)k * q;
+    float a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int kk = 0; kk < k; ++kk) {
+        a2 += P_col[(int64_t)node * k + kk] * __ldg(&W2[kk * q + qo]);
+        a3 += P_row[(int64_t)node * k + kk] * __ldg(&W3[kk * q + qo]);
+        a4 += __ldg(&P_cube[s * k + kk]) * __ldg(&W4[kk * q + qo]);
+    }
+    Q_col[t] = a2;
+    Q_row[t] = a3 + (a4 + __ldg(&bias[qo]));
+}
+
+__global__ void gl_edge_out_kernel(const float *__restrict__ H, const int32_t *__restrict__ col,
+                                   const float *__restrict__ W1, const float *__restrict__ Q_col,
+                                   const float *__restrict__ Q_row, int64_t c, int M, int k, int q, int relu,
+                                   float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c * q) return;
+    const int64_t e = t / q;
+    const int qo = (int)(t % q);
+    const float *h = H + e * k;
+    float z = 0.f;
+    for (int kk = 0; kk < k; ++kk) z += h[kk] * __ldg(&W1[kk * q + qo]);
+    z += __ldg(&Q_col[(int64_t)col[e] * q + qo]) + __ldg(&Q_row[(e / M) * q + qo]);
+    out[t] = (relu && z < 0.f) ? 0.f : z;
+}
+
+__global__ void gl_last_out_kernel(const float *__restrict__ H, const int32_t *__restrict__ col,
+                                   const float *__restrict__ W1, const float *__restrict__ Q_col,
+                                   const float *__restrict__ Q_row, int BN, int M, int k, int q, int relu,
+                                   float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * q) return;
+    const int node = (int)(t / q), qo = (int)(t % q);
+    const float qr = Q_row[t];
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) {
+        const int64_t e = (int64_t)node * M + m;
+        const float *h = H + e * k;
+        float z = 0.f;
+        for (int kk = 0; kk < k; ++kk) z += h[kk] * __ldg(&W1[kk * q + qo]);
+        acc += z + (__ldg(&Q_col[(int64_t)col[e] * q + qo]) + qr);
+    }
+    acc = acc / (float)M;   // graph.py:455 row-mean of the (c,q) output
+    out[t] = (relu && acc < 0.f) ? 0.f : acc;
+}
+
+// ------------------------------------------------------------------ graph layer backward
+// dZ accessor: gradient w.r.t. the (c,q) pre-activation, never materialised
+struct GlDz {
+    const float *g;      // dOut: (c,q), or (BN,q) when is_last
+    const float *hout;   // forward output (same shape as g), used only when relu
+    int relu, is_last, M, q;
+    __device__ __forceinline__ float at(int64_t e, int qo) const {
+        const int64_t r = is_last ? e / M : e;
+        float v = g[r * q + qo];
+        if (relu && !(hout[r * q + qo] > 0.f)) v = 0.f;
+        return is_last ? v / (float)M : v;
+    }
+};
+
+__global__ void glb_pool_kernel(GlDz dz, int BN, int M, int q, const int32_t *__restrict__ csrT_ptr,
+                                const int32_t *__restrict__ csrT_edge, float *__restrict__ dQ_row,
+                                float *__restrict__ dQ_col) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * q) return;
+    const int node = (int)(t / q), qo = (int)(t % q);
+    float rs = 0.f;
+    for (int m = 0; m < M; ++m) rs += dz.at((int64_t)node * M + m, qo);
+    dQ_row[t] = rs;
+    const int b = csrT_ptr[node], e = csrT_ptr[node + 1];
+    float cs = 0.f;
+    for (int p = b; p < e; ++p) cs += dz.at(csrT_edge[p], qo);
+    dQ_col[t] = cs;
+}
+
+__global__ void glb_bias_kernel(const float *__restrict__ dCq, int B, int q, float *__restrict__ dB) {
+    int qo = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qo >= q) return;
+    float acc = 0.f;
+    for (int s = 0; s < B; ++s) acc += dCq[s * q + qo];
+    dB[qo] = acc;
+}
+
+__global__ void glb_node_grad_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
+                                     const float *__restrict__ dCq, const float *__restrict__ W,
+                                     const int32_t *__restrict__ csrT_ptr, int BN, int N, int M, int k, int q,
+                                     float *__restrict__ G_col, float *__restrict__ G_row) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * k) return;
+    const int node = (int)(t / k), kk = (int)(t % k);
+    const int s = node / N;
+    const float *W2 = W + (int64_t)k * q, *W3 = W + 2 * (int64_t)k * q, *W4 = W + 3 * (int64_t)k * q;
+    float a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int qo = 0; qo < q; ++qo) {
+        a2 += dQ_col[(int64_t)node * q + qo] * __ldg(&W2[kk * q + qo]);
+        a3 += dQ_row[(int64_t)node * q + qo] * __ldg(&W3[kk * q + qo]);
+        a4 += __ldg(&dCq[s * q + qo]) * __ldg(&W4[kk * q + qo]);
+    }
+    const int indeg = csrT_ptr[node + 1] - csrT_ptr[node];
+    G_col[t] = a2 / (float)nbpc_max(indeg, 1);
+    G_row[t] = a3 / (float)M + a4 / ((float)N * (float)M);
+}
+
+__global__ void glb_edge_in_kernel(GlDz dz, const int32_t *__restrict__ col, const float *__restrict__ W1,
+                                   const float *__restrict__ G_col, const float *__restrict__ G_row, int64_t c,
+                                   int M, int k, int q, float *__restrict__ dH) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= c * k) return;
+    const int64_t e = t / k;
+    const int kk = (int)(t % k);
+    float a = 0.f;
+    for (int qo = 0; qo < q; ++qo) a += dz.at(e, qo) * __ldg(&W1[kk * q + qo]);
+    a += __ldg(&G_col[(int64_t)col[e] * k + kk]) + __ldg(&G_row[(e / M) * k + kk]);
+    dH[t] = a;
+}
+
+// ------------------------------------------------------------------ workspaces
+struct GlWorkspace {
+    float *Qc, *Qr;          // (BN, max(k,q)) each: Q_col/Q_row (fwd), dQ_col/dQ_row (bwd)
+    float *Gc, *Gr;          // (BN, k): G_col/G_row (bwd)
+    float *cube_partial;     // (B, nblk, max(k,q))
+    float *dCq;              // (B, q)
+    float *xty_partial;
+    size_t bytes;
+};
+
+static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int k, int q) {
+    NbpcArena a(ws, ws_bytes);
+    GlWorkspace w;
+    const size_t BN = (size_t)B * N;
+    const int mx = k > q ? k : q;
+    const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+    w.Qc = a.take<float>(BN * mx);
+    w.Qr = a.take<float>(BN * mx);
+    w.Gc = a.take<float>(BN * k);
+    w.Gr = a.take<float>(BN * k);
+    w.cube_partial = a.take<float>((size_t)B * nblk * mx);
+    w.dCq = a.take<float>((size_t)B * mx);
+    int rpc, nc;
+    xty_plan((int64_t)BN * M, k, q, &rpc, &nc);
+    w.xty_partial = a.take<float>((size_t)nc * k * q);
+    w.bytes = a.off;
+    return w;
+}
+
+extern "C" {
+
+int nbpc_edge_features_za(const float *pos, int ld_pos, const float *za, int ld_za, const int32_t *col,
+                          const int64_t *diag, int64_t n_diag, int BN, int M, float *edges_out, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(pos && col && edges_out, "null pointer");
+    NBPC_ARG(BN >= 1 && M >= 1 && ld_pos >= 3, "bad sizes");
+    const int64_t c = (int64_t)BN * M;
+    NBPC_LAUNCH(edge_features_kernel, nbpc_cdiv(c, GL_THREADS), GL_THREADS, 0, stream, pos, ld_pos, col, c, M, edges_out);
+    if (za && n_diag > 0) {
+        NBPC_ARG(diag && ld_za >= 3, "diag/za");
+        NBPC_LAUNCH(edge_add_diag_kernel, nbpc_cdiv(n_diag, GL_THREADS), GL_THREADS, 0, stream, za, ld_za, diag, n_diag, c,
+                    edges_out);
+    }
+    return nbpc_check_launch("nbpc_edge_features_za");
+}
+
+int nbpc_edge_features(const float *pos, int ld_pos, const int32_t *col, int BN, int M, float *edges_out,
+                       void *stream_) {
+    return nbpc_edge_features_za(pos, ld_pos, nullptr, 0, col, nullptr, 0, BN, M, edges_out, stream_);
+}
+
+int nbpc_include_node_features(const float *edges, int E, const float *nodes, int ld_nodes, int F,
+                               const int32_t *col, const float *redshift, int BN, int M, float *out,
+                               void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(edges && nodes && col && out, "null pointer");
+    NBPC_ARG(BN >= 1 && M >= 1 && E >= 1 && F >= 1 && ld_nodes >= F, "bad sizes");
+    const int64_t c = (int64_t)BN * M;
+    const int Wd = E + 2 * F + (redshift ? 1 : 0);
+    NBPC_LAUNCH(include_node_features_kernel, nbpc_cdiv(c * Wd, GL_THREADS), GL_THREADS, 0, stream, edges, E, nodes,
+                ld_nodes, F, col, redshift, c, M, out);
+    return nbpc_check_launch("nbpc_include_node_features");
+}
+
+int nbpc_segment_reduce(const float *h, int k, const int32_t *seg_ptr, const int32_t *seg_members, int num_segs,
+                        int mean, float *out, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(h && seg_ptr && seg_members && out, "null pointer");
+    NBPC_ARG(k >= 1 && num_segs >= 1, "bad sizes");
+    NBPC_LAUNCH(segment_reduce_kernel, nbpc_cdiv((int64_t)num_segs * k, GL_THREADS), GL_THREADS, 0, stream, h, k, seg_ptr,
+                seg_members, num_segs, mean, out);
+    return nbpc_check_launch("nbpc_segment_reduce");
+}
+
+int nbpc_gather_rows(const float *src, int k, const int32_t *ids, int64_t n_ids, const int32_t *seg_ptr,
+                     float *out, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(src && ids && out, "null pointer");
+    NBPC_ARG(k >= 1 && n_ids >= 0, "bad sizes");
+    if (n_ids == 0) return NBPC_OK;
+    NBPC_LAUNCH(gather_rows_kernel, nbpc_cdiv(n_ids * k, GL_THREADS), GL_THREADS, 0, stream, src, k, ids, n_ids, seg_ptr, out);
+    return nbpc_check_launch("nbpc_gather_rows");
+}
+
+size_t nbpc_graph_layer_workspace_bytes(int B, int N, int M, int k, int q) {
+    if (B < 1 || N < 1 || M < 1 || k < 1 || q < 1) return 0;
+    return gl_carve(nullptr, 0, B, N, M, k, q).bytes;
+}
+
+int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge,
+                         int B, int N, int M, int k, int q, const float *W, const float *bias, int is_last,
+                         int relu, float *H_out, float *P_col, float *P_row, float *P_cube, void *workspace,
+                         size_t ws_bytes, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(H_in && col && csrT_ptr && csrT_edge && W && bias && H_out && P_col && P_row && P_cube && workspace,
+             "null pointer");
+    NBPC_ARG(B >= 1 && N >= 1 && M >= 1 && k >= 1 && q >= 1, "bad sizes");
+    const int64_t BN = (int64_t)B * N, c = BN * M;
+    NBPC_ARG(c < ((int64_t)1 << 31), "B*N*M must fit int32");
+    GlWorkspace w = gl_carve(workspace, ws_bytes, B, N, M, k, q);
+    if (w.bytes > ws_bytes) {
+        nbpc_set_error("nbpc_graph_layer_fwd: workspace too small");
+        return NBPC_EWORKSPACE;
+    }
+    const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+    NBPC_LAUNCH(gl_pool_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, M, (int)BN, csrT_ptr,
+                csrT_edge, P_row, P_col);
+    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, P_row, k, N,
+                nblk, B, w.cube_partial);
+    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, k, nblk, B,
+                (float)N, P_cube);
+    NBPC_LAUNCH(gl_node_project_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, P_col, P_row, P_cube, W,
+                bias, (int)BN, N, k, q, w.Qc, w.Qr);
+    if (is_last) {
+        NBPC_LAUNCH(gl_last_out_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr,
+                    (int)BN, M, k, q, relu, H_out);
+    } else {
+        NBPC_LAUNCH(gl_edge_out_kernel, nbpc_cdiv(c * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr, c, M,
+                    k, q, relu, H_out);
+    }
+    return nbpc_check_launch("nbpc_graph_layer_fwd");
+}
+
+int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const int32_t *col,
+                         const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k, int q,
+                         const float *W, const float *P_col, const float *P_row, const float *P_cube, int is_last,
+                         int relu, float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes,
+                         void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(dOut && H_in && col && csrT_ptr && csrT_edge && W && P_col && P_row && P_cube && dW && dB && workspace,
+             "null pointer");
+    NBPC_ARG(!relu || H_out, "H_out is required when relu is set");
+    NBPC_ARG(B >= 1 && N >= 1 && M >= 1 && k >= 1 && q >= 1, "bad sizes");
+    const int64_t BN = (int64_t)B * N, c = BN * M;
+    NBPC_ARG(c < ((int64_t)1 << 31), "B*N*M must fit int32");
+    GlWorkspace w = gl_carve(workspace, ws_bytes, B, N, M, k, q);
+    if (w.bytes > ws_bytes) {
+        nbpc_set_error("nbpc_graph_layer_bwd: workspace too small");
+        return NBPC_EWORKSPACE;
+    }
+    const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+    GlDz dz;
+    dz.g = dOut; dz.hout = H_out; dz.relu = relu; dz.is_last = is_last; dz.M = M; dz.q = q;
+    float *dQ_col = w.Qc, *dQ_row = w.Qr;
+    const int64_t kq = (int64_t)k * q;
+
+    NBPC_LAUNCH(glb_pool_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, dz, (int)BN, M, q, csrT_ptr,
+                csrT_edge, dQ_row, dQ_col);
+    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dQ_row, q, N,
+                nblk, B, w.cube_partial);
+    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, q, nblk, B, 1.0f,
+                w.dCq);
+    NBPC_LAUNCH(glb_bias_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.dCq, B, q, dB);
+    // dW1 = H_in^T dZ (c rows), dW2 = P_col^T dQ_col, dW3 = P_row^T dQ_row (BN rows), dW4 = P_cube^T dCq (B rows)
+    GlPlain x, y;
+    x.ld = k; y.ld = q;
+    x.p = H_in;
+    xty(x, dz, c, k, q, w.xty_partial, dW, stream);
+    x.p = P_col; y.p = dQ_col;
+    xty(x, y, BN, k, q, w.xty_partial, dW + kq, stream);
+    x.p = P_row; y.p = dQ_row;
+    xty(x, y, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
+    x.p = P_cube; y.p = w.dCq;
+    xty(x, y, (int64_t)B, k, q, w.xty_partial, dW + 3 * kq, stream);
+    if (dH_in) {
+        NBPC_LAUNCH(glb_node_grad_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, dQ_col, dQ_row, w.dCq, W,
+                    csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
+        NBPC_LAUNCH(glb_edge_in_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0, stream, dz, col, W, w.Gc, w.Gr, c, M, k,
+                    q, dH_in);
+    }
+    return nbpc_check_launch("nbpc_graph_layer_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,420 @@
+// knn.cu - exact k-nearest-neighbour graph on a (periodic) particle box, bit-compatible with the
+// float64 KD-tree the reference calls (scikit-learn kneighbors_graph; /root/reference/graph.py:709,
+// 887) and with the reference's padded-cube periodic images (graph.py:801-917).
+//
+// Algorithm (cell list):
+//   1. bounding box per sample (non-periodic) or the unit box (periodic); G^3 uniform cells
+//   2. counting sort of the particles by cell (count -> exclusive scan -> scatter); sorted records
+//      are float4 {x, y, z, index | image-flags << 24}, x-fastest cell order so that a row of
+//      neighbouring cells is ONE contiguous range of records
+//   3. one thread per query, queries taken in sorted order (a warp = spatially adjacent queries,
+//      so candidate loads hit the same lines): visit cell shells R = 0,1,2,... around the query's
+//      cell; keep the k best in a register-resident sorted list; stop once the k-th best distance
+//      is strictly inside the region already covered.
+//
+// Bit-exactness: distances are float64, tmp = q - p; d = ((tx*tx) + (ty*ty)) + (tz*tz) with
+// separately rounded multiply/add (__dmul_rn/__dadd_rn: no FMA contraction), images are formed
+// as (double)x + shift before the subtraction.  Total order on candidates = (d2, index); the
+// result is therefore independent of the visiting order.
+#include "nbpc_common.cuh"
+#include "scan.cuh"
+
+#define KNN_IDX_MASK 0x00FFFFFF
+#define KNN_FLAG_SHIFT 24
+#define KNN_THREADS 128
+
+struct KnnGridInfo {  // per sample, device
+    float lo[3];
+    float inv_h;
+    double h;
+};
+
+__device__ __forceinline__ unsigned knn_enc_float(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float knn_dec_float(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__device__ __forceinline__ int knn_cell_coord(float x, float lo, float inv_h, int G) {
+    int c = (int)floorf((x - lo) * inv_h);
+    return nbpc_min(nbpc_max(c, 0), G - 1);
+}
+
+// ------------------------------------------------------------------ 1. bounding box
+__global__ void knn_bbox_init(unsigned *mm, int B) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * 6) mm[i] = ((i % 6) < 3) ? 0xFFFFFFFFu : 0u;  // [min xyz | max xyz]
+}
+
+__global__ void knn_bbox_reduce(const float *__restrict__ xyz, int64_t sb, int64_t sn, int N, unsigned *mm) {
+    const int b = blockIdx.y;
+    const float *p = xyz + (int64_t)b * sb;
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            float v = p[(int64_t)i * sn + d];
+            mn[d] = fminf(mn[d], v);
+            mx[d] = fmaxf(mx[d], v);
+        }
+    }
+#ifndef NBPC_HOST_EMU
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) != 0) return;
+#endif
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (mn[d] <= mx[d]) {
+            atomicMin(&mm[b * 6 + d], knn_enc_float(mn[d]));
+            atomicMax(&mm[b * 6 + 3 + d], knn_enc_float(mx[d]));
+        }
+    }
+}
+
+__global__ void knn_grid_setup(const unsigned *mm, int B, int G, int periodic, KnnGridInfo *info) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    KnnGridInfo gi;
+    if (periodic) {
+        gi.lo[0] = gi.lo[1] = gi.lo[2] = 0.f;
+        gi.inv_h = (float)G;
+        gi.h = 1.0 / (double)G;
+    } else {
+        float ext = 0.f;
+        for (int d = 0; d < 3; ++d) {
+            float lo = knn_dec_float(mm[b * 6 + d]), hi = knn_dec_float(mm[b * 6 + 3 + d]);
+            gi.lo[d] = lo;
+            ext = fmaxf(ext, hi - lo);
+        }
+        if (!(ext > 0.f)) ext = 1.f;
+        double h = (double)ext * (1.0 + 1e-6) / (double)G;
+        gi.h = h;
+        gi.inv_h = (float)(1.0 / h);
+    }
+    info[b] = gi;
+}
+
+// ------------------------------------------------------------------ 2. counting sort by cell
+__global__ void knn_count(const float *__restrict__ xyz, int64_t sb, int64_t sn, int B, int N, int G,
+                          const KnnGridInfo *__restrict__ info, int32_t *__restrict__ cell_of_point,
+                          int32_t *__restrict__ cell_count) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * N) return;
+    const int b = (int)(t / N), i = (int)(t % N);
+    const float *p = xyz + (int64_t)b * sb + (int64_t)i * sn;
+    const KnnGridInfo gi = info[b];
+    const int cx = knn_cell_coord(p[0], gi.lo[0], gi.inv_h, G);
+    const int cy = knn_cell_coord(p[1], gi.lo[1], gi.inv_h, G);
+    const int cz = knn_cell_coord(p[2], gi.lo[2], gi.inv_h, G);
+    const int cell = b * G * G * G + (cz * G + cy) * G + cx;
+    cell_of_point[t] = cell;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+__global__ void knn_scatter(const float *__restrict__ xyz, int64_t sb, int64_t sn, int B, int N,
+                            int periodic, float lower_f, float upper_f,
+                            const int32_t *__restrict__ cell_of_point, const int32_t *__restrict__ cell_start,
+                            int32_t *__restrict__ cell_fill, float4 *__restrict__ sorted) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)B * N) return;
+    const int b = (int)(t / N), i = (int)(t % N);
+    const float *p = xyz + (int64_t)b * sb + (int64_t)i * sn;
+    const float x = p[0], y = p[1], z = p[2];
+    int flags = 0;
+    if (periodic) {
+        // graph.py:842  bound = where(x >= upper, -1, where(x <= lower, +1, 0)), float32 compare
+        const int fx = (x >= upper_f) ? 2 : ((x <= lower_f) ? 1 : 0);
+        const int fy = (y >= upper_f) ? 2 : ((y <= lower_f) ? 1 : 0);
+        const int fz = (z >= upper_f) ? 2 : ((z <= lower_f) ? 1 : 0);
+        flags = fx | (fy << 2) | (fz << 4);
+    }
+    const int cell = cell_of_point[t];
+    const int pos = cell_start[cell] + atomicAdd(&cell_fill[cell], 1);
+    sorted[pos] = make_float4(x, y, z, __int_as_float(i | (flags << KNN_FLAG_SHIFT)));
+}
+
+// ------------------------------------------------------------------ 3. query
+template <int K>
+struct KnnTopK {
+    double d[K];
+    int id[K];
+    // slots [0, K-k) hold -inf sentinels so that d[K-1] is always the k-th best real entry
+    __device__ __forceinline__ void init(int k) {
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+            const bool sentinel = m < K - k;
+            d[m] = sentinel ? -INFINITY : INFINITY;
+            id[m] = sentinel ? -1 : 0x7FFFFFFF;
+        }
+    }
+    __device__ __forceinline__ bool accepts(double dd, int ii) const {
+        return dd < d[K - 1] || (dd == d[K - 1] && ii < id[K - 1]);
+    }
+    // precondition: accepts(dd, ii).  Fully predicated (no early exit): an early-exit loop makes the
+    // compiler index the arrays dynamically, which moves them from registers to local memory.
+    __device__ __forceinline__ void insert(double dd, int ii) {
+        bool below_m = true;  // new entry sorts before slot m (true for m = K-1 by the precondition)
+#pragma unroll
+        for (int m = K - 1; m > 0; --m) {
+            const bool below_m1 = dd < d[m - 1] || (dd == d[m - 1] && ii < id[m - 1]);
+            d[m] = below_m1 ? d[m - 1] : (below_m ? dd : d[m]);
+            id[m] = below_m1 ? id[m - 1] : (below_m ? ii : id[m]);
+            below_m = below_m1;
+        }
+        if (below_m) {
+            d[0] = dd;
+            id[0] = ii;
+        }
+    }
+    __device__ __forceinline__ void sort_ids_ascending() {  // bitonic network, K is a power of two
+#pragma unroll
+        for (int size = 2; size <= K; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+                for (int m = 0; m < K; ++m) {
+                    const int p = m ^ stride;
+                    if (p > m) {
+                        const bool asc = (m & size) == 0;
+                        const int a = id[m], b = id[p];
+                        const bool sw = asc ? (a > b) : (a < b);
+                        id[m] = sw ? b : a;
+                        id[p] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+};
+
+struct KnnQueryParams {
+    const float4 *sorted;
+    const int32_t *cell_start;
+    const KnnGridInfo *info;
+    int32_t *idx_out;
+    double *d2_out;
+    int B, N, G, k, include_self, order;
+};
+
+template <int K, bool PERIODIC>
+__global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= (int64_t)P.B * P.N) return;
+    const int b = (int)(s / P.N);
+    const int G = P.G;
+    const KnnGridInfo gi = P.info[b];
+    const float4 me = P.sorted[s];
+    const int my_id = __float_as_int(me.w) & KNN_IDX_MASK;
+    const double px = (double)me.x, py = (double)me.y, pz = (double)me.z;
+    const int cx = knn_cell_coord(me.x, gi.lo[0], gi.inv_h, G);
+    const int cy = knn_cell_coord(me.y, gi.lo[1], gi.inv_h, G);
+    const int cz = knn_cell_coord(me.z, gi.lo[2], gi.inv_h, G);
+    // distance (in cells) from the query to the nearest face of its own cell, clamped to [0, 0.5]
+    float margin;
+    {
+        const float fx = (me.x - gi.lo[0]) * gi.inv_h - (float)cx;
+        const float fy = (me.y - gi.lo[1]) * gi.inv_h - (float)cy;
+        const float fz = (me.z - gi.lo[2]) * gi.inv_h - (float)cz;
+        margin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
+        margin = fminf(fmaxf(margin, 0.f), 0.5f);
+    }
+    const int tmin = PERIODIC ? -G : 0, tmax = PERIODIC ? 2 * G - 1 : G - 1;  // extended cell coords
+    int Rmax = nbpc_max(nbpc_max(cx - tmin, tmax - cx), nbpc_max(nbpc_max(cy - tmin, tmax - cy), nbpc_max(cz - tmin, tmax - cz)));
+    const int64_t cellbase = (int64_t)b * G * G * G;
+    const bool skip_self = !P.include_self;
+
+    KnnTopK<K> top;
+    top.init(P.k);
+
+    for (int R = 0; R <= Rmax; ++R) {
+        for (int dz = -R; dz <= R; ++dz) {
+            int tz = cz + dz;
+            if (tz < tmin || tz > tmax) continue;
+            int sz = 0;
+            if (PERIODIC) {
+                if (tz < 0) { tz += G; sz = -1; } else if (tz >= G) { tz -= G; sz = 1; }
+            }
+            const bool zface = (dz == -R || dz == R);
+            for (int dy = -R; dy <= R; ++dy) {
+                int ty = cy + dy;
+                if (ty < tmin || ty > tmax) continue;
+                int sy = 0;
+                if (PERIODIC) {
+                    if (ty < 0) { ty += G; sy = -1; } else if (ty >= G) { ty -= G; sy = 1; }
+                }
+                const bool full_row = zface || dy == -R || dy == R;
+                const int64_t rowbase = cellbase + ((int64_t)tz * G + ty) * G;
+                // x ranges (extended coords): the whole run [cx-R, cx+R] on a shell face, otherwise its two ends
+                const int nparts = full_row ? 1 : 2;
+                for (int part = 0; part < nparts; ++part) {
+                    int x0 = full_row ? cx - R : (part == 0 ? cx - R : cx + R);
+                    int x1 = full_row ? cx + R : x0;
+                    if (full_row) {
+                        if (x0 < tmin) x0 = tmin;
+                        if (x1 > tmax) x1 = tmax;
+                    } else if (x0 < tmin || x0 > tmax) {
+                        continue;  // a single end cell outside the (extended) grid
+                    }
+                    // split into the shift -1 / 0 / +1 copies of the row
+                    const int nseg = PERIODIC ? 3 : 1;
+                    for (int seg = 0; seg < nseg; ++seg) {
+                        const int sx = PERIODIC ? seg - 1 : 0;
+                        const int lo = nbpc_max(x0, sx * G), hi = nbpc_min(x1, sx * G + G - 1);
+                        if (lo > hi) continue;
+                        const int jb = __ldg(&P.cell_start[rowbase + (lo - sx * G)]);
+                        const int je = __ldg(&P.cell_start[rowbase + (hi - sx * G) + 1]);
+                        // an image shifted by +1 exists only for particles flagged 1 (x <= lower),
+                        // by -1 only for particles flagged 2 (x >= upper)
+                        int req = 0, reqmask = 0;
+                        if (PERIODIC) {
+                            if (sx) { reqmask |= 3; req |= (sx > 0 ? 1 : 2); }
+                            if (sy) { reqmask |= 3 << 2; req |= (sy > 0 ? 1 : 2) << 2; }
+                            if (sz) { reqmask |= 3 << 4; req |= (sz > 0 ? 1 : 2) << 4; }
+                        }
+                        const bool unshifted = (sx | sy | sz) == 0;
+                        const double ox = (double)sx, oy = (double)sy, oz = (double)sz;
+                        for (int j = jb; j < je; ++j) {
+                            const float4 c = __ldg(&P.sorted[j]);
+                            const int w = __float_as_int(c.w);
+                            if (PERIODIC && (((w >> KNN_FLAG_SHIFT) & reqmask) != req)) continue;
+                            const int cid = w & KNN_IDX_MASK;
+                            if (skip_self && unshifted && cid == my_id) continue;
+                            const double tx = __dsub_rn(px, __dadd_rn((double)c.x, ox));
+                            const double ty2 = __dsub_rn(py, __dadd_rn((double)c.y, oy));
+                            const double tz2 = __dsub_rn(pz, __dadd_rn((double)c.z, oz));
+                            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty2, ty2)), __dmul_rn(tz2, tz2));
+                            if (top.accepts(dd, cid)) top.insert(dd, cid);
+                        }
+                    }
+                }
+            }
+        }
+        // everything not yet visited is at least (R + margin) cells away along some axis
+        const double g = ((double)R + (double)margin - 1e-3) * gi.h;
+        if (g > 0.0 && top.d[K - 1] < g * g) break;
+    }
+
+    const int64_t out = ((int64_t)b * P.N + my_id) * P.k;
+    if (P.d2_out) {
+#pragma unroll
+        for (int m = 0; m < K; ++m)
+            if (m >= K - P.k) P.d2_out[out + (m - (K - P.k))] = top.d[m];
+    }
+    if (P.order == NBPC_ORDER_INDEX) top.sort_ids_ascending();
+#pragma unroll
+    for (int m = 0; m < K; ++m)
+        if (m >= K - P.k) P.idx_out[out + (m - (K - P.k))] = top.id[m];
+}
+
+// ------------------------------------------------------------------ host side
+static int knn_grid_cells(int N) {
+    // ~2 particles per cell: with k=14 most queries finish after shell R=2 (125 cells, ~250 candidates)
+    int G = (int)floor(cbrt((double)N / 2.0));
+    if (G < 1) G = 1;
+    if (G > 256) G = 256;
+    return G;
+}
+
+struct KnnWorkspace {
+    unsigned *mm;
+    KnnGridInfo *info;
+    int32_t *cell_start;  // B*G^3 + 1
+    int32_t *cell_fill;   // B*G^3
+    int32_t *cell_of_point;
+    float4 *sorted;
+    int32_t *partials;
+    size_t bytes;
+};
+
+static KnnWorkspace knn_carve(void *ws, size_t ws_bytes, int B, int N, int G) {
+    NbpcArena a(ws, ws_bytes);
+    KnnWorkspace w;
+    const int64_t ncell = (int64_t)B * G * G * G;
+    w.mm = a.take<unsigned>((size_t)B * 6);
+    w.info = a.take<KnnGridInfo>((size_t)B);
+    w.cell_start = a.take<int32_t>((size_t)ncell + 1);
+    w.cell_fill = a.take<int32_t>((size_t)ncell);
+    w.cell_of_point = a.take<int32_t>((size_t)B * N);
+    w.sorted = a.take<float4>((size_t)B * N);
+    w.partials = a.take<int32_t>(nbpc_scan_partials_count(ncell + 1));
+    w.bytes = a.off;
+    return w;
+}
+
+template <int K>
+static void knn_launch_query(const KnnQueryParams &P, int periodic, cudaStream_t stream) {
+    const int grid = nbpc_cdiv((int64_t)P.B * P.N, KNN_THREADS);
+    void (*kern)(KnnQueryParams) = periodic ? knn_query<K, true> : knn_query<K, false>;
+    NBPC_LAUNCH(kern, grid, KNN_THREADS, 0, stream, P);
+}
+
+extern "C" {
+
+size_t nbpc_knn_workspace_bytes(int B, int N, int k, int periodic) {
+    (void)k; (void)periodic;
+    if (B < 1 || N < 1) return 0;
+    return knn_carve(nullptr, 0, B, N, knn_grid_cells(N)).bytes;
+}
+
+int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N, int k, int periodic,
+             double boundary_threshold, int include_self, int order, int32_t *idx_out, double *d2_out,
+             void *workspace, size_t ws_bytes, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(xyz && idx_out && workspace, "null pointer");
+    NBPC_ARG(B >= 1 && N >= 1, "B and N must be positive");
+    NBPC_ARG(N <= KNN_IDX_MASK, "N must be < 2^24");
+    NBPC_ARG((int64_t)B * N < (int64_t)1 << 31, "B*N must fit int32");
+    NBPC_ARG(k >= 1 && k <= NBPC_KNN_MAX_K, "k must be in [1, 64]");
+    NBPC_ARG(k <= N - (include_self ? 0 : 1), "k exceeds the number of available neighbours");
+    NBPC_ARG(stride_n >= 3, "stride_n must be >= 3");
+    NBPC_ARG(order == NBPC_ORDER_DISTANCE || order == NBPC_ORDER_INDEX, "bad order");
+    NBPC_ARG(!periodic || (boundary_threshold >= 0.0 && boundary_threshold <= 1.0), "boundary_threshold must be in [0,1]");
+    const int G = knn_grid_cells(N);
+    KnnWorkspace w = knn_carve(workspace, ws_bytes, B, N, G);
+    if (w.bytes > ws_bytes) {
+        nbpc_set_error("nbpc_knn: workspace too small");
+        return NBPC_EWORKSPACE;
+    }
+    const int64_t ncell = (int64_t)B * G * G * G;
+    const int64_t P_ = (int64_t)B * N;
+
+    if (!periodic) {
+        NBPC_LAUNCH(knn_bbox_init, nbpc_cdiv(B * 6, 64), 64, 0, stream, w.mm, B);
+        const int bx = nbpc_min(nbpc_cdiv(N, 256 * 8), 256);
+        NBPC_LAUNCH(knn_bbox_reduce, dim3(bx, B), 256, 0, stream, xyz, stride_b, stride_n, N, w.mm);
+    }
+    NBPC_LAUNCH(knn_grid_setup, nbpc_cdiv(B, 64), 64, 0, stream, w.mm, B, G, periodic, w.info);
+    if (nbpc_memset_async(w.cell_start, 0, sizeof(int32_t) * (size_t)(ncell + 1), stream) ||
+        nbpc_memset_async(w.cell_fill, 0, sizeof(int32_t) * (size_t)ncell, stream)) {
+        nbpc_set_error("nbpc_knn: memset failed");
+        return NBPC_ELAUNCH;
+    }
+    NBPC_LAUNCH(knn_count, nbpc_cdiv(P_, 256), 256, 0, stream, xyz, stride_b, stride_n, B, N, G, w.info,
+                w.cell_of_point, w.cell_start);
+    NBPC_TRY(nbpc_exclusive_scan_i32(w.cell_start, ncell + 1, w.partials, stream));
+    const float lower_f = (float)boundary_threshold, upper_f = (float)(1.0 - boundary_threshold);
+    NBPC_LAUNCH(knn_scatter, nbpc_cdiv(P_, 256), 256, 0, stream, xyz, stride_b, stride_n, B, N, periodic, lower_f,
+                upper_f, w.cell_of_point, w.cell_start, w.cell_fill, w.sorted);
+
+    KnnQueryParams P;
+    P.sorted = w.sorted; P.cell_start = w.cell_start; P.info = w.info;
+    P.idx_out = idx_out; P.d2_out = d2_out;
+    P.B = B; P.N = N; P.G = G; P.k = k; P.include_self = include_self; P.order = order;
+    if (k <= 8) knn_launch_query<8>(P, periodic, stream);
+    else if (k <= 16) knn_launch_query<16>(P, periodic, stream);
+    else if (k <= 32) knn_launch_query<32>(P, periodic, stream);
+    else knn_launch_query<64>(P, periodic, stream);
+    return nbpc_check_launch("nbpc_knn");
+}
+
+}  // extern "C"
