@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py - the reference's headline metric on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+metric  : particles/sec per train step (kNN + adjacency + features + fwd + bwd + Adam) at 32^3
+workload: BASELINE config 2 - 32^3 particles, k=14, 3-layer graph net [3,32,16,3], batch 8 per GPU
+          (weak scaling: every rank owns 8 samples; one NCCL all-reduce of the flat gradient per step).
+A "step" is one pass of the hot path over one batch of synthetic particle boxes.
+
+One JSON line on stdout (rank 0).  `value` = whole-job particles/s with inputs resident in HBM;
+`e2e` = the same through the public API with pinned HOST inputs copied H2D and the loss read back
+D2H inside every timed step.  `roofline` describes the dominant kernel (device time from CUDA events
+recorded by the library around each launch); `cpu_baseline` times the oracle port of the reference
+path on this box's host cores on a bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "particles/sec per train step (kNN+fwd+bwd) at 32^3"
+UNIT = "particles/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-side", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU")
+    ap.add_argument("--k", type=int, default=14)
+    ap.add_argument("--kind", default="uniform", choices=["uniform", "clustered"])
+    ap.add_argument("--channels", type=int, nargs="+", default=[3, 32, 16, 3])
+    ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the 128^3 kNN build timing")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.n_side}^3 particles, k={a.k}, graph net {a.channels}, batch {a.batch} per GPU, "
+            f"{a.kind} box, FP32 layers / FP64 kNN distances")
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_step(x, za, tgt, k, channels, params):
+    """One step of the reference path, restated op for op (oracle/): sklearn KD-tree kNN
+    (graph.py:704-713) -> COO (621-662) -> model_func_shift_inv_za (479-515) -> loss_ZA -> backward."""
+    from oracle import ref_graph, ref_layers
+    b, N, _ = x.shape
+    t0 = time.perf_counter()
+    A = ref_graph.get_kneighbor_list(x, k)
+    t1 = time.perf_counter()
+    coo, diag = ref_graph.to_coo_batch_ZA_diag(A)
+    t2 = time.perf_counter()
+    tp = [([torch.tensor(w, requires_grad=True) for w in Ws], torch.tensor(B, requires_grad=True)) for Ws, B in params]
+    mv = types.SimpleNamespace(channels=channels, get_layer_vars=lambda i: tp[i])
+    pred = ref_layers.model_func_shift_inv_za(torch.tensor(x), coo, torch.tensor(za), diag, mv, (b, N, k))
+    loss = ref_layers.loss_ZA(pred, torch.tensor(tgt))
+    t3 = time.perf_counter()
+    loss.backward()
+    t4 = time.perf_counter()
+    return {"knn": t1 - t0, "coo": t2 - t1, "fwd": t3 - t2, "bwd": t4 - t3, "total": t4 - t0, "loss": float(loss.detach())}
+
+
+def cpu_sample(a, syn, steps, warmup):
+    N = a.n_side ** 3
+    b = a.cpu_batch
+    params = syn.glorot_params(a.channels)
+    x = syn.make_box(a.kind, b, N, 0)
+    za, tgt = syn.za_features(b, N, 0)
+    for _ in range(warmup):
+        cpu_reference_step(x, za, tgt, a.k, a.channels, params)
+    parts, t0 = [], time.perf_counter()
+    for _ in range(steps):
+        parts.append(cpu_reference_step(x, za, tgt, a.k, a.channels, params))
+    dt = (time.perf_counter() - t0) / steps
+    stage = {s: float(np.mean([p[s] for p in parts])) for s in ("knn", "coo", "fwd", "bwd")}
+    return b * N / dt, dt, stage
+
+
+def run_reference(a):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port - the reference is
+    pure Python and /root/reference does not exist on the GPU box), all host threads torch can use."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    syn = importlib.import_module("n-body_pointcloudevolution_b200.synthetic")
+    value, dt, stage = cpu_sample(a, syn, a.steps, min(a.warmup, 1))
+    cores = torch.get_num_threads()
+    sample = (f"{a.cpu_batch} samples of the {a.n_side}^3 workload per step "
+              f"(kNN sklearn 1 thread, layers torch-CPU {cores} threads)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "reference_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "stage_s": stage},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+class ClockSampler:
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="nbpc_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={CLOCK_QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        try:
+            for line in open(self.path):
+                f = [c.strip() for c in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+# ----------------------------------------------------------------------------- roofline bookkeeping
+def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
+    """Algorithmic (minimum) bytes one launch of `name` must move (FP32, s = 4 B).
+    c = b*N*M edges, n = b*N nodes; node-level operands are counted once (they are L2-resident)."""
+    n, c = b * N, b * N * M
+    base, k, q = name, None, None
+    if "[" in name:
+        base, dims = name.split("[")
+        k, q = (int(t.split("=")[1]) for t in dims.rstrip("]").split(","))
+    relu = 2 if (k, q) in relu_by_layer and relu_by_layer[(k, q)] else 1   # masked dZ also reads H_out
+    if base == "knn_query":
+        return n * (12 + 4 * M)                      # xyz in, int32 idx out
+    if base == "gl_pool_kernel":
+        return c * (2 * 4 * k + 4) + n * (4 + 2 * 4 * k)
+    if base == "gl_edge_out_kernel":
+        return c * (4 * k + 4 + 4 * q) + n * 2 * 4 * q
+    if base == "gl_last_out_kernel":
+        return c * (4 * k + 4) + n * 3 * 4 * q
+    if base == "glb_pool_kernel":
+        return c * (2 * 4 * q * relu + 4) + n * (4 + 2 * 4 * q)
+    if base == "xty_partial_dW1":
+        return c * (4 * k + 4 * q * relu)
+    if base == "glb_edge_in_kernel":
+        return c * (4 * q * relu + 4 + 4 * k) + n * 2 * 4 * k
+    if base == "edge_features_kernel":
+        return c * (4 + 12) + n * 12
+    if base in ("adj_coo_kernel",):
+        return c * (4 + 12)
+    if base in ("seg_count_kernel", "seg_fill_kernel"):
+        return c * 8
+    return None
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(name):
+    """dram bytes per launch from the committed ncu capture, if one exists for this kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(name.split("[")[0])
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200 GPU (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group("nccl", device_id=dev)
+
+    nb = importlib.import_module("n-body_pointcloudevolution_b200")
+    syn, graph, nn_, tu, lib = nb.synthetic, nb.graph, nb.nn, nb.train_utils, nb._lib
+    nb.ops.device_check()
+
+    N, b, k, ch = a.n_side ** 3, a.batch, a.k, a.channels
+    store = tu.ParamStore(ch, device=dev)
+    store.load_numpy(syn.glorot_params(ch))
+    adam = tu.AdamTF(store, lr=0.01)
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+
+    # a pool of distinct batches (different boxes every step; every rank owns its own samples)
+    n_pool = 4
+    host = []
+    for i in range(n_pool):
+        seed = 1000 * rank + i
+        x = syn.make_box(a.kind, b, N, seed)
+        za, tgt = syn.za_features(b, N, seed)
+        host.append(tuple(torch.from_numpy(t).pin_memory() for t in (x, za, tgt)))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
+
+    def train_step(x, za, tgt, comm=True):
+        A = graph.get_kneighbor_list(x, k)                           # kNN rebuilt every step
+        coo, diag = graph.to_coo_batch_ZA_diag(A)
+        pred = graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
+        loss = nn_.loss_ZA(pred, tgt)
+        store.zero_grad()
+        loss.backward()
+        if comm:
+            tu.allreduce_gradients(store, world)
+        adam.step(grad_scale=1.0 / world)
+        return loss
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_resident(i):
+        train_step(*resident[i % n_pool])
+
+    def step_e2e(i):
+        hb = host[i % n_pool]
+        for d, h in zip(staging, hb):
+            d.copy_(h, non_blocking=True)                            # H2D from pinned memory
+        return float(train_step(*staging).item())                    # D2H read of the loss
+
+    # ---- warm-up, then the timed region (device-resident inputs)
+    for i in range(max(a.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.launch_count()
+    ms = timed(step_resident, a.steps)
+    launches = lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else {}
+    particles = world * b * N
+    value = particles * a.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, a.steps)
+    e2e_value = particles * a.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
+
+    # ---- per-kernel device times (library-side CUDA events on the launching stream), rank 0
+    prof_steps = 3
+    torch.cuda.synchronize()
+    lib.prof_enable(True)
+    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_ev0.record()
+    for i in range(prof_steps):
+        train_step(*resident[i % n_pool], comm=False)
+    t_ev1.record()
+    torch.cuda.synchronize()
+    report = lib.prof_report()
+    lib.prof_enable(False)
+    kern_ms = {n: tot / prof_steps for n, (cnt, tot) in report.items()}
+    kern_cnt = {n: cnt / prof_steps for n, (cnt, tot) in report.items()}
+    sum_ms = sum(kern_ms.values())
+    relu_by_layer = {(kk, qq): (li < len(ch) - 2) for li, (kk, qq) in enumerate(zip(ch[:-1], ch[1:]))}
+    peak, peak_src = measured_peak_gbs()
+    top = sorted(kern_ms.items(), key=lambda kv: -kv[1])
+    kernels = []
+    for name, t in top[:12]:
+        per_launch_ms = t / kern_cnt[name]
+        ab = kernel_algorithmic_bytes(name, b, N, k, relu_by_layer)
+        kernels.append({"kernel": name, "ms_per_step": round(t, 4), "launches_per_step": kern_cnt[name],
+                        "share": round(t / sum_ms, 4),
+                        "algorithmic_bytes": ab,
+                        "achieved_gbs": (ab / (per_launch_ms * 1e-3) / 1e9) if ab else None})
+    dom = kernels[0]
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s",
+                "frac": (dom["achieved_gbs"] / peak) if dom["achieved_gbs"] else None,
+                "traffic": ncu_traffic(dom["kernel"]), "share_of_step": dom["share"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
+                "step_algorithmic_bytes": None, "kernels": kernels}
+    # whole-step roofline (SURVEY §8d contract figure: 1428 B/edge + 68 B + 280 B per particle for [3,32,16,3], k=14)
+    if ch == [3, 32, 16, 3]:
+        c_edges = b * N * k
+        step_bytes = 1428 * c_edges + (12 + 4 * k) * b * N + 20 * c_edges + 16 * b * N
+        roofline["step_algorithmic_bytes"] = step_bytes
+        roofline["step_achieved"] = step_bytes / (ms / a.steps * 1e-3) / 1e9
+        roofline["step_frac"] = roofline["step_achieved"] / peak
+
+    # ---- secondary metric: kNN build ms at 128^3 (periodic, k=14)
+    extras = {}
+    if not a.no_extras:
+        for kind in ("uniform", "clustered"):
+            xb = torch.from_numpy(syn.make_box(kind, 1, 128 ** 3, 0)).to(dev)
+            for _ in range(2):
+                graph.get_pbc_kneighbors_csr(xb, 14, 0.05, include_self=True)
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            reps = 5
+            for _ in range(reps):
+                graph.get_pbc_kneighbors_csr(xb, 14, 0.05, include_self=True)
+            ev[1].record()
+            torch.cuda.synchronize()
+            t_ms = ev[0].elapsed_time(ev[1]) / reps
+            ab = 128 ** 3 * (12 + 4 * 14)
+            extras[f"knn_build_ms_128^3_{kind}"] = t_ms
+            extras[f"knn_128^3_{kind}_roofline_frac"] = ab / (t_ms * 1e-3) / 1e9 / peak
+            del xb
+
+    # ---- the reference's CPU path on this box's host cores (bounded sample)
+    cpu = None
+    if not a.no_cpu_baseline and world == 1:
+        v, dt, stage = cpu_sample(a, syn, 1, 1)
+        cores = torch.get_num_threads()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"1 step of {a.cpu_batch} samples of the same {a.n_side}^3/k={a.k} workload "
+                         f"(kNN: sklearn KD-tree, 1 thread as shipped; layers: torch-CPU, {cores} threads)",
+               "stage_s": stage}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "particles_per_step": particles, "edges_per_step": particles * k,
+                   "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)",
+                   "l2": "step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "extras": extras,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,15 @@ const char *nbpc_last_error_string(void);
 /* NBPC_OK if the current CUDA device is compute capability 10.0, else NBPC_EARCH. */
 int nbpc_device_check(void);
 
+/* Tracing (replaces the reference's single wall-clock timer around the training loop,
+ * train.py:84, 122-124).  nbpc_launch_count(): kernels launched by this library so far in the
+ * process.  nbpc_prof_enable(1) clears the records and starts bracketing every launch with CUDA
+ * events on its stream; nbpc_prof_report() writes "kernel\tlaunches\ttotal_ms\n" lines (it waits
+ * for the recorded events) and returns the buffer size needed.  Host-side only, not for hot loops. */
+long long nbpc_launch_count(void);
+int nbpc_prof_enable(int on);
+long long nbpc_prof_report(char *buf, size_t cap);
+
 /* ---------------------------------------------------------------- kNN graph
  * Replaces graph.get_kneighbor_list (graph.py:704-713; periodic=0) and
  * graph.get_pbc_kneighbors_csr + pad_cube_boundaries + get_pcube_csr (graph.py:801-917; periodic=1).

@@ -27,6 +27,9 @@ SIGNATURES = {
     "nbpc_version": (_i, []),
     "nbpc_last_error_string": (ctypes.c_char_p, []),
     "nbpc_device_check": (_i, []),
+    "nbpc_launch_count": (ctypes.c_longlong, []),
+    "nbpc_prof_enable": (_i, [_i]),
+    "nbpc_prof_report": (ctypes.c_longlong, [ctypes.c_char_p, _sz]),
     "nbpc_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "nbpc_knn": (_i, [_p, _i64, _i64, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _sz, _p]),
     "nbpc_adjacency_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -86,3 +89,25 @@ def last_error():
 def check(rc, what):
     if rc != NBPC_OK:
         raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def launch_count():
+    """Kernels launched by libnbpc.so so far in this process."""
+    return int(load().nbpc_launch_count())
+
+
+def prof_enable(on=True):
+    load().nbpc_prof_enable(int(bool(on)))
+
+
+def prof_report():
+    """{kernel name: (launches, total_ms)} since prof_enable(True); waits for the recorded events."""
+    L = load()
+    need = L.nbpc_prof_report(None, 0)
+    buf = ctypes.create_string_buffer(int(need) + 16)
+    L.nbpc_prof_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out

@@ -51,7 +51,81 @@ int nbpc_require_sm100() {
 #endif
 }
 
+// ------------------------------------------------------------------ launch counter + event profiler
+unsigned long long g_nbpc_launches = 0;
+int g_nbpc_prof_on = 0;
+
+#ifndef NBPC_HOST_EMU
+#include <map>
+#include <mutex>
+#include <vector>
+namespace {
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+std::mutex g_prof_mu;
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+void nbpc_prof_pre(const char *name, cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfRec r;
+    r.name = name; r.a = prof_event(); r.b = prof_event();
+    cudaEventRecord(r.a, stream);
+    g_prof_recs.push_back(r);
+}
+void nbpc_prof_post(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_recs.empty()) cudaEventRecord(g_prof_recs.back().b, stream);
+}
+#endif
+
 extern "C" {
+
+long long nbpc_launch_count(void) { return (long long)g_nbpc_launches; }
+
+int nbpc_prof_enable(int on) {
+#ifndef NBPC_HOST_EMU
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto &r : g_prof_recs) { g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b); }
+    g_prof_recs.clear();
+#endif
+    g_nbpc_prof_on = on ? 1 : 0;
+    return NBPC_OK;
+}
+
+// Writes "name\tlaunches\ttotal_ms\n" per kernel (aggregated over the records since the last
+// nbpc_prof_enable) into buf; returns the number of bytes needed (call again with a larger buffer if
+// it exceeds cap).  Synchronises on the recorded events.
+long long nbpc_prof_report(char *buf, size_t cap) {
+    std::string out;
+#ifndef NBPC_HOST_EMU
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<long long, double>> agg;
+    std::vector<std::string> order;
+    for (auto &r : g_prof_recs) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto it = agg.find(r.name);
+        if (it == agg.end()) { order.push_back(r.name); agg[r.name] = std::make_pair(1LL, (double)ms); }
+        else { it->second.first += 1; it->second.second += ms; }
+    }
+    for (auto &n : order) {
+        out += n + "\t" + std::to_string(agg[n].first) + "\t" + std::to_string(agg[n].second) + "\n";
+    }
+#endif
+    if (buf && cap > 0) {
+        size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return (long long)out.size() + 1;
+}
 
 int nbpc_version(void) { return 100; /* 0.1.0 */ }
 

@@ -331,19 +331,19 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
         return NBPC_EWORKSPACE;
     }
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
-    NBPC_LAUNCH(gl_pool_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, M, (int)BN, csrT_ptr,
+    NBPC_LAUNCH_N(NbpcKName("gl_pool_kernel", k, q).c_str(), gl_pool_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, M, (int)BN, csrT_ptr,
                 csrT_edge, P_row, P_col);
     NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, P_row, k, N,
                 nblk, B, w.cube_partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, k, nblk, B,
                 (float)N, P_cube);
-    NBPC_LAUNCH(gl_node_project_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, P_col, P_row, P_cube, W,
+    NBPC_LAUNCH_N(NbpcKName("gl_node_project_kernel", k, q).c_str(), gl_node_project_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, P_col, P_row, P_cube, W,
                 bias, (int)BN, N, k, q, w.Qc, w.Qr);
     if (is_last) {
-        NBPC_LAUNCH(gl_last_out_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr,
+        NBPC_LAUNCH_N(NbpcKName("gl_last_out_kernel", k, q).c_str(), gl_last_out_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr,
                     (int)BN, M, k, q, relu, H_out);
     } else {
-        NBPC_LAUNCH(gl_edge_out_kernel, nbpc_cdiv(c * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr, c, M,
+        NBPC_LAUNCH_N(NbpcKName("gl_edge_out_kernel", k, q).c_str(), gl_edge_out_kernel, nbpc_cdiv(c * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr, c, M,
                     k, q, relu, H_out);
     }
     return nbpc_check_launch("nbpc_graph_layer_fwd");
@@ -373,7 +373,7 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     float *dQ_col = w.Qc, *dQ_row = w.Qr;
     const int64_t kq = (int64_t)k * q;
 
-    NBPC_LAUNCH(glb_pool_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, dz, (int)BN, M, q, csrT_ptr,
+    NBPC_LAUNCH_N(NbpcKName("glb_pool_kernel", k, q).c_str(), glb_pool_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, dz, (int)BN, M, q, csrT_ptr,
                 csrT_edge, dQ_row, dQ_col);
     NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dQ_row, q, N,
                 nblk, B, w.cube_partial);
@@ -384,17 +384,17 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     GlPlain x, y;
     x.ld = k; y.ld = q;
     x.p = H_in;
-    xty(x, dz, c, k, q, w.xty_partial, dW, stream);
+    xty(NbpcKName("xty_partial_dW1", k, q).c_str(), x, dz, c, k, q, w.xty_partial, dW, stream);
     x.p = P_col; y.p = dQ_col;
-    xty(x, y, BN, k, q, w.xty_partial, dW + kq, stream);
+    xty("xty_partial_dW2", x, y, BN, k, q, w.xty_partial, dW + kq, stream);
     x.p = P_row; y.p = dQ_row;
-    xty(x, y, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
+    xty("xty_partial_dW3", x, y, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
     x.p = P_cube; y.p = w.dCq;
-    xty(x, y, (int64_t)B, k, q, w.xty_partial, dW + 3 * kq, stream);
+    xty("xty_partial_dW4", x, y, (int64_t)B, k, q, w.xty_partial, dW + 3 * kq, stream);
     if (dH_in) {
-        NBPC_LAUNCH(glb_node_grad_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, dQ_col, dQ_row, w.dCq, W,
+        NBPC_LAUNCH_N(NbpcKName("glb_node_grad_kernel", k, q).c_str(), glb_node_grad_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, dQ_col, dQ_row, w.dCq, W,
                     csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
-        NBPC_LAUNCH(glb_edge_in_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0, stream, dz, col, W, w.Gc, w.Gr, c, M, k,
+        NBPC_LAUNCH_N(NbpcKName("glb_edge_in_kernel", k, q).c_str(), glb_edge_in_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0, stream, dz, col, W, w.Gc, w.Gr, c, M, k,
                     q, dH_in);
     }
     return nbpc_check_launch("nbpc_graph_layer_bwd");

@@ -354,7 +354,7 @@ template <int K>
 static void knn_launch_query(const KnnQueryParams &P, int periodic, cudaStream_t stream) {
     const int grid = nbpc_cdiv((int64_t)P.B * P.N, KNN_THREADS);
     void (*kern)(KnnQueryParams) = periodic ? knn_query<K, true> : knn_query<K, false>;
-    NBPC_LAUNCH(kern, grid, KNN_THREADS, 0, stream, P);
+    NBPC_LAUNCH_N("knn_query", kern, grid, KNN_THREADS, 0, stream, P);
 }
 
 extern "C" {

@@ -130,7 +130,7 @@ static int loss_fwd_impl(const float *pred, int ldp, const float *truth, int ldt
     }
     float *partial = (float *)workspace;
     void (*kern)(const float *, int, const float *, int, int64_t, int, float *) = loss_partial_kernel<PBC>;
-    NBPC_LAUNCH(kern, nbpc_cdiv(nchunks, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows, nchunks, partial);
+    NBPC_LAUNCH_N("loss_partial_kernel", kern, nbpc_cdiv(nchunks, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows, nchunks, partial);
     NBPC_LAUNCH(loss_final_kernel, 1, 32, 0, stream, partial, nchunks, (float)rows, scale, loss_out);
     return nbpc_check_launch(name);
 }
@@ -142,7 +142,7 @@ static int loss_bwd_impl(const float *pred, int ldp, const float *truth, int ldt
     NBPC_ARG(pred && truth && dloss && dpred, "null pointer");
     NBPC_ARG(rows >= 1 && ldp >= 3 && ldt >= 3 && ldd >= 3, "bad sizes");
     void (*kern)(const float *, int, const float *, int, int64_t, float, const float *, float *, int) = loss_bwd_kernel<PBC>;
-    NBPC_LAUNCH(kern, nbpc_cdiv(rows * 3, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows, scale, dloss,
+    NBPC_LAUNCH_N("loss_bwd_kernel", kern, nbpc_cdiv(rows * 3, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows, scale, dloss,
                 dpred, ldd);
     return nbpc_check_launch(name);
 }

@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <stdio.h>
 
 #include <string>
 
@@ -60,7 +61,8 @@ static inline void nbpc_emu_launch(K kern, dim3 grid, dim3 block, A... args) {
             kern(args...);
         }
 }
-#define NBPC_LAUNCH(kern, grid, block, smem, stream, ...) nbpc_emu_launch(kern, dim3(grid), dim3(block), __VA_ARGS__)
+#define NBPC_LAUNCH_N(name, kern, grid, block, smem, stream, ...) nbpc_emu_launch(kern, dim3(grid), dim3(block), __VA_ARGS__)
+#define NBPC_LAUNCH(kern, grid, block, smem, stream, ...) NBPC_LAUNCH_N(#kern, kern, grid, block, smem, stream, __VA_ARGS__)
 static inline int nbpc_memset_async(void *p, int v, size_t n, cudaStream_t) { memset(p, v, n); return 0; }
 static inline int nbpc_launch_status() { return 0; }
 #else
@@ -68,11 +70,38 @@ static inline int nbpc_launch_status() { return 0; }
 #include <cuda_runtime.h>
 template <class T> __host__ __device__ __forceinline__ T nbpc_min(T a, T b) { return a < b ? a : b; }
 template <class T> __host__ __device__ __forceinline__ T nbpc_max(T a, T b) { return a > b ? a : b; }
-#define NBPC_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// Every kernel launch goes through this macro: it counts launches (nbpc_launch_count) and, when
+// profiling is enabled (nbpc_prof_enable), brackets the launch with CUDA events on the launching
+// stream so that bench.py can report per-kernel device times (nbpc_prof_report).
+extern int g_nbpc_prof_on;
+extern unsigned long long g_nbpc_launches;
+void nbpc_prof_pre(const char *name, cudaStream_t stream);
+void nbpc_prof_post(cudaStream_t stream);
+#define NBPC_LAUNCH_N(name, kern, grid, block, smem, stream, ...)       \
+    do {                                                                \
+        ++g_nbpc_launches;                                              \
+        if (g_nbpc_prof_on) nbpc_prof_pre(name, stream);                \
+        kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);       \
+        if (g_nbpc_prof_on) nbpc_prof_post(stream);                     \
+    } while (0)
+#define NBPC_LAUNCH(kern, grid, block, smem, stream, ...) NBPC_LAUNCH_N(#kern, kern, grid, block, smem, stream, __VA_ARGS__)
 static inline int nbpc_memset_async(void *p, int v, size_t n, cudaStream_t s) {
     return cudaMemsetAsync(p, v, n, s) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+// kernel name carrying the layer widths ("gl_edge_out_kernel[k=32,q=16]"); only built while profiling
+struct NbpcKName {
+    char buf[96];
+    const char *base;
+    NbpcKName(const char *b, int k, int q) : base(b) {
+        buf[0] = 0;
+#ifndef NBPC_HOST_EMU
+        if (g_nbpc_prof_on) snprintf(buf, sizeof(buf), "%s[k=%d,q=%d]", b, k, q);
+#endif
+    }
+    const char *c_str() const { return buf[0] ? buf : base; }
+};
 
 // ------------------------------------------------------------------ errors
 void nbpc_set_error(const std::string &msg);

@@ -74,10 +74,11 @@ static void xty_plan(int64_t n, int k, int q, int *rows_per_chunk, int *nchunks)
 }
 
 template <class XAcc, class YAcc>
-static void xty(XAcc X, YAcc Y, int64_t n, int k, int q, float *partial, float *out, cudaStream_t stream) {
+static void xty(const char *name, XAcc X, YAcc Y, int64_t n, int k, int q, float *partial, float *out, cudaStream_t stream) {
+    (void)name;
     int rpc, nc;
     xty_plan(n, k, q, &rpc, &nc);
     void (*kern)(XAcc, YAcc, int64_t, int, int, int, int, float *) = xty_partial_kernel<XAcc, YAcc>;
-    NBPC_LAUNCH(kern, nbpc_cdiv((int64_t)nc * k * q, GL_THREADS), GL_THREADS, 0, stream, X, Y, n, rpc, nc, k, q, partial);
+    NBPC_LAUNCH_N(name, kern, nbpc_cdiv((int64_t)nc * k * q, GL_THREADS), GL_THREADS, 0, stream, X, Y, n, rpc, nc, k, q, partial);
     NBPC_LAUNCH(xty_final_kernel, nbpc_cdiv(k * q, GL_THREADS), GL_THREADS, 0, stream, partial, nc, k * q, out);
 }

@@ -99,9 +99,9 @@ nbpc_scan_apply(int32_t *__restrict__ data, int64_t n, const int32_t *__restrict
 static inline int nbpc_exclusive_scan_i32(int32_t *data, int64_t n, int32_t *partials, cudaStream_t stream) {
     if (n <= 0) return NBPC_OK;
     const int nchunks = (int)((n + NBPC_SCAN_CHUNK - 1) / NBPC_SCAN_CHUNK);
-    nbpc_scan_chunk_sums<<<nchunks, NBPC_SCAN_THREADS, 0, stream>>>(data, n, partials);
-    nbpc_scan_partials<<<1, 1024, 0, stream>>>(partials, nchunks);
-    nbpc_scan_apply<<<nchunks, NBPC_SCAN_THREADS, 0, stream>>>(data, n, partials);
+    NBPC_LAUNCH(nbpc_scan_chunk_sums, nchunks, NBPC_SCAN_THREADS, 0, stream, data, n, partials);
+    NBPC_LAUNCH(nbpc_scan_partials, 1, 1024, 0, stream, partials, nchunks);
+    NBPC_LAUNCH(nbpc_scan_apply, nchunks, NBPC_SCAN_THREADS, 0, stream, data, n, partials);
     return nbpc_check_launch("nbpc_exclusive_scan_i32");
 }
 #endif

@@ -144,7 +144,7 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
     NBPC_LAUNCH(set_bias_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.colsum, B, q, dB);
     SetXCentered X;
     X.h = H_in; X.mu = mu; X.k = k; X.N = N;
-    xty(X, dz, rows, k, q, w.xty_partial, dW, stream);
+    xty("xty_partial_set_dW", X, dz, rows, k, q, w.xty_partial, dW, stream);
     if (dH_in)
         NBPC_LAUNCH(set_bwd_in_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, dz, w.colsum, W, rows, N, k, q,
                     dH_in);

@@ -1,0 +1,302 @@
+"""Drop-in for the hot-path functions of /root/reference/graph.py - same names, argument order
+and return structure, with torch CUDA tensors where the reference had NumPy arrays / TF tensors.
+
+Graph construction (reference: scikit-learn KD-tree on the host, every step) and every layer op
+(reference: TF stock ops) run as hand-written sm_100a kernels in libnbpc.so.  No CPU fallback.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * kNN results are `KnnCSR` objects exposing the SciPy-CSR attributes the reference touches
+    (`.indices`, `.indptr`, `.shape`, `.nonzero()`, `.tocoo()`) as device tensors;
+  * exact-distance ties are broken by ascending particle index (sklearn: KD-tree traversal order);
+  * `COO_feats` returned by `to_coo_batch*` carries the precomputed CSR transpose as an attribute;
+    a plain (3,c) tensor/array is accepted too (the transpose is then built on first use).
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import ops
+
+__all__ = [
+    "KnnCSR", "Adjacency", "get_kneighbor_list", "get_pbc_kneighbors_csr", "pad_cube_boundaries",
+    "get_indices_from_list_CSR", "to_coo_batch_ZA_diag", "to_coo_batch", "confirm_CSR_to_COO_index_integrity",
+    "include_node_features", "get_input_features_shift_inv_ZA", "get_input_features_shift_inv",
+    "shift_inv_conv", "shift_inv_layer", "network_func_shift_inv_za", "model_func_shift_inv_za",
+]
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("n-body_pointcloudevolution_b200 needs an sm_100 (B200) GPU; there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_cuda(x, dtype=None):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    elif not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if not x.is_cuda:
+        x = x.to(_dev(), non_blocking=True)
+    if dtype is not None and x.dtype != dtype:
+        x = x.to(dtype)
+    return x
+
+
+# =============================================================================== kNN results
+class KnnCSR:
+    """One sample's kNN graph: the subset of scipy.sparse.csr_matrix the reference uses."""
+
+    def __init__(self, batch_idx, sample, n_cols=None, offset=0):
+        self._batch = batch_idx          # (B, N, M) int32, shared by the whole batch (local indices)
+        self._sample = sample
+        self._offset = offset            # graph.py:710-711 offset_idx
+        self._n_cols = n_cols
+        _, self.N, self.M = batch_idx.shape
+
+    @property
+    def indices(self):
+        ind = self._batch[self._sample].reshape(-1)
+        return ind + self._offset if self._offset else ind
+
+    @property
+    def indptr(self):
+        return torch.arange(0, self.N * self.M + 1, self.M, dtype=torch.int32, device=self._batch.device)
+
+    @property
+    def data(self):
+        return torch.ones(self.N * self.M, dtype=torch.float32, device=self._batch.device)
+
+    @property
+    def shape(self):
+        n_cols = self._n_cols() if callable(self._n_cols) else (self._n_cols or self.N)
+        return (self.N, int(n_cols))
+
+    def nonzero(self):
+        rows = torch.arange(self.N, dtype=torch.int32, device=self._batch.device).repeat_interleave(self.M)
+        return rows, self.indices
+
+    def tocoo(self):
+        r, c = self.nonzero()
+        return SimpleNamespace(row=r, col=c, data=self.data, shape=self.shape)
+
+    def toarray_indices(self):
+        """(N, M) view of the neighbour indices."""
+        return self.indices.view(self.N, self.M)
+
+
+def _as_batch(A):
+    """list of KnnCSR produced by one kNN call -> the shared (B,N,M) tensor (no copy), else stack."""
+    if isinstance(A, torch.Tensor) and A.dim() == 3:
+        return _to_cuda(A, torch.int32)
+    if all(isinstance(a, KnnCSR) for a in A):
+        first = A[0]._batch
+        if (first.shape[0] == len(A) and all(a._batch is first and a._sample == i and not a._offset
+                                              for i, a in enumerate(A))):
+            return first
+        return torch.stack([a._batch[a._sample] for a in A])
+    # scipy CSR matrices (e.g. produced by the reference itself)
+    N = A[0].shape[0]
+    return _to_cuda(np.stack([np.asarray(a.indices).reshape(N, -1) for a in A]), torch.int32)
+
+
+def get_kneighbor_list(X_in, M, offset_idx=False, include_self=True):
+    """graph.py:704-713.  X_in (b,N,D>=3) -> list of b KnnCSR of shape (N,N); per-row indices in
+    ASCENDING COLUMN order, int32 (what `.astype(np.float32)` does to the sklearn result)."""
+    X = _to_cuda(X_in, torch.float32)
+    b, N, D = X.shape
+    idx, _ = ops.knn(X, int(M), False, 0.0, bool(include_self), ops._lib.ORDER_INDEX, False)
+    return [KnnCSR(idx, i, N, offset=(N * i if offset_idx else 0)) for i in range(b)]
+
+
+def _n_padded(X, thr):
+    """Number of points of the reference's padded cloud (graph.py:827-855): N + sum(2^nb - 1)."""
+    def f():
+        x = X[..., :3]
+        upper = torch.tensor(1 - thr, dtype=torch.float32, device=X.device)
+        lower = torch.tensor(thr, dtype=torch.float32, device=X.device)
+        nb = ((x >= upper) | (x <= lower)).sum(-1)
+        return X.shape[0] + int(((2 ** nb) - 1).sum().item())
+    return f
+
+
+def get_pbc_kneighbors_csr(X, K, boundary_threshold, include_self=False):
+    """graph.py:896-917 (+ pad_cube_boundaries 827-855, get_pcube_csr 877-894).  Unit periodic box;
+    rows stay DISTANCE-sorted, image columns are mapped back to the original particle."""
+    Xc = _to_cuda(X, torch.float32)
+    mb_size, N, D = Xc.shape
+    idx, _ = ops.knn(Xc, int(K), True, float(boundary_threshold), bool(include_self), ops._lib.ORDER_DISTANCE, False)
+    return [KnnCSR(idx, i, _n_padded(Xc[i], float(boundary_threshold))) for i in range(mb_size)]
+
+
+def pad_cube_boundaries(x, boundary_threshold):
+    raise NotImplementedError(
+        "pad_cube_boundaries (graph.py:827-855) is folded into the periodic kNN kernel: images are generated "
+        "on the fly from the same (x >= 1-thr / x <= thr) rule; call get_pbc_kneighbors_csr")
+
+
+# =============================================================================== adjacency
+class Adjacency:
+    """COO (3,c) + diagonals + CSR transpose of a fixed-degree batch graph (c = b*N*M edges)."""
+
+    def __init__(self, coo, diag, csrT_ptr, csrT_edge, status, b, N, M):
+        self.coo, self.diag, self.csrT_ptr, self.csrT_edge, self.status = coo, diag, csrT_ptr, csrT_edge, status
+        self.b, self.N, self.M = b, N, M
+        self._seg_cache = {}
+
+    @property
+    def col(self):
+        return self.coo[1]
+
+    def check(self):
+        """Host-synchronising sanity check: one self edge per row, all indices in range."""
+        bad_diag, bad_idx = self.status.tolist()
+        if bad_idx:
+            raise ValueError(f"adjacency: {bad_idx} neighbour indices out of range")
+        return bad_diag == 0
+
+
+def _attach(coo, adj):
+    coo._nbpc_adjacency = adj
+    return coo
+
+
+def _build_adjacency(A):
+    idx = _as_batch(A)
+    b, N, M = idx.shape
+    coo, diag, ptr, edge, status = ops.adjacency(idx)
+    return Adjacency(coo, diag, ptr, edge, status, b, N, M)
+
+
+def to_coo_batch_ZA_diag(A):
+    """graph.py:621-662 -> (COO_feats (3, b*N*M) int32, diagonals (b*N,) int64).
+    `diagonals[n]` is the flat position of row n's self edge (-1 if a row has none; the reference
+    would return a shorter array in that case)."""
+    adj = _build_adjacency(A)
+    return _attach(adj.coo, adj), adj.diag
+
+
+def to_coo_batch(A):
+    """graph.py:664-697"""
+    return to_coo_batch_ZA_diag(A)[0]
+
+
+def get_indices_from_list_CSR(A, offset=True):
+    """graph.py:593-610"""
+    idx = _as_batch(A)
+    b, N, M = idx.shape
+    off = (torch.arange(b, dtype=torch.int32, device=idx.device) * N).view(b, 1, 1)
+    return (idx + off).reshape(-1)
+
+
+def confirm_CSR_to_COO_index_integrity(A, COO_feats):
+    """graph.py:612-618"""
+    assert bool((get_indices_from_list_CSR(A) == _to_cuda(COO_feats[1], torch.int32)).all())
+
+
+_ADJ_CACHE = {}
+
+
+def _adjacency_of(COO_feats, b, N):
+    adj = getattr(COO_feats, "_nbpc_adjacency", None)
+    if adj is not None and adj.b * adj.N == b * N:
+        return adj
+    # plain (3,c) array/tensor: rebuild the CSR transpose (cached on identity of the storage)
+    coo = _to_cuda(COO_feats, torch.int32).contiguous()
+    key = (coo.data_ptr(), tuple(coo.shape), coo._version, b, N)
+    adj = _ADJ_CACHE.get(key)
+    if adj is None:
+        c = coo.shape[1]
+        if coo.shape[0] != 3 or c % (b * N) != 0:
+            raise ValueError(f"COO_feats must be (3, b*N*M); got {tuple(coo.shape)} for b*N={b * N}")
+        M = c // (b * N)
+        rows_ok = bool((coo[0] == torch.arange(c, device=coo.device, dtype=torch.int32) // M).all())
+        if not rows_ok:
+            raise ValueError("COO_feats[0] must be the fixed-degree CSR row index e // M (kNN graph layout)")
+        ptr, edge, status = ops.segment_csr(coo[1], b * N)
+        if int(status.item()):
+            raise ValueError("COO_feats[1] has indices outside [0, b*N)")
+        diag = torch.full((b * N,), -1, dtype=torch.int64, device=coo.device)
+        adj = Adjacency(coo, diag, ptr, edge, torch.zeros(2, dtype=torch.int32, device=coo.device), b, N, M)
+        if len(_ADJ_CACHE) > 8:
+            _ADJ_CACHE.clear()
+        _ADJ_CACHE[key] = adj
+    return adj
+
+
+# =============================================================================== input features
+def include_node_features(X_in_edges, X_in_nodes, COO_feats, redshift=None):
+    """graph.py:245-275: concat [edges, nodes[row], nodes[col], (redshift)] -> (c, 9|10)."""
+    nodes = _to_cuda(X_in_nodes, torch.float32)
+    adj = _adjacency_of(COO_feats, 1, nodes.shape[0])
+    rs = None if redshift is None else _to_cuda(redshift, torch.float32)
+    return ops.include_node_features(_to_cuda(X_in_edges, torch.float32), nodes, adj.col, rs, adj.M)
+
+
+def get_input_features_shift_inv_ZA(init_pos, ZA_displacement, coo, diag, dims):
+    """graph.py:289-343: edges[e] = pos[col[e]] - pos[row[e]], ZA displacement added on the self edge."""
+    b, N, M = dims
+    pos = _to_cuda(init_pos, torch.float32).reshape(b * N, -1)
+    za = _to_cuda(ZA_displacement, torch.float32).reshape(b * N, -1)
+    adj = _adjacency_of(coo, b, N)
+    return ops.edge_features(pos, za, adj.col, _to_cuda(diag, torch.int64), M)
+
+
+def get_input_features_shift_inv(X_in, coo, dims):
+    """graph.py:346-364: raw (non minimum-image) relative positions (c,3) and the node features X[...,3:]."""
+    b, N, M = dims
+    X = _to_cuda(X_in, torch.float32).reshape(b * N, -1)
+    adj = _adjacency_of(coo, b, N)
+    edges = ops.edge_features(X, None, adj.col, None, M)
+    return edges, X[:, 3:]
+
+
+# =============================================================================== layers
+def shift_inv_conv(h, pool_idx, num_segs, broadcast):
+    """graph.py:367-391: unsorted segment mean (+ gather back).  Deterministic: members of every
+    segment are summed in ascending order."""
+    h = _to_cuda(h, torch.float32)
+    ids = _to_cuda(pool_idx, torch.int32).contiguous()
+    ptr, members, _ = ops.segment_csr(ids, int(num_segs))
+    return ops.SegmentPool.apply(h, ids, ptr, members, bool(broadcast))
+
+
+def _is_relu(fn):
+    return fn in (torch.relu, torch.nn.functional.relu) or getattr(fn, "__name__", "") == "relu"
+
+
+def _layer(H_in, COO_feats, bN, layer_vars, is_last, relu):
+    b, N = bN
+    weights, B = layer_vars
+    adj = _adjacency_of(COO_feats, b, N)
+    W = weights if isinstance(weights, torch.Tensor) and weights.dim() == 3 else torch.stack(list(weights[:4]))
+    return ops.GraphLayer.apply(H_in, W, B, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M, bool(is_last), relu)
+
+
+def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
+    """graph.py:394-456.  H_in (c,k); layer_vars = ([W1..W4] each (k,q), B (q,)) -> (c,q), or (b,N,q) if is_last."""
+    return _layer(_to_cuda(H_in, torch.float32), COO_feats, bN, layer_vars, is_last, False)
+
+
+def network_func_shift_inv_za(edges, coo, num_layers, dims, activation, model_vars):
+    """graph.py:463-476.  A ReLU activation is fused into the layer kernel; any other callable is
+    applied to the un-activated layer output."""
+    fuse = _is_relu(activation)
+    H = _layer(_to_cuda(edges, torch.float32), coo, dims, model_vars.get_layer_vars(0), False, fuse)
+    if not fuse:
+        H = activation(H)
+    for layer_idx in range(1, num_layers):
+        is_last = layer_idx == num_layers - 1
+        H = _layer(H, coo, dims, model_vars.get_layer_vars(layer_idx), is_last, fuse and not is_last)
+        if not is_last and not fuse:
+            H = activation(H)
+    return H
+
+
+def model_func_shift_inv_za(init_pos, COO_feats, ZA_displacement, ZA_diagonal, model_vars, dims,
+                            activation=torch.relu):
+    """graph.py:479-515 -> predicted displacement error (b, N, q_last)."""
+    num_layers = len(model_vars.channels) - 1
+    edges = get_input_features_shift_inv_ZA(init_pos, ZA_displacement, COO_feats, ZA_diagonal, dims)
+    return network_func_shift_inv_za(edges, COO_feats, num_layers, dims[:-1], activation, model_vars)

@@ -1,0 +1,452 @@
+"""PyTorch custom ops (`torch.ops.nbpc.*`) over the C ABI of libnbpc.so, plus the autograd
+Functions that pair each forward with its hand-written backward.
+
+torch is plumbing here: device memory, the current CUDA stream and autograd bookkeeping.  Every
+op launches hand-written sm_100a kernels through ctypes; none has a CPU or eager-PyTorch
+fallback (a CPU tensor raises).
+"""
+import ctypes
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("nbpc ops need CUDA tensors on an sm_100 (B200) device; there is no CPU fallback")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def _i32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ================================================================== kNN
+@torch.library.custom_op("nbpc::knn", mutates_args=())
+def knn(xyz: torch.Tensor, k: int, periodic: bool, boundary_threshold: float, include_self: bool,
+        order: int, want_d2: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """xyz (B,N,D>=3) float32 (any strides with unit stride on the last dim) -> idx (B,N,k) int32
+    [, d2 (B,N,k) float64 in distance order; empty if not requested]."""
+    _need_cuda(xyz)
+    L = _lib.load()
+    if xyz.dtype != torch.float32:
+        xyz = xyz.to(torch.float32)
+    if xyz.dim() != 3 or xyz.shape[-1] < 3:
+        raise RuntimeError("knn: xyz must be (B, N, D>=3)")
+    if xyz.stride(-1) != 1:
+        xyz = xyz.contiguous()
+    B, N, _ = xyz.shape
+    idx = torch.empty((B, N, k), dtype=torch.int32, device=xyz.device)
+    d2 = torch.empty((B, N, k) if want_d2 else (0,), dtype=torch.float64, device=xyz.device)
+    ws = _workspace(L.nbpc_knn_workspace_bytes(B, N, k, int(periodic)), xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = L.nbpc_knn(_ptr(xyz), xyz.stride(0), xyz.stride(1), B, N, k, int(periodic), float(boundary_threshold),
+                        int(include_self), int(order), _ptr(idx), _ptr(d2) if want_d2 else None, _ptr(ws),
+                        ws.numel(), _stream())
+    _lib.check(rc, "nbpc_knn")
+    return idx, d2
+
+
+# ================================================================== adjacency
+@torch.library.custom_op("nbpc::adjacency", mutates_args=())
+def adjacency(idx: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """idx (B,N,M) int32 local -> coo (3,c) int32, diag (B*N) int64, csrT_ptr (B*N+1), csrT_edge (c), status (2)."""
+    _need_cuda(idx)
+    L = _lib.load()
+    idx = _i32c(idx)
+    B, N, M = idx.shape
+    c = B * N * M
+    dev = idx.device
+    coo = torch.empty((3, c), dtype=torch.int32, device=dev)
+    diag = torch.empty((B * N,), dtype=torch.int64, device=dev)
+    ptr = torch.empty((B * N + 1,), dtype=torch.int32, device=dev)
+    edge = torch.empty((c,), dtype=torch.int32, device=dev)
+    status = torch.empty((2,), dtype=torch.int32, device=dev)
+    ws = _workspace(L.nbpc_adjacency_workspace_bytes(B, N, M), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_adjacency(_ptr(idx), B, N, M, _ptr(coo), _ptr(diag), _ptr(ptr), _ptr(edge), _ptr(status),
+                              _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_adjacency")
+    return coo, diag, ptr, edge, status
+
+
+@torch.library.custom_op("nbpc::segment_csr", mutates_args=())
+def segment_csr(ids: torch.Tensor, num_segs: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _need_cuda(ids)
+    L = _lib.load()
+    ids = _i32c(ids).reshape(-1)
+    n = ids.numel()
+    dev = ids.device
+    ptr = torch.empty((num_segs + 1,), dtype=torch.int32, device=dev)
+    mem = torch.empty((n,), dtype=torch.int32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    ws = _workspace(L.nbpc_segment_csr_workspace_bytes(n, num_segs), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_segment_csr(_ptr(ids), n, num_segs, _ptr(ptr), _ptr(mem), _ptr(status), _ptr(ws), ws.numel(),
+                                _stream())
+    _lib.check(rc, "nbpc_segment_csr")
+    return ptr, mem, status
+
+
+# ================================================================== input features
+@torch.library.custom_op("nbpc::edge_features", mutates_args=())
+def edge_features(pos: torch.Tensor, za: Optional[torch.Tensor], col: torch.Tensor,
+                  diag: Optional[torch.Tensor], M: int) -> torch.Tensor:
+    """pos (BN, ld>=3), za (BN, ld>=3)|None, col (c) int32, diag (n) int64|None -> edges (c,3)."""
+    _need_cuda(pos, za, col, diag)
+    L = _lib.load()
+    pos = _f32c(pos)
+    BN = pos.shape[0]
+    col = _i32c(col)
+    out = torch.empty((BN * M, 3), dtype=torch.float32, device=pos.device)
+    with torch.cuda.device(pos.device):
+        if za is None:
+            rc = L.nbpc_edge_features(_ptr(pos), pos.shape[1], _ptr(col), BN, M, _ptr(out), _stream())
+        else:
+            za = _f32c(za)
+            diag = diag.to(torch.int64).contiguous()
+            rc = L.nbpc_edge_features_za(_ptr(pos), pos.shape[1], _ptr(za), za.shape[1], _ptr(col), _ptr(diag),
+                                         diag.numel(), BN, M, _ptr(out), _stream())
+    _lib.check(rc, "nbpc_edge_features")
+    return out
+
+
+@torch.library.custom_op("nbpc::include_node_features", mutates_args=())
+def include_node_features(edges: torch.Tensor, nodes: torch.Tensor, col: torch.Tensor,
+                          redshift: Optional[torch.Tensor], M: int) -> torch.Tensor:
+    _need_cuda(edges, nodes, col, redshift)
+    L = _lib.load()
+    edges, nodes, col = _f32c(edges), _f32c(nodes), _i32c(col)
+    c, E = edges.shape
+    BN, F = nodes.shape
+    if redshift is not None:
+        redshift = _f32c(redshift).reshape(-1)
+    out = torch.empty((c, E + 2 * F + (1 if redshift is not None else 0)), dtype=torch.float32, device=edges.device)
+    with torch.cuda.device(edges.device):
+        rc = L.nbpc_include_node_features(_ptr(edges), E, _ptr(nodes), F, F, _ptr(col), _ptr(redshift), BN, M,
+                                          _ptr(out), _stream())
+    _lib.check(rc, "nbpc_include_node_features")
+    return out
+
+
+# ================================================================== pooling primitive
+@torch.library.custom_op("nbpc::segment_reduce", mutates_args=())
+def segment_reduce(h: torch.Tensor, seg_ptr: torch.Tensor, seg_members: torch.Tensor, mean: bool) -> torch.Tensor:
+    _need_cuda(h, seg_ptr, seg_members)
+    L = _lib.load()
+    h = _f32c(h)
+    k = h.shape[1]
+    num_segs = seg_ptr.numel() - 1
+    out = torch.empty((num_segs, k), dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        rc = L.nbpc_segment_reduce(_ptr(h), k, _ptr(seg_ptr), _ptr(seg_members), num_segs, int(mean), _ptr(out),
+                                   _stream())
+    _lib.check(rc, "nbpc_segment_reduce")
+    return out
+
+
+@torch.library.custom_op("nbpc::gather_rows", mutates_args=())
+def gather_rows(src: torch.Tensor, ids: torch.Tensor, seg_ptr: Optional[torch.Tensor]) -> torch.Tensor:
+    _need_cuda(src, ids, seg_ptr)
+    L = _lib.load()
+    src, ids = _f32c(src), _i32c(ids).reshape(-1)
+    k = src.shape[1]
+    out = torch.empty((ids.numel(), k), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        rc = L.nbpc_gather_rows(_ptr(src), k, _ptr(ids), ids.numel(), _ptr(seg_ptr), _ptr(out), _stream())
+    _lib.check(rc, "nbpc_gather_rows")
+    return out
+
+
+class SegmentPool(torch.autograd.Function):
+    """shift_inv_conv (graph.py:367-391) with a deterministic backward."""
+
+    @staticmethod
+    def forward(ctx, h, ids, seg_ptr, seg_members, broadcast):
+        pooled = segment_reduce(h, seg_ptr, seg_members, True)
+        ctx.save_for_backward(ids, seg_ptr, seg_members)
+        ctx.broadcast = broadcast
+        return gather_rows(pooled, ids, None) if broadcast else pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        ids, seg_ptr, seg_members = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.broadcast:  # adjoint of the gather = segment sum
+            g = segment_reduce(g, seg_ptr, seg_members, False)
+        # adjoint of the mean = gather of g / max(count, 1)
+        return gather_rows(g, ids, seg_ptr), None, None, None, None
+
+
+# ================================================================== graph layer
+@torch.library.custom_op("nbpc::graph_layer_fwd", mutates_args=())
+def graph_layer_fwd(H_in: torch.Tensor, col: torch.Tensor, csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor,
+                    W: torch.Tensor, bias: torch.Tensor, B: int, N: int, M: int, is_last: bool,
+                    relu: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> H_out (c,q) | (B*N,q), P_col (BN,k), P_row (BN,k), P_cube (B,k)."""
+    _need_cuda(H_in, col, csrT_ptr, csrT_edge, W, bias)
+    L = _lib.load()
+    H_in, W, bias = _f32c(H_in), _f32c(W), _f32c(bias)
+    k, q = W.shape[1], W.shape[2]
+    c = B * N * M
+    if H_in.shape != (c, k) or W.shape[0] != 4 or bias.shape != (q,):
+        raise RuntimeError(f"graph_layer_fwd: shape mismatch H_in {tuple(H_in.shape)} vs (c={c}, k={k}); W {tuple(W.shape)}")
+    dev = H_in.device
+    out = torch.empty(((B * N) if is_last else c, q), dtype=torch.float32, device=dev)
+    P_col = torch.empty((B * N, k), dtype=torch.float32, device=dev)
+    P_row = torch.empty((B * N, k), dtype=torch.float32, device=dev)
+    P_cube = torch.empty((B, k), dtype=torch.float32, device=dev)
+    ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_graph_layer_fwd(_ptr(H_in), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge), B, N, M, k, q, _ptr(W),
+                                    _ptr(bias), int(is_last), int(relu), _ptr(out), _ptr(P_col), _ptr(P_row),
+                                    _ptr(P_cube), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_graph_layer_fwd")
+    return out, P_col, P_row, P_cube
+
+
+@torch.library.custom_op("nbpc::graph_layer_bwd", mutates_args=())
+def graph_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, col: torch.Tensor,
+                    csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor, W: torch.Tensor, P_col: torch.Tensor,
+                    P_row: torch.Tensor, P_cube: torch.Tensor, B: int, N: int, M: int, is_last: bool, relu: bool,
+                    need_dH: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> dH_in (c,k) (empty if not needed), dW (4,k,q), dB (q)."""
+    _need_cuda(dOut, H_in, H_out, W)
+    L = _lib.load()
+    dOut = _f32c(dOut)
+    k, q = W.shape[1], W.shape[2]
+    c = B * N * M
+    dev = H_in.device
+    dH = torch.empty((c, k) if need_dH else (0,), dtype=torch.float32, device=dev)
+    dW = torch.empty((4, k, q), dtype=torch.float32, device=dev)
+    dB = torch.empty((q,), dtype=torch.float32, device=dev)
+    ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_graph_layer_bwd(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge),
+                                    B, N, M, k, q, _ptr(W), _ptr(P_col), _ptr(P_row), _ptr(P_cube), int(is_last),
+                                    int(relu), _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB), _ptr(ws),
+                                    ws.numel(), _stream())
+    _lib.check(rc, "nbpc_graph_layer_bwd")
+    return dH, dW, dB
+
+
+class GraphLayer(torch.autograd.Function):
+    """shift_inv_layer (graph.py:394-456) [+ fused ReLU], backward through the CSR transpose."""
+
+    @staticmethod
+    def forward(ctx, H_in, W, bias, col, csrT_ptr, csrT_edge, B, N, M, is_last, relu):
+        H_in = _f32c(H_in)
+        out, P_col, P_row, P_cube = graph_layer_fwd(H_in, col, csrT_ptr, csrT_edge, W, bias, B, N, M, is_last, relu)
+        ctx.save_for_backward(H_in, out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube)
+        ctx.cfg = (B, N, M, is_last, relu)
+        if is_last:
+            out = out.view(B, N, -1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        H_in, out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube = ctx.saved_tensors
+        B, N, M, is_last, relu = ctx.cfg
+        need_dH = ctx.needs_input_grad[0]
+        g = g.reshape(out.shape)
+        dH, dW, dB = graph_layer_bwd(g, H_in, out, col, csrT_ptr, csrT_edge, W, P_col, P_row, P_cube, B, N, M,
+                                     is_last, relu, need_dH)
+        return (dH if need_dH else None), dW, dB, None, None, None, None, None, None, None, None
+
+
+# ================================================================== set layer
+@torch.library.custom_op("nbpc::set_layer_fwd", mutates_args=())
+def set_layer_fwd(H_in: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, relu: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    _need_cuda(H_in, W, bias)
+    L = _lib.load()
+    H_in, W, bias = _f32c(H_in), _f32c(W), _f32c(bias)
+    B, N, k = H_in.shape
+    q = W.shape[1]
+    dev = H_in.device
+    out = torch.empty((B, N, q), dtype=torch.float32, device=dev)
+    mu = torch.empty((B, k), dtype=torch.float32, device=dev)
+    ws = _workspace(L.nbpc_set_layer_workspace_bytes(B, N, k, q), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_set_layer_fwd(_ptr(H_in), B, N, k, q, _ptr(W), _ptr(bias), int(relu), _ptr(out), _ptr(mu),
+                                  _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_set_layer_fwd")
+    return out, mu
+
+
+@torch.library.custom_op("nbpc::set_layer_bwd", mutates_args=())
+def set_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, mu: torch.Tensor, W: torch.Tensor,
+                  relu: bool, need_dH: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _need_cuda(dOut, H_in, H_out, mu, W)
+    L = _lib.load()
+    dOut = _f32c(dOut)
+    B, N, k = H_in.shape
+    q = W.shape[1]
+    dev = H_in.device
+    dH = torch.empty((B, N, k) if need_dH else (0,), dtype=torch.float32, device=dev)
+    dW = torch.empty((k, q), dtype=torch.float32, device=dev)
+    dB = torch.empty((q,), dtype=torch.float32, device=dev)
+    ws = _workspace(L.nbpc_set_layer_workspace_bytes(B, N, k, q), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_set_layer_bwd(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(mu), B, N, k, q, _ptr(W), int(relu),
+                                  _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_set_layer_bwd")
+    return dH, dW, dB
+
+
+class SetLayer(torch.autograd.Function):
+    """set_layer (nn.py:10-28) [+ fused ReLU]."""
+
+    @staticmethod
+    def forward(ctx, H_in, W, bias, relu):
+        H_in = _f32c(H_in)
+        out, mu = set_layer_fwd(H_in, W, bias, relu)
+        ctx.save_for_backward(H_in, out, mu, W)
+        ctx.relu = relu
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        H_in, out, mu, W = ctx.saved_tensors
+        need_dH = ctx.needs_input_grad[0]
+        dH, dW, dB = set_layer_bwd(g, H_in, out, mu, W, ctx.relu, need_dH)
+        return (dH if need_dH else None), dW, dB, None
+
+
+# ================================================================== losses / readout
+def _rows_ld(t: torch.Tensor):
+    t = _f32c(t)
+    ld = t.shape[-1]
+    return t, t.numel() // ld, ld
+
+
+@torch.library.custom_op("nbpc::loss_fwd", mutates_args=())
+def loss_fwd(pred: torch.Tensor, truth: torch.Tensor, pbc: bool, scale_error: bool) -> torch.Tensor:
+    _need_cuda(pred, truth)
+    L = _lib.load()
+    pred, rows, ldp = _rows_ld(pred)
+    truth, rows_t, ldt = _rows_ld(truth)
+    if rows != rows_t or ldp < 3 or ldt < 3:
+        raise RuntimeError("loss: pred/truth must have the same leading shape and >= 3 channels")
+    out = torch.empty((), dtype=torch.float32, device=pred.device)
+    ws = _workspace(L.nbpc_loss_workspace_bytes(rows), pred.device)
+    with torch.cuda.device(pred.device):
+        if pbc:
+            rc = L.nbpc_pbc_loss_fwd(_ptr(pred), ldp, _ptr(truth), ldt, rows, int(scale_error), _ptr(out), _ptr(ws),
+                                     ws.numel(), _stream())
+        else:
+            rc = L.nbpc_loss_za_fwd(_ptr(pred), ldp, _ptr(truth), ldt, rows, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_loss_fwd")
+    return out
+
+
+@torch.library.custom_op("nbpc::loss_bwd", mutates_args=())
+def loss_bwd(pred: torch.Tensor, truth: torch.Tensor, dloss: torch.Tensor, pbc: bool, scale_error: bool) -> torch.Tensor:
+    _need_cuda(pred, truth, dloss)
+    L = _lib.load()
+    pred, rows, ldp = _rows_ld(pred)
+    truth, _, ldt = _rows_ld(truth)
+    dloss = _f32c(dloss).reshape(1)
+    dpred = torch.zeros_like(pred) if ldp > 3 else torch.empty_like(pred)
+    with torch.cuda.device(pred.device):
+        if pbc:
+            rc = L.nbpc_pbc_loss_bwd(_ptr(pred), ldp, _ptr(truth), ldt, rows, int(scale_error), _ptr(dloss),
+                                     _ptr(dpred), ldp, _stream())
+        else:
+            rc = L.nbpc_loss_za_bwd(_ptr(pred), ldp, _ptr(truth), ldt, rows, _ptr(dloss), _ptr(dpred), ldp, _stream())
+    _lib.check(rc, "nbpc_loss_bwd")
+    return dpred
+
+
+class Loss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, truth, pbc, scale_error):
+        ctx.save_for_backward(pred, truth)
+        ctx.cfg = (pbc, scale_error)
+        return loss_fwd(pred, truth, pbc, scale_error)
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, truth = ctx.saved_tensors
+        pbc, scale_error = ctx.cfg
+        return loss_bwd(pred, truth, g, pbc, scale_error).reshape(pred.shape), None, None, None
+
+
+@torch.library.custom_op("nbpc::periodic_boundary_dist", mutates_args=())
+def periodic_boundary_dist(pred: torch.Tensor, truth: torch.Tensor) -> torch.Tensor:
+    _need_cuda(pred, truth)
+    L = _lib.load()
+    pred, rows, ldp = _rows_ld(pred)
+    truth, _, ldt = _rows_ld(truth)
+    out = torch.empty(pred.shape[:-1] + (3,), dtype=torch.float32, device=pred.device)
+    with torch.cuda.device(pred.device):
+        rc = L.nbpc_periodic_boundary_dist(_ptr(pred), ldp, _ptr(truth), ldt, rows, _ptr(out), _stream())
+    _lib.check(rc, "nbpc_periodic_boundary_dist")
+    return out
+
+
+@torch.library.custom_op("nbpc::readout", mutates_args=())
+def readout(h: torch.Tensor) -> torch.Tensor:
+    _need_cuda(h)
+    L = _lib.load()
+    h, rows, C = _rows_ld(h)
+    out = torch.empty_like(h)
+    with torch.cuda.device(h.device):
+        rc = L.nbpc_readout(_ptr(h), rows, C, _ptr(out), _stream())
+    _lib.check(rc, "nbpc_readout")
+    return out
+
+
+class Readout(torch.autograd.Function):
+    """get_readout (nn.py:107-119): d readout / d h = 1 almost everywhere (tf.sign has zero gradient)."""
+
+    @staticmethod
+    def forward(ctx, h):
+        return readout(h)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+# ================================================================== optimiser
+def adam_tf_(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr: float,
+             beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    """In-place tf.train.AdamOptimizer step (train.py:70) on flat float32 buffers."""
+    _need_cuda(param, grad, m, v)
+    L = _lib.load()
+    for t in (param, grad, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("adam_tf_: buffers must be contiguous float32")
+    with torch.cuda.device(param.device):
+        rc = L.nbpc_adam_tf(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), lr, beta1, beta2, eps, step,
+                            grad_scale, _stream())
+    _lib.check(rc, "nbpc_adam_tf")
+
+
+def device_check() -> None:
+    """Raise unless the current CUDA device is an sm_100 part."""
+    _lib.check(_lib.load().nbpc_device_check(), "nbpc_device_check")

@@ -1,0 +1,99 @@
+"""Host-side glue the entry points need around the hot path: parameter store with the reference's
+`get_layer_vars(i) -> ([W0..W3], B)` contract (utils.py:292-385), the `ModelVars` tuple
+(utils.py:199-202), TF-form Adam on a flat buffer (train.py:70) and sample-sharded data-parallel
+gradient all-reduce (one NCCL all-reduce of the flat gradient buffer per step)."""
+import math
+from collections import namedtuple
+
+import torch
+
+from . import ops
+from .synthetic import PARAMS_SEED
+
+ModelVars = namedtuple("ModelVars", ["num_layers", "get_layer_vars", "activation"])  # utils.py:199-202
+
+
+class ParamStore:
+    """All layer weights/biases as views into ONE flat float32 buffer (so the gradient all-reduce and
+    the Adam step are a single kernel each).  Layout per layer: n_w weights (k,q) then the bias (q)."""
+
+    def __init__(self, channels, n_w=4, seed=PARAMS_SEED, device="cuda", var_scope="params"):
+        self.channels = list(channels)
+        self.var_scope = var_scope
+        self.num_layers = len(channels) - 1
+        self.n_w = n_w
+        sizes = []
+        for k, q in zip(channels[:-1], channels[1:]):
+            sizes.append(n_w * k * q + q)
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros_like(self.flat)
+        gen = torch.Generator(device="cpu").manual_seed(int(seed))
+        self._W, self._B = [], []
+        off = 0
+        for (k, q), _ in zip(zip(channels[:-1], channels[1:]), sizes):
+            W = self.flat[off:off + n_w * k * q].view(n_w, k, q)
+            Wg = self.flat_grad[off:off + n_w * k * q].view(n_w, k, q)
+            off += n_w * k * q
+            Bv = self.flat[off:off + q]
+            Bg = self.flat_grad[off:off + q]
+            off += q
+            sigma = math.sqrt(2.0 / (k + q))   # glorot normal (utils.py:178, 357)
+            init = torch.empty(n_w, k, q).normal_(0.0, sigma, generator=gen)
+            W.copy_(init)
+            Bv.fill_(1e-8)                     # utils.py:334
+            W.requires_grad_(True)
+            Bv.requires_grad_(True)
+            W.grad, Bv.grad = Wg, Bg           # autograd accumulates straight into the flat buffer
+            self._W.append(W)
+            self._B.append(Bv)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.step_count = 0
+
+    def get_layer_vars(self, i):
+        """([W_0..W_{n_w-1}] as one (n_w,k,q) tensor - indexable like the reference's list -, B)."""
+        return self._W[i], self._B[i]
+
+    def model_vars(self, activation=torch.relu):
+        return ModelVars(self.num_layers, self.get_layer_vars, activation)
+
+    def load_numpy(self, params):
+        """params: list over layers of ([W...], B) NumPy arrays (synthetic.glorot_params)."""
+        with torch.no_grad():
+            for i, (Ws, B) in enumerate(params):
+                for j, w in enumerate(Ws):
+                    self._W[i][j].copy_(torch.as_tensor(w))
+                self._B[i].copy_(torch.as_tensor(B).reshape(-1))
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def parameters(self):
+        return self._W + self._B
+
+
+class AdamTF:
+    """tf.train.AdamOptimizer(lr) (train.py:70): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps)."""
+
+    def __init__(self, store, lr=0.01, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.store, self.lr, self.beta1, self.beta2, self.eps = store, lr, beta1, beta2, eps
+
+    def step(self, grad_scale=1.0):
+        s = self.store
+        s.step_count += 1
+        ops.adam_tf_(s.flat, s.flat_grad, s.m, s.v, s.step_count, self.lr, self.beta1, self.beta2, self.eps, grad_scale)
+
+
+def allreduce_gradients(store, world_size):
+    """Sum the flat gradient buffer over ranks (NCCL over NVLink on GPUs; gloo in CPU tests)."""
+    if world_size > 1:
+        torch.distributed.all_reduce(store.flat_grad, op=torch.distributed.ReduceOp.SUM)
+
+
+def shard_samples(n_samples, rank, world_size):
+    """Contiguous block of sample indices owned by `rank` (samples are independent: block-diagonal
+    adjacency, graph.py:643-652)."""
+    per = n_samples // world_size
+    rem = n_samples % world_size
+    start = rank * per + min(rank, rem)
+    return range(start, start + per + (1 if rank < rem else 0))

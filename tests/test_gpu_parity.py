@@ -1,0 +1,396 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the reference-named Python
+API (which goes through the C ABI of libnbpc.so), against
+  * golden vectors produced by the UNMODIFIED reference (tests/golden, oracle/make_golden.py),
+  * the CPU oracle (oracle/) on seeded inputs,
+  * size-independent properties at the full BASELINE sizes.
+Tolerances: kNN indices / COO / diag / float64 distances / input features / readout: bit-exact.
+Layer outputs: rtol 2e-5, atol 2e-6 vs the float32 reference run (different association of the same
+sums, SURVEY.md §7 hard part 7); gradients: rtol 2e-4 vs the float64 reference run."""
+import hashlib
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ref_graph, ref_layers
+from oracle.knn_exact import knn_exact
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def idx_of(A):
+    return torch.stack([a.indices.view(a.N, a.M) for a in A]).cpu().numpy()
+
+
+def cuda_model_vars(g, channels, n_w=4):
+    tp = []
+    for li in range(len(channels) - 1):
+        Ws = [torch.tensor(g[f"W{li}_{wi}"], device=DEV, requires_grad=True) for wi in range(n_w)]
+        B = torch.tensor(g[f"B{li}"], device=DEV, requires_grad=True)
+        tp.append((Ws, B))
+    mv = types.SimpleNamespace(var_scope="params", channels=list(channels), num_layers=len(channels) - 1,
+                               activation=torch.relu, get_layer_vars=lambda i: tp[i])
+    return mv, tp
+
+
+# =============================================================================== kNN
+@pytest.mark.parametrize("kind", ["uniform", "clustered"])
+def test_knn_16_golden(nb, kind):
+    g = load_golden("knn_16.npz")
+    for seed in (0, 1, 2):
+        tag = f"{kind}_s{seed}"
+        x = g[f"x_{tag}"]
+        A = nb.graph.get_kneighbor_list(x, 14)
+        assert A[0].shape == (4096, 4096) and A[0].indices.dtype == torch.int32
+        assert np.array_equal(idx_of(A), g[f"knl_{tag}"])
+        assert np.array_equal(idx_of(nb.graph.get_pbc_kneighbors_csr(x, 14, 0.1)), g[f"pbc_{tag}"])
+        if seed == 0:
+            P = nb.graph.get_pbc_kneighbors_csr(x, 14, 0.1, include_self=True)
+            assert np.array_equal(idx_of(P), g[f"pbcself_{tag}"])
+            padded, _ = ref_graph.pad_cube_boundaries(x[0], 0.1)
+            assert P[0].shape == (4096, padded.shape[0])
+            assert np.array_equal(idx_of(nb.graph.get_pbc_kneighbors_csr(x, 8, 0.3)), g[f"pbc03_{tag}"])
+            assert np.array_equal(idx_of(nb.graph.get_kneighbor_list(x, 8, include_self=False)), g[f"knlnoself_{tag}"])
+            # offset_idx (graph.py:710-711)
+            Ao = nb.graph.get_kneighbor_list(x, 14, offset_idx=True)
+            assert np.array_equal(Ao[1].indices.cpu().numpy(), g[f"knl_{tag}"][1].reshape(-1).astype(np.int64) + 4096)
+
+
+def test_knn_32_golden_hashes(nb, syn):
+    g = load_golden("knn_32.npz")
+    for kind in ("uniform", "clustered"):
+        x = syn.make_box(kind, 1, 32768, 0)
+        assert sha(x) == str(g[f"x_sha_{kind}"])
+        for k in (8, 14, 32):
+            knl = idx_of(nb.graph.get_kneighbor_list(x, k))
+            assert np.array_equal(knl[:, :64], g[f"knl_head_{kind}_k{k}"])
+            assert sha(knl.astype(np.int32)) == str(g[f"knl_sha_{kind}_k{k}"]), (kind, k)
+        pbc = idx_of(nb.graph.get_pbc_kneighbors_csr(x, 14, 0.1, include_self=True))
+        assert sha(pbc.astype(np.int32)) == str(g[f"pbc_sha_{kind}_k14"]), kind
+
+
+@pytest.mark.parametrize("N,k,periodic,thr,inc", [
+    (5000, 1, False, 0.0, True), (5000, 64, False, 0.0, True), (777, 33, True, 0.5, True),
+    (3000, 14, True, 0.05, False), (64, 63, False, 0.0, False), (9, 8, True, 0.5, False), (1, 1, False, 0.0, True),
+])
+def test_knn_vs_exact_oracle(nb, N, k, periodic, thr, inc):
+    x = np.random.default_rng(N + k).random((2, N, 3)).astype(np.float32)
+    idx, d2 = nb.ops.knn(torch.tensor(x, device=DEV), k, periodic, thr, inc, 0, True)
+    for s in range(2):
+        cloud = ref_graph.pad_cube_boundaries(x[s], thr) if periodic else (x[s].astype(np.float64), None)
+        ridx, rd2 = knn_exact(cloud[0], N, k, inc, return_d2=True)
+        if periodic and len(cloud[1]):
+            ridx = np.where(ridx >= N, cloud[1][np.maximum(ridx - N, 0)], ridx)
+        assert np.array_equal(d2[s].cpu().numpy(), rd2)          # bit-exact float64 distances
+        assert np.array_equal(idx[s].cpu().numpy(), ridx)
+
+
+def test_knn_arbitrary_box_strided_and_ties(nb):
+    rng = np.random.default_rng(4)
+    X = (rng.random((2, 3000, 9)) * 128 - 5).astype(np.float32)    # reference layout (b,N,9), Mpc/h coordinates
+    A = nb.graph.get_kneighbor_list(torch.tensor(X, device=DEV), 14)
+    ref = ref_graph.get_kneighbor_list(X, 14, backend="exact")
+    assert np.array_equal(idx_of(A), np.stack([r.indices.reshape(3000, 14) for r in ref]))
+    g = load_golden("lattice_8.npz")       # tie-heavy lattice: distances are defined, order is (d2, index)
+    idx, d2 = nb.ops.knn(torch.tensor(g["x"], device=DEV), 14, False, 0.0, True, 0, True)
+    assert np.array_equal(d2[0].cpu().numpy(), g["knl_sorted_d2"])
+    assert np.array_equal(idx[0].cpu().numpy(), knn_exact(g["x"][0].astype(np.float64), 512, 14, True))
+
+
+def test_knn_errors(nb):
+    x = torch.rand(1, 10, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="k exceeds"):
+        nb.graph.get_kneighbor_list(x, 11)
+    with pytest.raises(RuntimeError, match="k exceeds"):
+        nb.graph.get_kneighbor_list(x, 10, include_self=False)
+    with pytest.raises(RuntimeError, match="k must be"):
+        nb.ops.knn(torch.rand(1, 100, 3, device=DEV), 65, False, 0.0, True, 0, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        nb.ops.knn(torch.rand(1, 100, 3), 4, False, 0.0, True, 0, False)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered"])
+def test_knn_128_cubed_properties(nb, syn, kind):
+    """BASELINE size (2 097 152 particles, k=14, periodic): properties + brute-force spot check."""
+    N, k = 128 ** 3, 14
+    x = torch.tensor(syn.make_box(kind, 1, N, 0), device=DEV)
+    idx, d2 = nb.ops.knn(x, k, True, 0.5, True, 0, True)
+    idx, d2 = idx[0], d2[0]
+    assert bool((idx[:, 0] == torch.arange(N, device=DEV)).all()) and bool((d2[:, 0] == 0).all())
+    assert bool((d2[:, 1:] >= d2[:, :-1]).all())
+    assert int(idx.min()) >= 0 and int(idx.max()) < N
+    # recompute the reported distances from the indices (minimum image, float64)
+    xd = x[0].double()
+    diff = xd[idx.long()] - xd[:, None, :]
+    diff = diff - torch.round(diff)
+    assert torch.allclose((diff * diff).sum(-1), d2, rtol=1e-12, atol=1e-18)
+    # brute force on 256 random queries
+    q = torch.randperm(N, device=DEV)[:256]
+    for chunk in q.split(32):
+        dd = xd[None, :, :] - xd[chunk][:, None, :]
+        dd = dd - torch.round(dd)
+        dist = (dd * dd).sum(-1)
+        ref = torch.topk(dist, k, dim=1, largest=False).values
+        assert torch.allclose(ref, d2[chunk], rtol=1e-12, atol=1e-18)
+
+
+# =============================================================================== adjacency + features
+def test_adjacency_golden(nb):
+    g = load_golden("knn_16.npz")
+    for kind in ("uniform", "clustered"):
+        tag = f"{kind}_s0"
+        A = nb.graph.get_kneighbor_list(g[f"x_{tag}"], 14)
+        coo, diag = nb.graph.to_coo_batch_ZA_diag(A)
+        assert coo.dtype == torch.int32 and tuple(coo.shape) == (3, 2 * 4096 * 14) and diag.dtype == torch.int64
+        assert sha(coo.cpu().numpy()) == str(g[f"coo_sha_{tag}"])
+        assert np.array_equal(diag.cpu().numpy(), g[f"diag_{tag}"])
+        assert torch.equal(nb.graph.to_coo_batch(A), coo)
+        assert torch.equal(nb.graph.get_indices_from_list_CSR(A), coo[1])
+        nb.graph.confirm_CSR_to_COO_index_integrity(A, coo)
+        adj = coo._nbpc_adjacency
+        assert adj.check()
+        order = np.argsort(coo[1].cpu().numpy(), kind="stable")
+        assert np.array_equal(adj.csrT_edge.cpu().numpy(), order)
+        assert np.array_equal(np.diff(adj.csrT_ptr.cpu().numpy()), np.bincount(coo[1].cpu().numpy(), minlength=8192))
+
+
+def test_input_features_golden(nb):
+    g = load_golden("layers_small.npz")
+    b, N = g["x"].shape[:2]; k = int(g["k"])
+    coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(g["x"], k))
+    assert np.array_equal(coo.cpu().numpy(), g["coo"]) and np.array_equal(diag.cpu().numpy(), g["diag"])
+    e = nb.graph.get_input_features_shift_inv_ZA(torch.tensor(g["x"], device=DEV), torch.tensor(g["za"], device=DEV),
+                                                 coo, diag, (b, N, k))
+    assert np.array_equal(e.cpu().numpy(), g["f32_edges"])
+    e2, n2 = nb.graph.get_input_features_shift_inv(torch.tensor(g["feat_X6"], device=DEV), coo, (b, N, k))
+    assert np.array_equal(e2.cpu().numpy(), g["feat_edges"]) and np.array_equal(n2.cpu().numpy(), g["feat_nodes"])
+    assert np.array_equal(nb.graph.include_node_features(e2, n2, coo).cpu().numpy(), g["feat_nodes9"])
+    rs = torch.full((b * N * k, 1), 0.75, device=DEV)
+    assert np.array_equal(nb.graph.include_node_features(e2, n2, coo, redshift=rs).cpu().numpy(), g["feat_nodes10"])
+    # NumPy COO (as the reference feeds it) is accepted too
+    e3 = nb.graph.get_input_features_shift_inv_ZA(g["x"], g["za"], g["coo"], g["diag"], (b, N, k))
+    assert np.array_equal(e3.cpu().numpy(), g["f32_edges"])
+
+
+# =============================================================================== graph layers
+def test_graph_layers_per_layer_golden(nb):
+    g = load_golden("layers_small.npz")
+    ch = list(g["channels"]); k = int(g["k"]); b, N = g["x"].shape[:2]
+    coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(g["x"], k))
+    mv, tp = cuda_model_vars(g, ch)
+    H = torch.tensor(g["f32_edges"], device=DEV)
+    L = len(ch) - 1
+    for li in range(L):
+        last = li == L - 1
+        H = nb.graph.shift_inv_layer(H, coo, (b, N), tp[li], is_last=last)
+        if not last:
+            H = torch.relu(H)
+        ref32, ref64 = g[f"f32_H{li}"], g[f"f64_H{li}"]
+        out = H.detach().cpu().numpy()
+        assert out.shape == ref32.shape
+        np.testing.assert_allclose(out, ref32, rtol=2e-5, atol=2e-6)
+        assert np.abs(out - ref64).max() <= 4 * max(np.abs(ref32 - ref64).max(), 1e-7)
+
+
+@pytest.mark.parametrize("plain_coo", [False, True])
+def test_graph_model_small_golden_fwd_bwd(nb, plain_coo):
+    g = load_golden("layers_small.npz")
+    ch = list(g["channels"]); k = int(g["k"]); b, N = g["x"].shape[:2]
+    if plain_coo:   # a bare (3,c) tensor, as a reference caller would feed it
+        coo, diag = torch.tensor(g["coo"], device=DEV), torch.tensor(g["diag"], device=DEV)
+    else:
+        coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(g["x"], k))
+    mv, tp = cuda_model_vars(g, ch)
+    pred = nb.graph.model_func_shift_inv_za(torch.tensor(g["x"], device=DEV), coo, torch.tensor(g["za"], device=DEV),
+                                            diag, mv, (b, N, k))
+    loss = nb.nn.loss_ZA(pred, torch.tensor(g["tgt"], device=DEV))
+    loss.backward()
+    assert tuple(pred.shape) == (b, N, 3)
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), g["f32_pred"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(loss.item(), g["f64_loss"], rtol=1e-5)
+    for li, (Ws, B) in enumerate(tp):
+        for wi, w in enumerate(Ws):
+            np.testing.assert_allclose(w.grad.cpu().numpy(), g[f"f64_gW{li}_{wi}"], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(B.grad.cpu().numpy(), g[f"f64_gB{li}"], rtol=2e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "clustered"])
+def test_graph_model_c1_golden(nb, syn, kind):
+    """BASELINE config 1: 16^3 particles, k=14, 3-layer graph net, batch 2, one fwd+bwd step."""
+    g = load_golden("model_16.npz")
+    ch = list(g["channels"]); k = int(g["k"]); b, N = 2, 4096
+    x = syn.make_box(kind, b, N, 0)
+    za, tgt = syn.za_features(b, N, 0)
+    assert sha(x) == str(g[f"x_sha_{kind}"]) and sha(za) == str(g[f"za_sha_{kind}"])
+    store = nb.train_utils.ParamStore(ch, device=DEV)
+    store.load_numpy(syn.glorot_params(ch))
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+    xt = torch.tensor(x, device=DEV)
+    A = nb.graph.get_kneighbor_list(xt, k)
+    coo, diag = nb.graph.to_coo_batch_ZA_diag(A)
+    pred = nb.graph.model_func_shift_inv_za(xt, coo, torch.tensor(za, device=DEV), diag, mv, (b, N, k))
+    loss = nb.nn.loss_ZA(pred, torch.tensor(tgt, device=DEV))
+    loss.backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), g[f"{kind}_f32_pred"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(loss.item(), g[f"{kind}_f64_loss"], rtol=1e-5)
+    for li in range(len(ch) - 1):
+        W, B = store.get_layer_vars(li)
+        for wi in range(4):
+            np.testing.assert_allclose(W.grad[wi].cpu().numpy(), g[f"{kind}_f64_gW{li}_{wi}"], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(B.grad.cpu().numpy(), g[f"{kind}_f64_gB{li}"], rtol=2e-4, atol=1e-7)
+
+
+def test_layer_odd_widths_and_conv_golden(nb):
+    g = load_golden("layers_small.npz")
+    b, N = g["x"].shape[:2]
+    coo = torch.tensor(g["coo"], device=DEV)
+    for last, t in ((False, "mid"), (True, "last")):
+        Ht = torch.tensor(g["odd_H_in"], device=DEV, requires_grad=True)
+        Wt = [torch.tensor(g[f"odd_W{i}"], device=DEV, requires_grad=True) for i in range(4)]
+        Bt = torch.tensor(g["odd_B"], device=DEV, requires_grad=True)
+        o = nb.graph.shift_inv_layer(Ht, coo, (b, N), (Wt, Bt), is_last=last)
+        (o * torch.tensor(g[f"odd_{t}_gout"], device=DEV)).sum().backward()
+        np.testing.assert_allclose(o.detach().cpu().numpy(), g[f"odd_{t}_out"], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(Ht.grad.cpu().numpy(), g[f"odd_{t}_gH"], rtol=1e-4, atol=1e-5)
+        for i in range(4):
+            np.testing.assert_allclose(Wt[i].grad.cpu().numpy(), g[f"odd_{t}_gW{i}"], rtol=1e-4, atol=2e-4)
+        np.testing.assert_allclose(Bt.grad.cpu().numpy(), g[f"odd_{t}_gB"], rtol=1e-4, atol=2e-4)
+    H = torch.tensor(g["odd_H_in"], device=DEV)
+    for ci, nm in ((0, "row"), (1, "col"), (2, "cube")):
+        for bc, suffix in ((True, "bc"), (False, "nobc")):
+            out = nb.graph.shift_inv_conv(H, coo[ci], b * N, bc)
+            np.testing.assert_allclose(out.cpu().numpy(), g[f"conv_{nm}_{suffix}"], rtol=2e-5, atol=2e-6)
+
+
+def test_shift_inv_conv_autograd_vs_oracle(nb):
+    rng = np.random.default_rng(8)
+    h = rng.standard_normal((4000, 6)).astype(np.float32)
+    ids = rng.integers(0, 300, size=4000).astype(np.int32)      # arbitrary, unsorted, some segments empty
+    gout = rng.standard_normal((4000, 6)).astype(np.float32)
+    for bc in (True, False):
+        ht = torch.tensor(h, device=DEV, requires_grad=True)
+        o = nb.graph.shift_inv_conv(ht, torch.tensor(ids, device=DEV), 320, bc)
+        hc = torch.tensor(h, dtype=torch.float64, requires_grad=True)
+        oc = ref_layers.shift_inv_conv(hc, ids, 320, bc)
+        go = gout if bc else gout[:320]
+        (o * torch.tensor(go, device=DEV)).sum().backward()
+        (oc * torch.tensor(go, dtype=torch.float64)).sum().backward()
+        np.testing.assert_allclose(o.detach().cpu().numpy(), oc.detach().numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ht.grad.cpu().numpy(), hc.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_graph_step_is_deterministic(nb, syn):
+    ch = [3, 32, 16, 3]; b, N, k = 2, 4096, 14
+    x = torch.tensor(syn.clustered_box(b, N, 3), device=DEV)
+    za, tgt = (torch.tensor(a, device=DEV) for a in syn.za_features(b, N, 3))
+    outs = []
+    for _ in range(2):
+        store = nb.train_utils.ParamStore(ch, device=DEV)
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+        coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, k))
+        pred = nb.graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
+        loss = nb.nn.loss_ZA(pred, tgt)
+        loss.backward()
+        outs.append((pred.detach().clone(), loss.detach().clone(), store.flat_grad.clone()))
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)     # bit-identical: no float atomics anywhere
+
+
+def test_graph_model_properties_c2(nb, syn):
+    """BASELINE config 2 size (32^3, b=8, k=14): shift invariance and particle-relabelling equivariance."""
+    ch = [3, 32, 16, 3]; b, N, k = 8, 32768, 14
+    # coordinates on a 2^-20 lattice inside [0.25, 0.75): adding 0.125 is then exact in float32
+    x = torch.round(torch.tensor(syn.uniform_box(b, N, 1), device=DEV) * 2 ** 19) / 2 ** 20 + 0.25
+    za = torch.tensor(syn.za_features(b, N, 1)[0], device=DEV)
+    store = nb.train_utils.ParamStore(ch, device=DEV)
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+
+    def run(xx, zz):
+        coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(xx, k))
+        with torch.no_grad():
+            return nb.graph.model_func_shift_inv_za(xx, coo, zz, diag, mv, (b, N, k))
+    base = run(x, za)
+    assert tuple(base.shape) == (b, N, 3) and bool(torch.isfinite(base).all())
+    perm = torch.randperm(N, device=DEV)
+    assert torch.allclose(run(x[:, perm], za[:, perm]), base[:, perm], rtol=1e-4, atol=1e-6)
+    assert torch.equal(run(x + 0.125, za), base)      # exact shift => identical graph, edges and output
+
+
+# =============================================================================== set model + losses
+def test_set_model_golden(nb):
+    g = load_golden("set_small.npz")
+    ch = list(g["channels"]); L = len(ch) - 1
+    mv, tp = cuda_model_vars(g, ch)
+    H = torch.tensor(g["X"], device=DEV)
+    for li in range(L):
+        H = nb.nn.set_layer(H, tp[li])
+        if li < L - 1:
+            H = torch.relu(H)
+        np.testing.assert_allclose(H.detach().cpu().numpy(), g[f"f32_H{li}"], rtol=2e-5, atol=2e-6)
+    pred = nb.nn.model_func_set(torch.tensor(g["X"], device=DEV), mv)
+    loss = nb.nn.loss_ZA(pred, torch.tensor(g["Y"], device=DEV))
+    loss.backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), g["f32_pred"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(loss.item(), g["f64_loss"], rtol=1e-5)
+    for li, (Ws, B) in enumerate(tp):
+        np.testing.assert_allclose(Ws[0].grad.cpu().numpy(), g[f"f64_gW{li}"], rtol=2e-4, atol=1e-7)
+        np.testing.assert_allclose(B.grad.cpu().numpy(), g[f"f64_gB{li}"], rtol=2e-4, atol=1e-7)
+        assert all(w.grad is None for w in Ws[1:])      # nn.py:22: only W[0] takes part
+
+
+def test_set_layer_properties(nb):
+    """with B = 0 the output has zero mean over N; permutation equivariance."""
+    H = torch.randn(3, 1000, 7, device=DEV) * 3 + 5
+    W = [torch.randn(7, 11, device=DEV)]
+    out = nb.nn.set_layer(H, (W, torch.zeros(11, device=DEV)))
+    assert float(out.mean(dim=1).abs().max()) < 1e-4
+    perm = torch.randperm(1000, device=DEV)
+    assert torch.allclose(nb.nn.set_layer(H[:, perm], (W, torch.zeros(11, device=DEV))), out[:, perm], atol=1e-5)
+
+
+def test_losses_and_readout_golden(nb):
+    g = load_golden("losses.npz")
+    p = torch.tensor(g["pred"], device=DEV, requires_grad=True)
+    t = torch.tensor(g["truth"], device=DEV)
+    ro = nb.nn.get_readout(p)
+    assert np.array_equal(ro.detach().cpu().numpy(), g["f32_readout"])
+    assert np.array_equal(nb.nn.get_readout(p[..., :3]).detach().cpu().numpy(), g["f32_readout3"])
+    assert np.array_equal(nb.nn.periodic_boundary_dist(ro, t).cpu().numpy(), g["f32_pbd"])
+    l1 = nb.nn.pbc_loss(ro, t)
+    l1.backward()
+    np.testing.assert_allclose(l1.item(), g["f64_pbc_loss"], rtol=1e-5)
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g["f64_pbc_loss_gpred"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(nb.nn.pbc_loss(ro, t, scale_error=False).item(), g["f64_pbc_loss_unscaled"], rtol=1e-5)
+    p2 = torch.tensor(g["pred"][..., :3], device=DEV, requires_grad=True)
+    l2 = nb.nn.loss_ZA(p2, t[..., :3])
+    l2.backward()
+    np.testing.assert_allclose(l2.item(), g["f64_loss_za"], rtol=1e-5)
+    np.testing.assert_allclose(p2.grad.cpu().numpy(), g["f64_loss_za_gpred"], rtol=1e-5, atol=1e-9)
+    # reference quirk preserved: readout(0) = readout(1) = 0.5 (nn.py:112-115 with sign(0) = 0)
+    q = nb.nn.get_readout(torch.tensor([[[0.0, 1.0, 0.25]]], device=DEV))
+    assert q.flatten().tolist() == [0.5, 0.5, 0.25]
+
+
+def test_adam_tf_matches_tf_formula(nb):
+    rng = np.random.default_rng(0)
+    p = rng.standard_normal(1000).astype(np.float32); m = np.zeros_like(p); v = np.zeros_like(p)
+    pt, mt, vt = (torch.tensor(a, device=DEV) for a in (p, m, v))
+    lr, b1, b2, eps = 0.01, 0.9, 0.999, 1e-8
+    p64, m64, v64 = p.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for t in range(1, 6):
+        gr = rng.standard_normal(1000).astype(np.float32)
+        nb.ops.adam_tf_(pt, torch.tensor(gr, device=DEV), mt, vt, t, lr, b1, b2, eps, 0.5)
+        g64 = gr.astype(np.float64) * 0.5
+        lr_t = lr * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        m64 = b1 * m64 + (1 - b1) * g64
+        v64 = b2 * v64 + (1 - b2) * g64 * g64
+        p64 = p64 - lr_t * m64 / (np.sqrt(v64) + eps)
+    np.testing.assert_allclose(pt.cpu().numpy(), p64, rtol=1e-5, atol=1e-6)
