@@ -339,7 +339,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     top = sorted(kern_ms.items(), key=lambda kv: -kv[1])
     kernels = []
-    for name, t in top[:12]:
+    for name, t in top[:40]:
         per_launch_ms = t / kern_cnt[name]
         ab = kernel_algorithmic_bytes(name, b, N, k, relu_by_layer)
         kernels.append({"kernel": name, "ms_per_step": round(t, 4), "launches_per_step": kern_cnt[name],

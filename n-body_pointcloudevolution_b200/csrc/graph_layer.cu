@@ -14,6 +14,8 @@
 //
 // This file holds the barrier-free baseline kernels (one thread per output element).  They are the
 // correctness anchor for the tiled / tensor-core kernels and also compile under NBPC_HOST_EMU.
+#include <stdlib.h>
+
 #include "nbpc_common.cuh"
 #include "reduce.cuh"
 
@@ -222,12 +224,48 @@ __global__ void glb_edge_in_kernel(GlDz dz, const int32_t *__restrict__ col, con
 }
 
 // ------------------------------------------------------------------ workspaces
+#include "graph_layer_fast.cuh"
+
+// NBPC_BASELINE=1 forces the barrier-free baseline kernels (used to cross-check the tiled ones)
+static bool gl_use_fast() {
+#ifdef NBPC_HOST_EMU
+    return false;
+#else
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("NBPC_BASELINE");
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1;
+#endif
+}
+
+static int gl_edge_bwd_tiles_per_block(int64_t c) {
+    const int64_t ntiles = (c + 127) / 128;
+    int64_t tpb = (ntiles + 1183) / 1184;   // ~8 blocks per SM worth of partials at most
+    return (int)(tpb < 1 ? 1 : tpb);
+}
+static int gl_edge_bwd_grid(int64_t c) {
+    const int64_t ntiles = (c + 127) / 128;
+    const int tpb = gl_edge_bwd_tiles_per_block(c);
+    return (int)((ntiles + tpb - 1) / tpb);
+}
+static int gl_node_xty_rows_per_block(int64_t n) {
+    int64_t rpb = (n + 591) / 592;
+    rpb = (rpb + 31) / 32 * 32;
+    return (int)(rpb < 32 ? 32 : rpb);
+}
+static int gl_node_xty_grid(int64_t n) {
+    const int rpb = gl_node_xty_rows_per_block(n);
+    return (int)((n + rpb - 1) / rpb);
+}
+
 struct GlWorkspace {
     float *Qc, *Qr;          // (BN, max(k,q)) each: Q_col/Q_row (fwd), dQ_col/dQ_row (bwd)
     float *Gc, *Gr;          // (BN, k): G_col/G_row (bwd)
     float *cube_partial;     // (B, nblk, max(k,q))
     float *dCq;              // (B, q)
-    float *xty_partial;
+    float *xty_partial;      // per-block partials of the X^T Y reductions
     size_t bytes;
 };
 
@@ -245,10 +283,98 @@ static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int 
     w.dCq = a.take<float>((size_t)B * mx);
     int rpc, nc;
     xty_plan((int64_t)BN * M, k, q, &rpc, &nc);
-    w.xty_partial = a.take<float>((size_t)nc * k * q);
+    size_t nparts = (size_t)nc;
+    nparts = nbpc_max(nparts, (size_t)gl_edge_bwd_grid((int64_t)BN * M));
+    nparts = nbpc_max(nparts, (size_t)gl_node_xty_grid((int64_t)BN));
+    w.xty_partial = a.take<float>(nparts * k * q);
     w.bytes = a.off;
     return w;
 }
+
+#ifndef NBPC_HOST_EMU
+// ---- template dispatch over the compiled (K, Q) shapes of the edge-level kernels
+#define GLF_FOR_KQ(X)  X(3, 16) X(3, 32) X(3, 64) X(16, 16) X(16, 32) X(16, 64) X(32, 16) X(32, 32) X(32, 64) X(64, 16) X(64, 32) X(64, 64)
+
+static bool glf_edge_shape_ok(int k, int q) {
+#define X(K_, Q_) if (k == K_ && q == Q_) return true;
+    GLF_FOR_KQ(X)
+#undef X
+    return false;
+}
+
+template <class F>
+static int glf_set_smem(F kern, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+    }
+    return 0;
+}
+
+template <int K, int Q>
+static int glf_launch_edge_out(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
+                               int64_t c, int M, int relu, float *out, cudaStream_t stream) {
+    constexpr int KS = (K == 3) ? 3 : glf_stride(K), QS = glf_stride(Q);
+    const size_t smem = sizeof(float) * (size_t)(K * Q + GLF_TE * KS + GLF_TE * QS);
+    const int grid = (int)((c + GLF_TE - 1) / GLF_TE);
+    if (relu) {
+        auto kern = glf_edge_out_kernel<K, Q, true>;
+        if (glf_set_smem(kern, smem)) return 1;
+        NBPC_LAUNCH_N(NbpcKName("glf_edge_out_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, H, col, W1, Qc, Qr, c, M, out);
+    } else {
+        auto kern = glf_edge_out_kernel<K, Q, false>;
+        if (glf_set_smem(kern, smem)) return 1;
+        NBPC_LAUNCH_N(NbpcKName("glf_edge_out_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, H, col, W1, Qc, Qr, c, M, out);
+    }
+    return 0;
+}
+
+template <int K, int Q, bool RELU, bool HAS_DH>
+static int glf_launch_edge_bwd_t(const float *dOut, const float *Hout, const float *H, const int32_t *col, const float *W1,
+                                 const float *Gc, const float *Gr, int64_t c, int M, float *dH, float *partial,
+                                 cudaStream_t stream) {
+    constexpr int KP = (K == 3) ? 4 : K;
+    constexpr int KS = glf_stride(KP), QS = glf_stride(Q);
+    const size_t smem = sizeof(float) * (size_t)(Q * KP + 2 * GLF_TE * KS + GLF_TE * QS);
+    auto kern = glf_edge_bwd_kernel<K, Q, RELU, HAS_DH>;
+    if (glf_set_smem(kern, smem)) return 1;
+    const int tpb = gl_edge_bwd_tiles_per_block(c), grid = gl_edge_bwd_grid(c);
+    NBPC_LAUNCH_N(NbpcKName("glf_edge_bwd_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, dOut, Hout, H, col, W1,
+                  Gc, Gr, c, M, tpb, dH, partial);
+    return 0;
+}
+
+template <int K, int Q>
+static int glf_launch_edge_bwd(const float *dOut, const float *Hout, const float *H, const int32_t *col, const float *W1,
+                               const float *Gc, const float *Gr, int64_t c, int M, int relu, float *dH, float *partial,
+                               float *dW1, cudaStream_t stream) {
+    int rc;
+    if constexpr (K % 4 == 0) {
+        if (dH) rc = relu ? glf_launch_edge_bwd_t<K, Q, true, true>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
+                          : glf_launch_edge_bwd_t<K, Q, false, true>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+        else rc = relu ? glf_launch_edge_bwd_t<K, Q, true, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
+                       : glf_launch_edge_bwd_t<K, Q, false, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+    } else {
+        rc = relu ? glf_launch_edge_bwd_t<K, Q, true, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
+                  : glf_launch_edge_bwd_t<K, Q, false, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+    }
+    if (rc) return rc;
+    NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(K * Q, 128), 128, 0, stream, partial, gl_edge_bwd_grid(c), K * Q, dW1);
+    return 0;
+}
+
+// X^T Y over n node rows -> out (k,q); deterministic
+static void glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, int k, int q, float *partial,
+                         float *out, cudaStream_t stream) {
+    const int rpb = gl_node_xty_rows_per_block(n), grid = gl_node_xty_grid(n);
+    const size_t smem = sizeof(float) * (size_t)GLF_XTY_ROWS * (k + q);
+    NBPC_LAUNCH_N(name, glf_node_xty_kernel, grid, 256, smem, stream, X, Y, n, rpb, k, q, partial);
+    NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(k * q, 128), 128, 0, stream, partial, grid, k * q, out);
+}
+#endif  // !NBPC_HOST_EMU
+
 
 extern "C" {
 
@@ -331,21 +457,66 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
         return NBPC_EWORKSPACE;
     }
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
-    NBPC_LAUNCH_N(NbpcKName("gl_pool_kernel", k, q).c_str(), gl_pool_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, M, (int)BN, csrT_ptr,
-                csrT_edge, P_row, P_col);
+    const bool fast = gl_use_fast();
+    (void)fast;
+    // ---- pooling: P_row, P_col
+    bool done = false;
+#ifndef NBPC_HOST_EMU
+    if (fast && (k == 16 || k == 32 || k == 64)) {
+        const int grid = nbpc_cdiv(BN * (k / 4), 256);
+        if (k == 16) NBPC_LAUNCH_N(NbpcKName("glf_pool_kernel", k, q).c_str(), glf_pool_kernel<16>, grid, 256, 0, stream, H_in, M, (int)BN, csrT_ptr, csrT_edge, P_row, P_col);
+        if (k == 32) NBPC_LAUNCH_N(NbpcKName("glf_pool_kernel", k, q).c_str(), glf_pool_kernel<32>, grid, 256, 0, stream, H_in, M, (int)BN, csrT_ptr, csrT_edge, P_row, P_col);
+        if (k == 64) NBPC_LAUNCH_N(NbpcKName("glf_pool_kernel", k, q).c_str(), glf_pool_kernel<64>, grid, 256, 0, stream, H_in, M, (int)BN, csrT_ptr, csrT_edge, P_row, P_col);
+        done = true;
+    }
+#endif
+    if (!done)
+        NBPC_LAUNCH_N(NbpcKName("gl_pool_kernel", k, q).c_str(), gl_pool_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream,
+                      H_in, k, M, (int)BN, csrT_ptr, csrT_edge, P_row, P_col);
     NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, P_row, k, N,
                 nblk, B, w.cube_partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, k, nblk, B,
                 (float)N, P_cube);
-    NBPC_LAUNCH_N(NbpcKName("gl_node_project_kernel", k, q).c_str(), gl_node_project_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, P_col, P_row, P_cube, W,
-                bias, (int)BN, N, k, q, w.Qc, w.Qr);
-    if (is_last) {
-        NBPC_LAUNCH_N(NbpcKName("gl_last_out_kernel", k, q).c_str(), gl_last_out_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr,
-                    (int)BN, M, k, q, relu, H_out);
-    } else {
-        NBPC_LAUNCH_N(NbpcKName("gl_edge_out_kernel", k, q).c_str(), gl_edge_out_kernel, nbpc_cdiv(c * q, GL_THREADS), GL_THREADS, 0, stream, H_in, col, W, w.Qc, w.Qr, c, M,
-                    k, q, relu, H_out);
+    // ---- node-level projections Q_col, Q_row
+    done = false;
+#ifndef NBPC_HOST_EMU
+    if (fast && (size_t)3 * k * q * sizeof(float) <= 48 * 1024) {
+        NBPC_LAUNCH_N(NbpcKName("glf_node_project_kernel", k, q).c_str(), glf_node_project_kernel, nbpc_cdiv(BN * q, 256), 256,
+                      sizeof(float) * 3 * k * q, stream, P_col, P_row, P_cube, W, bias, (int)BN, N, k, q, w.Qc, w.Qr);
+        done = true;
     }
+#endif
+    if (!done)
+        NBPC_LAUNCH_N(NbpcKName("gl_node_project_kernel", k, q).c_str(), gl_node_project_kernel, nbpc_cdiv(BN * q, GL_THREADS),
+                      GL_THREADS, 0, stream, P_col, P_row, P_cube, W, bias, (int)BN, N, k, q, w.Qc, w.Qr);
+    // ---- output
+    if (is_last) {
+#ifndef NBPC_HOST_EMU
+        if (fast) {
+            NBPC_LAUNCH_N(NbpcKName("glf_last_out_kernel", k, q).c_str(), glf_last_out_kernel, nbpc_cdiv(BN * q, 256), 256, 0, stream,
+                          P_row, col, W, w.Qc, w.Qr, (int)BN, M, k, q, relu, H_out);
+            return nbpc_check_launch("nbpc_graph_layer_fwd");
+        }
+#endif
+        NBPC_LAUNCH_N(NbpcKName("gl_last_out_kernel", k, q).c_str(), gl_last_out_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0,
+                      stream, H_in, col, W, w.Qc, w.Qr, (int)BN, M, k, q, relu, H_out);
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
+#ifndef NBPC_HOST_EMU
+    if (fast && glf_edge_shape_ok(k, q)) {
+        int rc = 1;
+#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_out<K_, Q_>(H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+        GLF_FOR_KQ(X)
+#undef X
+        if (rc) {
+            nbpc_set_error("nbpc_graph_layer_fwd: could not configure shared memory");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
+#endif
+    NBPC_LAUNCH_N(NbpcKName("gl_edge_out_kernel", k, q).c_str(), gl_edge_out_kernel, nbpc_cdiv(c * q, GL_THREADS), GL_THREADS, 0,
+                  stream, H_in, col, W, w.Qc, w.Qr, c, M, k, q, relu, H_out);
     return nbpc_check_launch("nbpc_graph_layer_fwd");
 }
 
@@ -372,31 +543,102 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     dz.g = dOut; dz.hout = H_out; dz.relu = relu; dz.is_last = is_last; dz.M = M; dz.q = q;
     float *dQ_col = w.Qc, *dQ_row = w.Qr;
     const int64_t kq = (int64_t)k * q;
+    const bool fast = gl_use_fast();
+    (void)fast;
 
-    NBPC_LAUNCH_N(NbpcKName("glb_pool_kernel", k, q).c_str(), glb_pool_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream, dz, (int)BN, M, q, csrT_ptr,
-                csrT_edge, dQ_row, dQ_col);
+    // ---- dQ_row, dQ_col
+    bool done = false;
+#ifndef NBPC_HOST_EMU
+    if (fast && is_last) {
+        NBPC_LAUNCH_N(NbpcKName("glf_last_bwd_pool_kernel", k, q).c_str(), glf_last_bwd_pool_kernel, nbpc_cdiv(BN * q, 256), 256, 0,
+                      stream, dOut, H_out, relu, (int)BN, M, q, csrT_ptr, csrT_edge, dQ_row, dQ_col);
+        done = true;
+    } else if (fast && (q == 16 || q == 32 || q == 64)) {
+        const int grid = nbpc_cdiv(BN * (q / 4), 256);
+#define GLF_BP(Q_)                                                                                                        \
+    if (q == Q_) {                                                                                                       \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("glf_bwd_pool_kernel", k, q).c_str(), (glf_bwd_pool_kernel<Q_, true>), grid, 256, 0, stream, dOut, H_out, M, (int)BN, csrT_ptr, csrT_edge, dQ_row, dQ_col); \
+        else NBPC_LAUNCH_N(NbpcKName("glf_bwd_pool_kernel", k, q).c_str(), (glf_bwd_pool_kernel<Q_, false>), grid, 256, 0, stream, dOut, H_out, M, (int)BN, csrT_ptr, csrT_edge, dQ_row, dQ_col); \
+    }
+        GLF_BP(16) GLF_BP(32) GLF_BP(64)
+#undef GLF_BP
+        done = true;
+    }
+#endif
+    if (!done)
+        NBPC_LAUNCH_N(NbpcKName("glb_pool_kernel", k, q).c_str(), glb_pool_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream,
+                      dz, (int)BN, M, q, csrT_ptr, csrT_edge, dQ_row, dQ_col);
     NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dQ_row, q, N,
                 nblk, B, w.cube_partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, q, nblk, B, 1.0f,
                 w.dCq);
     NBPC_LAUNCH(glb_bias_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.dCq, B, q, dB);
-    // dW1 = H_in^T dZ (c rows), dW2 = P_col^T dQ_col, dW3 = P_row^T dQ_row (BN rows), dW4 = P_cube^T dCq (B rows)
+
+    // ---- node-level weight gradients: dW2 = P_col^T dQ_col, dW3 = P_row^T dQ_row, dW4 = P_cube^T dCq
     GlPlain x, y;
     x.ld = k; y.ld = q;
-    x.p = H_in;
-    xty(NbpcKName("xty_partial_dW1", k, q).c_str(), x, dz, c, k, q, w.xty_partial, dW, stream);
-    x.p = P_col; y.p = dQ_col;
-    xty("xty_partial_dW2", x, y, BN, k, q, w.xty_partial, dW + kq, stream);
-    x.p = P_row; y.p = dQ_row;
-    xty("xty_partial_dW3", x, y, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
+    done = false;
+#ifndef NBPC_HOST_EMU
+    if (fast && kq <= 4096) {
+        glf_node_xty("glf_node_xty_dW2", P_col, dQ_col, BN, k, q, w.xty_partial, dW + kq, stream);
+        glf_node_xty("glf_node_xty_dW3", P_row, dQ_row, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
+        done = true;
+    }
+#endif
+    if (!done) {
+        x.p = P_col; y.p = dQ_col;
+        xty("xty_partial_dW2", x, y, BN, k, q, w.xty_partial, dW + kq, stream);
+        x.p = P_row; y.p = dQ_row;
+        xty("xty_partial_dW3", x, y, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
+    }
     x.p = P_cube; y.p = w.dCq;
     xty("xty_partial_dW4", x, y, (int64_t)B, k, q, w.xty_partial, dW + 3 * kq, stream);
+
+    // ---- node-level input-gradient terms G_col, G_row
     if (dH_in) {
-        NBPC_LAUNCH_N(NbpcKName("glb_node_grad_kernel", k, q).c_str(), glb_node_grad_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream, dQ_col, dQ_row, w.dCq, W,
-                    csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
-        NBPC_LAUNCH_N(NbpcKName("glb_edge_in_kernel", k, q).c_str(), glb_edge_in_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0, stream, dz, col, W, w.Gc, w.Gr, c, M, k,
-                    q, dH_in);
+        done = false;
+#ifndef NBPC_HOST_EMU
+        if (fast && (size_t)3 * kq * sizeof(float) <= 48 * 1024) {
+            NBPC_LAUNCH_N(NbpcKName("glf_node_grad_kernel", k, q).c_str(), glf_node_grad_kernel, nbpc_cdiv(BN * k, 256), 256,
+                          sizeof(float) * 3 * kq, stream, dQ_col, dQ_row, w.dCq, W, csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
+            done = true;
+        }
+#endif
+        if (!done)
+            NBPC_LAUNCH_N(NbpcKName("glb_node_grad_kernel", k, q).c_str(), glb_node_grad_kernel, nbpc_cdiv(BN * k, GL_THREADS),
+                          GL_THREADS, 0, stream, dQ_col, dQ_row, w.dCq, W, csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
     }
+
+    // ---- edge level: dW1 = H^T dZ and dH = dZ W1^T + G_col[col] + G_row[row]
+#ifndef NBPC_HOST_EMU
+    if (fast && is_last && kq <= 4096 && (!dH_in || k % 4 == 0)) {
+        // row-mean output: dZ[e] = dOutM[e/M]/M  =>  dW1 = P_row^T dOutM (= dW3), dH[e] = R[e/M] + G_col[col[e]]
+        NBPC_LAUNCH(glf_copy_kernel, nbpc_cdiv(kq, 128), 128, 0, stream, dW + 2 * kq, dW, (int)kq);
+        if (dH_in) {
+            NBPC_LAUNCH_N(NbpcKName("glf_last_rowterm_kernel", k, q).c_str(), glf_last_rowterm_kernel, nbpc_cdiv(BN * k, 256), 256, 0,
+                          stream, dQ_row, W, (int)BN, M, k, q, w.Gr);
+            NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256,
+                          0, stream, col, w.Gr, w.Gc, c, M, k, dH_in);
+        }
+        return nbpc_check_launch("nbpc_graph_layer_bwd");
+    }
+    if (fast && !is_last && glf_edge_shape_ok(k, q) && (!dH_in || k % 4 == 0)) {
+        int rc = 1;
+#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, dH_in, w.xty_partial, dW, stream);
+        GLF_FOR_KQ(X)
+#undef X
+        if (rc) {
+            nbpc_set_error("nbpc_graph_layer_bwd: could not configure shared memory");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_graph_layer_bwd");
+    }
+#endif
+    x.p = H_in;
+    xty(NbpcKName("xty_partial_dW1", k, q).c_str(), x, dz, c, k, q, w.xty_partial, dW, stream);
+    if (dH_in)
+        NBPC_LAUNCH_N(NbpcKName("glb_edge_in_kernel", k, q).c_str(), glb_edge_in_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0,
+                      stream, dz, col, W, w.Gc, w.Gr, c, M, k, q, dH_in);
     return nbpc_check_launch("nbpc_graph_layer_bwd");
 }
 

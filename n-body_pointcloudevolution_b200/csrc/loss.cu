@@ -3,7 +3,8 @@
 #include "nbpc_common.cuh"
 
 #define LOSS_THREADS 256
-#define LOSS_CHUNK 1024  // rows per partial
+#define LOSS_CHUNK 64    // rows per first-level partial
+#define LOSS_FAN 64      // first-level partials per second-level partial
 
 __device__ __forceinline__ float sq_rn(float a) { return __fmul_rn(a, a); }
 
@@ -44,6 +45,15 @@ __global__ void loss_partial_kernel(const float *__restrict__ pred, int ldp, con
         acc = __fadd_rn(acc, rs);
     }
     partial[ch] = acc;
+}
+
+__global__ void loss_mid_kernel(const float *__restrict__ partial, int n1, int n2, float *__restrict__ partial2) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n2) return;
+    const int i0 = j * LOSS_FAN, i1 = nbpc_min(i0 + LOSS_FAN, n1);
+    float acc = 0.f;
+    for (int i = i0; i < i1; ++i) acc = __fadd_rn(acc, partial[i]);
+    partial2[j] = acc;
 }
 
 __global__ void loss_final_kernel(const float *__restrict__ partial, int nchunks, float rows, float scale,
@@ -124,14 +134,17 @@ static int loss_fwd_impl(const float *pred, int ldp, const float *truth, int ldt
     NBPC_ARG(pred && truth && loss_out && workspace, "null pointer");
     NBPC_ARG(rows >= 1 && ldp >= 3 && ldt >= 3, "bad sizes");
     const int nchunks = nbpc_cdiv(rows, LOSS_CHUNK);
-    if (nbpc_align_up((size_t)nchunks * sizeof(float)) > ws_bytes) {
+    const int n2 = nbpc_cdiv(nchunks, LOSS_FAN);
+    if (nbpc_align_up((size_t)(nchunks + n2) * sizeof(float)) > ws_bytes) {
         nbpc_set_error(std::string(name) + ": workspace too small");
         return NBPC_EWORKSPACE;
     }
     float *partial = (float *)workspace;
+    float *partial2 = partial + nchunks;
     void (*kern)(const float *, int, const float *, int, int64_t, int, float *) = loss_partial_kernel<PBC>;
     NBPC_LAUNCH_N("loss_partial_kernel", kern, nbpc_cdiv(nchunks, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows, nchunks, partial);
-    NBPC_LAUNCH(loss_final_kernel, 1, 32, 0, stream, partial, nchunks, (float)rows, scale, loss_out);
+    NBPC_LAUNCH(loss_mid_kernel, nbpc_cdiv(n2, LOSS_THREADS), LOSS_THREADS, 0, stream, partial, nchunks, n2, partial2);
+    NBPC_LAUNCH(loss_final_kernel, 1, 32, 0, stream, partial2, n2, (float)rows, scale, loss_out);
     return nbpc_check_launch(name);
 }
 
@@ -151,7 +164,8 @@ extern "C" {
 
 size_t nbpc_loss_workspace_bytes(int64_t rows) {
     if (rows < 1) return 0;
-    return nbpc_align_up((size_t)nbpc_cdiv(rows, LOSS_CHUNK) * sizeof(float));
+    const size_t n1 = (size_t)nbpc_cdiv(rows, LOSS_CHUNK);
+    return nbpc_align_up((n1 + (n1 + LOSS_FAN - 1) / LOSS_FAN) * sizeof(float));
 }
 
 int nbpc_loss_za_fwd(const float *pred, int ld_pred, const float *truth, int ld_truth, int64_t rows, float *loss_out,

@@ -394,3 +394,74 @@ def test_adam_tf_matches_tf_formula(nb):
         v64 = b2 * v64 + (1 - b2) * g64 * g64
         p64 = p64 - lr_t * m64 / (np.sqrt(v64) + eps)
     np.testing.assert_allclose(pt.cpu().numpy(), p64, rtol=1e-5, atol=1e-6)
+
+
+# =============================================================================== every compiled layer shape
+@pytest.mark.parametrize("k,q", [(3, 16), (3, 32), (3, 64), (16, 16), (16, 32), (16, 64), (32, 16), (32, 32), (32, 64),
+                                 (64, 16), (64, 32), (64, 64), (16, 3), (32, 3), (9, 32), (10, 8), (8, 128), (128, 8)])
+@pytest.mark.parametrize("is_last,relu", [(False, True), (False, False), (True, False)])
+def test_graph_layer_shapes_vs_oracle(nb, k, q, is_last, relu):
+    """Tiled kernels (and the baseline fallback for shapes they do not cover) against the float64 oracle,
+    forward + all gradients, on a graph whose edge count is not a multiple of the 128-edge tile."""
+    b, N, M = 2, 601, 10
+    rng = np.random.default_rng(k * 131 + q)
+    x = rng.random((b, N, 3)).astype(np.float32)
+    coo, _ = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, M))
+    coo_np = coo.cpu().numpy()
+    c = b * N * M
+    H = rng.standard_normal((c, k)).astype(np.float32)
+    Ws = [(rng.standard_normal((k, q)) / np.sqrt(k)).astype(np.float32) for _ in range(4)]
+    Bv = (0.1 * rng.standard_normal(q)).astype(np.float32)
+    gout = rng.standard_normal(((b, N, q) if is_last else (c, q))).astype(np.float32)
+
+    Ht = torch.tensor(H, device=DEV, requires_grad=True)
+    Wt = [torch.tensor(w, device=DEV, requires_grad=True) for w in Ws]
+    Bt = torch.tensor(Bv, device=DEV, requires_grad=True)
+    if relu:   # the fused-activation path the network functions use
+        o = nb.graph._layer(Ht, coo, (b, N), (Wt, Bt), is_last, True)
+    else:
+        o = nb.graph.shift_inv_layer(Ht, coo, (b, N), (Wt, Bt), is_last=is_last)
+    (o * torch.tensor(gout, device=DEV)).sum().backward()
+
+    Hc = torch.tensor(H, dtype=torch.float64, requires_grad=True)
+    Wc = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in Ws]
+    Bc = torch.tensor(Bv, dtype=torch.float64, requires_grad=True)
+    oc = ref_layers.shift_inv_layer(Hc, coo_np, (b, N), (Wc, Bc), is_last=is_last)
+    if relu:
+        oc = torch.relu(oc)
+    (oc * torch.tensor(gout, dtype=torch.float64)).sum().backward()
+
+    np.testing.assert_allclose(o.detach().cpu().numpy(), oc.detach().numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(Ht.grad.cpu().numpy(), Hc.grad.numpy(), rtol=2e-4, atol=2e-5)
+    scale = float(np.abs(Wc[0].grad.numpy()).max())
+    for i in range(4):
+        np.testing.assert_allclose(Wt[i].grad.cpu().numpy(), Wc[i].grad.numpy(), rtol=2e-4, atol=2e-5 * max(scale, 1.0))
+    np.testing.assert_allclose(Bt.grad.cpu().numpy(), Bc.grad.numpy(), rtol=2e-4, atol=2e-4)
+
+
+def test_fast_and_baseline_kernels_agree(nb, syn):
+    """NBPC_BASELINE=1 (barrier-free baseline kernels) vs the tiled kernels, whole model, in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import importlib, sys, types, torch, numpy as np
+sys.path.insert(0, %r)
+nb = importlib.import_module("n-body_pointcloudevolution_b200")
+syn = nb.synthetic
+ch = [3, 32, 16, 3]; b, N, k = 2, 4096, 14
+x = torch.tensor(syn.uniform_box(b, N, 2), device="cuda"); za, tgt = (torch.tensor(a, device="cuda") for a in syn.za_features(b, N, 2))
+store = nb.train_utils.ParamStore(ch, device="cuda")
+mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, k))
+pred = nb.graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k)); loss = nb.nn.loss_ZA(pred, tgt); loss.backward()
+np.savez(sys.argv[1], pred=pred.detach().cpu().numpy(), grad=store.flat_grad.cpu().numpy())
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),)
+    outs = []
+    for flag in ("0", "1"):
+        path = f"/tmp/nbpc_fb_{flag}.npz"
+        env = dict(os.environ, NBPC_BASELINE=flag)
+        subprocess.check_call([sys.executable, "-c", code, path], env=env)
+        outs.append(np.load(path))
+    np.testing.assert_allclose(outs[0]["pred"], outs[1]["pred"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(outs[0]["grad"], outs[1]["grad"], rtol=1e-4, atol=1e-7)
