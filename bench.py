@@ -181,18 +181,25 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
     relu = 2 if (k, q) in relu_by_layer and relu_by_layer[(k, q)] else 1   # masked dZ also reads H_out
     if base == "knn_query":
         return n * (12 + 4 * M)                      # xyz in, int32 idx out
-    if base == "gl_pool_kernel":
+    if base in ("gl_pool_kernel", "glf_pool_kernel"):          # H read for the row pool + gathered for the col pool
         return c * (2 * 4 * k + 4) + n * (4 + 2 * 4 * k)
-    if base == "gl_edge_out_kernel":
+    if base in ("gl_edge_out_kernel", "glf_edge_out_kernel"):  # H in, col in, H_out out (+ node tables)
         return c * (4 * k + 4 + 4 * q) + n * 2 * 4 * q
     if base == "gl_last_out_kernel":
         return c * (4 * k + 4) + n * 3 * 4 * q
-    if base == "glb_pool_kernel":
-        return c * (2 * 4 * q * relu + 4) + n * (4 + 2 * 4 * q)
+    if base == "glf_last_out_kernel":
+        return c * 4 + n * (4 * k + 3 * 4 * q)
+    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel"):     # dZ read twice (row sums + gathered); the network
+        return c * (2 * 4 * q + 4) + n * (4 + 2 * 4 * q)       # path delivers dZ pre-masked (no H_out read)
     if base == "xty_partial_dW1":
         return c * (4 * k + 4 * q * relu)
     if base == "glb_edge_in_kernel":
         return c * (4 * q * relu + 4 + 4 * k) + n * 2 * 4 * k
+    if base == "glf_edge_bwd_kernel":                          # dZ + H in, dH out (not for the first layer), col
+        first = (k == 3)
+        return c * (4 * q + 4 * k + (0 if first else 4 * k + 4)) + (0 if first else n * 2 * 4 * k)
+    if base == "glf_last_edge_in_kernel":                      # col in, H (mask) in, dH out
+        return c * (4 + 2 * 4 * k) + n * 2 * 4 * k
     if base == "edge_features_kernel":
         return c * (4 + 12) + n * 12
     if base in ("adj_coo_kernel",):

@@ -134,7 +134,10 @@ int nbpc_gather_rows(const float *src, int k, const int32_t *ids, int64_t n_ids,
  * W: float32 (4, k, q) = [W1, W2, W3, W4]; bias (q).
  * Saved for backward (caller-allocated): P_col (BN,k), P_row (BN,k), P_cube (B,k).
  * Backward returns dH_in (c,k; NULL to skip - first layer), dW (4,k,q), dB (q); all sums run in
- * a fixed order (CSR transpose + two-level trees; no float atomics) => bit-reproducible. */
+ * a fixed order (CSR transpose + two-level trees; no float atomics) => bit-reproducible.
+ * relu (bwd): dOut is masked by [H_out > 0] first (pass 0 if the caller already did).
+ * mask_input: dH_in is multiplied by [H_in > 0], i.e. the ReLU backward of the layer that produced
+ *   H_in is fused here, where H_in is already on chip (its producer then passes relu = 0). */
 size_t nbpc_graph_layer_workspace_bytes(int B, int N, int M, int k, int q);
 int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *csrT_ptr,
                          const int32_t *csrT_edge, int B, int N, int M, int k, int q,
@@ -145,8 +148,8 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                          const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge,
                          int B, int N, int M, int k, int q, const float *W, const float *P_col,
                          const float *P_row, const float *P_cube, int is_last, int relu,
-                         float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes,
-                         void *stream);
+                         int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
+                         size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------- set layer
  * nn.set_layer (nn.py:10-28): out = (H - mean_N H) W + B on (B,N,k) -> (B,N,q); relu optional

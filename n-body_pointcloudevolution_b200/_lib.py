@@ -43,7 +43,7 @@ SIGNATURES = {
     "nbpc_gather_rows": (_i, [_p, _i, _p, _i64, _p, _p, _p]),
     "nbpc_graph_layer_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "nbpc_graph_layer_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
-    "nbpc_graph_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i,
+    "nbpc_graph_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i,
                                   _p, _p, _p, _p, _sz, _p]),
     "nbpc_set_layer_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "nbpc_set_layer_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),

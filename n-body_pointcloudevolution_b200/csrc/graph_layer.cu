@@ -210,6 +210,12 @@ __global__ void glb_node_grad_kernel(const float *__restrict__ dQ_col, const flo
     G_row[t] = a3 / (float)M + a4 / ((float)N * (float)M);
 }
 
+// ReLU backward of the layer that produced H_in, applied to this layer's dH_in (mask_input)
+__global__ void glb_mask_input_kernel(const float *__restrict__ H, int64_t n, float *__restrict__ dH) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && !(H[t] > 0.f)) dH[t] = 0.f;
+}
+
 __global__ void glb_edge_in_kernel(GlDz dz, const int32_t *__restrict__ col, const float *__restrict__ W1,
                                    const float *__restrict__ G_col, const float *__restrict__ G_row, int64_t c,
                                    int M, int k, int q, float *__restrict__ dH) {
@@ -240,16 +246,22 @@ static bool gl_use_fast() {
 #endif
 }
 
-static int gl_edge_bwd_tiles_per_block(int64_t c) {
-    const int64_t ntiles = (c + 127) / 128;
-    int64_t tpb = (ntiles + 1183) / 1184;   // ~8 blocks per SM worth of partials at most
-    return (int)(tpb < 1 ? 1 : tpb);
+#ifndef NBPC_HOST_EMU
+static int gl_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    return sms;
 }
-static int gl_edge_bwd_grid(int64_t c) {
-    const int64_t ntiles = (c + 127) / 128;
-    const int tpb = gl_edge_bwd_tiles_per_block(c);
-    return (int)((ntiles + tpb - 1) / tpb);
-}
+#else
+static int gl_num_sms() { return 148; }
+#endif
+// upper bound on the number of per-block partials any X^T Y reduction writes (persistent grids never
+// exceed 8 resident blocks per SM)
+static int gl_max_partial_blocks() { return gl_num_sms() * 8; }
 static int gl_node_xty_rows_per_block(int64_t n) {
     int64_t rpb = (n + 591) / 592;
     rpb = (rpb + 31) / 32 * 32;
@@ -284,7 +296,7 @@ static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int 
     int rpc, nc;
     xty_plan((int64_t)BN * M, k, q, &rpc, &nc);
     size_t nparts = (size_t)nc;
-    nparts = nbpc_max(nparts, (size_t)gl_edge_bwd_grid((int64_t)BN * M));
+    nparts = nbpc_max(nparts, (size_t)gl_max_partial_blocks());
     nparts = nbpc_max(nparts, (size_t)gl_node_xty_grid((int64_t)BN));
     w.xty_partial = a.take<float>(nparts * k * q);
     w.bytes = a.off;
@@ -302,76 +314,120 @@ static bool glf_edge_shape_ok(int k, int q) {
     return false;
 }
 
+// persistent grid: blocks/SM from the occupancy calculator (cached per kernel instance)
 template <class F>
-static int glf_set_smem(F kern, size_t bytes) {
-    if (bytes > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+static int glf_persistent_grid(F kern, int threads, size_t smem) {
+    if (smem > 48 * 1024) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
             cudaGetLastError();
-            return 1;
+            return -1;
         }
     }
-    return 0;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        return -1;
+    }
+    if (occ > 8) occ = 8;
+    return gl_num_sms() * occ;
 }
 
+template <int K, int Q, bool RELU>
+static int glf_launch_edge_out_t(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
+                                 int64_t c, int M, float *out, cudaStream_t stream) {
+    constexpr int KS = (K == 3) ? 0 : glf_stride(K), QS = glf_stride(Q);
+    const size_t smem = sizeof(float) * (size_t)(((K * Q + 3) / 4) * 4 + GLF_TE * QS + 2 * GLF_TE * KS);
+    auto kern = glf_edge_out_kernel<K, Q, RELU>;
+    static int grid_cache = 0;
+    const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;
+    if (!grid_cache) grid_cache = glf_persistent_grid(kern, GLF_THREADS, smem);
+    if (grid_cache < 0) return 1;
+    const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
+    NBPC_LAUNCH_N(NbpcKName("glf_edge_out_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, H, col, W1, Qc, Qr, c, M, out);
+    return 0;
+}
 template <int K, int Q>
 static int glf_launch_edge_out(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
                                int64_t c, int M, int relu, float *out, cudaStream_t stream) {
-    constexpr int KS = (K == 3) ? 3 : glf_stride(K), QS = glf_stride(Q);
-    const size_t smem = sizeof(float) * (size_t)(K * Q + GLF_TE * KS + GLF_TE * QS);
-    const int grid = (int)((c + GLF_TE - 1) / GLF_TE);
-    if (relu) {
-        auto kern = glf_edge_out_kernel<K, Q, true>;
-        if (glf_set_smem(kern, smem)) return 1;
-        NBPC_LAUNCH_N(NbpcKName("glf_edge_out_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, H, col, W1, Qc, Qr, c, M, out);
-    } else {
-        auto kern = glf_edge_out_kernel<K, Q, false>;
-        if (glf_set_smem(kern, smem)) return 1;
-        NBPC_LAUNCH_N(NbpcKName("glf_edge_out_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, H, col, W1, Qc, Qr, c, M, out);
-    }
-    return 0;
+    return relu ? glf_launch_edge_out_t<K, Q, true>(H, col, W1, Qc, Qr, c, M, out, stream)
+                : glf_launch_edge_out_t<K, Q, false>(H, col, W1, Qc, Qr, c, M, out, stream);
 }
 
-template <int K, int Q, bool RELU, bool HAS_DH>
-static int glf_launch_edge_bwd_t(const float *dOut, const float *Hout, const float *H, const int32_t *col, const float *W1,
-                                 const float *Gc, const float *Gr, int64_t c, int M, float *dH, float *partial,
-                                 cudaStream_t stream) {
+// launches the edge backward kernel; returns the number of per-block partials written (<= 0 on error)
+template <int K, int Q, bool RELU, bool HAS_DH, bool MASK_IN>
+static int glf_launch_edge_bwd_t(const char *name, const float *dOut, const float *Hout, const float *H, const int32_t *col,
+                                 const float *W1, const float *Gc, const float *Gr, int64_t c, int M, float *dH,
+                                 float *partial, cudaStream_t stream) {
     constexpr int KP = (K == 3) ? 4 : K;
     constexpr int KS = glf_stride(KP), QS = glf_stride(Q);
-    const size_t smem = sizeof(float) * (size_t)(Q * KP + 2 * GLF_TE * KS + GLF_TE * QS);
-    auto kern = glf_edge_bwd_kernel<K, Q, RELU, HAS_DH>;
-    if (glf_set_smem(kern, smem)) return 1;
-    const int tpb = gl_edge_bwd_tiles_per_block(c), grid = gl_edge_bwd_grid(c);
-    NBPC_LAUNCH_N(NbpcKName("glf_edge_bwd_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, dOut, Hout, H, col, W1,
-                  Gc, Gr, c, M, tpb, dH, partial);
-    return 0;
+    constexpr int TILE = GLF_TE * (KS + QS + (RELU ? QS : 0));
+    const size_t smem = sizeof(float) * (size_t)(Q * KP + 2 * TILE);
+    auto kern = glf_edge_bwd_kernel<K, Q, RELU, HAS_DH, MASK_IN>;
+    static int grid_cache = 0;
+    if (!grid_cache) grid_cache = glf_persistent_grid(kern, GLF_THREADS, smem);
+    if (grid_cache < 0) return -1;
+    const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;
+    int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
+    const int tpb = (int)((ntiles + grid - 1) / grid);
+    grid = (int)((ntiles + tpb - 1) / tpb);
+    NBPC_LAUNCH_N(name, kern, grid, GLF_THREADS, smem, stream, dOut, Hout, H, col, W1, Gc, Gr, c, M, tpb, dH, partial);
+    return grid;
+}
+
+static void glf_reduce_partials(const float *partial, int nblocks, int rows, int cols, int transpose, float *out,
+                                cudaStream_t stream) {
+    NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(rows * cols, 32), 1024, 0, stream, partial, nblocks, rows, cols, transpose, out);
 }
 
 template <int K, int Q>
 static int glf_launch_edge_bwd(const float *dOut, const float *Hout, const float *H, const int32_t *col, const float *W1,
-                               const float *Gc, const float *Gr, int64_t c, int M, int relu, float *dH, float *partial,
-                               float *dW1, cudaStream_t stream) {
-    int rc;
+                               const float *Gc, const float *Gr, int64_t c, int M, int relu, int mask_in, float *dH,
+                               float *partial, float *dW1, cudaStream_t stream) {
+    int nb = -1;
+    const NbpcKName nm("glf_edge_bwd_kernel", K, Q);
+    const char *n = nm.c_str();
     if constexpr (K % 4 == 0) {
-        if (dH) rc = relu ? glf_launch_edge_bwd_t<K, Q, true, true>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
-                          : glf_launch_edge_bwd_t<K, Q, false, true>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-        else rc = relu ? glf_launch_edge_bwd_t<K, Q, true, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
-                       : glf_launch_edge_bwd_t<K, Q, false, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-    } else {
-        rc = relu ? glf_launch_edge_bwd_t<K, Q, true, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
-                  : glf_launch_edge_bwd_t<K, Q, false, false>(dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+        if (dH) {
+            if (relu && mask_in) nb = glf_launch_edge_bwd_t<K, Q, true, true, true>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+            else if (relu) nb = glf_launch_edge_bwd_t<K, Q, true, true, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+            else if (mask_in) nb = glf_launch_edge_bwd_t<K, Q, false, true, true>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+            else nb = glf_launch_edge_bwd_t<K, Q, false, true, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+        }
     }
-    if (rc) return rc;
-    NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(K * Q, 128), 128, 0, stream, partial, gl_edge_bwd_grid(c), K * Q, dW1);
+    if (!dH) {
+        nb = relu ? glf_launch_edge_bwd_t<K, Q, true, false, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
+                  : glf_launch_edge_bwd_t<K, Q, false, false, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+    }
+    if (nb <= 0) return 1;
+    glf_reduce_partials(partial, nb, K, Q, 0, dW1, stream);
     return 0;
 }
 
-// X^T Y over n node rows -> out (k,q); deterministic
-static void glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, int k, int q, float *partial,
-                         float *out, cudaStream_t stream) {
+// X^T Y over n node rows -> out (k,q); deterministic.  Uses the micro-tile kernel when (k,q) or (q,k)
+// is a compiled shape, else the generic kernel.
+static int glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, int k, int q, float *partial,
+                        float *out, cudaStream_t stream) {
+    int nb = 0;
+#define XN(K_, Q_)                                                                                                    \
+    if (!nb && k == K_ && q == Q_) {                                                                                 \
+        nb = glf_launch_edge_bwd_t<K_, Q_, false, false, false>(name, Y, nullptr, X, nullptr, nullptr, nullptr, nullptr, n, 1, \
+                                                                nullptr, partial, stream);                          \
+        if (nb > 0) glf_reduce_partials(partial, nb, k, q, 0, out, stream);                                          \
+    }                                                                                                                \
+    if (!nb && k == Q_ && q == K_ && K_ != Q_) {                                                                     \
+        nb = glf_launch_edge_bwd_t<K_, Q_, false, false, false>(name, X, nullptr, Y, nullptr, nullptr, nullptr, nullptr, n, 1, \
+                                                                nullptr, partial, stream);                          \
+        if (nb > 0) glf_reduce_partials(partial, nb, q, k, 1, out, stream);                                          \
+    }
+    GLF_FOR_KQ(XN)
+#undef XN
+    if (nb < 0) return 1;
+    if (nb > 0) return 0;
     const int rpb = gl_node_xty_rows_per_block(n), grid = gl_node_xty_grid(n);
     const size_t smem = sizeof(float) * (size_t)GLF_XTY_ROWS * (k + q);
     NBPC_LAUNCH_N(name, glf_node_xty_kernel, grid, 256, smem, stream, X, Y, n, rpb, k, q, partial);
-    NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(k * q, 128), 128, 0, stream, partial, grid, k * q, out);
+    glf_reduce_partials(partial, grid, k, q, 0, out, stream);
+    return 0;
 }
 #endif  // !NBPC_HOST_EMU
 
@@ -481,7 +537,7 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
     done = false;
 #ifndef NBPC_HOST_EMU
     if (fast && (size_t)3 * k * q * sizeof(float) <= 48 * 1024) {
-        NBPC_LAUNCH_N(NbpcKName("glf_node_project_kernel", k, q).c_str(), glf_node_project_kernel, nbpc_cdiv(BN * q, 256), 256,
+        NBPC_LAUNCH_N(NbpcKName("glf_node_project_kernel", k, q).c_str(), glf_node_project_kernel, nbpc_min(nbpc_cdiv(BN * q, 256), gl_num_sms() * 8), 256,
                       sizeof(float) * 3 * k * q, stream, P_col, P_row, P_cube, W, bias, (int)BN, N, k, q, w.Qc, w.Qr);
         done = true;
     }
@@ -523,8 +579,8 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
 int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const int32_t *col,
                          const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k, int q,
                          const float *W, const float *P_col, const float *P_row, const float *P_cube, int is_last,
-                         int relu, float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes,
-                         void *stream_) {
+                         int relu, int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
+                         size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
     NBPC_ARG(dOut && H_in && col && csrT_ptr && csrT_edge && W && P_col && P_row && P_cube && dW && dB && workspace,
@@ -580,8 +636,11 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     done = false;
 #ifndef NBPC_HOST_EMU
     if (fast && kq <= 4096) {
-        glf_node_xty("glf_node_xty_dW2", P_col, dQ_col, BN, k, q, w.xty_partial, dW + kq, stream);
-        glf_node_xty("glf_node_xty_dW3", P_row, dQ_row, BN, k, q, w.xty_partial, dW + 2 * kq, stream);
+        if (glf_node_xty("glf_node_xty_dW2", P_col, dQ_col, BN, k, q, w.xty_partial, dW + kq, stream) ||
+            glf_node_xty("glf_node_xty_dW3", P_row, dQ_row, BN, k, q, w.xty_partial, dW + 2 * kq, stream)) {
+            nbpc_set_error("nbpc_graph_layer_bwd: could not configure the X^T Y kernel");
+            return NBPC_ELAUNCH;
+        }
         done = true;
     }
 #endif
@@ -599,7 +658,7 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
         done = false;
 #ifndef NBPC_HOST_EMU
         if (fast && (size_t)3 * kq * sizeof(float) <= 48 * 1024) {
-            NBPC_LAUNCH_N(NbpcKName("glf_node_grad_kernel", k, q).c_str(), glf_node_grad_kernel, nbpc_cdiv(BN * k, 256), 256,
+            NBPC_LAUNCH_N(NbpcKName("glf_node_grad_kernel", k, q).c_str(), glf_node_grad_kernel, nbpc_min(nbpc_cdiv(BN * k, 256), gl_num_sms() * 8), 256,
                           sizeof(float) * 3 * kq, stream, dQ_col, dQ_row, w.dCq, W, csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
             done = true;
         }
@@ -618,13 +677,13 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
             NBPC_LAUNCH_N(NbpcKName("glf_last_rowterm_kernel", k, q).c_str(), glf_last_rowterm_kernel, nbpc_cdiv(BN * k, 256), 256, 0,
                           stream, dQ_row, W, (int)BN, M, k, q, w.Gr);
             NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256,
-                          0, stream, col, w.Gr, w.Gc, c, M, k, dH_in);
+                          0, stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, c, M, k, dH_in);
         }
         return nbpc_check_launch("nbpc_graph_layer_bwd");
     }
     if (fast && !is_last && glf_edge_shape_ok(k, q) && (!dH_in || k % 4 == 0)) {
         int rc = 1;
-#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, dH_in, w.xty_partial, dW, stream);
+#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, dW, stream);
         GLF_FOR_KQ(X)
 #undef X
         if (rc) {
@@ -636,9 +695,12 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
 #endif
     x.p = H_in;
     xty(NbpcKName("xty_partial_dW1", k, q).c_str(), x, dz, c, k, q, w.xty_partial, dW, stream);
-    if (dH_in)
+    if (dH_in) {
         NBPC_LAUNCH_N(NbpcKName("glb_edge_in_kernel", k, q).c_str(), glb_edge_in_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0,
                       stream, dz, col, W, w.Gc, w.Gr, c, M, k, q, dH_in);
+        if (mask_input)
+            NBPC_LAUNCH(glb_mask_input_kernel, nbpc_cdiv(c * k, GL_THREADS), GL_THREADS, 0, stream, H_in, c * k, dH_in);
+    }
     return nbpc_check_launch("nbpc_graph_layer_bwd");
 }
 

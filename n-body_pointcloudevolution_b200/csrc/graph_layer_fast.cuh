@@ -2,16 +2,18 @@
 //
 // Same math and the same fixed summation orders as the baseline kernels in graph_layer.cu, but laid
 // out for HBM throughput:
-//   * edge tiles of 128 consecutive edges are staged into shared memory with 16-byte cp.async
-//     copies (fully coalesced 512 B per warp instruction) into rows padded so that a thread reading
-//     its own row with LDS.128 is bank-conflict free;
+//   * persistent blocks walk 128-edge tiles; the NEXT tile is prefetched into the other shared-memory
+//     buffer with 16-byte cp.async copies (512 contiguous bytes per warp instruction) while the
+//     current one is consumed; tile rows are padded so that a thread reading its own row with LDS.128
+//     is bank-conflict free;
 //   * the edge-level GEMM  Z = H W1  runs thread-per-edge-row with the row in registers and W1 read
-//     from shared memory as broadcast LDS.128 (4 FMAs per shared load, no divergence);
-//   * outputs leave through a per-warp shared staging buffer so that every global store instruction
-//     writes 512 contiguous bytes;
+//     from shared memory as broadcast LDS.128 (4 FMAs per shared load, no divergence); the epilogue
+//     gathers (Q_col[col[e]], Q_row[e/M]) are issued before the FMA loop so their L2 latency hides;
+//   * outputs leave through a per-warp shared staging area so every global store instruction writes
+//     512 contiguous bytes;
 //   * pooling gathers use float4 channel groups (a 128 B edge row is read by 8 adjacent lanes);
-//   * dW1 = H^T dZ is accumulated per block in registers with 4x4 micro-tiles and reduced over
-//     blocks in a fixed order (no float atomics => bit-reproducible).
+//   * X^T Y reductions (dW1 over edges, dW2/dW3 over nodes) accumulate 4x4 register micro-tiles per
+//     block and are reduced over blocks in a fixed order (no float atomics => bit-reproducible).
 // Compile-time channel widths: K in {3,16,32,64}, Q in {16,32,64} for the edge-level kernels; any
 // other shape falls back to the baseline kernels.
 #pragma once
@@ -26,9 +28,8 @@ __device__ __forceinline__ void glf_cp_async16(void *smem, const void *gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
-__device__ __forceinline__ void glf_cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
+__device__ __forceinline__ void glf_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void glf_cp_async_wait0() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ float4 glf_ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 // row stride (floats) for a C-wide tile row: multiple of 4, (stride/4) odd => conflict-free LDS.128 per row
@@ -43,6 +44,15 @@ __device__ __forceinline__ void glf_stage_tile(float *smem, const float *__restr
         float *dst = smem + r * CS + 4 * ch;
         if (row0 + r < rows_total) glf_cp_async16(dst, g + (row0 + r) * C + 4 * ch);
         else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// 3-wide rows (input edges): plain loads, zero-padded to 4 floats per row
+template <int CS>
+__device__ __forceinline__ void glf_stage_tile3(float *smem, const float *__restrict__ g, int64_t row0, int64_t rows_total) {
+    for (int i = threadIdx.x; i < GLF_TE * 4; i += GLF_THREADS) {
+        const int r = i / 4, kk = i % 4;
+        smem[r * CS + kk] = (kk < 3 && row0 + r < rows_total) ? __ldg(&g[(row0 + r) * 3 + kk]) : 0.f;
     }
 }
 
@@ -130,11 +140,13 @@ __global__ void __launch_bounds__(256) glf_bwd_pool_kernel(const float *__restri
     const int b = csrT_ptr[node], e = csrT_ptr[node + 1];
     float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
     int p = b;
-    for (; p + 2 <= e; p += 2) {
-        const int e0 = __ldg(&csrT_edge[p]), e1 = __ldg(&csrT_edge[p + 1]);
-        const float4 v0 = dz(e0), v1 = dz(e1);
+    for (; p + 4 <= e; p += 4) {
+        const int e0 = __ldg(&csrT_edge[p]), e1 = __ldg(&csrT_edge[p + 1]), e2 = __ldg(&csrT_edge[p + 2]), e3 = __ldg(&csrT_edge[p + 3]);
+        const float4 v0 = dz(e0), v1 = dz(e1), v2 = dz(e2), v3 = dz(e3);
         cs.x += v0.x; cs.y += v0.y; cs.z += v0.z; cs.w += v0.w;
         cs.x += v1.x; cs.y += v1.y; cs.z += v1.z; cs.w += v1.w;
+        cs.x += v2.x; cs.y += v2.y; cs.z += v2.z; cs.w += v2.w;
+        cs.x += v3.x; cs.y += v3.y; cs.z += v3.z; cs.w += v3.w;
     }
     for (; p < e; ++p) {
         const float4 v = dz(__ldg(&csrT_edge[p]));
@@ -144,76 +156,159 @@ __global__ void __launch_bounds__(256) glf_bwd_pool_kernel(const float *__restri
 }
 
 // ------------------------------------------------------------------ forward: edge GEMM + epilogue
-//   out[e] = act( H[e] W1 + Q_col[col[e]] + Q_row[e / M] )
+//   out[e] = act( H[e] W1 + Q_col[col[e]] + Q_row[e / M] )        persistent blocks, double-buffered tiles
 template <int K, int Q, bool RELU>
 __global__ void __launch_bounds__(GLF_THREADS) glf_edge_out_kernel(const float *__restrict__ H, const int32_t *__restrict__ col,
                                                                     const float *__restrict__ W1,
                                                                     const float *__restrict__ Q_col,
                                                                     const float *__restrict__ Q_row, int64_t c, int M,
                                                                     float *__restrict__ out) {
-    constexpr int KS = (K == 3) ? 3 : glf_stride(K);
+    constexpr int KS = (K == 3) ? 0 : glf_stride(K);      // K == 3: rows are read straight into registers
     constexpr int QS = glf_stride(Q);
+    constexpr bool EARLY = (K + 2 * Q <= 112);            // prefetch the epilogue gathers before the FMA loop
     extern __shared__ __align__(16) float smem[];
-    float *Ws = smem;                         // [K][Q]
-    float *Hs = Ws + K * Q;                   // [TE][KS]   (K == 3: dense, scalar reads)
-    float *Os = Hs + GLF_TE * KS;             // [TE][QS]   (GLF_TE * KS and K * Q are multiples of 4)
+    float *Ws = smem;                          // [K][Q]
+    float *Os = Ws + ((K * Q + 3) / 4) * 4;    // [TE][QS]
+    float *Hs = Os + GLF_TE * QS;              // [2][TE][KS]
     const int tid = threadIdx.x;
-    const int64_t e0 = (int64_t)blockIdx.x * GLF_TE;
+    const int ntiles = (int)((c + GLF_TE - 1) / GLF_TE);
     for (int i = tid; i < K * Q; i += GLF_THREADS) Ws[i] = __ldg(&W1[i]);
-    if constexpr (K == 3) {
-        for (int i = tid; i < GLF_TE * 3; i += GLF_THREADS) Hs[i] = (e0 * 3 + i < c * 3) ? __ldg(&H[e0 * 3 + i]) : 0.f;
-    } else {
-        glf_stage_tile<K, KS>(Hs, H, e0, c);
-        glf_cp_async_wait_all();
+    int t = blockIdx.x, buf = 0;
+    if constexpr (K != 3) {
+        if (t < ntiles) glf_stage_tile<K, KS>(Hs, H, (int64_t)t * GLF_TE, c);
+        glf_cp_async_commit();
     }
-    __syncthreads();
-
-    const int64_t e = e0 + tid;
-    float h[K];
-    if constexpr (K == 3) {
-#pragma unroll
-        for (int kk = 0; kk < K; ++kk) h[kk] = Hs[tid * 3 + kk];
-    } else {
-#pragma unroll
-        for (int j = 0; j < K / 4; ++j) {
-            const float4 v = *reinterpret_cast<const float4 *>(Hs + tid * KS + 4 * j);
-            h[4 * j] = v.x; h[4 * j + 1] = v.y; h[4 * j + 2] = v.z; h[4 * j + 3] = v.w;
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        if constexpr (K != 3) glf_cp_async_wait0();
+        __syncthreads();     // tile t has landed (and Ws on the first pass); the other buffer is free
+        if constexpr (K != 3) {
+            const int tn = t + gridDim.x;
+            if (tn < ntiles) glf_stage_tile<K, KS>(Hs + (buf ^ 1) * GLF_TE * KS, H, (int64_t)tn * GLF_TE, c);
+            glf_cp_async_commit();
         }
-    }
-    float acc[Q];
+        const int64_t e0 = (int64_t)t * GLF_TE, e = e0 + tid;
+        const bool valid = e < c;
+        const float *qc = Q_col + (valid ? (int64_t)__ldg(&col[e]) : 0) * Q;
+        const float *qr = Q_row + (valid ? e / M : 0) * Q;
+        float acc[Q];
+        if constexpr (EARLY) {
 #pragma unroll
-    for (int qo = 0; qo < Q; ++qo) acc[qo] = 0.f;
+            for (int j = 0; j < Q / 4; ++j) {
+                const float4 a = glf_ldg4(qc + 4 * j), b = glf_ldg4(qr + 4 * j);
+                acc[4 * j] = a.x + b.x; acc[4 * j + 1] = a.y + b.y; acc[4 * j + 2] = a.z + b.z; acc[4 * j + 3] = a.w + b.w;
+            }
+        }
+        float h[K];
+        if constexpr (K == 3) {
 #pragma unroll
-    for (int kk = 0; kk < K; ++kk) {
+            for (int kk = 0; kk < 3; ++kk) h[kk] = valid ? __ldg(&H[e * 3 + kk]) : 0.f;
+        } else {
+            const float *hrow = Hs + buf * GLF_TE * KS + tid * KS;
+#pragma unroll
+            for (int j = 0; j < K / 4; ++j) {
+                const float4 v = *reinterpret_cast<const float4 *>(hrow + 4 * j);
+                h[4 * j] = v.x; h[4 * j + 1] = v.y; h[4 * j + 2] = v.z; h[4 * j + 3] = v.w;
+            }
+        }
+        float z[Q];
+#pragma unroll
+        for (int qo = 0; qo < Q; ++qo) z[qo] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) {
+#pragma unroll
+            for (int j = 0; j < Q / 4; ++j) {
+                const float4 w = *reinterpret_cast<const float4 *>(Ws + kk * Q + 4 * j);   // broadcast
+                z[4 * j] += h[kk] * w.x; z[4 * j + 1] += h[kk] * w.y; z[4 * j + 2] += h[kk] * w.z; z[4 * j + 3] += h[kk] * w.w;
+            }
+        }
+        if constexpr (!EARLY) {
+#pragma unroll
+            for (int j = 0; j < Q / 4; ++j) {
+                const float4 a = glf_ldg4(qc + 4 * j), b = glf_ldg4(qr + 4 * j);
+                acc[4 * j] = a.x + b.x; acc[4 * j + 1] = a.y + b.y; acc[4 * j + 2] = a.z + b.z; acc[4 * j + 3] = a.w + b.w;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < Q / 4; ++j) {
-            const float4 w = *reinterpret_cast<const float4 *>(Ws + kk * Q + 4 * j);   // broadcast
-            acc[4 * j] += h[kk] * w.x; acc[4 * j + 1] += h[kk] * w.y;
-            acc[4 * j + 2] += h[kk] * w.z; acc[4 * j + 3] += h[kk] * w.w;
+            float4 o = make_float4(z[4 * j] + acc[4 * j], z[4 * j + 1] + acc[4 * j + 1], z[4 * j + 2] + acc[4 * j + 2],
+                                   z[4 * j + 3] + acc[4 * j + 3]);
+            if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            *reinterpret_cast<float4 *>(Os + tid * QS + 4 * j) = o;
         }
+        __syncwarp();
+        const int w = tid >> 5;
+        glf_store_warp_rows<Q, QS>(Os + w * 32 * QS, out, e0 + w * 32, c);
+        __syncwarp();
     }
-    if (e < c) {
-        const float *qc = Q_col + (int64_t)__ldg(&col[e]) * Q;
-        const float *qr = Q_row + (e / M) * Q;
-#pragma unroll
-        for (int j = 0; j < Q / 4; ++j) {
-            const float4 a = glf_ldg4(qc + 4 * j), b = glf_ldg4(qr + 4 * j);
-            float4 z = make_float4(acc[4 * j] + (a.x + b.x), acc[4 * j + 1] + (a.y + b.y), acc[4 * j + 2] + (a.z + b.z),
-                                   acc[4 * j + 3] + (a.w + b.w));
-            if (RELU) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
-            *reinterpret_cast<float4 *>(Os + tid * QS + 4 * j) = z;
-        }
-    }
-    __syncwarp();
-    const int w = tid >> 5;
-    glf_store_warp_rows<Q, QS>(Os + w * 32 * QS, out, e0 + w * 32, c);
+    if constexpr (K != 3) glf_cp_async_wait0();
 }
 
+// ------------------------------------------------------------------ X^T Y micro-tile machinery
+// The (KP x Q) result is cut into 4x4 micro-tiles.  NT threads form an accumulator set (one or MT
+// micro-tiles per thread); NSETS sets split a tile's rows (set s takes rows s, s+NSETS, ...).
+template <int KP, int Q>
+struct GlfXty {
+    static constexpr int KG = KP / 4, QG = Q / 4, NMT = KG * QG;
+    static constexpr int MT = (NMT > GLF_THREADS) ? NMT / GLF_THREADS : 1;
+    static constexpr int NT = (NMT > GLF_THREADS) ? GLF_THREADS : NMT;
+    static constexpr int NSETS = GLF_THREADS / NT;
+    static_assert(GLF_THREADS % NT == 0 && NMT % NT == 0, "unsupported shape");
+    float acc[MT][4][4];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int j = 0; j < MT; ++j)
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[j][a][b] = 0.f;
+    }
+    template <int KS, int QS>
+    __device__ __forceinline__ void accumulate(const float *Xs, const float *Ys) {
+        const int my_set = threadIdx.x / NT;
+#pragma unroll 2
+        for (int r = my_set; r < GLF_TE; r += NSETS) {
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                const int mt = (threadIdx.x % NT) + j * NT, tk = mt % KG, tq = mt / KG;
+                const float4 hv = *reinterpret_cast<const float4 *>(Xs + r * KS + 4 * tk);
+                const float4 zv = *reinterpret_cast<const float4 *>(Ys + r * QS + 4 * tq);
+                acc[j][0][0] += hv.x * zv.x; acc[j][0][1] += hv.x * zv.y; acc[j][0][2] += hv.x * zv.z; acc[j][0][3] += hv.x * zv.w;
+                acc[j][1][0] += hv.y * zv.x; acc[j][1][1] += hv.y * zv.y; acc[j][1][2] += hv.y * zv.z; acc[j][1][3] += hv.y * zv.w;
+                acc[j][2][0] += hv.z * zv.x; acc[j][2][1] += hv.z * zv.y; acc[j][2][2] += hv.z * zv.z; acc[j][2][3] += hv.z * zv.w;
+                acc[j][3][0] += hv.w * zv.x; acc[j][3][1] += hv.w * zv.y; acc[j][3][2] += hv.w * zv.z; acc[j][3][3] += hv.w * zv.w;
+            }
+        }
+    }
+    // reduce the NSETS sets in a fixed order through `red` (>= NSETS*KP*Q floats of smem, all threads
+    // must have finished with it) and write rows kk < K of this block's partial [K][Q]
+    __device__ __forceinline__ void finish(float *red, int K, float *__restrict__ partial_block) {
+        const int my_set = threadIdx.x / NT;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < MT; ++j) {
+            const int mt = (threadIdx.x % NT) + j * NT, tk = mt % KG, tq = mt / KG;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) red[(my_set * KP + 4 * tk + a) * Q + 4 * tq + b] = acc[j][a][b];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * Q; i += GLF_THREADS) {
+            float s = 0.f;
+            for (int st = 0; st < NSETS; ++st) s += red[st * KP * Q + i];
+            partial_block[i] = s;
+        }
+    }
+};
+
 // ------------------------------------------------------------------ backward: edge kernel
-//   dZ[e]  = dOut[e] * [Hout[e] > 0]                      (RELU: mask of this layer's activation)
-//   dH[e]  = dZ[e] W1^T + G_col[col[e]] + G_row[e / M]    (HAS_DH)
+//   dZ[e]  = dOut[e] * [Hout[e] > 0]                      (RELU: mask of this layer's own activation)
 //   dW1   += H[e]^T dZ[e]                                  (per-block partial, fixed-order reduce later)
-template <int K, int Q, bool RELU, bool HAS_DH>
+//   dH[e]  = dZ[e] W1^T + G_col[col[e]] + G_row[e / M]    (HAS_DH; MASK_IN: times [H[e] > 0], i.e. the
+//            ReLU backward of the layer that produced H is applied here, where H is already on chip)
+// With HAS_DH = false and RELU = false this is a plain deterministic X^T Y (X = H, Y = dOut) and is
+// reused for the node-level dW2 / dW3.
+template <int K, int Q, bool RELU, bool HAS_DH, bool MASK_IN>
 __global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout,
                                                                     const float *__restrict__ H, const int32_t *__restrict__ col,
                                                                     const float *__restrict__ W1,
@@ -221,76 +316,73 @@ __global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *
                                                                     const float *__restrict__ G_row, int64_t c, int M,
                                                                     int tiles_per_block, float *__restrict__ dH,
                                                                     float *__restrict__ dW_partial) {
-    constexpr int KP = (K == 3) ? 4 : K;           // H tile rows are zero-padded to a multiple of 4 for the micro-tiles
+    constexpr int KP = (K == 3) ? 4 : K;           // 3-wide rows are zero-padded to 4 for the micro-tiles
     constexpr int KS = glf_stride(KP), QS = glf_stride(Q);
-    constexpr int KG = KP / 4, QG = Q / 4;         // 4x4 micro-tiles of dW1
-    constexpr int NMT = KG * QG;                   // micro-tiles of the (K x Q) result
-    constexpr int MT = (NMT > GLF_THREADS) ? NMT / GLF_THREADS : 1;     // micro-tiles per thread
-    constexpr int NT = (NMT > GLF_THREADS) ? GLF_THREADS : NMT;         // threads per accumulator set
-    static_assert(GLF_THREADS % NT == 0 && NMT % NT == 0, "unsupported shape");
-    constexpr int NSETS = GLF_THREADS / NT;        // sets split the tile's edges (set s: edges s, s+NSETS, ..)
+    constexpr int TILE = GLF_TE * (KS + QS + (RELU ? QS : 0));   // floats per pipeline stage: Hs | Zs | (Ms)
     extern __shared__ __align__(16) float smem[];
     float *Wt = smem;                              // [Q][KP]  (W1 transposed: 4 consecutive kk per LDS.128)
-    float *Hs = Wt + Q * KP;                       // [TE][KS]
-    float *Zs = Hs + GLF_TE * KS;                  // [TE][QS]  masked dZ
-    float *Ds = Zs + GLF_TE * QS;                  // [TE][KS]  dH staging (HAS_DH) / cross-set reduction scratch
+    float *stage0 = Wt + Q * KP;
     const int tid = threadIdx.x;
-    for (int i = tid; i < Q * KP; i += GLF_THREADS) {
-        const int qo = i / KP, kk = i % KP;
-        Wt[i] = (kk < K) ? __ldg(&W1[kk * Q + qo]) : 0.f;
-    }
-    const int my_set = tid / NT;
-    float wacc[MT][4][4];
-#pragma unroll
-    for (int j = 0; j < MT; ++j)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) wacc[j][a][b] = 0.f;
-
-    for (int it = 0; it < tiles_per_block; ++it) {
-        const int64_t e0 = ((int64_t)blockIdx.x * tiles_per_block + it) * GLF_TE;
-        if (e0 >= c) break;
-        __syncthreads();   // previous tile fully consumed
-        // ---- stage H tile and dOut tile
-        if constexpr (K == 3) {
-            for (int i = tid; i < GLF_TE * KP; i += GLF_THREADS) {
-                const int r = i / KP, kk = i % KP;
-                Hs[r * KS + kk] = (kk < 3 && e0 + r < c) ? __ldg(&H[(e0 + r) * 3 + kk]) : 0.f;
-            }
-        } else {
-            glf_stage_tile<KP, KS>(Hs, H, e0, c);
+    if constexpr (HAS_DH) {
+        for (int i = tid; i < Q * KP; i += GLF_THREADS) {
+            const int qo = i / KP, kk = i % KP;
+            Wt[i] = (kk < K) ? __ldg(&W1[kk * Q + qo]) : 0.f;
         }
-        glf_stage_tile<Q, QS>(Zs, dOut, e0, c);
-        glf_cp_async_wait_all();
-        if constexpr (RELU) {   // mask own chunks in place (each thread masks exactly the chunks it staged)
+    }
+    GlfXty<KP, Q> xty;
+    xty.clear();
+
+    const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;
+    const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_block;
+    const int64_t t_end = nbpc_min(t_begin + tiles_per_block, ntiles);
+    auto issue = [&](int64_t t, int b) {
+        float *Hs = stage0 + b * TILE, *Zs = Hs + GLF_TE * KS;
+        if constexpr (K == 3) glf_stage_tile3<KS>(Hs, H, t * GLF_TE, c);
+        else glf_stage_tile<KP, KS>(Hs, H, t * GLF_TE, c);
+        glf_stage_tile<Q, QS>(Zs, dOut, t * GLF_TE, c);
+        if constexpr (RELU) glf_stage_tile<Q, QS>(Zs + GLF_TE * QS, Hout, t * GLF_TE, c);
+    };
+    if (t_begin < t_end) issue(t_begin, 0);
+    glf_cp_async_commit();
+    int buf = 0;
+    for (int64_t t = t_begin; t < t_end; ++t, buf ^= 1) {
+        float *Hs = stage0 + buf * TILE, *Zs = Hs + GLF_TE * KS;
+        glf_cp_async_wait0();
+        if constexpr (RELU) {   // mask in place; every thread masks exactly the chunks it copied itself
             constexpr int CH = Q / 4;
+            const float *Ms = Zs + GLF_TE * QS;
             for (int i = tid; i < GLF_TE * CH; i += GLF_THREADS) {
                 const int r = i / CH, ch = i % CH;
-                if (e0 + r < c) {
-                    const float4 ho = glf_ldg4(Hout + (e0 + r) * Q + 4 * ch);
-                    float4 *z = reinterpret_cast<float4 *>(Zs + r * QS + 4 * ch);
-                    float4 v = *z;
-                    v.x = ho.x > 0.f ? v.x : 0.f; v.y = ho.y > 0.f ? v.y : 0.f;
-                    v.z = ho.z > 0.f ? v.z : 0.f; v.w = ho.w > 0.f ? v.w : 0.f;
-                    *z = v;
-                }
+                const float4 ho = *reinterpret_cast<const float4 *>(Ms + r * QS + 4 * ch);
+                float4 *zp = reinterpret_cast<float4 *>(Zs + r * QS + 4 * ch);
+                float4 v = *zp;
+                v.x = ho.x > 0.f ? v.x : 0.f; v.y = ho.y > 0.f ? v.y : 0.f;
+                v.z = ho.z > 0.f ? v.z : 0.f; v.w = ho.w > 0.f ? v.w : 0.f;
+                *zp = v;
             }
         }
-        __syncthreads();
+        __syncthreads();       // tile t complete in smem; the other stage is no longer in use
+        if (t + 1 < t_end) issue(t + 1, buf ^ 1);
+        glf_cp_async_commit();
 
-        // ---- dH: thread per edge row
+        const int64_t e0 = t * GLF_TE, e = e0 + tid;
+        float dh[HAS_DH ? KP : 1];
         if constexpr (HAS_DH) {
-            static_assert(K % 4 == 0, "dH path needs K % 4 == 0");
-            const int64_t e = e0 + tid;
+            static_assert(!HAS_DH || K % 4 == 0, "dH path needs K % 4 == 0");
+            const bool valid = e < c;
+            const float *gc = G_col + (valid ? (int64_t)__ldg(&col[e]) : 0) * K;
+            const float *gr = G_row + (valid ? e / M : 0) * K;
+#pragma unroll
+            for (int j = 0; j < K / 4; ++j) {   // issue the gathers first: their latency hides behind the FMAs
+                const float4 a = glf_ldg4(gc + 4 * j), b = glf_ldg4(gr + 4 * j);
+                dh[4 * j] = a.x + b.x; dh[4 * j + 1] = a.y + b.y; dh[4 * j + 2] = a.z + b.z; dh[4 * j + 3] = a.w + b.w;
+            }
             float dz[Q];
 #pragma unroll
             for (int j = 0; j < Q / 4; ++j) {
                 const float4 v = *reinterpret_cast<const float4 *>(Zs + tid * QS + 4 * j);
                 dz[4 * j] = v.x; dz[4 * j + 1] = v.y; dz[4 * j + 2] = v.z; dz[4 * j + 3] = v.w;
             }
-            const int64_t ce = (e < c) ? (int64_t)__ldg(&col[e]) : 0;
-            const int64_t re = (e < c) ? e / M : 0;
 #pragma unroll
             for (int j = 0; j < K / 4; ++j) {
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -299,48 +391,49 @@ __global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *
                     const float4 w = *reinterpret_cast<const float4 *>(Wt + qo * KP + 4 * j);   // broadcast
                     a.x += dz[qo] * w.x; a.y += dz[qo] * w.y; a.z += dz[qo] * w.z; a.w += dz[qo] * w.w;
                 }
-                const float4 gc = glf_ldg4(G_col + ce * K + 4 * j), gr = glf_ldg4(G_row + re * K + 4 * j);
-                a.x += gc.x + gr.x; a.y += gc.y + gr.y; a.z += gc.z + gr.z; a.w += gc.w + gr.w;
-                *reinterpret_cast<float4 *>(Ds + tid * KS + 4 * j) = a;
+                dh[4 * j] += a.x; dh[4 * j + 1] += a.y; dh[4 * j + 2] += a.z; dh[4 * j + 3] += a.w;
+                if constexpr (MASK_IN) {
+                    const float4 hv = *reinterpret_cast<const float4 *>(Hs + tid * KS + 4 * j);
+                    dh[4 * j] = hv.x > 0.f ? dh[4 * j] : 0.f; dh[4 * j + 1] = hv.y > 0.f ? dh[4 * j + 1] : 0.f;
+                    dh[4 * j + 2] = hv.z > 0.f ? dh[4 * j + 2] : 0.f; dh[4 * j + 3] = hv.w > 0.f ? dh[4 * j + 3] : 0.f;
+                }
             }
+        }
+        xty.template accumulate<KS, QS>(Hs, Zs);
+        if constexpr (HAS_DH) {
+            __syncthreads();   // everyone is done reading Hs: reuse it as the dH staging area
+#pragma unroll
+            for (int j = 0; j < K / 4; ++j)
+                *reinterpret_cast<float4 *>(Hs + tid * KS + 4 * j) = make_float4(dh[4 * j], dh[4 * j + 1], dh[4 * j + 2], dh[4 * j + 3]);
             __syncwarp();
             const int w = tid >> 5;
-            glf_store_warp_rows<KP, KS>(Ds + w * 32 * KS, dH, e0 + w * 32, c);
-        }
-
-        // ---- dW1 micro-tiles: set s takes edges s, s + NSETS, ...
-#pragma unroll 2
-        for (int r = my_set; r < GLF_TE; r += NSETS) {
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                const int mt = (tid % NT) + j * NT, tk = mt % KG, tq = mt / KG;
-                const float4 hv = *reinterpret_cast<const float4 *>(Hs + r * KS + 4 * tk);
-                const float4 zv = *reinterpret_cast<const float4 *>(Zs + r * QS + 4 * tq);
-                wacc[j][0][0] += hv.x * zv.x; wacc[j][0][1] += hv.x * zv.y; wacc[j][0][2] += hv.x * zv.z; wacc[j][0][3] += hv.x * zv.w;
-                wacc[j][1][0] += hv.y * zv.x; wacc[j][1][1] += hv.y * zv.y; wacc[j][1][2] += hv.y * zv.z; wacc[j][1][3] += hv.y * zv.w;
-                wacc[j][2][0] += hv.z * zv.x; wacc[j][2][1] += hv.z * zv.y; wacc[j][2][2] += hv.z * zv.z; wacc[j][2][3] += hv.z * zv.w;
-                wacc[j][3][0] += hv.w * zv.x; wacc[j][3][1] += hv.w * zv.y; wacc[j][3][2] += hv.w * zv.z; wacc[j][3][3] += hv.w * zv.w;
-            }
+            glf_store_warp_rows<KP, KS>(Hs + w * 32 * KS, dH, e0 + w * 32, c);
         }
     }
+    glf_cp_async_wait0();
+    static_assert(2 * TILE >= GlfXty<KP, Q>::NSETS * KP * Q, "reduction scratch too small");
+    xty.finish(stage0, K, dW_partial + (int64_t)blockIdx.x * K * Q);
+}
 
-    // ---- reduce the NSETS accumulator sets in a fixed order, write this block's partial [K][Q]
+// out = sum over blocks of partial[b] (rows x cols), fixed order; transpose: out is (cols x rows).
+// block = 32 lanes x 32 warps: 32 consecutive outputs, warp w sums blocks b = w, w+32, ...
+__global__ void __launch_bounds__(1024) glf_partial_reduce_kernel(const float *__restrict__ partial, int nblocks, int rows,
+                                                                   int cols, int transpose, float *__restrict__ out) {
+    __shared__ float red[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = rows * cols;
+    const int i = blockIdx.x * 32 + lane;
+    float s = 0.f;
+    if (i < n)
+        for (int b = w; b < nblocks; b += 32) s += partial[(int64_t)b * n + i];
+    red[w][lane] = s;
     __syncthreads();
-    float *red = Hs;   // NSETS * KP * Q floats, spans the contiguous Hs|Zs region
-    static_assert(GLF_TE * (KS + QS) >= NSETS * KP * Q, "reduction scratch too small");
+    if (w == 0 && i < n) {
+        float tot = 0.f;
 #pragma unroll
-    for (int j = 0; j < MT; ++j) {
-        const int mt = (tid % NT) + j * NT, tk = mt % KG, tq = mt / KG;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) red[(my_set * KP + 4 * tk + a) * Q + 4 * tq + b] = wacc[j][a][b];
-    }
-    __syncthreads();
-    for (int i = tid; i < K * Q; i += GLF_THREADS) {
-        float s = 0.f;
-        for (int st = 0; st < NSETS; ++st) s += red[st * KP * Q + i];   // i = kk*Q + qo with kk < K <= KP
-        dW_partial[(int64_t)blockIdx.x * K * Q + i] = s;
+        for (int ww = 0; ww < 32; ++ww) tot += red[ww][lane];
+        const int r = i / cols, cc = i % cols;
+        out[transpose ? cc * rows + r : i] = tot;
     }
 }
 
@@ -349,21 +442,33 @@ __global__ void glf_copy_kernel(const float *__restrict__ src, float *__restrict
     if (i < n) dst[i] = src[i];
 }
 
-// out[i] = sum_b partial[b][i], fixed order
-__global__ void glf_partial_reduce_kernel(const float *__restrict__ partial, int nblocks, int n, float *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nblocks; b += 4) {
-        s0 += partial[(int64_t)b * n + i]; s1 += partial[(int64_t)(b + 1) * n + i];
-        s2 += partial[(int64_t)(b + 2) * n + i]; s3 += partial[(int64_t)(b + 3) * n + i];
+// ------------------------------------------------------------------ node-level kernels (runtime k, q)
+// persistent grid-stride blocks: the weights are staged in shared memory once per block
+// Q_col = P_col W2;  Q_row = P_row W3 + (P_cube W4 + B)
+__global__ void __launch_bounds__(256) glf_node_project_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
+                                                                const float *__restrict__ P_cube, const float *__restrict__ W,
+                                                                const float *__restrict__ bias, int BN, int N, int k, int q,
+                                                                float *__restrict__ Q_col, float *__restrict__ Q_row) {
+    extern __shared__ __align__(16) float smem[];   // W2, W3, W4: [k][q] each
+    for (int i = threadIdx.x; i < 3 * k * q; i += blockDim.x) smem[i] = __ldg(&W[(int64_t)k * q + i]);
+    __syncthreads();
+    const float *W2 = smem, *W3 = smem + k * q, *W4 = smem + 2 * k * q;
+    const int64_t total = (int64_t)BN * q, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int node = (int)(t / q), qo = (int)(t % q);
+        const int s = node / N;
+        const float *pc = P_col + (int64_t)node * k, *pr = P_row + (int64_t)node * k, *pq = P_cube + s * k;
+        float a2 = 0.f, a3 = 0.f, a4 = 0.f;
+        for (int kk = 0; kk < k; ++kk) {
+            a2 += __ldg(&pc[kk]) * W2[kk * q + qo];
+            a3 += __ldg(&pr[kk]) * W3[kk * q + qo];
+            a4 += __ldg(&pq[kk]) * W4[kk * q + qo];
+        }
+        Q_col[t] = a2;
+        Q_row[t] = a3 + (a4 + __ldg(&bias[qo]));
     }
-    for (; b < nblocks; ++b) s0 += partial[(int64_t)b * n + i];
-    out[i] = (s0 + s1) + (s2 + s3);
 }
 
-// ------------------------------------------------------------------ node-level kernels (runtime k, q)
 // G_col = (dQ_col W2^T)/max(indeg,1);  G_row = (dQ_row W3^T)/M + (dCq W4^T)/(N M)
 __global__ void __launch_bounds__(256) glf_node_grad_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
                                                              const float *__restrict__ dCq, const float *__restrict__ W,
@@ -378,46 +483,24 @@ __global__ void __launch_bounds__(256) glf_node_grad_kernel(const float *__restr
         W4t[i] = __ldg(&W[3 * (int64_t)k * q + kk * q + qo]);
     }
     __syncthreads();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)BN * k) return;
-    const int node = (int)(t / k), kk = (int)(t % k);
-    const int s = node / N;
-    float a2 = 0.f, a3 = 0.f, a4 = 0.f;
-    for (int qo = 0; qo < q; ++qo) {
-        a2 += __ldg(&dQ_col[(int64_t)node * q + qo]) * W2t[qo * k + kk];
-        a3 += __ldg(&dQ_row[(int64_t)node * q + qo]) * W3t[qo * k + kk];
-        a4 += __ldg(&dCq[s * q + qo]) * W4t[qo * k + kk];
+    const int64_t total = (int64_t)BN * k, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int node = (int)(t / k), kk = (int)(t % k);
+        const int s = node / N;
+        const float *dc = dQ_col + (int64_t)node * q, *dr = dQ_row + (int64_t)node * q, *dq = dCq + s * q;
+        float a2 = 0.f, a3 = 0.f, a4 = 0.f;
+        for (int qo = 0; qo < q; ++qo) {
+            a2 += __ldg(&dc[qo]) * W2t[qo * k + kk];
+            a3 += __ldg(&dr[qo]) * W3t[qo * k + kk];
+            a4 += __ldg(&dq[qo]) * W4t[qo * k + kk];
+        }
+        const int indeg = csrT_ptr[node + 1] - csrT_ptr[node];
+        G_col[t] = a2 / (float)nbpc_max(indeg, 1);
+        G_row[t] = a3 / (float)M + a4 / ((float)N * (float)M);
     }
-    const int indeg = csrT_ptr[node + 1] - csrT_ptr[node];
-    G_col[t] = a2 / (float)nbpc_max(indeg, 1);
-    G_row[t] = a3 / (float)M + a4 / ((float)N * (float)M);
 }
 
-// Q_col = P_col W2;  Q_row = P_row W3 + (P_cube W4 + B)        thread per (node, qo), W in smem
-__global__ void __launch_bounds__(256) glf_node_project_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
-                                                                const float *__restrict__ P_cube, const float *__restrict__ W,
-                                                                const float *__restrict__ bias, int BN, int N, int k, int q,
-                                                                float *__restrict__ Q_col, float *__restrict__ Q_row) {
-    extern __shared__ __align__(16) float smem[];   // W2, W3, W4: [k][q] each
-    for (int i = threadIdx.x; i < 3 * k * q; i += blockDim.x) smem[i] = __ldg(&W[(int64_t)k * q + i]);
-    __syncthreads();
-    const float *W2 = smem, *W3 = smem + k * q, *W4 = smem + 2 * k * q;
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)BN * q) return;
-    const int node = (int)(t / q), qo = (int)(t % q);
-    const int s = node / N;
-    float a2 = 0.f, a3 = 0.f, a4 = 0.f;
-    for (int kk = 0; kk < k; ++kk) {
-        a2 += __ldg(&P_col[(int64_t)node * k + kk]) * W2[kk * q + qo];
-        a3 += __ldg(&P_row[(int64_t)node * k + kk]) * W3[kk * q + qo];
-        a4 += __ldg(&P_cube[s * k + kk]) * W4[kk * q + qo];
-    }
-    Q_col[t] = a2;
-    Q_row[t] = a3 + (a4 + __ldg(&bias[qo]));
-}
-
-// X^T Y over n node rows (runtime k, q): block handles a contiguous chunk of rows staged through smem,
-// thread owns pairs p = tid, tid + 256, ... of the (k x q) result; per-block partial, fixed-order reduce later
+// generic X^T Y over n node rows (runtime k, q; used when no micro-tile instance fits)
 #define GLF_XTY_ROWS 32
 __global__ void __launch_bounds__(256) glf_node_xty_kernel(const float *__restrict__ X, const float *__restrict__ Y, int64_t n,
                                                             int rows_per_block, int k, int q, float *__restrict__ partial) {
@@ -504,9 +587,10 @@ __global__ void __launch_bounds__(256) glf_last_rowterm_kernel(const float *__re
     G_row[t] = a / (float)M + G_row[t];
 }
 
-// dH[e] = R[e / M] + G_col[col[e]]      thread per (edge, 4-channel group); k % 4 == 0
+// dH[e] = (R[e / M] + G_col[col[e]]) [* (H[e] > 0) if Hmask]     thread per (edge, 4-channel group); k % 4 == 0
 __global__ void __launch_bounds__(256) glf_last_edge_in_kernel(const int32_t *__restrict__ col, const float *__restrict__ R,
-                                                                const float *__restrict__ G_col, int64_t c, int M, int k,
+                                                                const float *__restrict__ G_col,
+                                                                const float *__restrict__ Hmask, int64_t c, int M, int k,
                                                                 float *__restrict__ dH) {
     const int G = k / 4;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -515,7 +599,12 @@ __global__ void __launch_bounds__(256) glf_last_edge_in_kernel(const int32_t *__
     const int g = (int)(t % G);
     const float4 r = glf_ldg4(R + (e / M) * k + 4 * g);
     const float4 gc = glf_ldg4(G_col + (int64_t)__ldg(&col[e]) * k + 4 * g);
-    *reinterpret_cast<float4 *>(dH + e * k + 4 * g) = make_float4(r.x + gc.x, r.y + gc.y, r.z + gc.z, r.w + gc.w);
+    float4 o = make_float4(r.x + gc.x, r.y + gc.y, r.z + gc.z, r.w + gc.w);
+    if (Hmask) {
+        const float4 h = glf_ldg4(Hmask + e * k + 4 * g);
+        o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+    }
+    *reinterpret_cast<float4 *>(dH + e * k + 4 * g) = o;
 }
 
 #endif  // !NBPC_HOST_EMU

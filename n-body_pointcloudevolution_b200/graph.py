@@ -266,12 +266,13 @@ def _is_relu(fn):
     return fn in (torch.relu, torch.nn.functional.relu) or getattr(fn, "__name__", "") == "relu"
 
 
-def _layer(H_in, COO_feats, bN, layer_vars, is_last, relu):
+def _layer(H_in, COO_feats, bN, layer_vars, is_last, relu, input_relu=False, grad_premasked=False):
     b, N = bN
     weights, B = layer_vars
     adj = _adjacency_of(COO_feats, b, N)
     W = weights if isinstance(weights, torch.Tensor) and weights.dim() == 3 else torch.stack(list(weights[:4]))
-    return ops.GraphLayer.apply(H_in, W, B, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M, bool(is_last), relu)
+    return ops.GraphLayer.apply(H_in, W, B, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M, bool(is_last), relu,
+                                input_relu, grad_premasked)
 
 
 def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
@@ -283,12 +284,17 @@ def network_func_shift_inv_za(edges, coo, num_layers, dims, activation, model_va
     """graph.py:463-476.  A ReLU activation is fused into the layer kernel; any other callable is
     applied to the un-activated layer output."""
     fuse = _is_relu(activation)
-    H = _layer(_to_cuda(edges, torch.float32), coo, dims, model_vars.get_layer_vars(0), False, fuse)
+    # inside this function every hidden tensor has exactly one consumer (the next layer), so the ReLU
+    # backward of layer l is applied by layer l+1's edge kernel (input_relu) and layer l skips its own mask
+    chain = fuse and num_layers > 1
+    H = _layer(_to_cuda(edges, torch.float32), coo, dims, model_vars.get_layer_vars(0), False, fuse,
+               input_relu=False, grad_premasked=chain)
     if not fuse:
         H = activation(H)
     for layer_idx in range(1, num_layers):
         is_last = layer_idx == num_layers - 1
-        H = _layer(H, coo, dims, model_vars.get_layer_vars(layer_idx), is_last, fuse and not is_last)
+        H = _layer(H, coo, dims, model_vars.get_layer_vars(layer_idx), is_last, fuse and not is_last,
+                   input_relu=fuse, grad_premasked=fuse and not is_last)
         if not is_last and not fuse:
             H = activation(H)
     return H

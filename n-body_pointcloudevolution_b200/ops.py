@@ -233,8 +233,10 @@ def graph_layer_fwd(H_in: torch.Tensor, col: torch.Tensor, csrT_ptr: torch.Tenso
 def graph_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, col: torch.Tensor,
                     csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor, W: torch.Tensor, P_col: torch.Tensor,
                     P_row: torch.Tensor, P_cube: torch.Tensor, B: int, N: int, M: int, is_last: bool, relu: bool,
-                    need_dH: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """-> dH_in (c,k) (empty if not needed), dW (4,k,q), dB (q)."""
+                    mask_input: bool, need_dH: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> dH_in (c,k) (empty if not needed), dW (4,k,q), dB (q).
+    relu: mask dOut by [H_out > 0]; mask_input: multiply dH_in by [H_in > 0] (fused ReLU backward of the
+    layer that produced H_in)."""
     _need_cuda(dOut, H_in, H_out, W)
     L = _lib.load()
     dOut = _f32c(dOut)
@@ -248,21 +250,27 @@ def graph_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor,
     with torch.cuda.device(dev):
         rc = L.nbpc_graph_layer_bwd(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge),
                                     B, N, M, k, q, _ptr(W), _ptr(P_col), _ptr(P_row), _ptr(P_cube), int(is_last),
-                                    int(relu), _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB), _ptr(ws),
-                                    ws.numel(), _stream())
+                                    int(relu), int(mask_input), _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB),
+                                    _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "nbpc_graph_layer_bwd")
     return dH, dW, dB
 
 
 class GraphLayer(torch.autograd.Function):
-    """shift_inv_layer (graph.py:394-456) [+ fused ReLU], backward through the CSR transpose."""
+    """shift_inv_layer (graph.py:394-456) [+ fused ReLU], backward through the CSR transpose.
+
+    input_relu: H_in is the output of a ReLU-fused layer whose ONLY consumer is this layer; the ReLU
+      backward of that layer is then applied to dH_in inside this layer's edge kernel (H_in is on chip).
+    grad_premasked: the converse - this layer fused a ReLU and its only consumer applies the mask, so
+      backward does not re-read H_out.  graph.network_func_shift_inv_za sets both consistently."""
 
     @staticmethod
-    def forward(ctx, H_in, W, bias, col, csrT_ptr, csrT_edge, B, N, M, is_last, relu):
+    def forward(ctx, H_in, W, bias, col, csrT_ptr, csrT_edge, B, N, M, is_last, relu, input_relu=False,
+                grad_premasked=False):
         H_in = _f32c(H_in)
         out, P_col, P_row, P_cube = graph_layer_fwd(H_in, col, csrT_ptr, csrT_edge, W, bias, B, N, M, is_last, relu)
         ctx.save_for_backward(H_in, out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube)
-        ctx.cfg = (B, N, M, is_last, relu)
+        ctx.cfg = (B, N, M, is_last, relu and not grad_premasked, input_relu)
         if is_last:
             out = out.view(B, N, -1)
         return out
@@ -270,12 +278,12 @@ class GraphLayer(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         H_in, out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube = ctx.saved_tensors
-        B, N, M, is_last, relu = ctx.cfg
+        B, N, M, is_last, relu, input_relu = ctx.cfg
         need_dH = ctx.needs_input_grad[0]
         g = g.reshape(out.shape)
         dH, dW, dB = graph_layer_bwd(g, H_in, out, col, csrT_ptr, csrT_edge, W, P_col, P_row, P_cube, B, N, M,
-                                     is_last, relu, need_dH)
-        return (dH if need_dH else None), dW, dB, None, None, None, None, None, None, None, None
+                                     is_last, relu, input_relu, need_dH)
+        return (dH if need_dH else None), dW, dB, None, None, None, None, None, None, None, None, None, None
 
 
 # ================================================================== set layer

@@ -107,7 +107,7 @@ def graph_layer_fwd(H, col, ptr, edge, B, N, M, W, bias, is_last, relu):
     return out, (Pc, Pr, Pq)
 
 
-def graph_layer_bwd(dOut, H, Hout, col, ptr, edge, B, N, M, W, saved, is_last, relu, need_dH=True):
+def graph_layer_bwd(dOut, H, Hout, col, ptr, edge, B, N, M, W, saved, is_last, relu, need_dH=True, mask_input=False):
     L = lib()
     k, q = W.shape[1], W.shape[2]
     c = B * N * M
@@ -117,7 +117,7 @@ def graph_layer_bwd(dOut, H, Hout, col, ptr, edge, B, N, M, W, saved, is_last, r
     Pc, Pr, Pq = saved
     w = ws(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q))
     ok(L.nbpc_graph_layer_bwd(P(dOut), P(H), P(Hout), P(col), P(ptr), P(edge), B, N, M, k, q, P(W), P(Pc), P(Pr),
-                              P(Pq), int(is_last), int(relu), P(dH), P(dW), P(dB), P(w), w.nbytes, None))
+                              P(Pq), int(is_last), int(relu), int(mask_input), P(dH), P(dW), P(dB), P(w), w.nbytes, None))
     return dH, dW, dB
 
 
