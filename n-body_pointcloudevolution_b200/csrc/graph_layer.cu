@@ -432,6 +432,22 @@ static int glf_node_xty(const char *name, const float *X, const float *Y, int64_
 #endif  // !NBPC_HOST_EMU
 
 
+// per-sample column sums of a node tensor X (B*N, ch): out[s] = sum_n X[s,n] / divisor
+static void gl_colsum(const float *X, int ch, int N, int B, int nblk, float divisor, float *partial, float *out, bool fast,
+                      cudaStream_t stream) {
+#ifndef NBPC_HOST_EMU
+    if (fast) {
+        NBPC_LAUNCH(glf_colsum_partial_kernel, dim3(nblk, B), 256, 0, stream, X, ch, N, GL_CUBE_CHUNK, partial);
+        NBPC_LAUNCH(glf_colsum_final_kernel, B, 256, 0, stream, partial, ch, nblk, divisor, out);
+        return;
+    }
+#endif
+    (void)fast;
+    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * ch, GL_THREADS), GL_THREADS, 0, stream, X, ch, N, nblk, B,
+                partial);
+    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * ch, GL_THREADS), GL_THREADS, 0, stream, partial, ch, nblk, B, divisor, out);
+}
+
 extern "C" {
 
 int nbpc_edge_features_za(const float *pos, int ld_pos, const float *za, int ld_za, const int32_t *col,
@@ -529,14 +545,18 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
     if (!done)
         NBPC_LAUNCH_N(NbpcKName("gl_pool_kernel", k, q).c_str(), gl_pool_kernel, nbpc_cdiv(BN * k, GL_THREADS), GL_THREADS, 0, stream,
                       H_in, k, M, (int)BN, csrT_ptr, csrT_edge, P_row, P_col);
-    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, P_row, k, N,
-                nblk, B, w.cube_partial);
-    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, k, nblk, B,
-                (float)N, P_cube);
+    gl_colsum(P_row, k, N, B, nblk, (float)N, w.cube_partial, P_cube, fast, stream);
     // ---- node-level projections Q_col, Q_row
     done = false;
 #ifndef NBPC_HOST_EMU
-    if (fast && (size_t)3 * k * q * sizeof(float) <= 48 * 1024) {
+    if (fast && k % 4 == 0 && q % 4 == 0 && (size_t)2 * k * q * sizeof(float) <= 48 * 1024) {
+        float *Cq = w.dCq;   // (B,q): per-sample constant P_cube W4 + bias
+        NBPC_LAUNCH(glf_cube_project_kernel, nbpc_cdiv(B * q, 128), 128, 0, stream, P_cube, W + 3 * (int64_t)k * q, bias, B, k, q, Cq);
+        NBPC_LAUNCH_N(NbpcKName("glf_node_project4_kernel", k, q).c_str(), glf_node_project4_kernel,
+                      nbpc_min(nbpc_cdiv(BN * (q / 4), 256), gl_num_sms() * 8), 256, sizeof(float) * 2 * k * q, stream, P_col,
+                      P_row, Cq, W, (int)BN, N, k, q, w.Qc, w.Qr);
+        done = true;
+    } else if (fast && (size_t)3 * k * q * sizeof(float) <= 48 * 1024) {
         NBPC_LAUNCH_N(NbpcKName("glf_node_project_kernel", k, q).c_str(), glf_node_project_kernel, nbpc_min(nbpc_cdiv(BN * q, 256), gl_num_sms() * 8), 256,
                       sizeof(float) * 3 * k * q, stream, P_col, P_row, P_cube, W, bias, (int)BN, N, k, q, w.Qc, w.Qr);
         done = true;
@@ -624,10 +644,7 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     if (!done)
         NBPC_LAUNCH_N(NbpcKName("glb_pool_kernel", k, q).c_str(), glb_pool_kernel, nbpc_cdiv(BN * q, GL_THREADS), GL_THREADS, 0, stream,
                       dz, (int)BN, M, q, csrT_ptr, csrT_edge, dQ_row, dQ_col);
-    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dQ_row, q, N,
-                nblk, B, w.cube_partial);
-    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.cube_partial, q, nblk, B, 1.0f,
-                w.dCq);
+    gl_colsum(dQ_row, q, N, B, nblk, 1.0f, w.cube_partial, w.dCq, fast, stream);
     NBPC_LAUNCH(glb_bias_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.dCq, B, q, dB);
 
     // ---- node-level weight gradients: dW2 = P_col^T dQ_col, dW3 = P_row^T dQ_row, dW4 = P_cube^T dCq
@@ -657,7 +674,14 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     if (dH_in) {
         done = false;
 #ifndef NBPC_HOST_EMU
-        if (fast && (size_t)3 * kq * sizeof(float) <= 48 * 1024) {
+        if (fast && k % 4 == 0 && q % 4 == 0 && (size_t)2 * kq * sizeof(float) <= 48 * 1024) {
+            float *Gq = w.cube_partial;   // (B,k): per-sample constant dCq W4^T / (N M); the colsum partials are consumed
+            NBPC_LAUNCH(glf_cube_grad_kernel, nbpc_cdiv(B * k, 128), 128, 0, stream, w.dCq, W + 3 * kq, B, N, M, k, q, Gq);
+            NBPC_LAUNCH_N(NbpcKName("glf_node_grad4_kernel", k, q).c_str(), glf_node_grad4_kernel,
+                          nbpc_min(nbpc_cdiv(BN * (k / 4), 256), gl_num_sms() * 8), 256, sizeof(float) * 2 * kq, stream, dQ_col,
+                          dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
+            done = true;
+        } else if (fast && (size_t)3 * kq * sizeof(float) <= 48 * 1024) {
             NBPC_LAUNCH_N(NbpcKName("glf_node_grad_kernel", k, q).c_str(), glf_node_grad_kernel, nbpc_min(nbpc_cdiv(BN * k, 256), gl_num_sms() * 8), 256,
                           sizeof(float) * 3 * kq, stream, dQ_col, dQ_row, w.dCq, W, csrT_ptr, (int)BN, N, M, k, q, w.Gc, w.Gr);
             done = true;

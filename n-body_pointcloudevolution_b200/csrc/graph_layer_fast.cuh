@@ -500,6 +500,148 @@ __global__ void __launch_bounds__(256) glf_node_grad_kernel(const float *__restr
     }
 }
 
+// ---- 4-wide node kernels (k % 4 == 0 and q % 4 == 0): float4 row loads, LDS.128 weights, 4 outputs / thread
+// per-sample constants are hoisted into tiny kernels:  Cq[s] = P_cube[s] W4 + bias,  Gq[s] = dCq[s] W4^T / (N M)
+__global__ void glf_cube_project_kernel(const float *__restrict__ P_cube, const float *__restrict__ W4,
+                                        const float *__restrict__ bias, int B, int k, int q, float *__restrict__ Cq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * q) return;
+    const int s = t / q, qo = t % q;
+    float a = 0.f;
+    for (int kk = 0; kk < k; ++kk) a += P_cube[s * k + kk] * W4[kk * q + qo];
+    Cq[t] = a + bias[qo];
+}
+__global__ void glf_cube_grad_kernel(const float *__restrict__ dCq, const float *__restrict__ W4, int B, int N, int M, int k,
+                                     int q, float *__restrict__ Gq) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * k) return;
+    const int s = t / k, kk = t % k;
+    float a = 0.f;
+    for (int qo = 0; qo < q; ++qo) a += dCq[s * q + qo] * W4[kk * q + qo];
+    Gq[t] = a / ((float)N * (float)M);
+}
+
+__global__ void __launch_bounds__(256) glf_node_project4_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
+                                                                 const float *__restrict__ Cq, const float *__restrict__ W,
+                                                                 int BN, int N, int k, int q, float *__restrict__ Q_col,
+                                                                 float *__restrict__ Q_row) {
+    extern __shared__ __align__(16) float smem[];   // W2, W3: [k][q] each
+    for (int i = threadIdx.x; i < 2 * k * q; i += blockDim.x) smem[i] = __ldg(&W[(int64_t)k * q + i]);
+    __syncthreads();
+    const float *W2 = smem, *W3 = smem + k * q;
+    const int QG = q / 4;
+    const int64_t total = (int64_t)BN * QG, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int node = (int)(t / QG), j = (int)(t % QG);
+        const float *pc = P_col + (int64_t)node * k, *pr = P_row + (int64_t)node * k;
+        float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f), a3 = a2;
+        for (int k4 = 0; k4 < k; k4 += 4) {
+            const float4 c4 = glf_ldg4(pc + k4), r4 = glf_ldg4(pr + k4);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 w2 = *reinterpret_cast<const float4 *>(W2 + (k4 + i) * q + 4 * j);
+                const float4 w3 = *reinterpret_cast<const float4 *>(W3 + (k4 + i) * q + 4 * j);
+                a2.x += cv[i] * w2.x; a2.y += cv[i] * w2.y; a2.z += cv[i] * w2.z; a2.w += cv[i] * w2.w;
+                a3.x += rv[i] * w3.x; a3.y += rv[i] * w3.y; a3.z += rv[i] * w3.z; a3.w += rv[i] * w3.w;
+            }
+        }
+        const float4 cq = glf_ldg4(Cq + (node / N) * q + 4 * j);
+        *reinterpret_cast<float4 *>(Q_col + (int64_t)node * q + 4 * j) = a2;
+        *reinterpret_cast<float4 *>(Q_row + (int64_t)node * q + 4 * j) = make_float4(a3.x + cq.x, a3.y + cq.y, a3.z + cq.z, a3.w + cq.w);
+    }
+}
+
+__global__ void __launch_bounds__(256) glf_node_grad4_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
+                                                              const float *__restrict__ Gq, const float *__restrict__ W,
+                                                              const int32_t *__restrict__ csrT_ptr, int BN, int N, int M,
+                                                              int k, int q, float *__restrict__ G_col, float *__restrict__ G_row) {
+    extern __shared__ __align__(16) float smem[];   // W2t, W3t: [q][k] each
+    float *W2t = smem, *W3t = smem + k * q;
+    for (int i = threadIdx.x; i < k * q; i += blockDim.x) {
+        const int qo = i / k, kk = i % k;
+        W2t[i] = __ldg(&W[(int64_t)k * q + kk * q + qo]);
+        W3t[i] = __ldg(&W[2 * (int64_t)k * q + kk * q + qo]);
+    }
+    __syncthreads();
+    const int KG = k / 4;
+    const int64_t total = (int64_t)BN * KG, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int node = (int)(t / KG), j = (int)(t % KG);
+        const float *dc = dQ_col + (int64_t)node * q, *dr = dQ_row + (int64_t)node * q;
+        float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f), a3 = a2;
+        for (int q4 = 0; q4 < q; q4 += 4) {
+            const float4 c4 = glf_ldg4(dc + q4), r4 = glf_ldg4(dr + q4);
+            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, rv[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 w2 = *reinterpret_cast<const float4 *>(W2t + (q4 + i) * k + 4 * j);
+                const float4 w3 = *reinterpret_cast<const float4 *>(W3t + (q4 + i) * k + 4 * j);
+                a2.x += cv[i] * w2.x; a2.y += cv[i] * w2.y; a2.z += cv[i] * w2.z; a2.w += cv[i] * w2.w;
+                a3.x += rv[i] * w3.x; a3.y += rv[i] * w3.y; a3.z += rv[i] * w3.z; a3.w += rv[i] * w3.w;
+            }
+        }
+        const float fi = (float)nbpc_max(csrT_ptr[node + 1] - csrT_ptr[node], 1), fm = (float)M;
+        const float4 gq = glf_ldg4(Gq + (node / N) * k + 4 * j);
+        *reinterpret_cast<float4 *>(G_col + (int64_t)node * k + 4 * j) = make_float4(a2.x / fi, a2.y / fi, a2.z / fi, a2.w / fi);
+        *reinterpret_cast<float4 *>(G_row + (int64_t)node * k + 4 * j) =
+            make_float4(a3.x / fm + gq.x, a3.y / fm + gq.y, a3.z / fm + gq.z, a3.w / fm + gq.w);
+    }
+}
+
+// ---- per-sample column sums (cube pool / dCq): block = 32 lanes (channels) x 8 warps (row slices)
+// partial[s][blk][ch] = sum of rows [blk*rpb, (blk+1)*rpb) of sample s;   grid (nblk, B)
+__global__ void __launch_bounds__(256) glf_colsum_partial_kernel(const float *__restrict__ X, int ch, int N, int rpb,
+                                                                  float *__restrict__ partial) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int blk = blockIdx.x, s = blockIdx.y, nblk = gridDim.x;
+    const int r0 = blk * rpb, r1 = nbpc_min(r0 + rpb, N);
+    for (int c0 = 0; c0 < ch; c0 += 32) {
+        const int cc = c0 + lane;
+        float a0 = 0.f, a1 = 0.f;
+        if (cc < ch) {
+            int r = r0 + w;
+            for (; r + 8 < r1; r += 16) {
+                a0 += __ldg(&X[((int64_t)s * N + r) * ch + cc]);
+                a1 += __ldg(&X[((int64_t)s * N + r + 8) * ch + cc]);
+            }
+            if (r < r1) a0 += __ldg(&X[((int64_t)s * N + r) * ch + cc]);
+        }
+        red[w][lane] = a0 + a1;
+        __syncthreads();
+        if (w == 0 && cc < ch) {
+            float tot = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) tot += red[ww][lane];
+            partial[((int64_t)s * nblk + blk) * ch + cc] = tot;
+        }
+        __syncthreads();
+    }
+}
+// out[s][ch] = (sum_blk partial[s][blk][ch]) / divisor;   grid (B)
+__global__ void __launch_bounds__(256) glf_colsum_final_kernel(const float *__restrict__ partial, int ch, int nblk, float divisor,
+                                                                float *__restrict__ out) {
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int s = blockIdx.x;
+    for (int c0 = 0; c0 < ch; c0 += 32) {
+        const int cc = c0 + lane;
+        float a = 0.f;
+        if (cc < ch)
+            for (int b = w; b < nblk; b += 8) a += partial[((int64_t)s * nblk + b) * ch + cc];
+        red[w][lane] = a;
+        __syncthreads();
+        if (w == 0 && cc < ch) {
+            float tot = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < 8; ++ww) tot += red[ww][lane];
+            out[s * ch + cc] = tot / divisor;
+        }
+        __syncthreads();
+    }
+}
+
 // generic X^T Y over n node rows (runtime k, q; used when no micro-tile instance fits)
 #define GLF_XTY_ROWS 32
 __global__ void __launch_bounds__(256) glf_node_xty_kernel(const float *__restrict__ X, const float *__restrict__ Y, int64_t n,

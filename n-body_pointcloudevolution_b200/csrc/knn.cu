@@ -16,12 +16,18 @@
 // separately rounded multiply/add (__dmul_rn/__dadd_rn: no FMA contraction), images are formed
 // as (double)x + shift before the subtraction.  Total order on candidates = (d2, index); the
 // result is therefore independent of the visiting order.
+#include <stdlib.h>
+
 #include "nbpc_common.cuh"
 #include "scan.cuh"
 
 #define KNN_IDX_MASK 0x00FFFFFF
 #define KNN_FLAG_SHIFT 24
 #define KNN_THREADS 128
+#define KNN_PEND 4          // per-lane queue of accepted-but-not-yet-inserted candidates
+// Deferred insertion measured SLOWER on B200 (0.62 vs 0.57 ms at 8x32^3, k=14: lanes of a warp are rarely
+// converged inside the candidate loop, so the queue flushes per small lane group); kept for reference.
+#define KNN_DEFERRED 0
 
 struct KnnGridInfo {  // per sample, device
     float lo[3];
@@ -218,15 +224,16 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
     const int cx = knn_cell_coord(me.x, gi.lo[0], gi.inv_h, G);
     const int cy = knn_cell_coord(me.y, gi.lo[1], gi.inv_h, G);
     const int cz = knn_cell_coord(me.z, gi.lo[2], gi.inv_h, G);
-    // distance (in cells) from the query to the nearest face of its own cell, clamped to [0, 0.5]
-    float margin;
-    {
-        const float fx = (me.x - gi.lo[0]) * gi.inv_h - (float)cx;
-        const float fy = (me.y - gi.lo[1]) * gi.inv_h - (float)cy;
-        const float fz = (me.z - gi.lo[2]) * gi.inv_h - (float)cz;
-        margin = fminf(fminf(fminf(fx, 1.f - fx), fminf(fy, 1.f - fy)), fminf(fz, 1.f - fz));
-        margin = fminf(fmaxf(margin, 0.f), 0.5f);
-    }
+    // position inside the own cell in cell units (clamped to [0,1]: the cell index itself was clamped)
+    const float frx = fminf(fmaxf((me.x - gi.lo[0]) * gi.inv_h - (float)cx, 0.f), 1.f);
+    const float fry = fminf(fmaxf((me.y - gi.lo[1]) * gi.inv_h - (float)cy, 0.f), 1.f);
+    const float frz = fminf(fmaxf((me.z - gi.lo[2]) * gi.inv_h - (float)cz, 0.f), 1.f);
+    // distance (in cells) from the query to the nearest face of its own cell, in [0, 0.5]
+    const float margin = fminf(fminf(fminf(frx, 1.f - frx), fminf(fry, 1.f - fry)), fminf(frz, 1.f - frz));
+    const float inv_h2 = gi.inv_h * gi.inv_h * 1.0001f;
+    // lower bound (cell units, minus a slack covering float cell-assignment fuzz) on the distance along one
+    // axis between the query and any point of the cell at offset o
+#define KNN_GAP(o, fr) fmaxf(((o) > 0 ? (float)(o) - (fr) : ((o) < 0 ? (float)(-(o)-1) + (fr) : 0.f)) - 1e-3f, 0.f)
     const int tmin = PERIODIC ? -G : 0, tmax = PERIODIC ? 2 * G - 1 : G - 1;  // extended cell coords
     int Rmax = nbpc_max(nbpc_max(cx - tmin, tmax - cx), nbpc_max(nbpc_max(cy - tmin, tmax - cy), nbpc_max(cz - tmin, tmax - cz)));
     const int64_t cellbase = (int64_t)b * G * G * G;
@@ -234,6 +241,24 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
 
     KnnTopK<K> top;
     top.init(P.k);
+#if !defined(NBPC_HOST_EMU) && KNN_DEFERRED
+    __shared__ double pend_d_s[KNN_PEND * KNN_THREADS];
+    __shared__ int pend_i_s[KNN_PEND * KNN_THREADS];
+    double *pend_d = pend_d_s + threadIdx.x;
+    int *pend_i = pend_i_s + threadIdx.x;
+    int npend = 0;
+#define KNN_FLUSH()                                                            \
+    do {                                                                       \
+        _Pragma("unroll") for (int f = 0; f < KNN_PEND; ++f) {                 \
+            if (f < npend) {                                                   \
+                const double fd = pend_d[f * KNN_THREADS];                     \
+                const int fi = pend_i[f * KNN_THREADS];                        \
+                if (top.accepts(fd, fi)) top.insert(fd, fi);                   \
+            }                                                                  \
+        }                                                                      \
+        npend = 0;                                                             \
+    } while (0)
+#endif
 
     for (int R = 0; R <= Rmax; ++R) {
         for (int dz = -R; dz <= R; ++dz) {
@@ -244,9 +269,17 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
                 if (tz < 0) { tz += G; sz = -1; } else if (tz >= G) { tz -= G; sz = 1; }
             }
             const bool zface = (dz == -R || dz == R);
+            const float gz = KNN_GAP(dz, frz);
+            if (gz * gz > (float)top.d[K - 1] * inv_h2) continue;   // whole plane is beyond the current k-th distance
             for (int dy = -R; dy <= R; ++dy) {
                 int ty = cy + dy;
                 if (ty < tmin || ty > tmax) continue;
+                // prune with the CURRENT k-th distance (cell units): skip rows / row ends that cannot hold a closer point
+                const float gy = KNN_GAP(dy, fry);
+                const float rem = (float)top.d[K - 1] * inv_h2 - (gz * gz + gy * gy);
+                if (rem < 0.f) continue;
+                const float xr = fminf(sqrtf(rem) + 1e-3f, 8192.f);
+                const int x_lo = (int)floorf((float)cx + frx - xr), x_hi = (int)floorf((float)cx + frx + xr);
                 int sy = 0;
                 if (PERIODIC) {
                     if (ty < 0) { ty += G; sy = -1; } else if (ty >= G) { ty -= G; sy = 1; }
@@ -259,10 +292,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
                     int x0 = full_row ? cx - R : (part == 0 ? cx - R : cx + R);
                     int x1 = full_row ? cx + R : x0;
                     if (full_row) {
-                        if (x0 < tmin) x0 = tmin;
-                        if (x1 > tmax) x1 = tmax;
-                    } else if (x0 < tmin || x0 > tmax) {
-                        continue;  // a single end cell outside the (extended) grid
+                        x0 = nbpc_max(x0, nbpc_max(tmin, x_lo));
+                        x1 = nbpc_min(x1, nbpc_min(tmax, x_hi));
+                    } else if (x0 < tmin || x0 > tmax || x0 < x_lo || x0 > x_hi) {
+                        continue;  // a single end cell outside the (extended) grid or out of reach
                     }
                     // split into the shift -1 / 0 / +1 copies of the row
                     const int nseg = PERIODIC ? 3 : 1;
@@ -292,12 +325,28 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
                             const double ty2 = __dsub_rn(py, __dadd_rn((double)c.y, oy));
                             const double tz2 = __dsub_rn(pz, __dadd_rn((double)c.z, oz));
                             const double dd = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty2, ty2)), __dmul_rn(tz2, tz2));
+#if defined(NBPC_HOST_EMU) || !KNN_DEFERRED
                             if (top.accepts(dd, cid)) top.insert(dd, cid);
+#else
+                            // Deferred insertion: a candidate that beats the (possibly stale) k-th best is parked in
+                            // a small per-lane queue; the ~K*10-instruction insert runs only when some lane of the
+                            // converged group has a full queue, and then for all lanes together.  (With immediate
+                            // insertion nearly every iteration pays the insert for the sake of one or two lanes.)
+                            if (top.accepts(dd, cid)) {
+                                pend_d[npend * KNN_THREADS] = dd;
+                                pend_i[npend * KNN_THREADS] = cid;
+                                ++npend;
+                            }
+                            if (__any_sync(__activemask(), npend == KNN_PEND)) KNN_FLUSH();
+#endif
                         }
                     }
                 }
             }
         }
+#if !defined(NBPC_HOST_EMU) && KNN_DEFERRED
+        if (__any_sync(__activemask(), npend > 0)) KNN_FLUSH();   // the termination test needs the true k-th best
+#endif
         // everything not yet visited is at least (R + margin) cells away along some axis
         const double g = ((double)R + (double)margin - 1e-3) * gi.h;
         if (g > 0.0 && top.d[K - 1] < g * g) break;
@@ -317,8 +366,15 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
 
 // ------------------------------------------------------------------ host side
 static int knn_grid_cells(int N) {
-    // ~2 particles per cell: with k=14 most queries finish after shell R=2 (125 cells, ~250 candidates)
-    int G = (int)floor(cbrt((double)N / 2.0));
+    // ~1 particle per cell by default (NBPC_KNN_RHO overrides): with the per-row pruning above a query
+    // only touches the cells that intersect its current k-th-neighbour ball
+    static double rho = 0.0;
+    if (rho == 0.0) {
+        const char *e = getenv("NBPC_KNN_RHO");
+        rho = e ? atof(e) : 1.0;
+        if (!(rho > 0.01 && rho < 1000.0)) rho = 1.0;
+    }
+    int G = (int)floor(cbrt((double)N / rho));
     if (G < 1) G = 1;
     if (G > 256) G = 256;
     return G;

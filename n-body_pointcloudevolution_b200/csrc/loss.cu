@@ -3,7 +3,7 @@
 #include "nbpc_common.cuh"
 
 #define LOSS_THREADS 256
-#define LOSS_CHUNK 64    // rows per first-level partial
+#define LOSS_CHUNK 16    // rows per first-level partial
 #define LOSS_FAN 64      // first-level partials per second-level partial
 
 __device__ __forceinline__ float sq_rn(float a) { return __fmul_rn(a, a); }
