@@ -221,7 +221,8 @@ def ncu_traffic(name):
     """dram bytes per launch from the committed ncu capture, if one exists for this kernel."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            return json.load(f).get(name.split("[")[0])
+            e = json.load(f).get(name.split("[")[0])
+            return e["bytes_per_launch"] if isinstance(e, dict) else e
     except Exception:
         return None
 
