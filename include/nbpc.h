@@ -47,6 +47,21 @@ const char *nbpc_last_error_string(void);
 /* NBPC_OK if the current CUDA device is compute capability 10.0, else NBPC_EARCH. */
 int nbpc_device_check(void);
 
+/* Arithmetic of the edge-level channel projections of the graph layer (H W1, dZ W1^T, H^T dZ) for channel
+ * widths in {16,32,64}.  All modes run on the GPU; they differ in which pipe does the multiply-adds:
+ *   NBPC_MATH_FP32    CUDA-core FP32 FMAs;
+ *   NBPC_MATH_TF32X3  tcgen05 tensor cores, operands split x = hi + lo into two TF32 values and three MMAs
+ *                     (lo*hi + hi*lo + hi*hi) accumulated in FP32 in TMEM: FP32-class accuracy (same test tolerance);
+ *   NBPC_MATH_TF32    one tcgen05 pass on 10-bit-mantissa operands: ~1e-3 relative (better than BF16).
+ * The process default comes from the environment variable NBPC_MATH (fp32 | tf32x3 | tf32), else
+ * NBPC_MATH_DEFAULT.  The mode is process-global (not per stream). */
+#define NBPC_MATH_FP32 0
+#define NBPC_MATH_TF32X3 1
+#define NBPC_MATH_TF32 2
+#define NBPC_MATH_DEFAULT NBPC_MATH_FP32
+int nbpc_set_math_mode(int mode);
+int nbpc_get_math_mode(void);
+
 /* Tracing (replaces the reference's single wall-clock timer around the training loop,
  * train.py:84, 122-124).  nbpc_launch_count(): kernels launched by this library so far in the
  * process.  nbpc_prof_enable(1) clears the records and starts bracketing every launch with CUDA

@@ -27,6 +27,8 @@ SIGNATURES = {
     "nbpc_version": (_i, []),
     "nbpc_last_error_string": (ctypes.c_char_p, []),
     "nbpc_device_check": (_i, []),
+    "nbpc_set_math_mode": (_i, [_i]),
+    "nbpc_get_math_mode": (_i, []),
     "nbpc_launch_count": (ctypes.c_longlong, []),
     "nbpc_prof_enable": (_i, [_i]),
     "nbpc_prof_report": (ctypes.c_longlong, [ctypes.c_char_p, _sz]),
@@ -89,6 +91,20 @@ def last_error():
 def check(rc, what):
     if rc != NBPC_OK:
         raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+MATH_MODES = {"fp32": 0, "tf32x3": 1, "tf32": 2}
+
+
+def set_math_mode(mode):
+    """Arithmetic of the edge-level channel projections: 'fp32' (CUDA cores), 'tf32x3' (tcgen05, error-compensated,
+    FP32-class accuracy) or 'tf32' (tcgen05, one pass).  Process-global; see include/nbpc.h."""
+    check(load().nbpc_set_math_mode(MATH_MODES[mode] if isinstance(mode, str) else int(mode)), "nbpc_set_math_mode")
+
+
+def get_math_mode():
+    m = int(load().nbpc_get_math_mode())
+    return {v: k for k, v in MATH_MODES.items()}[m]
 
 
 def launch_count():

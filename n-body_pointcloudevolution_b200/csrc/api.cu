@@ -1,4 +1,6 @@
 // api.cu - library-level entry points: version, error string, device check.
+#include <stdlib.h>
+
 #include "nbpc_common.cuh"
 
 static thread_local std::string g_last_error;
@@ -84,7 +86,29 @@ void nbpc_prof_post(cudaStream_t stream) {
 }
 #endif
 
+// NBPC_MATH=fp32|tf32|tf32x3 selects the default; nbpc_set_math_mode overrides it
+static int nbpc_math_mode_from_env() {
+    const char *e = getenv("NBPC_MATH");
+    if (!e) return NBPC_MATH_DEFAULT;
+    if (!strcmp(e, "fp32")) return NBPC_MATH_FP32;
+    if (!strcmp(e, "tf32")) return NBPC_MATH_TF32;
+    if (!strcmp(e, "tf32x3")) return NBPC_MATH_TF32X3;
+    return NBPC_MATH_DEFAULT;
+}
+int g_nbpc_math_mode = nbpc_math_mode_from_env();
+
 extern "C" {
+
+int nbpc_set_math_mode(int mode) {
+    if (mode != NBPC_MATH_FP32 && mode != NBPC_MATH_TF32 && mode != NBPC_MATH_TF32X3) {
+        nbpc_set_error("nbpc_set_math_mode: unknown mode");
+        return NBPC_EINVAL;
+    }
+    g_nbpc_math_mode = mode;
+    return NBPC_OK;
+}
+
+int nbpc_get_math_mode(void) { return g_nbpc_math_mode; }
 
 long long nbpc_launch_count(void) { return (long long)g_nbpc_launches; }
 

@@ -431,6 +431,7 @@ static int glf_node_xty(const char *name, const float *X, const float *Y, int64_
 }
 #endif  // !NBPC_HOST_EMU
 
+#include "graph_layer_tc.h"
 
 // per-sample column sums of a node tensor X (B*N, ch): out[s] = sum_n X[s,n] / divisor
 static void gl_colsum(const float *X, int ch, int N, int B, int nblk, float divisor, float *partial, float *out, bool fast,
@@ -579,6 +580,17 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
 #ifndef NBPC_HOST_EMU
+    if (fast && g_nbpc_math_mode != NBPC_MATH_FP32 && glt_fwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3)) {
+        // tcgen05 / TMEM / TMA path (graph_layer_tc.cuh)
+        int rc = 1;
+        const int x3 = g_nbpc_math_mode == NBPC_MATH_TF32X3;
+        rc = glt_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, x3, H_out, stream);
+        if (rc) {
+            nbpc_set_error("nbpc_graph_layer_fwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
     if (fast && glf_edge_shape_ok(k, q)) {
         int rc = 1;
 #define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_out<K_, Q_>(H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
@@ -702,6 +714,21 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                           stream, dQ_row, W, (int)BN, M, k, q, w.Gr);
             NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256,
                           0, stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, c, M, k, dH_in);
+        }
+        return nbpc_check_launch("nbpc_graph_layer_bwd");
+    }
+    if (fast && !is_last && !relu && dH_in && g_nbpc_math_mode != NBPC_MATH_FP32 &&
+        glt_bwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3, c)) {
+        int rc = 1;
+        const int x3 = g_nbpc_math_mode == NBPC_MATH_TF32X3;
+        const int nb = glt_edge_bwd(k, q, dOut, H_in, col, W, w.Gc, w.Gr, c, M, mask_input, x3, dH_in, w.xty_partial, stream);
+        if (nb > 0) {
+            glf_reduce_partials(w.xty_partial, nb, k, q, 0, dW, stream);
+            rc = 0;
+        }
+        if (rc) {
+            nbpc_set_error("nbpc_graph_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+            return NBPC_ELAUNCH;
         }
         return nbpc_check_launch("nbpc_graph_layer_bwd");
     }

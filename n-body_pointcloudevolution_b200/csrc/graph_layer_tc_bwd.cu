@@ -1,0 +1,303 @@
+// graph_layer_tc_bwd.cu - tcgen05 backward edge kernel (see graph_layer_tc.cuh)
+#include "graph_layer_tc.cuh"
+#ifndef NBPC_HOST_EMU
+// ------------------------------------------------------------------ backward kernel
+//
+// dW1 = H^T dZ contracts over the edges, i.e. over the ROWS of both tiles: both operands are MN-major.  For 32-bit
+// operands tcgen05 accepts an MN-major shared-memory operand only in the "128-byte swizzle, 32-byte atom" layout
+// (descriptor layout type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): rows of exactly 128 bytes, 4 rows per swizzle
+// atom.  Tensors with 16 channels are therefore viewed as (c/2, 32) - P = 2 edges per 128-byte "packed row" - and so
+// is the other operand, (c/2, 2K): the MMA then yields the (P K) x (P Q) matrix [H_even H_odd]^T [Z_even Z_odd] whose
+// P diagonal K x Q blocks sum to the tile's dW1 (the off-diagonal blocks are ignored; the tensor pipe is idle anyway).
+// dH = dZ W1^T needs dZ K-major (standard swizzle), so the dZ tile is landed twice (the second copy comes from L2).
+template <int K, int Q>
+struct GltBwdCfg {
+    using TZ = GltTile<Q>;
+    static constexpr int P = (K == 16 || Q == 16) ? 2 : 1;               // edges per packed row
+    static constexpr int R = GLT_TILE / P;                               // packed rows per tile
+    static constexpr int HCH = K * P / 32, ZCH = Q * P / 32;             // 32-float column chunks of the packed tiles
+    static constexpr int PCHUNK = R * 128;                               // bytes per packed chunk
+    static constexpr int H_BYTES = HCH * PCHUNK;                         // packed H            (MN-major operand of D2)
+    static constexpr int Z_BYTES = TZ::NCH * TZ::chunk_bytes(GLT_TILE);  // dZ, K-major         (A operand of D1)
+    static constexpr int Z2_BYTES = ZCH * PCHUNK;                        // packed dZ           (MN-major operand of D2)
+    static constexpr int STAGE = H_BYTES + Z_BYTES + Z2_BYTES;
+    static constexpr int B_BYTES = TZ::NCH * TZ::chunk_bytes(K);         // W1 as (N = K rows) x Q, K(=q)-major
+    static constexpr int KS = glf_stride(K);
+    static constexpr int OS_BYTES = GLT_TILE * KS * 4;
+    static constexpr int M2 = (K * P <= 64) ? 64 : 128, N2 = Q * P;      // D2 MMA shape
+    static constexpr int ACC_COLS = K + N2;                              // D1 (dH tile) | D2 (dW1 tile partial blocks)
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
+    static constexpr int SMEM_MAX = 227 * 1024;
+    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 256; }
+    __host__ __device__ static constexpr int stages(bool x3) {
+        const int s = (int)((SMEM_MAX - fixed_bytes(x3)) / ((size_t)STAGE * (x3 ? 2 : 1)));
+        return s > 6 ? 6 : s;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(bool x3) { return fixed_bytes(x3) + (size_t)stages(x3) * STAGE * (x3 ? 2 : 1); }
+    // byte offset of channel j (multiple of 4) of tile edge `row` inside the packed H tile
+    __device__ static __forceinline__ int h_offset(int row, int j) {
+        const int pr = row / P, colp = (row % P) * K + j, jj = colp & 31;
+        return (colp >> 5) * PCHUNK + pr * 128 + ((((jj >> 3) ^ pr) & 3) << 5) + ((jj & 7) << 2);
+    }
+};
+
+template <int K, int Q, bool MASK_IN, bool X3>
+__global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_constant__ CUtensorMap tmH,
+                                                                    const __grid_constant__ CUtensorMap tmZ,
+                                                                    const __grid_constant__ CUtensorMap tmZ2,
+                                                                    const int32_t *__restrict__ col,
+                                                                    const float *__restrict__ W1,
+                                                                    const float *__restrict__ G_col,
+                                                                    const float *__restrict__ G_row, int64_t c, int M,
+                                                                    float *__restrict__ dH, float *__restrict__ dW_partial) {
+    using Cfg = GltBwdCfg<K, Q>;
+    using TZ = typename Cfg::TZ;
+    constexpr int S = Cfg::stages(X3), KS = Cfg::KS, P = Cfg::P;
+    static_assert(S >= 2, "shape does not fit shared memory with two pipeline stages");
+    extern __shared__ __align__(16) unsigned char glt_smem_raw[];
+    unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
+    unsigned char *St = base;                                       // [S][H' | Z | Z']  raw -> hi
+    unsigned char *Sl = St + S * Cfg::STAGE;                        // [S][H' | Z | Z']  lo (X3 only)
+    unsigned char *Bh = Sl + (X3 ? S * Cfg::STAGE : 0);
+    unsigned char *Bl = Bh + Cfg::B_BYTES;                          // (X3 only)
+    float *Os = reinterpret_cast<float *>(Bh + Cfg::B_BYTES * (X3 ? 2 : 1));   // [128][KS]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + Cfg::OS_BYTES);
+    const uint32_t bar0 = glt_smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto TFULL = [&](int a) { return bar0 + 8u * (3 * S + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * S + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE);
+
+    if (tid == 0) {
+        // a stage is free again when its MMAs have read it AND (MASK_IN) the epilogue warps have read their H rows
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), MASK_IN ? 5 : 1); glt_mbar_init(CONV(s), 4); }
+        for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
+        glt_fence_barrier_init();
+        glt_prefetch_tmap(&tmH);
+        glt_prefetch_tmap(&tmZ);
+        glt_prefetch_tmap(&tmZ2);
+    }
+    if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    // B operand of dH = dZ W1^T: row n = input channel k, column = output channel q: W1[k][q] (as stored)
+    glt_fill_operand<Q>(reinterpret_cast<char *>(Bh), X3 ? reinterpret_cast<char *>(Bl) : nullptr, K,
+                        [&](int n, int qq) { return __ldg(&W1[n * Q + qq]); }, tid, GLT_THREADS);
+    glt_fence_proxy_async();
+    glt_tc_fence_before();
+    __syncthreads();
+    glt_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                glt_mbar_wait(EMPTY(s), ph ^ 1);
+                glt_mbar_expect_tx(FULL(s), Cfg::STAGE);
+                unsigned char *st = St + s * Cfg::STAGE;
+#pragma unroll
+                for (int ch = 0; ch < Cfg::HCH; ++ch)
+                    glt_tma_load_2d(glt_smem_u32(st + ch * Cfg::PCHUNK), &tmH, FULL(s), ch * 32, t * Cfg::R);
+#pragma unroll
+                for (int ch = 0; ch < TZ::NCH; ++ch)
+                    glt_tma_load_2d(glt_smem_u32(st + Cfg::H_BYTES + ch * TZ::chunk_bytes(GLT_TILE)), &tmZ, FULL(s), ch * TZ::CW, t * GLT_TILE);
+#pragma unroll
+                for (int ch = 0; ch < Cfg::ZCH; ++ch)
+                    glt_tma_load_2d(glt_smem_u32(st + Cfg::H_BYTES + Cfg::Z_BYTES + ch * Cfg::PCHUNK), &tmZ2, FULL(s), ch * 32, t * Cfg::R);
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer
+            constexpr uint32_t idesc1 = glt_idesc_tf32(GLT_TILE, K, 0, 0);   // D1 (128 x K) = dZ (K-major) * W1^T
+            constexpr uint32_t idesc2 = glt_idesc_tf32(Cfg::M2, Cfg::N2, 1, 1);  // D2 (P K x P Q) = H'^T (MN-major) * dZ' (MN-major)
+            int s = 0, ph = 0, a = 0, aph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                glt_mbar_wait(TEMPTY(a), aph ^ 1);
+                glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
+                glt_tc_fence_after();
+                const uint32_t d1 = tmem_base + a * Cfg::ACC_COLS, d2 = d1 + K;
+                const uint32_t h_hi = glt_smem_u32(St + s * Cfg::STAGE), z_hi = h_hi + Cfg::H_BYTES;
+                const uint32_t h_lo = glt_smem_u32(Sl + s * Cfg::STAGE), z_lo = h_lo + Cfg::H_BYTES;
+                const uint32_t z2_hi = z_hi + Cfg::Z_BYTES, z2_lo = z_lo + Cfg::Z_BYTES;
+                const uint32_t b_hi = glt_smem_u32(Bh), b_lo = glt_smem_u32(Bl);
+                uint32_t acc1 = 0, acc2 = 0;
+#pragma unroll
+                for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {
+                    const uint32_t zb = (pass == 0) ? z_lo : z_hi, bb = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+                    for (int ch = 0; ch < TZ::NCH; ++ch)
+#pragma unroll
+                        for (int k8 = 0; k8 < TZ::CW / 8; ++k8) {
+                            const uint64_t da = glt_smem_desc(zb + ch * TZ::chunk_bytes(GLT_TILE) + k8 * 32, 16, TZ::ATOM, TZ::SWZ);
+                            const uint64_t db = glt_smem_desc(bb + ch * TZ::chunk_bytes(K) + k8 * 32, 16, TZ::ATOM, TZ::SWZ);
+                            glt_mma_tf32(d1, da, db, idesc1, acc1);
+                            acc1 = 1;
+                        }
+                }
+#pragma unroll
+                for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {
+                    const uint32_t hb = (pass == 0) ? h_lo : h_hi, zb = (pass == 1) ? z2_lo : z2_hi;
+                    // reduction dimension = the packed rows of the tile, 8 per MMA = two 4-row swizzle atoms (SBO = 512 B);
+                    // MN groups of 32 floats are one column chunk apart (LBO)
+#pragma unroll
+                    for (int k8 = 0; k8 < Cfg::R / 8; ++k8) {
+                        const uint64_t da = glt_smem_desc(hb + k8 * 1024, Cfg::PCHUNK, 512, 1);
+                        const uint64_t db = glt_smem_desc(zb + k8 * 1024, Cfg::PCHUNK, 512, 1);
+                        glt_mma_tf32(d2, da, db, idesc2, acc2);
+                        acc2 = 1;
+                    }
+                }
+                glt_tc_commit(EMPTY(s));
+                glt_tc_commit(TFULL(a));
+                if (++s == S) { s = 0; ph ^= 1; }
+                if (++a == 2) { a = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps
+        const int qd = warp & 3, row = qd * 32 + lane, wtid = tid - 64;
+        // D2: M2 = 64 puts row r in lane (r % 16) + 32 (r / 16), M2 = 128 in lane r; row r = p K + k belongs to the
+        // diagonal block p (warp-uniform) whose columns are [p Q, p Q + Q)
+        constexpr int RPQ = (Cfg::M2 == 64) ? 16 : 32;
+        const int r2 = qd * RPQ + lane, p2 = (qd * RPQ) / K, krow = r2 - p2 * K;
+        const bool warp_has_dw = qd * RPQ < K * P;
+        const bool has_dw = warp_has_dw && lane < RPQ;
+        float dw[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) dw[j] = 0.f;
+        int s = 0, ph = 0, a = 0, aph = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            unsigned char *st = St + s * Cfg::STAGE;
+            if constexpr (X3 || MASK_IN) glt_mbar_wait(FULL(s), ph);   // the epilogue warps touch the landed tile themselves
+            if constexpr (X3) {
+                glt_split_inplace(reinterpret_cast<float *>(st), reinterpret_cast<float *>(Sl + s * Cfg::STAGE), Cfg::STAGE / 4, wtid, 128);
+                glt_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(CONV(s));
+            }
+            const int64_t e0 = (int64_t)t * GLT_TILE, e = e0 + row;
+            const bool valid = e < c;
+            const float *gc = G_col + (valid ? (int64_t)__ldg(&col[e]) : 0) * K;
+            const float *gr = G_row + (valid ? e / M : 0) * K;
+            float g[K];
+#pragma unroll
+            for (int j = 0; j < K / 4; ++j) {
+                const float4 x = glf_ldg4(gc + 4 * j), y = glf_ldg4(gr + 4 * j);
+                g[4 * j] = x.x + y.x; g[4 * j + 1] = x.y + y.y; g[4 * j + 2] = x.z + y.z; g[4 * j + 3] = x.w + y.w;
+            }
+            glt_mbar_wait(TFULL(a), aph);
+            glt_tc_fence_after();
+            const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * Cfg::ACC_COLS;
+#pragma unroll
+            for (int cb = 0; cb < K; cb += 16) {   // dH: 16 accumulator columns at a time
+                float v[16];
+                glt_tmem_ld16(tq + cb, v);
+                glt_tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int jj = cb + 4 * j;
+                    float4 o = make_float4(v[4 * j] + g[jj], v[4 * j + 1] + g[jj + 1], v[4 * j + 2] + g[jj + 2], v[4 * j + 3] + g[jj + 3]);
+                    if constexpr (MASK_IN) {   // ReLU backward of the producer of H: H (X3: its TF32 head, same sign) is still in the stage
+                        const float4 h = *reinterpret_cast<const float4 *>(st + Cfg::h_offset(row, jj));
+                        o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
+                    }
+                    *reinterpret_cast<float4 *>(Os + row * KS + jj) = o;
+                }
+            }
+            if (warp_has_dw) {
+#pragma unroll
+                for (int cb = 0; cb < Q; cb += 16) {   // dW1 tile partial: rows = input channels of diagonal block p2
+                    float w[16];
+                    glt_tmem_ld16(tq + K + p2 * Q + cb, w);
+                    glt_tc_wait_ld();
+                    if (has_dw) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dw[cb + j] += w[j];
+                    }
+                }
+            }
+            glt_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) glt_mbar_arrive(TEMPTY(a));
+            if (++a == 2) { a = 0; aph ^= 1; }
+            __syncwarp();
+            if constexpr (MASK_IN) {
+                if (lane == 0) glt_mbar_arrive(EMPTY(s));
+            }
+            if (++s == S) { s = 0; ph ^= 1; }
+            glf_store_warp_rows<K, KS>(Os + qd * 32 * KS, dH, e0 + qd * 32, c);
+            __syncwarp();
+        }
+        if (has_dw) {
+            float *dst = dW_partial + (((int64_t)blockIdx.x * P + p2) * K + krow) * Q;
+#pragma unroll
+            for (int j = 0; j < Q / 4; ++j)
+                *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(dw[4 * j], dw[4 * j + 1], dw[4 * j + 2], dw[4 * j + 3]);
+        }
+    }
+    glt_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        glt_tc_fence_after();
+        glt_tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// returns the number of per-block dW1 partials written (<= 0 on error)
+template <int K, int Q, bool MASK_IN, bool X3>
+static int glt_launch_edge_bwd_t(const float *dZ, const float *H, const int32_t *col, const float *W1, const float *Gc, const float *Gr,
+                                 int64_t c, int M, float *dH, float *partial, cudaStream_t stream) {
+    using Cfg = GltBwdCfg<K, Q>;
+    if constexpr (Cfg::stages(X3) < 2) return -1;
+    else {
+    if (c % Cfg::P) return -1;   // the packed view needs whole rows
+    CUtensorMap tmH, tmZ, tmZ2;
+    if (glt_make_tmap_packed(&tmH, H, c / Cfg::P, K * Cfg::P, Cfg::R) || glt_make_tmap<Q>(&tmZ, dZ, c) ||
+        glt_make_tmap_packed(&tmZ2, dZ, c / Cfg::P, Q * Cfg::P, Cfg::R))
+        return -1;
+    auto kern = glt_edge_bwd_kernel<K, Q, MASK_IN, X3>;
+    const size_t smem = Cfg::smem_bytes(X3);
+    static int grid_cache = 0;
+    if (!grid_cache) grid_cache = glt_grid(kern, smem, 1);
+    if (grid_cache < 0) return -1;
+    const int64_t ntiles = (c + GLT_TILE - 1) / GLT_TILE;
+    const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
+    NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_bwd_tf32x3" : "glt_edge_bwd_tf32", K, Q).c_str(), kern, grid, GLT_THREADS, smem, stream, tmH, tmZ, tmZ2,
+                  col, W1, Gc, Gr, c, M, dH, partial);
+    return grid * Cfg::P;
+    }
+}
+template <int K, int Q>
+static int glt_launch_edge_bwd(const float *dZ, const float *H, const int32_t *col, const float *W1, const float *Gc, const float *Gr,
+                               int64_t c, int M, int mask_in, int x3, float *dH, float *partial, cudaStream_t stream) {
+    int nb;
+    if (mask_in) nb = x3 ? glt_launch_edge_bwd_t<K, Q, true, true>(dZ, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
+                         : glt_launch_edge_bwd_t<K, Q, true, false>(dZ, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+    else nb = x3 ? glt_launch_edge_bwd_t<K, Q, false, true>(dZ, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
+                 : glt_launch_edge_bwd_t<K, Q, false, false>(dZ, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
+    return nb;
+}
+
+int glt_max_partial_blocks() { return 2 * gl_num_sms(); }
+
+// (k, q, mode) combinations whose stage ring fits shared memory at least twice; c must be a multiple of the packing
+bool glt_bwd_shape_ok(int k, int q, int x3, int64_t c) {
+#define X(K_, Q_) if (k == K_ && q == Q_) return GltBwdCfg<K_, Q_>::stages(x3 != 0) >= 2 && c % GltBwdCfg<K_, Q_>::P == 0;
+    GLT_FOR_KQ(X)
+#undef X
+    return false;
+}
+
+int glt_edge_bwd(int k, int q, const float *dZ, const float *H, const int32_t *col, const float *W1, const float *Gc, const float *Gr,
+                 int64_t c, int M, int mask_in, int x3, float *dH, float *partial, cudaStream_t stream) {
+#define X(K_, Q_) if (k == K_ && q == Q_) return glt_launch_edge_bwd<K_, Q_>(dZ, H, col, W1, Gc, Gr, c, M, mask_in, x3, dH, partial, stream);
+    GLT_FOR_KQ(X)
+#undef X
+    return -1;
+}
+#endif

@@ -1,0 +1,218 @@
+// graph_layer_tc_fwd.cu - tcgen05 forward edge kernel (see graph_layer_tc.cuh)
+#include "graph_layer_tc.cuh"
+#ifndef NBPC_HOST_EMU
+// ------------------------------------------------------------------ forward kernel
+template <int K, int Q>
+struct GltFwdCfg {
+    using TA = GltTile<K>;
+    static constexpr int A_STAGE = TA::NCH * TA::chunk_bytes(GLT_TILE);    // raw / hi tile
+    static constexpr int B_BYTES = TA::NCH * TA::chunk_bytes(Q);           // W1^T as (N = Q rows) x K, K-major
+    static constexpr int QS = glf_stride(Q);
+    static constexpr int OS_BYTES = GLT_TILE * QS * 4;
+    static constexpr int TMEM_COLS = (2 * Q <= 32) ? 32 : (2 * Q <= 64 ? 64 : (2 * Q <= 128 ? 128 : 256));
+    static constexpr int SMEM_MAX = 227 * 1024;
+    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 256; }
+    __host__ __device__ static constexpr int stages_in(bool x3, int budget) {
+        return (int)((budget - (int)fixed_bytes(x3)) / (A_STAGE * (x3 ? 2 : 1)));
+    }
+    // two CTAs per SM when a 3-deep ring fits half the shared memory, else one
+    __host__ __device__ static constexpr int ctas(bool x3) { return stages_in(x3, SMEM_MAX / 2) >= 3 ? 2 : 1; }
+    __host__ __device__ static constexpr int stages(bool x3) {
+        const int s = stages_in(x3, SMEM_MAX / ctas(x3));
+        return s > 4 ? 4 : s;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(bool x3) { return fixed_bytes(x3) + (size_t)stages(x3) * A_STAGE * (x3 ? 2 : 1); }
+};
+
+template <int K, int Q, bool RELU, bool X3>
+__global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_constant__ CUtensorMap tmH,
+                                                                    const int32_t *__restrict__ col,
+                                                                    const float *__restrict__ W1,
+                                                                    const float *__restrict__ Q_col,
+                                                                    const float *__restrict__ Q_row, int64_t c, int M,
+                                                                    float *__restrict__ out) {
+    using Cfg = GltFwdCfg<K, Q>;
+    using TA = typename Cfg::TA;
+    constexpr int S = Cfg::stages(X3), QS = Cfg::QS;
+    static_assert(S >= 2, "shape does not fit shared memory with two pipeline stages");
+    extern __shared__ __align__(16) unsigned char glt_smem_raw[];
+    unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
+    unsigned char *As = base;                                      // [S][A_STAGE]   raw -> hi
+    unsigned char *Al = As + S * Cfg::A_STAGE;                     // [S][A_STAGE]   lo (X3 only)
+    unsigned char *Bh = Al + (X3 ? S * Cfg::A_STAGE : 0);          // [B_BYTES]
+    unsigned char *Bl = Bh + Cfg::B_BYTES;                         // [B_BYTES]      (X3 only)
+    float *Os = reinterpret_cast<float *>(Bh + Cfg::B_BYTES * (X3 ? 2 : 1));   // [128][QS]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + Cfg::OS_BYTES);
+    // barriers: full[S] | empty[S] | conv[S] | tmem_full[2] | tmem_empty[2]
+    const uint32_t bar0 = glt_smem_u32(bars);
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto TFULL = [&](int a) { return bar0 + 8u * (3 * S + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * S + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE);
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
+        for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
+        glt_fence_barrier_init();
+        glt_prefetch_tmap(&tmH);
+    }
+    if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    // B operand: row n = output channel, column kk = input channel: W1[kk][n]
+    glt_fill_operand<K>(reinterpret_cast<char *>(Bh), X3 ? reinterpret_cast<char *>(Bl) : nullptr, Q,
+                        [&](int n, int kk) { return __ldg(&W1[kk * Q + n]); }, tid, GLT_THREADS);
+    glt_fence_proxy_async();
+    glt_tc_fence_before();
+    __syncthreads();
+    glt_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                glt_mbar_wait(EMPTY(s), ph ^ 1);
+                glt_mbar_expect_tx(FULL(s), Cfg::A_STAGE);
+#pragma unroll
+                for (int ch = 0; ch < TA::NCH; ++ch)
+                    glt_tma_load_2d(glt_smem_u32(As + s * Cfg::A_STAGE + ch * TA::chunk_bytes(GLT_TILE)), &tmH, FULL(s), ch * TA::CW, t * GLT_TILE);
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer
+            constexpr uint32_t idesc = glt_idesc_tf32(GLT_TILE, Q, 0, 0);
+            int s = 0, ph = 0, a = 0, aph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                glt_mbar_wait(TEMPTY(a), aph ^ 1);
+                glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
+                glt_tc_fence_after();
+                const uint32_t d = tmem_base + a * Q;
+                const uint32_t a_hi = glt_smem_u32(As + s * Cfg::A_STAGE), a_lo = glt_smem_u32(Al + s * Cfg::A_STAGE);
+                const uint32_t b_hi = glt_smem_u32(Bh), b_lo = glt_smem_u32(Bl);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {   // small terms first: lo*hi, hi*lo, hi*hi
+                    const uint32_t ab = (pass == 0) ? a_lo : a_hi, bb = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+                    for (int ch = 0; ch < TA::NCH; ++ch)
+#pragma unroll
+                        for (int k8 = 0; k8 < TA::CW / 8; ++k8) {
+                            const uint64_t da = glt_smem_desc(ab + ch * TA::chunk_bytes(GLT_TILE) + k8 * 32, 16, TA::ATOM, TA::SWZ);
+                            const uint64_t db = glt_smem_desc(bb + ch * TA::chunk_bytes(Q) + k8 * 32, 16, TA::ATOM, TA::SWZ);
+                            glt_mma_tf32(d, da, db, idesc, acc);
+                            acc = 1;
+                        }
+                }
+                glt_tc_commit(EMPTY(s));    // the stage may be refilled once these MMAs have read it
+                glt_tc_commit(TFULL(a));    // accumulator ready for the epilogue
+                if (++s == S) { s = 0; ph ^= 1; }
+                if (++a == 2) { a = 0; aph ^= 1; }
+            }
+        }
+    } else {
+        // ---------------- epilogue warps: quadrant = warp % 4 owns TMEM lanes / tile rows [32 qd, 32 qd + 32)
+        const int qd = warp & 3, row = qd * 32 + lane, wtid = tid - 64;
+        int s = 0, ph = 0, a = 0, aph = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            if constexpr (X3) {
+                glt_mbar_wait(FULL(s), ph);
+                glt_split_inplace(reinterpret_cast<float *>(As + s * Cfg::A_STAGE), reinterpret_cast<float *>(Al + s * Cfg::A_STAGE),
+                                  Cfg::A_STAGE / 4, wtid, 128);
+                glt_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(CONV(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+            const int64_t e0 = (int64_t)t * GLT_TILE, e = e0 + row;
+            const bool valid = e < c;
+            const float *qc = Q_col + (valid ? (int64_t)__ldg(&col[e]) : 0) * Q;
+            const float *qr = Q_row + (valid ? e / M : 0) * Q;
+            float acc[Q];
+#pragma unroll
+            for (int j = 0; j < Q / 4; ++j) {
+                const float4 x = glf_ldg4(qc + 4 * j), y = glf_ldg4(qr + 4 * j);
+                acc[4 * j] = x.x + y.x; acc[4 * j + 1] = x.y + y.y; acc[4 * j + 2] = x.z + y.z; acc[4 * j + 3] = x.w + y.w;
+            }
+            glt_mbar_wait(TFULL(a), aph);
+            glt_tc_fence_after();
+            const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * Q;
+#pragma unroll
+            for (int cb = 0; cb < Q; cb += 16) {   // 16 accumulator columns at a time
+                float z[16];
+                glt_tmem_ld16(tq + cb, z);
+                glt_tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 o = make_float4(z[4 * j] + acc[cb + 4 * j], z[4 * j + 1] + acc[cb + 4 * j + 1], z[4 * j + 2] + acc[cb + 4 * j + 2],
+                                           z[4 * j + 3] + acc[cb + 4 * j + 3]);
+                    if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4 *>(Os + row * QS + cb + 4 * j) = o;
+                }
+            }
+            glt_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) glt_mbar_arrive(TEMPTY(a));
+            if (++a == 2) { a = 0; aph ^= 1; }
+            __syncwarp();
+            glf_store_warp_rows<Q, QS>(Os + qd * 32 * QS, out, e0 + qd * 32, c);
+            __syncwarp();
+        }
+    }
+    glt_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        glt_tc_fence_after();
+        glt_tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int K, int Q, bool RELU, bool X3>
+static int glt_launch_edge_out_t(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c, int M,
+                                 float *out, cudaStream_t stream) {
+    using Cfg = GltFwdCfg<K, Q>;
+    if constexpr (Cfg::stages(X3) < 2) return 1;
+    else {
+    CUtensorMap tm;
+    if (glt_make_tmap<K>(&tm, H, c)) return 1;
+    auto kern = glt_edge_out_kernel<K, Q, RELU, X3>;
+    const size_t smem = Cfg::smem_bytes(X3);
+    static int grid_cache = 0;
+    if (!grid_cache) grid_cache = glt_grid(kern, smem, Cfg::ctas(X3));
+    if (grid_cache < 0) return 1;
+    const int64_t ntiles = (c + GLT_TILE - 1) / GLT_TILE;
+    const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
+    NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_out_tf32x3" : "glt_edge_out_tf32", K, Q).c_str(), kern, grid, GLT_THREADS, smem, stream, tm, col, W1, Qc,
+                  Qr, c, M, out);
+    return 0;
+    }
+}
+template <int K, int Q>
+static int glt_launch_edge_out(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c, int M,
+                               int relu, int x3, float *out, cudaStream_t stream) {
+    if (relu) return x3 ? glt_launch_edge_out_t<K, Q, true, true>(H, col, W1, Qc, Qr, c, M, out, stream)
+                        : glt_launch_edge_out_t<K, Q, true, false>(H, col, W1, Qc, Qr, c, M, out, stream);
+    return x3 ? glt_launch_edge_out_t<K, Q, false, true>(H, col, W1, Qc, Qr, c, M, out, stream)
+              : glt_launch_edge_out_t<K, Q, false, false>(H, col, W1, Qc, Qr, c, M, out, stream);
+}
+
+
+bool glt_fwd_shape_ok(int k, int q, int x3) {
+#define X(K_, Q_) if (k == K_ && q == Q_) return GltFwdCfg<K_, Q_>::stages(x3 != 0) >= 2;
+    GLT_FOR_KQ(X)
+#undef X
+    return false;
+}
+
+int glt_edge_out(int k, int q, const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c, int M,
+                 int relu, int x3, float *out, cudaStream_t stream) {
+#define X(K_, Q_) if (k == K_ && q == Q_) return glt_launch_edge_out<K_, Q_>(H, col, W1, Qc, Qr, c, M, relu, x3, out, stream);
+    GLT_FOR_KQ(X)
+#undef X
+    return 1;
+}
+#endif

@@ -103,6 +103,9 @@ struct NbpcKName {
     const char *c_str() const { return buf[0] ? buf : base; }
 };
 
+// arithmetic of the edge-level GEMMs (nbpc_set_math_mode / NBPC_MATH)
+extern int g_nbpc_math_mode;
+
 // ------------------------------------------------------------------ errors
 void nbpc_set_error(const std::string &msg);
 int nbpc_check_launch(const char *where);   // cudaGetLastError() -> NBPC_ELAUNCH (no sync)
