@@ -39,7 +39,7 @@ UNIT = "particles/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=32)
@@ -126,46 +126,67 @@ CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.ac
 
 
 class ClockSampler:
-    def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(prefix="nbpc_clocks_", suffix=".csv")
-        self.proc = None
-        try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={CLOCK_QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=self.fh, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+    """Samples SM clock, power and the throttle reasons of one GPU DURING the timed region, from a background thread
+    through NVML (the same counters `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.*` prints; an
+    nvidia-smi child process polling next to the benchmark stalled the launching thread by milliseconds per query)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def stop(self):
+    def __init__(self, gpu_index, period_s=0.05):
+        import threading
+        self.samples, self.period, self._stop, self.thread, self.h = [], period_s, threading.Event(), None, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].strip().isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.h = None
+
+    def _sample(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        try:
+            power = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            power = float("nan")
+        return time.time(), sm, mask, power
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self._sample())
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def wait_ready(self, timeout=5.0):
+        t0 = time.time()
+        while self.h is not None and not self.samples and time.time() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, since=0.0):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        if self.h is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.fh.close()
-        sm, mx, reasons, power = [], [], set(), []
-        try:
-            for line in open(self.path):
-                f = [c.strip() for c in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+        self._stop.set()
+        self.thread.join(timeout=2)
+        rows = [r for r in self.samples if r[0] >= since]
+        if rows:
+            reasons = sorted({name for _, _, mask, _ in rows for name, bit in self.REASONS if mask & bit})
+            out.update(sm_mhz=float(np.median([r[1] for r in rows])), sm_max_mhz=self.max_sm, reasons=reasons,
+                       samples=len(rows), power_w_max=float(np.nanmax([r[3] for r in rows])), source="NVML thread, 50 ms period")
         return out
 
 
@@ -305,13 +326,17 @@ def main():
         return float(train_step(*staging).item())                    # D2H read of the loss
 
     # ---- warm-up, then the timed region (device-resident inputs)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(max(a.warmup, 3)):
         step_resident(i)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    skip = 0
+    if sampler:
+        sampler.wait_ready()
+        skip = sampler.mark()
     l0 = lib.launch_count()
     ms = timed(step_resident, a.steps)
     launches = lib.launch_count() - l0
-    clocks = sampler.stop() if sampler else {}
+    clocks = sampler.stop(skip) if sampler else {}
     particles = world * b * N
     value = particles * a.steps / (ms * 1e-3)
 

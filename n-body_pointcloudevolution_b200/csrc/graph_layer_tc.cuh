@@ -23,12 +23,15 @@
 // work off the issue slots so that the kernel can run at memory speed, not for its flop rate.
 #pragma once
 #ifndef NBPC_HOST_EMU
+#include <stdio.h>
+#include <stdlib.h>
 #include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
 
 #include "nbpc_common.cuh"
 #include "graph_layer_tc.h"
 
-#define GLT_THREADS 192
+#define GLT_THREADS 192      // TMA warp, MMA warp, 4 epilogue warps
+#define GLT_THREADS_X3 320   // + 4 converter warps (TF32 hi / lo split)
 #define GLT_TILE 128
 #define GLT_SPIN_LIMIT (1u << 22)
 
@@ -261,18 +264,44 @@ static int glt_make_tmap_packed(CUtensorMap *tm, const float *ptr, int64_t rows,
                ? 0 : 1;
 }
 
+// tuning override "ctas,stages" from the environment (unset or malformed: keep the defaults)
+static void glt_env_cfg(const char *name, int *ctas, int *stages) {
+    const char *e = getenv(name);
+    int a = 0, b = 0;
+    if (e && sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1) { *ctas = a; *stages = b; }
+}
+
+// persistent grid = SMs x co-resident CTAs.  The co-residency is computed from the SM's budgets (shared memory with
+// the carve-out forced to its maximum, registers, threads) instead of cudaOccupancyMaxActiveBlocksPerMultiprocessor,
+// which answered 1 for these kernels (it evaluates the default carve-out).  NBPC_GLT_DEBUG=1 prints both.
 template <class F>
-static int glt_grid(F kern, size_t smem, int ctas_per_sm_cap) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+static int glt_grid(F kern, int threads, size_t smem, int ctas_per_sm_cap) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GLT_THREADS, smem) != cudaSuccess || occ < 1) {
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) {
         cudaGetLastError();
         return -1;
     }
+    int api = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&api, kern, threads, smem) != cudaSuccess) {
+        cudaGetLastError();
+        api = 0;
+    }
+    const int regs_per_thread = (fa.numRegs + 7) / 8 * 8;
+    const int by_regs = 65536 / (regs_per_thread * ((threads + 31) / 32 * 32));
+    const int by_smem = (int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024));
+    const int by_threads = 2048 / threads;
+    int occ = by_regs < by_smem ? by_regs : by_smem;
+    occ = occ < by_threads ? occ : by_threads;
     if (occ > ctas_per_sm_cap) occ = ctas_per_sm_cap;
+    if (getenv("NBPC_GLT_DEBUG"))
+        fprintf(stderr, "libnbpc: glt_grid threads=%d smem=%zu regs=%d: occupancy api=%d regs=%d smem=%d threads=%d cap=%d -> %d CTAs/SM\n",
+                threads, smem, fa.numRegs, api, by_regs, by_smem, by_threads, ctas_per_sm_cap, occ);
+    if (occ < 1) return -1;
     return gl_num_sms() * occ;
 }
 

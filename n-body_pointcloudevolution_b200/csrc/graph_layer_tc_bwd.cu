@@ -28,12 +28,13 @@ struct GltBwdCfg {
     static constexpr int ACC_COLS = K + N2;                              // D1 (dH tile) | D2 (dW1 tile partial blocks)
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
     static constexpr int SMEM_MAX = 227 * 1024;
-    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 256; }
-    __host__ __device__ static constexpr int stages(bool x3) {
-        const int s = (int)((SMEM_MAX - fixed_bytes(x3)) / ((size_t)STAGE * (x3 ? 2 : 1)));
-        return s > 6 ? 6 : s;
+    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 512; }
+    // deepest stage ring (<= 8) that fits when `ctas` CTAs share an SM
+    __host__ __device__ static constexpr int stages_for(bool x3, int ctas) {
+        const int s = (int)((SMEM_MAX / ctas - 1024 - (int)fixed_bytes(x3)) / (STAGE * (x3 ? 2 : 1)));
+        return s > 8 ? 8 : s;
     }
-    __host__ __device__ static constexpr size_t smem_bytes(bool x3) { return fixed_bytes(x3) + (size_t)stages(x3) * STAGE * (x3 ? 2 : 1); }
+    __host__ __device__ static constexpr size_t smem_bytes(bool x3, int S) { return fixed_bytes(x3) + (size_t)S * STAGE * (x3 ? 2 : 1); }
     // byte offset of channel j (multiple of 4) of tile edge `row` inside the packed H tile
     __device__ static __forceinline__ int h_offset(int row, int j) {
         const int pr = row / P, colp = (row % P) * K + j, jj = colp & 31;
@@ -42,18 +43,17 @@ struct GltBwdCfg {
 };
 
 template <int K, int Q, bool MASK_IN, bool X3>
-__global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_constant__ CUtensorMap tmH,
+__global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bwd_kernel(const __grid_constant__ CUtensorMap tmH,
                                                                     const __grid_constant__ CUtensorMap tmZ,
                                                                     const __grid_constant__ CUtensorMap tmZ2,
                                                                     const int32_t *__restrict__ col,
                                                                     const float *__restrict__ W1,
                                                                     const float *__restrict__ G_col,
                                                                     const float *__restrict__ G_row, int64_t c, int M,
-                                                                    float *__restrict__ dH, float *__restrict__ dW_partial) {
+                                                                    float *__restrict__ dH, float *__restrict__ dW_partial, const int S) {
     using Cfg = GltBwdCfg<K, Q>;
     using TZ = typename Cfg::TZ;
-    constexpr int S = Cfg::stages(X3), KS = Cfg::KS, P = Cfg::P;
-    static_assert(S >= 2, "shape does not fit shared memory with two pipeline stages");
+    constexpr int KS = Cfg::KS, P = Cfg::P;
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
     unsigned char *St = base;                                       // [S][H' | Z | Z']  raw -> hi
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE);
+    const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE), G = gridDim.x;
 
     if (tid == 0) {
         // a stage is free again when its MMAs have read it AND (MASK_IN) the epilogue warps have read their H rows
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
     if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), Cfg::TMEM_COLS);
     // B operand of dH = dZ W1^T: row n = input channel k, column = output channel q: W1[k][q] (as stored)
     glt_fill_operand<Q>(reinterpret_cast<char *>(Bh), X3 ? reinterpret_cast<char *>(Bl) : nullptr, K,
-                        [&](int n, int qq) { return __ldg(&W1[n * Q + qq]); }, tid, GLT_THREADS);
+                        [&](int n, int qq) { return __ldg(&W1[n * Q + qq]); }, tid, blockDim.x);
     glt_fence_proxy_async();
     glt_tc_fence_before();
     __syncthreads();
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
     if (warp == 0) {
         if (lane == 0) {   // ---------------- TMA producer
             int s = 0, ph = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(EMPTY(s), ph ^ 1);
                 glt_mbar_expect_tx(FULL(s), Cfg::STAGE);
                 unsigned char *st = St + s * Cfg::STAGE;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
             constexpr uint32_t idesc1 = glt_idesc_tf32(GLT_TILE, K, 0, 0);   // D1 (128 x K) = dZ (K-major) * W1^T
             constexpr uint32_t idesc2 = glt_idesc_tf32(Cfg::M2, Cfg::N2, 1, 1);  // D2 (P K x P Q) = H'^T (MN-major) * dZ' (MN-major)
             int s = 0, ph = 0, a = 0, aph = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(TEMPTY(a), aph ^ 1);
                 glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
                 glt_tc_fence_after();
@@ -158,38 +158,49 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
                 if (++a == 2) { a = 0; aph ^= 1; }
             }
         }
-    } else {
-        // ---------------- epilogue warps
-        const int qd = warp & 3, row = qd * 32 + lane, wtid = tid - 64;
+    } else if (warp < 6) {
+        // ---------------- epilogue warps (software pipelined like the forward kernel)
+        const int qd = warp & 3, row = qd * 32 + lane;
         // D2: M2 = 64 puts row r in lane (r % 16) + 32 (r / 16), M2 = 128 in lane r; row r = p K + k belongs to the
         // diagonal block p (warp-uniform) whose columns are [p Q, p Q + Q)
         constexpr int RPQ = (Cfg::M2 == 64) ? 16 : 32;
         const int r2 = qd * RPQ + lane, p2 = (qd * RPQ) / K, krow = r2 - p2 * K;
         const bool warp_has_dw = qd * RPQ < K * P;
         const bool has_dw = warp_has_dw && lane < RPQ;
+        const bool small = c < ((int64_t)1 << 31);
+        auto edge_row = [&](int64_t e) -> int64_t { return small ? (int64_t)((uint32_t)e / (uint32_t)M) : e / M; };
+        auto load_col = [&](int t) -> int {
+            const int64_t e = (int64_t)t * GLT_TILE + row;
+            return (t < ntiles && e < c) ? __ldg(&col[e]) : -1;
+        };
+        auto gather = [&](int t, int cidx, float *dst) {
+            if (cidx >= 0) {
+                const int64_t e = (int64_t)t * GLT_TILE + row;
+                const float *gc = G_col + (int64_t)cidx * K, *gr = G_row + edge_row(e) * K;
+#pragma unroll
+                for (int j = 0; j < K / 4; ++j) {
+                    const float4 x = glf_ldg4(gc + 4 * j), y = glf_ldg4(gr + 4 * j);
+                    dst[4 * j] = x.x + y.x; dst[4 * j + 1] = x.y + y.y; dst[4 * j + 2] = x.z + y.z; dst[4 * j + 3] = x.w + y.w;
+                }
+            }
+        };
         float dw[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) dw[j] = 0.f;
-        int s = 0, ph = 0, a = 0, aph = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            unsigned char *st = St + s * Cfg::STAGE;
-            if constexpr (X3 || MASK_IN) glt_mbar_wait(FULL(s), ph);   // the epilogue warps touch the landed tile themselves
-            if constexpr (X3) {
-                glt_split_inplace(reinterpret_cast<float *>(st), reinterpret_cast<float *>(Sl + s * Cfg::STAGE), Cfg::STAGE / 4, wtid, 128);
-                glt_fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) glt_mbar_arrive(CONV(s));
-            }
-            const int64_t e0 = (int64_t)t * GLT_TILE, e = e0 + row;
-            const bool valid = e < c;
-            const float *gc = G_col + (valid ? (int64_t)__ldg(&col[e]) : 0) * K;
-            const float *gr = G_row + (valid ? e / M : 0) * K;
-            float g[K];
+        float g[K], gn[K];
 #pragma unroll
-            for (int j = 0; j < K / 4; ++j) {
-                const float4 x = glf_ldg4(gc + 4 * j), y = glf_ldg4(gr + 4 * j);
-                g[4 * j] = x.x + y.x; g[4 * j + 1] = x.y + y.y; g[4 * j + 2] = x.z + y.z; g[4 * j + 3] = x.w + y.w;
-            }
+        for (int j = 0; j < K; ++j) g[j] = gn[j] = 0.f;
+        int s = 0, ph = 0, a = 0, aph = 0;
+        int t = blockIdx.x;
+        gather(t, load_col(t), g);
+        int c_next = load_col(t + G);
+        for (; t < ntiles; t += G) {
+            gather(t + G, c_next, gn);
+            c_next = load_col(t + 2 * G);
+            unsigned char *st = St + s * Cfg::STAGE;
+            const int64_t e0 = (int64_t)t * GLT_TILE;
+            // the epilogue reads H (X3: its TF32 head, same sign) from the stage for the ReLU mask
+            if constexpr (MASK_IN) glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
             glt_mbar_wait(TFULL(a), aph);
             glt_tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * Cfg::ACC_COLS;
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
                 for (int j = 0; j < 4; ++j) {
                     const int jj = cb + 4 * j;
                     float4 o = make_float4(v[4 * j] + g[jj], v[4 * j + 1] + g[jj + 1], v[4 * j + 2] + g[jj + 2], v[4 * j + 3] + g[jj + 3]);
-                    if constexpr (MASK_IN) {   // ReLU backward of the producer of H: H (X3: its TF32 head, same sign) is still in the stage
+                    if constexpr (MASK_IN) {   // ReLU backward of the producer of H
                         const float4 h = *reinterpret_cast<const float4 *>(st + Cfg::h_offset(row, jj));
                         o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
                     }
@@ -223,21 +234,37 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_bwd_kernel(const __grid_
             }
             glt_tc_fence_before();
             __syncwarp();
-            if (lane == 0) glt_mbar_arrive(TEMPTY(a));
-            if (++a == 2) { a = 0; aph ^= 1; }
-            __syncwarp();
-            if constexpr (MASK_IN) {
-                if (lane == 0) glt_mbar_arrive(EMPTY(s));
+            if (lane == 0) {
+                glt_mbar_arrive(TEMPTY(a));
+                if constexpr (MASK_IN) glt_mbar_arrive(EMPTY(s));
             }
+            if (++a == 2) { a = 0; aph ^= 1; }
             if (++s == S) { s = 0; ph ^= 1; }
             glf_store_warp_rows<K, KS>(Os + qd * 32 * KS, dH, e0 + qd * 32, c);
             __syncwarp();
+#pragma unroll
+            for (int j = 0; j < K; ++j) g[j] = gn[j];
         }
         if (has_dw) {
             float *dst = dW_partial + (((int64_t)blockIdx.x * P + p2) * K + krow) * Q;
 #pragma unroll
             for (int j = 0; j < Q / 4; ++j)
                 *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(dw[4 * j], dw[4 * j + 1], dw[4 * j + 2], dw[4 * j + 3]);
+        }
+    } else {
+        // ---------------- converter warps (X3 only): split the landed tiles into TF32 hi / lo in place
+        if constexpr (X3) {
+            const int wtid = tid - 192;
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += G) {
+                glt_mbar_wait(FULL(s), ph);
+                glt_split_inplace(reinterpret_cast<float *>(St + s * Cfg::STAGE), reinterpret_cast<float *>(Sl + s * Cfg::STAGE),
+                                  Cfg::STAGE / 4, wtid, 128);
+                glt_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(CONV(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
         }
     }
     glt_tc_fence_before();
@@ -253,7 +280,7 @@ template <int K, int Q, bool MASK_IN, bool X3>
 static int glt_launch_edge_bwd_t(const float *dZ, const float *H, const int32_t *col, const float *W1, const float *Gc, const float *Gr,
                                  int64_t c, int M, float *dH, float *partial, cudaStream_t stream) {
     using Cfg = GltBwdCfg<K, Q>;
-    if constexpr (Cfg::stages(X3) < 2) return -1;
+    if constexpr (Cfg::stages_for(X3, 1) < 2) return -1;
     else {
     if (c % Cfg::P) return -1;   // the packed view needs whole rows
     CUtensorMap tmH, tmZ, tmZ2;
@@ -261,14 +288,24 @@ static int glt_launch_edge_bwd_t(const float *dZ, const float *H, const int32_t 
         glt_make_tmap_packed(&tmZ2, dZ, c / Cfg::P, Q * Cfg::P, Cfg::R))
         return -1;
     auto kern = glt_edge_bwd_kernel<K, Q, MASK_IN, X3>;
-    const size_t smem = Cfg::smem_bytes(X3);
-    static int grid_cache = 0;
-    if (!grid_cache) grid_cache = glt_grid(kern, smem, 1);
+    constexpr int threads = X3 ? GLT_THREADS_X3 : GLT_THREADS;
+    static int grid_cache = 0, S = 0;
+    if (!grid_cache) {
+        int ctas = 1;
+        for (int t = 2; t >= 1; --t)
+            if (Cfg::stages_for(X3, t) >= 2 && t * Cfg::TMEM_COLS <= 512) { ctas = t; break; }
+        S = Cfg::stages_for(X3, ctas);
+        S = S > 6 ? 6 : S;
+        glt_env_cfg("NBPC_GLT_BWD", &ctas, &S);
+        if (S < 1 || S > Cfg::stages_for(X3, 1) || ctas * Cfg::TMEM_COLS > 512) return -1;
+        grid_cache = glt_grid(kern, threads, Cfg::smem_bytes(X3, S), ctas);
+    }
+    const size_t smem = Cfg::smem_bytes(X3, S);
     if (grid_cache < 0) return -1;
     const int64_t ntiles = (c + GLT_TILE - 1) / GLT_TILE;
     const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
-    NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_bwd_tf32x3" : "glt_edge_bwd_tf32", K, Q).c_str(), kern, grid, GLT_THREADS, smem, stream, tmH, tmZ, tmZ2,
-                  col, W1, Gc, Gr, c, M, dH, partial);
+    NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_bwd_tf32x3" : "glt_edge_bwd_tf32", K, Q).c_str(), kern, grid, threads, smem, stream, tmH, tmZ, tmZ2,
+                  col, W1, Gc, Gr, c, M, dH, partial, S);
     return grid * Cfg::P;
     }
 }
@@ -283,11 +320,11 @@ static int glt_launch_edge_bwd(const float *dZ, const float *H, const int32_t *c
     return nb;
 }
 
-int glt_max_partial_blocks() { return 2 * gl_num_sms(); }
+int glt_max_partial_blocks() { return 2 * 2 * gl_num_sms(); }
 
 // (k, q, mode) combinations whose stage ring fits shared memory at least twice; c must be a multiple of the packing
 bool glt_bwd_shape_ok(int k, int q, int x3, int64_t c) {
-#define X(K_, Q_) if (k == K_ && q == Q_) return GltBwdCfg<K_, Q_>::stages(x3 != 0) >= 2 && c % GltBwdCfg<K_, Q_>::P == 0;
+#define X(K_, Q_) if (k == K_ && q == Q_) return GltBwdCfg<K_, Q_>::stages_for(x3 != 0, 1) >= 2 && c % GltBwdCfg<K_, Q_>::P == 0;
     GLT_FOR_KQ(X)
 #undef X
     return false;

@@ -11,30 +11,25 @@ struct GltFwdCfg {
     static constexpr int OS_BYTES = GLT_TILE * QS * 4;
     static constexpr int TMEM_COLS = (2 * Q <= 32) ? 32 : (2 * Q <= 64 ? 64 : (2 * Q <= 128 ? 128 : 256));
     static constexpr int SMEM_MAX = 227 * 1024;
-    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 256; }
-    __host__ __device__ static constexpr int stages_in(bool x3, int budget) {
-        return (int)((budget - (int)fixed_bytes(x3)) / (A_STAGE * (x3 ? 2 : 1)));
+    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 512; }
+    // deepest stage ring (<= 8) that fits when `ctas` CTAs share an SM (each CTA also pays 1 KB of system shared memory)
+    __host__ __device__ static constexpr int stages_for(bool x3, int ctas) {
+        const int s = (int)((SMEM_MAX / ctas - 1024 - (int)fixed_bytes(x3)) / (A_STAGE * (x3 ? 2 : 1)));
+        return s > 8 ? 8 : s;
     }
-    // two CTAs per SM when a 3-deep ring fits half the shared memory, else one
-    __host__ __device__ static constexpr int ctas(bool x3) { return stages_in(x3, SMEM_MAX / 2) >= 3 ? 2 : 1; }
-    __host__ __device__ static constexpr int stages(bool x3) {
-        const int s = stages_in(x3, SMEM_MAX / ctas(x3));
-        return s > 4 ? 4 : s;
-    }
-    __host__ __device__ static constexpr size_t smem_bytes(bool x3) { return fixed_bytes(x3) + (size_t)stages(x3) * A_STAGE * (x3 ? 2 : 1); }
+    __host__ __device__ static constexpr size_t smem_bytes(bool x3, int S) { return fixed_bytes(x3) + (size_t)S * A_STAGE * (x3 ? 2 : 1); }
 };
 
 template <int K, int Q, bool RELU, bool X3>
-__global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_constant__ CUtensorMap tmH,
-                                                                    const int32_t *__restrict__ col,
-                                                                    const float *__restrict__ W1,
-                                                                    const float *__restrict__ Q_col,
-                                                                    const float *__restrict__ Q_row, int64_t c, int M,
-                                                                    float *__restrict__ out) {
+__global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_out_kernel(const __grid_constant__ CUtensorMap tmH,
+                                                                                         const int32_t *__restrict__ col,
+                                                                                         const float *__restrict__ W1,
+                                                                                         const float *__restrict__ Q_col,
+                                                                                         const float *__restrict__ Q_row, int64_t c, int M,
+                                                                                         float *__restrict__ out, const int S) {
     using Cfg = GltFwdCfg<K, Q>;
     using TA = typename Cfg::TA;
-    constexpr int S = Cfg::stages(X3), QS = Cfg::QS;
-    static_assert(S >= 2, "shape does not fit shared memory with two pipeline stages");
+    constexpr int QS = Cfg::QS;
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
     unsigned char *As = base;                                      // [S][A_STAGE]   raw -> hi
@@ -53,7 +48,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE);
+    const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE), G = gridDim.x;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
@@ -64,7 +59,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
     if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), Cfg::TMEM_COLS);
     // B operand: row n = output channel, column kk = input channel: W1[kk][n]
     glt_fill_operand<K>(reinterpret_cast<char *>(Bh), X3 ? reinterpret_cast<char *>(Bl) : nullptr, Q,
-                        [&](int n, int kk) { return __ldg(&W1[kk * Q + n]); }, tid, GLT_THREADS);
+                        [&](int n, int kk) { return __ldg(&W1[kk * Q + n]); }, tid, blockDim.x);
     glt_fence_proxy_async();
     glt_tc_fence_before();
     __syncthreads();
@@ -74,7 +69,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
     if (warp == 0) {
         if (lane == 0) {   // ---------------- TMA producer
             int s = 0, ph = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(EMPTY(s), ph ^ 1);
                 glt_mbar_expect_tx(FULL(s), Cfg::A_STAGE);
 #pragma unroll
@@ -87,7 +82,7 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
         if (lane == 0) {   // ---------------- MMA issuer
             constexpr uint32_t idesc = glt_idesc_tf32(GLT_TILE, Q, 0, 0);
             int s = 0, ph = 0, a = 0, aph = 0;
-            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(TEMPTY(a), aph ^ 1);
                 glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
                 glt_tc_fence_after();
@@ -114,30 +109,39 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
                 if (++a == 2) { a = 0; aph ^= 1; }
             }
         }
-    } else {
-        // ---------------- epilogue warps: quadrant = warp % 4 owns TMEM lanes / tile rows [32 qd, 32 qd + 32)
-        const int qd = warp & 3, row = qd * 32 + lane, wtid = tid - 64;
-        int s = 0, ph = 0, a = 0, aph = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            if constexpr (X3) {
-                glt_mbar_wait(FULL(s), ph);
-                glt_split_inplace(reinterpret_cast<float *>(As + s * Cfg::A_STAGE), reinterpret_cast<float *>(Al + s * Cfg::A_STAGE),
-                                  Cfg::A_STAGE / 4, wtid, 128);
-                glt_fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) glt_mbar_arrive(CONV(s));
-                if (++s == S) { s = 0; ph ^= 1; }
-            }
-            const int64_t e0 = (int64_t)t * GLT_TILE, e = e0 + row;
-            const bool valid = e < c;
-            const float *qc = Q_col + (valid ? (int64_t)__ldg(&col[e]) : 0) * Q;
-            const float *qr = Q_row + (valid ? e / M : 0) * Q;
-            float acc[Q];
+    } else if (warp < 6) {
+        // ---------------- epilogue warps: quadrant = warp % 4 owns TMEM lanes / tile rows [32 qd, 32 qd + 32).
+        // Software pipelined: the node-level terms of tile i+1 are gathered (and the column index of tile i+2 is loaded)
+        // before the accumulator of tile i is awaited, so the dependent-load chain is off the critical path.
+        const int qd = warp & 3, row = qd * 32 + lane;
+        const bool small = c < ((int64_t)1 << 31);
+        auto edge_row = [&](int64_t e) -> int64_t { return small ? (int64_t)((uint32_t)e / (uint32_t)M) : e / M; };
+        auto load_col = [&](int t) -> int {
+            const int64_t e = (int64_t)t * GLT_TILE + row;
+            return (t < ntiles && e < c) ? __ldg(&col[e]) : -1;
+        };
+        auto gather = [&](int t, int cidx, float *dst) {
+            if (cidx >= 0) {
+                const int64_t e = (int64_t)t * GLT_TILE + row;
+                const float *qc = Q_col + (int64_t)cidx * Q, *qr = Q_row + edge_row(e) * Q;
 #pragma unroll
-            for (int j = 0; j < Q / 4; ++j) {
-                const float4 x = glf_ldg4(qc + 4 * j), y = glf_ldg4(qr + 4 * j);
-                acc[4 * j] = x.x + y.x; acc[4 * j + 1] = x.y + y.y; acc[4 * j + 2] = x.z + y.z; acc[4 * j + 3] = x.w + y.w;
+                for (int j = 0; j < Q / 4; ++j) {
+                    const float4 x = glf_ldg4(qc + 4 * j), y = glf_ldg4(qr + 4 * j);
+                    dst[4 * j] = x.x + y.x; dst[4 * j + 1] = x.y + y.y; dst[4 * j + 2] = x.z + y.z; dst[4 * j + 3] = x.w + y.w;
+                }
             }
+        };
+        int a = 0, aph = 0;
+        int t = blockIdx.x;
+        float cur[Q], nxt[Q];
+#pragma unroll
+        for (int j = 0; j < Q; ++j) cur[j] = nxt[j] = 0.f;
+        gather(t, load_col(t), cur);
+        int c_next = load_col(t + G);
+        for (; t < ntiles; t += G) {
+            gather(t + G, c_next, nxt);
+            c_next = load_col(t + 2 * G);
+            const int64_t e0 = (int64_t)t * GLT_TILE;
             glt_mbar_wait(TFULL(a), aph);
             glt_tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * Q;
@@ -148,8 +152,8 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
                 glt_tc_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float4 o = make_float4(z[4 * j] + acc[cb + 4 * j], z[4 * j + 1] + acc[cb + 4 * j + 1], z[4 * j + 2] + acc[cb + 4 * j + 2],
-                                           z[4 * j + 3] + acc[cb + 4 * j + 3]);
+                    float4 o = make_float4(z[4 * j] + cur[cb + 4 * j], z[4 * j + 1] + cur[cb + 4 * j + 1], z[4 * j + 2] + cur[cb + 4 * j + 2],
+                                           z[4 * j + 3] + cur[cb + 4 * j + 3]);
                     if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     *reinterpret_cast<float4 *>(Os + row * QS + cb + 4 * j) = o;
                 }
@@ -158,9 +162,25 @@ __global__ void __launch_bounds__(GLT_THREADS) glt_edge_out_kernel(const __grid_
             __syncwarp();
             if (lane == 0) glt_mbar_arrive(TEMPTY(a));
             if (++a == 2) { a = 0; aph ^= 1; }
-            __syncwarp();
             glf_store_warp_rows<Q, QS>(Os + qd * 32 * QS, out, e0 + qd * 32, c);
             __syncwarp();
+#pragma unroll
+            for (int j = 0; j < Q; ++j) cur[j] = nxt[j];
+        }
+    } else {
+        // ---------------- converter warps (X3 only): split the landed tile into TF32 hi / lo in place
+        if constexpr (X3) {
+            const int wtid = tid - 192;
+            int s = 0, ph = 0;
+            for (int t = blockIdx.x; t < ntiles; t += G) {
+                glt_mbar_wait(FULL(s), ph);
+                glt_split_inplace(reinterpret_cast<float *>(As + s * Cfg::A_STAGE), reinterpret_cast<float *>(Al + s * Cfg::A_STAGE),
+                                  Cfg::A_STAGE / 4, wtid, 128);
+                glt_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(CONV(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
         }
     }
     glt_tc_fence_before();
@@ -175,19 +195,32 @@ template <int K, int Q, bool RELU, bool X3>
 static int glt_launch_edge_out_t(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c, int M,
                                  float *out, cudaStream_t stream) {
     using Cfg = GltFwdCfg<K, Q>;
-    if constexpr (Cfg::stages(X3) < 2) return 1;
+    if constexpr (Cfg::stages_for(X3, 1) < 2) return 1;
     else {
     CUtensorMap tm;
     if (glt_make_tmap<K>(&tm, H, c)) return 1;
     auto kern = glt_edge_out_kernel<K, Q, RELU, X3>;
-    const size_t smem = Cfg::smem_bytes(X3);
-    static int grid_cache = 0;
-    if (!grid_cache) grid_cache = glt_grid(kern, smem, Cfg::ctas(X3));
+    constexpr int threads = X3 ? GLT_THREADS_X3 : GLT_THREADS;
+    // CTAs per SM / ring depth: as many CTAs (<= 4) as keep a 2-deep ring: each CTA is an independent
+    // load -> MMA -> epilogue pipeline, so co-resident CTAs hide each other's latencies (measured on B200, k=32 q=16, 3.67 M
+    // edges: 1 CTA x 4 stages 272 us, 2 x 4 170 us, 3 x 3 150 us, 4 x 2 148 us).  NBPC_GLT_FWD="ctas,stages" overrides.
+    static int grid_cache = 0, S = 0;
+    if (!grid_cache) {
+        int ctas = 1;
+        for (int t = 4; t >= 1; --t)
+            if (Cfg::stages_for(X3, t) >= 2 && t * Cfg::TMEM_COLS <= 512) { ctas = t; break; }
+        S = Cfg::stages_for(X3, ctas);
+        S = S > 4 ? 4 : S;
+        glt_env_cfg("NBPC_GLT_FWD", &ctas, &S);
+        if (S < 1 || S > Cfg::stages_for(X3, 1)) return 1;
+        grid_cache = glt_grid(kern, threads, Cfg::smem_bytes(X3, S), ctas);
+    }
+    const size_t smem = Cfg::smem_bytes(X3, S);
     if (grid_cache < 0) return 1;
     const int64_t ntiles = (c + GLT_TILE - 1) / GLT_TILE;
     const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
-    NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_out_tf32x3" : "glt_edge_out_tf32", K, Q).c_str(), kern, grid, GLT_THREADS, smem, stream, tm, col, W1, Qc,
-                  Qr, c, M, out);
+    NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_out_tf32x3" : "glt_edge_out_tf32", K, Q).c_str(), kern, grid, threads, smem, stream, tm, col, W1, Qc,
+                  Qr, c, M, out, S);
     return 0;
     }
 }
@@ -202,7 +235,7 @@ static int glt_launch_edge_out(const float *H, const int32_t *col, const float *
 
 
 bool glt_fwd_shape_ok(int k, int q, int x3) {
-#define X(K_, Q_) if (k == K_ && q == Q_) return GltFwdCfg<K_, Q_>::stages(x3 != 0) >= 2;
+#define X(K_, Q_) if (k == K_ && q == Q_) return GltFwdCfg<K_, Q_>::stages_for(x3 != 0, 1) >= 2;
     GLT_FOR_KQ(X)
 #undef X
     return false;

@@ -465,3 +465,123 @@ np.savez(sys.argv[1], pred=pred.detach().cpu().numpy(), grad=store.flat_grad.cpu
         outs.append(np.load(path))
     np.testing.assert_allclose(outs[0]["pred"], outs[1]["pred"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(outs[0]["grad"], outs[1]["grad"], rtol=1e-4, atol=1e-7)
+
+
+# =============================================================================== tensor-core (tcgen05) math modes
+@pytest.fixture
+def math_mode(nb):
+    """Sets the arithmetic of the edge-level projections for one test and restores the process default."""
+    before = nb._lib.get_math_mode()
+
+    def setter(mode):
+        nb._lib.set_math_mode(mode)
+    yield setter
+    nb._lib.set_math_mode(before)
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("k,q", [(16, 16), (16, 32), (16, 64), (32, 16), (32, 32), (32, 64), (64, 16), (64, 32), (64, 64)])
+@pytest.mark.parametrize("chain", [False, True])
+def test_tensor_core_layer_vs_oracle(nb, math_mode, mode, k, q, chain):
+    """tcgen05 edge kernels (forward, dH, dW1) against the float64 oracle.  tf32x3 (error-compensated) must meet the
+    FP32 tolerances of the CUDA-core path; tf32 (one pass, 10-bit mantissa operands) is held to 4e-3 of the tensor scale.
+    chain=True exercises the fused ReLU-backward mask of the input (the path the network functions take)."""
+    math_mode(mode)
+    assert nb._lib.get_math_mode() == mode
+    b, N, M = 2, 601, 10           # 12020 edges: not a multiple of the 128-edge tile
+    rng = np.random.default_rng(k * 17 + q)
+    x = rng.random((b, N, 3)).astype(np.float32)
+    coo, _ = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, M))
+    coo_np = coo.cpu().numpy()
+    c = b * N * M
+    H0 = rng.standard_normal((c, k)).astype(np.float32)
+    Ws = [(rng.standard_normal((k, q)) / np.sqrt(k)).astype(np.float32) for _ in range(4)]
+    Bv = (0.1 * rng.standard_normal(q)).astype(np.float32)
+    gout = rng.standard_normal((c, q)).astype(np.float32)
+
+    H0t = torch.tensor(H0, device=DEV, requires_grad=True)
+    Wt = [torch.tensor(w, device=DEV, requires_grad=True) for w in Ws]
+    Bt = torch.tensor(Bv, device=DEV, requires_grad=True)
+    if chain:    # H = relu(H0) with the mask applied by this layer's backward kernel (input_relu)
+        Ht = torch.relu(H0t.detach()).requires_grad_(True)
+        o = nb.graph._layer(Ht, coo, (b, N), (Wt, Bt), False, False, input_relu=True)
+    else:
+        Ht = H0t
+        o = nb.graph.shift_inv_layer(Ht, coo, (b, N), (Wt, Bt))
+    (o * torch.tensor(gout, device=DEV)).sum().backward()
+
+    Hc0 = torch.tensor(H0, dtype=torch.float64, requires_grad=True)
+    Hc = torch.relu(Hc0) if chain else Hc0
+    Wc = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in Ws]
+    Bc = torch.tensor(Bv, dtype=torch.float64, requires_grad=True)
+    oc = ref_layers.shift_inv_layer(Hc, coo_np, (b, N), (Wc, Bc), is_last=False)
+    (oc * torch.tensor(gout, dtype=torch.float64)).sum().backward()
+
+    got = [o.detach().cpu().numpy(), Ht.grad.cpu().numpy()] + [w.grad.cpu().numpy() for w in Wt] + [Bt.grad.cpu().numpy()]
+    ref = [oc.detach().numpy(), Hc0.grad.numpy()] + [w.grad.numpy() for w in Wc] + [Bc.grad.numpy()]
+    if mode == "tf32x3":
+        np.testing.assert_allclose(got[0], ref[0], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(got[1], ref[1], rtol=2e-4, atol=2e-5)
+        scale = max(float(np.abs(ref[2]).max()), 1.0)
+        for i in range(2, 6):
+            np.testing.assert_allclose(got[i], ref[i], rtol=2e-4, atol=2e-5 * scale)
+        np.testing.assert_allclose(got[6], ref[6], rtol=2e-4, atol=2e-4)
+    else:
+        for g_, r_ in zip(got, ref):
+            assert np.abs(g_ - r_).max() <= 4e-3 * max(float(np.abs(r_).max()), 1e-6)
+
+
+def test_tensor_core_odd_edge_count_falls_back(nb, math_mode):
+    """An odd number of edges cannot be viewed as packed 128-byte rows: the backward must take the CUDA-core kernel
+    (still on the GPU) and stay within the FP32 tolerance."""
+    math_mode("tf32x3")
+    b, N, M, k, q = 1, 601, 9, 32, 16
+    rng = np.random.default_rng(5)
+    x = rng.random((b, N, 3)).astype(np.float32)
+    coo, _ = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, M))
+    c = b * N * M
+    assert c % 2 == 1
+    H = rng.standard_normal((c, k)).astype(np.float32)
+    Ws = [(rng.standard_normal((k, q)) / np.sqrt(k)).astype(np.float32) for _ in range(4)]
+    Bv = np.zeros(q, np.float32)
+    Ht = torch.tensor(H, device=DEV, requires_grad=True)
+    Wt = [torch.tensor(w, device=DEV, requires_grad=True) for w in Ws]
+    o = nb.graph.shift_inv_layer(Ht, coo, (b, N), (Wt, torch.tensor(Bv, device=DEV, requires_grad=True)))
+    o.sum().backward()
+    Hc = torch.tensor(H, dtype=torch.float64, requires_grad=True)
+    Wc = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in Ws]
+    oc = ref_layers.shift_inv_layer(Hc, coo.cpu().numpy(), (b, N), (Wc, torch.tensor(Bv, dtype=torch.float64)), is_last=False)
+    oc.sum().backward()
+    np.testing.assert_allclose(o.detach().cpu().numpy(), oc.detach().numpy(), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(Ht.grad.cpu().numpy(), Hc.grad.numpy(), rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(Wt[0].grad.cpu().numpy(), Wc[0].grad.numpy(), rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+def test_tensor_core_model_c1_golden(nb, syn, math_mode, mode):
+    """BASELINE config 1 in the tensor-core modes against the reference's own outputs (model_16 golden)."""
+    math_mode(mode)
+    kind = "uniform"
+    g = load_golden("model_16.npz")
+    ch = list(g["channels"]); k = int(g["k"]); b, N = 2, 4096
+    x = syn.make_box(kind, b, N, 0)
+    za, tgt = syn.za_features(b, N, 0)
+    store = nb.train_utils.ParamStore(ch, device=DEV)
+    store.load_numpy(syn.glorot_params(ch))
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+    xt = torch.tensor(x, device=DEV)
+    coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(xt, k))
+    pred = nb.graph.model_func_shift_inv_za(xt, coo, torch.tensor(za, device=DEV), diag, mv, (b, N, k))
+    loss = nb.nn.loss_ZA(pred, torch.tensor(tgt, device=DEV))
+    loss.backward()
+    x3 = mode == "tf32x3"
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), g[f"{kind}_f32_pred"], rtol=2e-5 if x3 else 5e-3, atol=2e-6 if x3 else 2e-4)
+    np.testing.assert_allclose(loss.item(), g[f"{kind}_f64_loss"], rtol=1e-5 if x3 else 2e-3)
+    for li in range(len(ch) - 1):
+        W, B = store.get_layer_vars(li)
+        for wi in range(4):
+            ref = g[f"{kind}_f64_gW{li}_{wi}"]
+            if x3:
+                np.testing.assert_allclose(W.grad[wi].cpu().numpy(), ref, rtol=2e-4, atol=1e-7)
+            else:
+                assert np.abs(W.grad[wi].cpu().numpy() - ref).max() <= 5e-3 * float(np.abs(ref).max()) + 1e-9, (li, wi)
