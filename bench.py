@@ -303,15 +303,25 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_stats = {}
+
+    def timed(fn, steps, tag):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        host = []
+        ev[0].record()
+        t0 = time.perf_counter()
         for i in range(steps):
             fn(i)
-        e1.record()
+            ev[i + 1].record()
+            host.append(time.perf_counter() - t0)
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+        hd = np.diff(np.array([0.0] + host)) * 1e3
+        step_stats[tag] = {"device_ms_median": float(np.median(per)), "device_ms_max": float(per.max()),
+                           "device_ms_min": float(per.min()), "host_enqueue_ms_median": float(np.median(hd)),
+                           "host_enqueue_ms_max": float(hd.max()), "argmax": int(per.argmax())}
+        ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
         if world > 1:
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return float(ms.item())
@@ -334,7 +344,7 @@ def main():
         sampler.wait_ready()
         skip = sampler.mark()
     l0 = lib.launch_count()
-    ms = timed(step_resident, a.steps)
+    ms = timed(step_resident, a.steps, "resident")
     launches = lib.launch_count() - l0
     clocks = sampler.stop(skip) if sampler else {}
     particles = world * b * N
@@ -343,7 +353,7 @@ def main():
     # ---- end to end through the public API with host buffers
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, a.steps)
+    ms_e2e = timed(step_e2e, a.steps, "e2e")
     e2e_value = particles * a.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
 
@@ -428,14 +438,17 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "particles_per_step": particles, "edges_per_step": particles * k,
+        "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 TF32x3 error-compensated, FP32-class accuracy)",
+                  "tf32": "tf32 (tcgen05 single pass, FP32 accumulate)"}[lib.get_math_mode()],
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "math_mode": lib.get_math_mode(), "particles_per_step": particles, "edges_per_step": particles * k,
                    "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)",
                    "l2": "step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
+        "step_stats": step_stats,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "extras": extras,

@@ -58,7 +58,7 @@ int nbpc_device_check(void);
 #define NBPC_MATH_FP32 0
 #define NBPC_MATH_TF32X3 1
 #define NBPC_MATH_TF32 2
-#define NBPC_MATH_DEFAULT NBPC_MATH_FP32
+#define NBPC_MATH_DEFAULT NBPC_MATH_TF32X3
 int nbpc_set_math_mode(int mode);
 int nbpc_get_math_mode(void);
 

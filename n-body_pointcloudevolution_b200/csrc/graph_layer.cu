@@ -432,6 +432,42 @@ static int glf_node_xty(const char *name, const float *X, const float *Y, int64_
 #endif  // !NBPC_HOST_EMU
 
 #include "graph_layer_tc.h"
+#include "graph_layer_k3.cuh"
+
+#ifndef NBPC_HOST_EMU
+// ---- first-layer (k = 3) streaming kernels
+static bool glk3_shape_ok(int k, int q) { return k == 3 && (q == 16 || q == 32 || q == 64); }
+static void glk3_launch_edge_out(int q, const float *E, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c,
+                                 int M, int relu, float *out, cudaStream_t stream) {
+    const uint32_t magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)M);
+#define X(Q_)                                                                                                              \
+    if (q == Q_) {                                                                                                        \
+        const int epb = GLK3_THREADS / (Q_ / 4) * GLK3_UNROLL;                                                            \
+        const int grid = (int)((c + epb - 1) / epb);                                                                      \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_kernel", 3, q).c_str(), (glk3_edge_out_kernel<Q_, true>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)c, (uint32_t)M, magic, out); \
+        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_kernel", 3, q).c_str(), (glk3_edge_out_kernel<Q_, false>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)c, (uint32_t)M, magic, out); \
+    }
+    X(16) X(32) X(64)
+#undef X
+}
+// dW1 = E^T dZ; returns the number of per-block partials
+static int glk3_launch_edge_dw(int q, const float *E, const float *dOut, const float *Hout, int64_t c, int relu, float *partial,
+                               cudaStream_t stream) {
+    int nb = 0;
+#define X(Q_)                                                                                                              \
+    if (q == Q_) {                                                                                                        \
+        const int64_t unit = GLK3_THREADS / (Q_ / 4) * GLK3_UNROLL;                                                       \
+        int64_t epb = (c + gl_num_sms() * 8 - 1) / (gl_num_sms() * 8);                                                    \
+        epb = (epb + unit - 1) / unit * unit;                                                                             \
+        nb = (int)((c + epb - 1) / epb);                                                                                  \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_dw_kernel", 3, q).c_str(), (glk3_edge_dw_kernel<Q_, true>), nb, GLK3_THREADS, 0, stream, E, dOut, Hout, (uint32_t)c, (uint32_t)epb, partial); \
+        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_dw_kernel", 3, q).c_str(), (glk3_edge_dw_kernel<Q_, false>), nb, GLK3_THREADS, 0, stream, E, dOut, Hout, (uint32_t)c, (uint32_t)epb, partial); \
+    }
+    X(16) X(32) X(64)
+#undef X
+    return nb;
+}
+#endif
 
 // per-sample column sums of a node tensor X (B*N, ch): out[s] = sum_n X[s,n] / divisor
 static void gl_colsum(const float *X, int ch, int N, int B, int nblk, float divisor, float *partial, float *out, bool fast,
@@ -591,6 +627,10 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
         }
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
+    if (fast && glk3_shape_ok(k, q)) {
+        glk3_launch_edge_out(q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
     if (fast && glf_edge_shape_ok(k, q)) {
         int rc = 1;
 #define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_out<K_, Q_>(H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
@@ -730,6 +770,11 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
             nbpc_set_error("nbpc_graph_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
             return NBPC_ELAUNCH;
         }
+        return nbpc_check_launch("nbpc_graph_layer_bwd");
+    }
+    if (fast && !is_last && !dH_in && glk3_shape_ok(k, q)) {
+        const int nb = glk3_launch_edge_dw(q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
+        glf_reduce_partials(w.xty_partial, nb, k, q, 0, dW, stream);
         return nbpc_check_launch("nbpc_graph_layer_bwd");
     }
     if (fast && !is_last && glf_edge_shape_ok(k, q) && (!dH_in || k % 4 == 0)) {

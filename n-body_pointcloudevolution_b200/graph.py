@@ -13,6 +13,8 @@ Differences a caller can observe (all documented in DESIGN.md):
 """
 from types import SimpleNamespace
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -141,9 +143,19 @@ class Adjacency:
     """COO (3,c) + diagonals + CSR transpose of a fixed-degree batch graph (c = b*N*M edges)."""
 
     def __init__(self, coo, diag, csrT_ptr, csrT_edge, status, b, N, M):
-        self.coo, self.diag, self.csrT_ptr, self.csrT_edge, self.status = coo, diag, csrT_ptr, csrT_edge, status
+        self._coo, self._coo_ref = coo, None
+        self.diag, self.csrT_ptr, self.csrT_edge, self.status = diag, csrT_ptr, csrT_edge, status
         self.b, self.N, self.M = b, N, M
         self._seg_cache = {}
+
+    @property
+    def coo(self):
+        return self._coo if self._coo_ref is None else self._coo_ref()
+
+    def weaken(self):
+        """Called when this object is hung on its own COO tensor (`_attach`): keep only a weak reference back, or
+        tensor and adjacency form a cycle that pins ~60 MB of device memory per step until the cyclic GC runs."""
+        self._coo_ref, self._coo = weakref.ref(self._coo), None
 
     @property
     def col(self):
@@ -159,6 +171,7 @@ class Adjacency:
 
 def _attach(coo, adj):
     coo._nbpc_adjacency = adj
+    adj.weaken()
     return coo
 
 

@@ -8,6 +8,8 @@ syn, graph, nn_, tu, lib = nb.synthetic, nb.graph, nb.nn, nb.train_utils, nb._li
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=30)
 ap.add_argument("--batch", type=int, default=8)
+ap.add_argument("--nogc", action="store_true")
+ap.add_argument("--pool", type=int, default=1)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, b, k, ch = 32 ** 3, a.batch, 14, [3, 32, 16, 3]
@@ -28,6 +30,9 @@ def step():
     adam.step(grad_scale=1.0)
     return loss
 
+import gc
+if a.nogc:
+    gc.disable()
 for _ in range(3):
     step()
 torch.cuda.synchronize()
@@ -39,6 +44,9 @@ for i in range(a.steps):
     step()
     ev[i + 1].record()
     host.append((time.perf_counter() - t0) * 1e3)
+    if i % 10 == 0:
+        print(i, "alloc GB", round(torch.cuda.memory_allocated() / 2**30, 2), "reserved GB", round(torch.cuda.memory_reserved() / 2**30, 2),
+              "gc", gc.get_count(), "mallocs", torch.cuda.memory_stats()["num_device_alloc"], flush=True)
 torch.cuda.synchronize()
 print("math", lib.get_math_mode())
 print("device ms/step:", [round(ev[i].elapsed_time(ev[i + 1]), 2) for i in range(a.steps)])
