@@ -277,7 +277,9 @@ struct GlWorkspace {
     float *Gc, *Gr;          // (BN, k): G_col/G_row (bwd)
     float *cube_partial;     // (B, nblk, max(k,q))
     float *dCq;              // (B, q)
-    float *xty_partial;      // per-block partials of the X^T Y reductions
+    float *xty_partial;      // per-block partials of the X^T Y reductions (dW1)
+    float *xty_partial2;     // ... dW2
+    float *xty_partial3;     // ... dW3
     size_t bytes;
 };
 
@@ -286,12 +288,13 @@ static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int 
     GlWorkspace w;
     const size_t BN = (size_t)B * N;
     const int mx = k > q ? k : q;
-    const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+    // column-sum partials: one row per pooling block (>= 16 nodes) or per GL_CUBE_CHUNK rows
+    const int nblk = nbpc_max(nbpc_cdiv(N, GL_CUBE_CHUNK), nbpc_cdiv(N, 16));
     w.Qc = a.take<float>(BN * mx);
     w.Qr = a.take<float>(BN * mx);
     w.Gc = a.take<float>(BN * k);
     w.Gr = a.take<float>(BN * k);
-    w.cube_partial = a.take<float>((size_t)B * nblk * mx);
+    w.cube_partial = a.take<float>((size_t)B * nblk * mx + (size_t)B * mx);   // + Gq (B,k) behind the partials
     w.dCq = a.take<float>((size_t)B * mx);
     int rpc, nc;
     xty_plan((int64_t)BN * M, k, q, &rpc, &nc);
@@ -299,6 +302,8 @@ static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int 
     nparts = nbpc_max(nparts, (size_t)gl_max_partial_blocks());
     nparts = nbpc_max(nparts, (size_t)gl_node_xty_grid((int64_t)BN));
     w.xty_partial = a.take<float>(nparts * k * q);
+    w.xty_partial2 = a.take<float>(nparts * k * q);
+    w.xty_partial3 = a.take<float>(nparts * k * q);
     w.bytes = a.off;
     return w;
 }
@@ -379,10 +384,11 @@ static void glf_reduce_partials(const float *partial, int nblocks, int rows, int
     NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(rows * cols, 32), 1024, 0, stream, partial, nblocks, rows, cols, transpose, out);
 }
 
+// dW1 == nullptr: leave the nb per-block partials for the caller to reduce (*nb_out)
 template <int K, int Q>
 static int glf_launch_edge_bwd(const float *dOut, const float *Hout, const float *H, const int32_t *col, const float *W1,
                                const float *Gc, const float *Gr, int64_t c, int M, int relu, int mask_in, float *dH,
-                               float *partial, float *dW1, cudaStream_t stream) {
+                               float *partial, float *dW1, cudaStream_t stream, int *nb_out = nullptr) {
     int nb = -1;
     const NbpcKName nm("glf_edge_bwd_kernel", K, Q);
     const char *n = nm.c_str();
@@ -399,34 +405,42 @@ static int glf_launch_edge_bwd(const float *dOut, const float *Hout, const float
                   : glf_launch_edge_bwd_t<K, Q, false, false, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
     }
     if (nb <= 0) return 1;
-    glf_reduce_partials(partial, nb, K, Q, 0, dW1, stream);
+    if (nb_out) *nb_out = nb;
+    if (dW1) glf_reduce_partials(partial, nb, K, Q, 0, dW1, stream);
     return 0;
 }
 
 // X^T Y over n node rows -> out (k,q); deterministic.  Uses the micro-tile kernel when (k,q) or (q,k)
 // is a compiled shape, else the generic kernel.
+// out == nullptr: leave the partials (count -> *nb_out, layout (q,k) instead of (k,q) -> *transposed) for the caller
 static int glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, int k, int q, float *partial,
-                        float *out, cudaStream_t stream) {
+                        float *out, cudaStream_t stream, int *nb_out = nullptr, int *transposed = nullptr) {
     int nb = 0;
+    if (transposed) *transposed = 0;
 #define XN(K_, Q_)                                                                                                    \
     if (!nb && k == K_ && q == Q_) {                                                                                 \
         nb = glf_launch_edge_bwd_t<K_, Q_, false, false, false>(name, Y, nullptr, X, nullptr, nullptr, nullptr, nullptr, n, 1, \
                                                                 nullptr, partial, stream);                          \
-        if (nb > 0) glf_reduce_partials(partial, nb, k, q, 0, out, stream);                                          \
+        if (nb > 0 && out) glf_reduce_partials(partial, nb, k, q, 0, out, stream);                                   \
     }                                                                                                                \
     if (!nb && k == Q_ && q == K_ && K_ != Q_) {                                                                     \
         nb = glf_launch_edge_bwd_t<K_, Q_, false, false, false>(name, X, nullptr, Y, nullptr, nullptr, nullptr, nullptr, n, 1, \
                                                                 nullptr, partial, stream);                          \
-        if (nb > 0) glf_reduce_partials(partial, nb, q, k, 1, out, stream);                                          \
+        if (nb > 0 && out) glf_reduce_partials(partial, nb, q, k, 1, out, stream);                                   \
+        if (nb > 0 && transposed) *transposed = 1;                                                                   \
     }
     GLF_FOR_KQ(XN)
 #undef XN
     if (nb < 0) return 1;
-    if (nb > 0) return 0;
+    if (nb > 0) {
+        if (nb_out) *nb_out = nb;
+        return 0;
+    }
     const int rpb = gl_node_xty_rows_per_block(n), grid = gl_node_xty_grid(n);
     const size_t smem = sizeof(float) * (size_t)GLF_XTY_ROWS * (k + q);
     NBPC_LAUNCH_N(name, glf_node_xty_kernel, grid, 256, smem, stream, X, Y, n, rpb, k, q, partial);
-    glf_reduce_partials(partial, grid, k, q, 0, out, stream);
+    if (out) glf_reduce_partials(partial, grid, k, q, 0, out, stream);
+    if (nb_out) *nb_out = grid;
     return 0;
 }
 #endif  // !NBPC_HOST_EMU
@@ -484,6 +498,171 @@ static void gl_colsum(const float *X, int ch, int N, int B, int nblk, float divi
                 partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * ch, GL_THREADS), GL_THREADS, 0, stream, partial, ch, nblk, B, divisor, out);
 }
+
+#include "graph_layer_node.cuh"
+
+#ifndef NBPC_HOST_EMU
+// ================================================================== fused node-level pipeline (graph_layer_node.cuh)
+#define GLN_FOR_KQ(X)                                                                                                   \
+    X(3, 16) X(3, 32) X(3, 64) X(16, 3) X(16, 16) X(16, 32) X(16, 64) X(32, 3) X(32, 16) X(32, 32) X(32, 64) X(64, 3) X(64, 16) \
+    X(64, 32) X(64, 64)
+static bool gln_shape_ok(int k, int q) {
+#define X(K_, Q_) if (k == K_ && q == Q_) return true;
+    GLN_FOR_KQ(X)
+#undef X
+    return false;
+}
+static int gln_node_grid(int64_t BN) { return (int)nbpc_min((int64_t)nbpc_cdiv(BN, GLN_THREADS), (int64_t)gl_num_sms() * 8); }
+
+// pooling + per-block column sums of P_row; returns the number of partial blocks per sample
+static int gln_launch_pool(const float *H, int k, int q, int B, int N, int M, const int32_t *csrT_ptr, const int32_t *csrT_edge,
+                           float *P_row, float *P_col, float *partial, cudaStream_t stream) {
+    int nblk = 0;
+#define X(K_)                                                                                                           \
+    if (k == K_) {                                                                                                     \
+        nblk = nbpc_cdiv(N, gln_pool_nodes_per_block(K_));                                                             \
+        NBPC_LAUNCH_N(NbpcKName("gln_pool_kernel", k, q).c_str(), gln_pool_kernel<K_>, dim3(nblk, B), GLN_THREADS, 0, stream, H, M, N, \
+                      csrT_ptr, csrT_edge, P_row, P_col, partial);                                                     \
+    }
+    X(16) X(32) X(64)
+#undef X
+    if (!nblk) {
+        int KP = 1;
+        while (KP < k) KP <<= 1;
+        nblk = nbpc_cdiv(N, GLN_THREADS / KP);
+        NBPC_LAUNCH_N(NbpcKName("gln_pool_generic_kernel", k, q).c_str(), gln_pool_generic_kernel, dim3(nblk, B), GLN_THREADS, 0, stream, H,
+                      k, KP, M, N, csrT_ptr, csrT_edge, P_row, P_col, partial);
+    }
+    return nblk;
+}
+
+static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M,
+                        int k, int q, const float *W, const float *bias, int is_last, int relu, float *H_out, float *P_col,
+                        float *P_row, float *P_cube, GlWorkspace &w, cudaStream_t stream) {
+    const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
+    const int nblk = gln_launch_pool(H_in, k, q, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream);
+    float *Cq = w.dCq;
+    NBPC_LAUNCH(gln_cube_fwd_kernel, B, GLN_TINY_THREADS, 0, stream, w.cube_partial, nblk, N, k, q, W + 3 * kq, bias, P_cube, Cq);
+#define X(K_, Q_)                                                                                                       \
+    if (k == K_ && q == Q_)                                                                                            \
+        NBPC_LAUNCH_N(NbpcKName("gln_node_project_kernel", k, q).c_str(), (gln_node_project_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, \
+                      0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);
+    GLN_FOR_KQ(X)
+#undef X
+    if (is_last) {
+        NBPC_LAUNCH_N(NbpcKName("glf_last_out_kernel", k, q).c_str(), glf_last_out_kernel, nbpc_cdiv(BN * q, 256), 256, 0, stream, P_row,
+                      col, W, w.Qc, w.Qr, (int)BN, M, k, q, relu, H_out);
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
+    if (g_nbpc_math_mode != NBPC_MATH_FP32 && glt_fwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3)) {
+        if (glt_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, g_nbpc_math_mode == NBPC_MATH_TF32X3, H_out, stream)) {
+            nbpc_set_error("nbpc_graph_layer_fwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
+    if (glk3_shape_ok(k, q)) {
+        glk3_launch_edge_out(q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
+    int rc = 1;
+#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_out<K_, Q_>(H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+    GLF_FOR_KQ(X)
+#undef X
+    if (rc) {
+        nbpc_set_error("nbpc_graph_layer_fwd: could not configure shared memory");
+        return NBPC_ELAUNCH;
+    }
+    return nbpc_check_launch("nbpc_graph_layer_fwd");
+}
+
+// the fused path covers every (k, q) of GLN_FOR_KQ whose edge-level kernels exist
+static bool gl_fused_ok(int k, int q, int is_last) {
+    if (!gln_shape_ok(k, q)) return false;
+    if (is_last) return true;                       // node-level output
+    return glf_edge_shape_ok(k, q);                 // q in {16,32,64}
+}
+
+static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out, const int32_t *col, const int32_t *csrT_ptr,
+                        const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *P_col,
+                        const float *P_row, const float *P_cube, int is_last, int relu, int mask_input, float *dH_in, float *dW,
+                        float *dB, GlWorkspace &w, cudaStream_t stream) {
+    const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
+    float *dQ_col = w.Qc, *dQ_row = w.Qr;
+    // ---- dQ_row, dQ_col (+ column sums of dQ_row)
+    int nblk = 0;
+    if (is_last) {
+        NBPC_LAUNCH_N(NbpcKName("glf_last_bwd_pool_kernel", k, q).c_str(), glf_last_bwd_pool_kernel, nbpc_cdiv(BN * q, 256), 256, 0, stream,
+                      dOut, H_out, relu, (int)BN, M, q, csrT_ptr, csrT_edge, dQ_row, dQ_col);
+        nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+        NBPC_LAUNCH(glf_colsum_partial_kernel, dim3(nblk, B), 256, 0, stream, dQ_row, q, N, GL_CUBE_CHUNK, w.cube_partial);
+    } else {
+#define X(Q_)                                                                                                           \
+    if (q == Q_) {                                                                                                     \
+        nblk = nbpc_cdiv(N, gln_pool_nodes_per_block(Q_));                                                             \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, true>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial); \
+        else NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, false>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial); \
+    }
+        X(16) X(32) X(64)
+#undef X
+    }
+    float *Gq = w.cube_partial + (size_t)B * nblk * q;   // (B,k), behind the partials
+    NBPC_LAUNCH(gln_cube_bwd_kernel, B, GLN_TINY_THREADS, 0, stream, w.cube_partial, nblk, N, M, k, q, W + 3 * kq, w.dCq, dH_in ? Gq : (float *)nullptr);
+    // ---- G_col, G_row
+    if (dH_in) {
+#define X(K_, Q_)                                                                                                       \
+    if (k == K_ && q == Q_)                                                                                            \
+        NBPC_LAUNCH_N(NbpcKName("gln_node_grad_kernel", k, q).c_str(), (gln_node_grad_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, 0,  \
+                      stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, w.Gc, w.Gr);
+        GLN_FOR_KQ(X)
+#undef X
+    }
+    // ---- per-block partials of dW2 = P_col^T dQ_col, dW3 = P_row^T dQ_row
+    GlnFinalArgs fa;
+    for (int i = 0; i < 3; ++i) { fa.part[i] = nullptr; fa.n[i] = 0; fa.tr[i] = 0; }
+    fa.part[1] = w.xty_partial2;
+    fa.part[2] = w.xty_partial3;
+    if (glf_node_xty("glf_node_xty_dW2", P_col, dQ_col, BN, k, q, w.xty_partial2, nullptr, stream, &fa.n[1], &fa.tr[1]) ||
+        glf_node_xty("glf_node_xty_dW3", P_row, dQ_row, BN, k, q, w.xty_partial3, nullptr, stream, &fa.n[2], &fa.tr[2])) {
+        nbpc_set_error("nbpc_graph_layer_bwd: could not configure the X^T Y kernel");
+        return NBPC_ELAUNCH;
+    }
+    // ---- edge level: dW1 = H^T dZ and dH = dZ W1^T + G_col[col] + G_row[row]
+    if (is_last) {
+        // row-mean output: dZ[e] = dOutM[e/M]/M  =>  dW1 = P_row^T dOutM (= dW3), dH[e] = R[e/M] + G_col[col[e]]
+        fa.part[0] = fa.part[2]; fa.n[0] = fa.n[2]; fa.tr[0] = fa.tr[2];
+        if (dH_in) {
+            NBPC_LAUNCH_N(NbpcKName("glf_last_rowterm_kernel", k, q).c_str(), glf_last_rowterm_kernel, nbpc_cdiv(BN * k, 256), 256, 0, stream,
+                          dQ_row, W, (int)BN, M, k, q, w.Gr);
+            NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256, 0,
+                          stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, c, M, k, dH_in);
+        }
+    } else if (!relu && dH_in && g_nbpc_math_mode != NBPC_MATH_FP32 && glt_bwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3, c)) {
+        const int nb = glt_edge_bwd(k, q, dOut, H_in, col, W, w.Gc, w.Gr, c, M, mask_input, g_nbpc_math_mode == NBPC_MATH_TF32X3, dH_in,
+                                    w.xty_partial, stream);
+        if (nb <= 0) {
+            nbpc_set_error("nbpc_graph_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+            return NBPC_ELAUNCH;
+        }
+        fa.part[0] = w.xty_partial; fa.n[0] = nb;
+    } else if (!dH_in && glk3_shape_ok(k, q)) {
+        fa.part[0] = w.xty_partial;
+        fa.n[0] = glk3_launch_edge_dw(q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
+    } else {
+        int rc = 1, nb = 0;
+#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, nullptr, stream, &nb);
+        GLF_FOR_KQ(X)
+#undef X
+        if (rc) {
+            nbpc_set_error("nbpc_graph_layer_bwd: could not configure shared memory");
+            return NBPC_ELAUNCH;
+        }
+        fa.part[0] = w.xty_partial; fa.n[0] = nb;
+    }
+    NBPC_LAUNCH(gln_final_kernel, dim3(nbpc_cdiv(kq, 32), 4), 1024, 0, stream, fa, P_cube, w.dCq, B, k, q, dW, dB);
+    return nbpc_check_launch("nbpc_graph_layer_bwd");
+}
+#endif  // !NBPC_HOST_EMU
 
 extern "C" {
 
@@ -568,6 +747,10 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
     const bool fast = gl_use_fast();
     (void)fast;
+#ifndef NBPC_HOST_EMU
+    if (fast && gl_fused_ok(k, q, is_last))
+        return gl_fwd_fused(H_in, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, H_out, P_col, P_row, P_cube, w, stream);
+#endif
     // ---- pooling: P_row, P_col
     bool done = false;
 #ifndef NBPC_HOST_EMU
@@ -673,6 +856,11 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     const int64_t kq = (int64_t)k * q;
     const bool fast = gl_use_fast();
     (void)fast;
+#ifndef NBPC_HOST_EMU
+    if (fast && gl_fused_ok(k, q, is_last) && (!dH_in || k % 4 == 0))
+        return gl_bwd_fused(dOut, H_in, H_out, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, P_col, P_row, P_cube, is_last, relu,
+                            mask_input, dH_in, dW, dB, w, stream);
+#endif
 
     // ---- dQ_row, dQ_col
     bool done = false;

@@ -189,14 +189,30 @@ __device__ __forceinline__ float glt_to_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ void glt_split_inplace(float *hi, float *lo, int n_floats, int tid, int nthreads) {
-    for (int i = tid * 4; i < n_floats; i += nthreads * 4) {
-        const float4 x = *reinterpret_cast<const float4 *>(hi + i);
-        float4 h, l;
-        h.x = glt_to_tf32(x.x); h.y = glt_to_tf32(x.y); h.z = glt_to_tf32(x.z); h.w = glt_to_tf32(x.w);
-        l.x = glt_to_tf32(x.x - h.x); l.y = glt_to_tf32(x.y - h.y); l.z = glt_to_tf32(x.z - h.z); l.w = glt_to_tf32(x.w - h.w);
-        *reinterpret_cast<float4 *>(hi + i) = h;
-        *reinterpret_cast<float4 *>(lo + i) = l;
+// Error-compensated split of a landed FP32 tile for the TF32 tensor pipe.  tcgen05 kind::tf32 reads the top 19 bits of
+// each 32-bit operand (the low 13 mantissa bits are ignored), so the landed tile itself already IS the "hi" operand
+// trunc(x); only the residual lo = x - trunc(x) (exact in FP32, < 2^-10 |x|; the pipe keeps its top 11 bits) has to be
+// produced, at the same position of a second buffer.  hi * hi + hi * lo + lo * hi then carries ~2^-20 relative error per
+// product instead of 2^-11.  128 converter threads, one 16-byte granule per thread per step, 4 loads in flight.
+__device__ __forceinline__ float glt_residual(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+template <int N_FLOATS>
+__device__ __forceinline__ void glt_split_inplace(const float *hi, float *lo, int tid) {
+    constexpr int STEP = 128 * 4, NSTEP = N_FLOATS / STEP;
+    static_assert(N_FLOATS % STEP == 0, "tile size must be a multiple of 512 floats");
+    int s = 0;
+#pragma unroll 1
+    for (; s + 4 <= NSTEP; s += 4) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = *reinterpret_cast<const float4 *>(hi + (s + u) * STEP + tid * 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<float4 *>(lo + (s + u) * STEP + tid * 4) =
+                make_float4(glt_residual(x[u].x), glt_residual(x[u].y), glt_residual(x[u].z), glt_residual(x[u].w));
+    }
+    for (; s < NSTEP; ++s) {
+        const float4 x = *reinterpret_cast<const float4 *>(hi + s * STEP + tid * 4);
+        *reinterpret_cast<float4 *>(lo + s * STEP + tid * 4) = make_float4(glt_residual(x.x), glt_residual(x.y), glt_residual(x.z), glt_residual(x.w));
     }
 }
 
@@ -209,9 +225,9 @@ __device__ __forceinline__ void glt_fill_operand(char *hi, char *lo, int R, F sr
         const int ch = jj / T::CW, j = jj % T::CW;
         const int off = ch * T::chunk_bytes(R) + T::offset(r, j);
         const float x = src(r, jj);
-        const float h = glt_to_tf32(x);
-        *reinterpret_cast<float *>(hi + off) = h;
-        if (lo) *reinterpret_cast<float *>(lo + off) = glt_to_tf32(x - h);
+        // split mode: hi = the raw value (the pipe truncates it), lo = the exact residual; single pass: round to nearest
+        *reinterpret_cast<float *>(hi + off) = lo ? x : glt_to_tf32(x);
+        if (lo) *reinterpret_cast<float *>(lo + off) = glt_residual(x);
     }
 }
 
@@ -264,11 +280,13 @@ static int glt_make_tmap_packed(CUtensorMap *tm, const float *ptr, int64_t rows,
                ? 0 : 1;
 }
 
-// tuning override "ctas,stages" from the environment (unset or malformed: keep the defaults)
-static void glt_env_cfg(const char *name, int *ctas, int *stages) {
+// tuning override "ctas,stages[,lo]" from the environment (unset or malformed: keep the defaults)
+static void glt_env_cfg(const char *name, int *ctas, int *stages, int *lo) {
     const char *e = getenv(name);
-    int a = 0, b = 0;
-    if (e && sscanf(e, "%d,%d", &a, &b) == 2 && a >= 1 && b >= 1) { *ctas = a; *stages = b; }
+    int a = 0, b = 0, l = 0;
+    const int n = e ? sscanf(e, "%d,%d,%d", &a, &b, &l) : 0;
+    if (n >= 2 && a >= 1 && b >= 1) { *ctas = a; *stages = b; }
+    if (n == 3 && l >= 1) *lo = l;
 }
 
 // persistent grid = SMs x co-resident CTAs.  The co-residency is computed from the SM's budgets (shared memory with

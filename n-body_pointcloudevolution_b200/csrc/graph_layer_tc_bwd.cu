@@ -28,13 +28,22 @@ struct GltBwdCfg {
     static constexpr int ACC_COLS = K + N2;                              // D1 (dH tile) | D2 (dW1 tile partial blocks)
     static constexpr int TMEM_COLS = (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512));
     static constexpr int SMEM_MAX = 227 * 1024;
-    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 512; }
+    // epilogue warp sets per CTA: the split mode runs one CTA per SM (its hi / lo stages fill the shared memory), so it
+    // gets two sets that take alternate tiles (= accumulator stages); the single-pass mode runs two CTAs per SM instead
+    __host__ __device__ static constexpr int nsets(bool x3) { return x3 ? 2 : 1; }
+    __host__ __device__ static constexpr int threads(bool x3) { return 32 * (2 + 4 * nsets(x3) + (x3 ? 4 : 0)); }
+    __host__ __device__ static constexpr size_t fixed_bytes(bool x3) {
+        return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + (size_t)OS_BYTES * nsets(x3) + 512;
+    }
     // deepest stage ring (<= 8) that fits when `ctas` CTAs share an SM
-    __host__ __device__ static constexpr int stages_for(bool x3, int ctas) {
-        const int s = (int)((SMEM_MAX / ctas - 1024 - (int)fixed_bytes(x3)) / (STAGE * (x3 ? 2 : 1)));
+    // (the split mode also needs `lo` residual buffers of one stage each)
+    __host__ __device__ static constexpr int stages_for(bool x3, int ctas, int lo = 1) {
+        const int s = (int)((SMEM_MAX / ctas - 1024 - (int)fixed_bytes(x3) - (x3 ? lo * STAGE : 0)) / STAGE);
         return s > 8 ? 8 : s;
     }
-    __host__ __device__ static constexpr size_t smem_bytes(bool x3, int S) { return fixed_bytes(x3) + (size_t)S * STAGE * (x3 ? 2 : 1); }
+    __host__ __device__ static constexpr size_t smem_bytes(bool x3, int S, int L) {
+        return fixed_bytes(x3) + (size_t)S * STAGE + (x3 ? (size_t)L * STAGE : 0);
+    }
     // byte offset of channel j (multiple of 4) of tile edge `row` inside the packed H tile
     __device__ static __forceinline__ int h_offset(int row, int j) {
         const int pr = row / P, colp = (row % P) * K + j, jj = colp & 31;
@@ -43,39 +52,41 @@ struct GltBwdCfg {
 };
 
 template <int K, int Q, bool MASK_IN, bool X3>
-__global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bwd_kernel(const __grid_constant__ CUtensorMap tmH,
+__global__ void __launch_bounds__(GltBwdCfg<K, Q>::threads(X3)) glt_edge_bwd_kernel(const __grid_constant__ CUtensorMap tmH,
                                                                     const __grid_constant__ CUtensorMap tmZ,
                                                                     const __grid_constant__ CUtensorMap tmZ2,
                                                                     const int32_t *__restrict__ col,
                                                                     const float *__restrict__ W1,
                                                                     const float *__restrict__ G_col,
                                                                     const float *__restrict__ G_row, int64_t c, int M,
-                                                                    float *__restrict__ dH, float *__restrict__ dW_partial, const int S) {
+                                                                    float *__restrict__ dH, float *__restrict__ dW_partial, const int S, const int L) {
     using Cfg = GltBwdCfg<K, Q>;
     using TZ = typename Cfg::TZ;
-    constexpr int KS = Cfg::KS, P = Cfg::P;
+    constexpr int KS = Cfg::KS, P = Cfg::P, NSETS = Cfg::nsets(X3), EPI_END = 2 + 4 * NSETS;
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
-    unsigned char *St = base;                                       // [S][H' | Z | Z']  raw -> hi
-    unsigned char *Sl = St + S * Cfg::STAGE;                        // [S][H' | Z | Z']  lo (X3 only)
-    unsigned char *Bh = Sl + (X3 ? S * Cfg::STAGE : 0);
+    unsigned char *St = base;                                       // [S][H' | Z | Z']  landed tiles (= the hi operands)
+    unsigned char *Sl = St + S * Cfg::STAGE;                        // [L][H' | Z | Z']  residuals lo (X3 only)
+    unsigned char *Bh = Sl + (X3 ? L * Cfg::STAGE : 0);
     unsigned char *Bl = Bh + Cfg::B_BYTES;                          // (X3 only)
     float *Os = reinterpret_cast<float *>(Bh + Cfg::B_BYTES * (X3 ? 2 : 1));   // [128][KS]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + Cfg::OS_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + Cfg::OS_BYTES * NSETS);
     const uint32_t bar0 = glt_smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
-    auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };
-    auto TFULL = [&](int a) { return bar0 + 8u * (3 * S + a); };
-    auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * S + 2 + a); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
+    auto CONV = [&](int l) { return bar0 + 8u * (2 * S + l); };
+    auto LOFREE = [&](int l) { return bar0 + 8u * (2 * S + L + l); };
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * S + 2 * L + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * S + 2 * L + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * L + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE), G = gridDim.x;
 
     if (tid == 0) {
         // a stage is free again when its MMAs have read it AND (MASK_IN) the epilogue warps have read their H rows
-        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), MASK_IN ? 5 : 1); glt_mbar_init(CONV(s), 4); }
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), MASK_IN ? 5 : 1); }
+        for (int l = 0; l < L; ++l) { glt_mbar_init(CONV(l), 4); glt_mbar_init(LOFREE(l), 1); }
         for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
         glt_fence_barrier_init();
         glt_prefetch_tmap(&tmH);
@@ -115,14 +126,15 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bw
         if (lane == 0) {   // ---------------- MMA issuer
             constexpr uint32_t idesc1 = glt_idesc_tf32(GLT_TILE, K, 0, 0);   // D1 (128 x K) = dZ (K-major) * W1^T
             constexpr uint32_t idesc2 = glt_idesc_tf32(Cfg::M2, Cfg::N2, 1, 1);  // D2 (P K x P Q) = H'^T (MN-major) * dZ' (MN-major)
-            int s = 0, ph = 0, a = 0, aph = 0;
+            int s = 0, ph = 0, a = 0, aph = 0, l = 0, lph = 0;
             for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(TEMPTY(a), aph ^ 1);
-                glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
+                if constexpr (X3) glt_mbar_wait(CONV(l), lph);   // the residuals are ready (their producer had waited for FULL(s))
+                else glt_mbar_wait(FULL(s), ph);
                 glt_tc_fence_after();
                 const uint32_t d1 = tmem_base + a * Cfg::ACC_COLS, d2 = d1 + K;
                 const uint32_t h_hi = glt_smem_u32(St + s * Cfg::STAGE), z_hi = h_hi + Cfg::H_BYTES;
-                const uint32_t h_lo = glt_smem_u32(Sl + s * Cfg::STAGE), z_lo = h_lo + Cfg::H_BYTES;
+                const uint32_t h_lo = glt_smem_u32(Sl + l * Cfg::STAGE), z_lo = h_lo + Cfg::H_BYTES;
                 const uint32_t z2_hi = z_hi + Cfg::Z_BYTES, z2_lo = z_lo + Cfg::Z_BYTES;
                 const uint32_t b_hi = glt_smem_u32(Bh), b_lo = glt_smem_u32(Bl);
                 uint32_t acc1 = 0, acc2 = 0;
@@ -153,14 +165,20 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bw
                     }
                 }
                 glt_tc_commit(EMPTY(s));
+                if constexpr (X3) glt_tc_commit(LOFREE(l));
                 glt_tc_commit(TFULL(a));
                 if (++s == S) { s = 0; ph ^= 1; }
                 if (++a == 2) { a = 0; aph ^= 1; }
+                if (++l == L) { l = 0; lph ^= 1; }
             }
         }
-    } else if (warp < 6) {
-        // ---------------- epilogue warps (software pipelined like the forward kernel)
-        const int qd = warp & 3, row = qd * 32 + lane;
+    } else if (warp < EPI_END) {
+        // ---------------- epilogue warps: set = (warp - 2) / 4 takes the tiles i = set, set + NSETS, ... of this CTA's
+        // sequence (tile i uses accumulator i % 2 and stage i % S).  Software pipelined: the raw G_col rows of the set's
+        // NEXT tile are gathered into registers (un-added) and its G_row lines prefetched into L1 before the accumulator
+        // of the current tile is awaited.
+        const int set = (warp - 2) >> 2, qd = warp & 3, row = qd * 32 + lane;
+        float *Oset = Os + set * (Cfg::OS_BYTES / 4);
         // D2: M2 = 64 puts row r in lane (r % 16) + 32 (r / 16), M2 = 128 in lane r; row r = p K + k belongs to the
         // diagonal block p (warp-uniform) whose columns are [p Q, p Q + Q)
         constexpr int RPQ = (Cfg::M2 == 64) ? 16 : 32;
@@ -173,14 +191,32 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bw
             const int64_t e = (int64_t)t * GLT_TILE + row;
             return (t < ntiles && e < c) ? __ldg(&col[e]) : -1;
         };
-        auto gather = [&](int t, int cidx, float *dst) {
+        auto gather_col = [&](int cidx, float *dst) {
             if (cidx >= 0) {
-                const int64_t e = (int64_t)t * GLT_TILE + row;
-                const float *gc = G_col + (int64_t)cidx * K, *gr = G_row + edge_row(e) * K;
+                const float *gc = G_col + (int64_t)cidx * K;
 #pragma unroll
                 for (int j = 0; j < K / 4; ++j) {
-                    const float4 x = glf_ldg4(gc + 4 * j), y = glf_ldg4(gr + 4 * j);
-                    dst[4 * j] = x.x + y.x; dst[4 * j + 1] = x.y + y.y; dst[4 * j + 2] = x.z + y.z; dst[4 * j + 3] = x.w + y.w;
+                    const float4 x = glf_ldg4(gc + 4 * j);
+                    dst[4 * j] = x.x; dst[4 * j + 1] = x.y; dst[4 * j + 2] = x.z; dst[4 * j + 3] = x.w;
+                }
+            }
+        };
+        auto prefetch_row = [&](int t) {
+            const int64_t e = (int64_t)t * GLT_TILE + row;
+            if (t < ntiles && e < c) {
+                const float *gr = G_row + edge_row(e) * K;
+#pragma unroll
+                for (int j = 0; j < K; j += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(gr + j));
+            }
+        };
+        auto add_row = [&](int t, float *dst) {
+            const int64_t e = (int64_t)t * GLT_TILE + row;
+            if (e < c) {
+                const float *gr = G_row + edge_row(e) * K;
+#pragma unroll
+                for (int j = 0; j < K / 4; ++j) {
+                    const float4 y = glf_ldg4(gr + 4 * j);
+                    dst[4 * j] += y.x; dst[4 * j + 1] += y.y; dst[4 * j + 2] += y.z; dst[4 * j + 3] += y.w;
                 }
             }
         };
@@ -190,63 +226,61 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bw
         float g[K], gn[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) g[j] = gn[j] = 0.f;
-        int s = 0, ph = 0, a = 0, aph = 0;
-        int t = blockIdx.x;
-        gather(t, load_col(t), g);
-        int c_next = load_col(t + G);
-        for (; t < ntiles; t += G) {
-            gather(t + G, c_next, gn);
-            c_next = load_col(t + 2 * G);
+        const int TS = NSETS * G;                       // tile stride of this set
+        int i = set, t = blockIdx.x + set * G;
+        gather_col(load_col(t), g);
+        int c_next = load_col(t + TS);
+        for (; t < ntiles; t += TS, i += NSETS) {
+            gather_col(c_next, gn);
+            c_next = load_col(t + 2 * TS);
+            prefetch_row(t + TS);
+            add_row(t, g);
+            const int s = i % S, ph = (i / S) & 1, a = i & 1, aph = (i >> 1) & 1;
             unsigned char *st = St + s * Cfg::STAGE;
             const int64_t e0 = (int64_t)t * GLT_TILE;
-            // the epilogue reads H (X3: its TF32 head, same sign) from the stage for the ReLU mask
-            if constexpr (MASK_IN) glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
+            // ReLU mask of the producer of H: the sign bits of this thread's row are packed as soon as the tile has
+            // landed (the landed tile is never modified), and the stage is released before the accumulator is awaited
+            unsigned long long hmask = 0ull;
+            if constexpr (MASK_IN) {
+                glt_mbar_wait(FULL(s), ph);
+#pragma unroll
+                for (int jj = 0; jj < K; jj += 4) {
+                    const float4 h = *reinterpret_cast<const float4 *>(st + Cfg::h_offset(row, jj));
+                    hmask |= (unsigned long long)((h.x > 0.f ? 1u : 0u) | (h.y > 0.f ? 2u : 0u) | (h.z > 0.f ? 4u : 0u) | (h.w > 0.f ? 8u : 0u)) << jj;
+                }
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(EMPTY(s));
+            }
             glt_mbar_wait(TFULL(a), aph);
             glt_tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * Cfg::ACC_COLS;
+            float v[K], w[Q];
+            glt_tmem_ld<K>(tq, v);                      // all accumulator loads in flight, one wait
+            if (warp_has_dw) glt_tmem_ld<Q>(tq + K + p2 * Q, w);
+            glt_tc_wait_ld();
 #pragma unroll
-            for (int cb = 0; cb < K; cb += 16) {   // dH: 16 accumulator columns at a time
-                float v[16];
-                glt_tmem_ld16(tq + cb, v);
-                glt_tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int jj = cb + 4 * j;
-                    float4 o = make_float4(v[4 * j] + g[jj], v[4 * j + 1] + g[jj + 1], v[4 * j + 2] + g[jj + 2], v[4 * j + 3] + g[jj + 3]);
-                    if constexpr (MASK_IN) {   // ReLU backward of the producer of H
-                        const float4 h = *reinterpret_cast<const float4 *>(st + Cfg::h_offset(row, jj));
-                        o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f;
-                    }
-                    *reinterpret_cast<float4 *>(Os + row * KS + jj) = o;
+            for (int jj = 0; jj < K; jj += 4) {
+                float4 o = make_float4(v[jj] + g[jj], v[jj + 1] + g[jj + 1], v[jj + 2] + g[jj + 2], v[jj + 3] + g[jj + 3]);
+                if constexpr (MASK_IN) {   // ReLU backward of the producer of H
+                    const unsigned m4 = (unsigned)(hmask >> jj);
+                    o.x = (m4 & 1u) ? o.x : 0.f; o.y = (m4 & 2u) ? o.y : 0.f; o.z = (m4 & 4u) ? o.z : 0.f; o.w = (m4 & 8u) ? o.w : 0.f;
                 }
+                *reinterpret_cast<float4 *>(Oset + row * KS + jj) = o;
             }
-            if (warp_has_dw) {
+            if (has_dw) {
 #pragma unroll
-                for (int cb = 0; cb < Q; cb += 16) {   // dW1 tile partial: rows = input channels of diagonal block p2
-                    float w[16];
-                    glt_tmem_ld16(tq + K + p2 * Q + cb, w);
-                    glt_tc_wait_ld();
-                    if (has_dw) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) dw[cb + j] += w[j];
-                    }
-                }
+                for (int j = 0; j < Q; ++j) dw[j] += w[j];
             }
             glt_tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                glt_mbar_arrive(TEMPTY(a));
-                if constexpr (MASK_IN) glt_mbar_arrive(EMPTY(s));
-            }
-            if (++a == 2) { a = 0; aph ^= 1; }
-            if (++s == S) { s = 0; ph ^= 1; }
-            glf_store_warp_rows<K, KS>(Os + qd * 32 * KS, dH, e0 + qd * 32, c);
+            if (lane == 0) glt_mbar_arrive(TEMPTY(a));
+            glf_store_warp_rows<K, KS>(Oset + qd * 32 * KS, dH, e0 + qd * 32, c);
             __syncwarp();
 #pragma unroll
             for (int j = 0; j < K; ++j) g[j] = gn[j];
         }
         if (has_dw) {
-            float *dst = dW_partial + (((int64_t)blockIdx.x * P + p2) * K + krow) * Q;
+            float *dst = dW_partial + ((((int64_t)blockIdx.x * NSETS + set) * P + p2) * K + krow) * Q;
 #pragma unroll
             for (int j = 0; j < Q / 4; ++j)
                 *reinterpret_cast<float4 *>(dst + 4 * j) = make_float4(dw[4 * j], dw[4 * j + 1], dw[4 * j + 2], dw[4 * j + 3]);
@@ -254,16 +288,18 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_bw
     } else {
         // ---------------- converter warps (X3 only): split the landed tiles into TF32 hi / lo in place
         if constexpr (X3) {
-            const int wtid = tid - 192;
-            int s = 0, ph = 0;
+            const int wtid = tid - 32 * EPI_END;
+            int s = 0, ph = 0, l = 0, lph = 0;
             for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(FULL(s), ph);
-                glt_split_inplace(reinterpret_cast<float *>(St + s * Cfg::STAGE), reinterpret_cast<float *>(Sl + s * Cfg::STAGE),
-                                  Cfg::STAGE / 4, wtid, 128);
+                glt_mbar_wait(LOFREE(l), lph ^ 1);
+                glt_split_inplace<Cfg::STAGE / 4>(reinterpret_cast<const float *>(St + s * Cfg::STAGE),
+                                                  reinterpret_cast<float *>(Sl + l * Cfg::STAGE), wtid);
                 glt_fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) glt_mbar_arrive(CONV(s));
+                if (lane == 0) glt_mbar_arrive(CONV(l));
                 if (++s == S) { s = 0; ph ^= 1; }
+                if (++l == L) { l = 0; lph ^= 1; }
             }
         }
     }
@@ -288,25 +324,30 @@ static int glt_launch_edge_bwd_t(const float *dZ, const float *H, const int32_t 
         glt_make_tmap_packed(&tmZ2, dZ, c / Cfg::P, Q * Cfg::P, Cfg::R))
         return -1;
     auto kern = glt_edge_bwd_kernel<K, Q, MASK_IN, X3>;
-    constexpr int threads = X3 ? GLT_THREADS_X3 : GLT_THREADS;
-    static int grid_cache = 0, S = 0;
+    constexpr int threads = Cfg::threads(X3);
+    static int grid_cache = 0, S = 0, L = 1;
     if (!grid_cache) {
         int ctas = 1;
-        for (int t = 2; t >= 1; --t)
-            if (Cfg::stages_for(X3, t) >= 2 && t * Cfg::TMEM_COLS <= 512) { ctas = t; break; }
+        if (!X3)
+            for (int t = 2; t >= 1; --t)
+                if (Cfg::stages_for(X3, t) >= 2 && t * Cfg::TMEM_COLS <= 512) { ctas = t; break; }
         S = Cfg::stages_for(X3, ctas);
         S = S > 6 ? 6 : S;
-        glt_env_cfg("NBPC_GLT_BWD", &ctas, &S);
-        if (S < 1 || S > Cfg::stages_for(X3, 1) || ctas * Cfg::TMEM_COLS > 512) return -1;
-        grid_cache = glt_grid(kern, threads, Cfg::smem_bytes(X3, S), ctas);
+        // split mode: this kernel is bound by shared-memory bandwidth (landing + residual pass + three operand passes +
+        // output staging move ~0.4 MB per tile), not by bytes in flight: 2 landing stages + 2 residual buffers measured
+        // best (355 us vs 385 us for 4 + 1 at k=32, q=16, 3.67 M edges)
+        if (X3 && Cfg::stages_for(X3, 1, 2) >= 2) { S = 2; L = 2; }
+        glt_env_cfg("NBPC_GLT_BWD", &ctas, &S, &L);
+        if (S < 1 || S > 8 || L < 1 || L > 8 || Cfg::smem_bytes(X3, S, L) > (size_t)Cfg::SMEM_MAX || ctas * Cfg::TMEM_COLS > 512) return -1;
+        grid_cache = glt_grid(kern, threads, Cfg::smem_bytes(X3, S, L), ctas);
     }
-    const size_t smem = Cfg::smem_bytes(X3, S);
+    const size_t smem = Cfg::smem_bytes(X3, S, L);
     if (grid_cache < 0) return -1;
     const int64_t ntiles = (c + GLT_TILE - 1) / GLT_TILE;
     const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
     NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_bwd_tf32x3" : "glt_edge_bwd_tf32", K, Q).c_str(), kern, grid, threads, smem, stream, tmH, tmZ, tmZ2,
-                  col, W1, Gc, Gr, c, M, dH, partial, S);
-    return grid * Cfg::P;
+                  col, W1, Gc, Gr, c, M, dH, partial, S, L);
+    return grid * Cfg::P * Cfg::nsets(X3);
     }
 }
 template <int K, int Q>
@@ -320,7 +361,7 @@ static int glt_launch_edge_bwd(const float *dZ, const float *H, const int32_t *c
     return nb;
 }
 
-int glt_max_partial_blocks() { return 2 * 2 * gl_num_sms(); }
+int glt_max_partial_blocks() { return 2 * 2 * 2 * gl_num_sms(); }
 
 // (k, q, mode) combinations whose stage ring fits shared memory at least twice; c must be a multiple of the packing
 bool glt_bwd_shape_ok(int k, int q, int x3, int64_t c) {

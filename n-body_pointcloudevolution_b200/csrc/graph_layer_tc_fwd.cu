@@ -13,11 +13,14 @@ struct GltFwdCfg {
     static constexpr int SMEM_MAX = 227 * 1024;
     __host__ __device__ static constexpr size_t fixed_bytes(bool x3) { return 1024 + (size_t)B_BYTES * (x3 ? 2 : 1) + OS_BYTES + 512; }
     // deepest stage ring (<= 8) that fits when `ctas` CTAs share an SM (each CTA also pays 1 KB of system shared memory)
-    __host__ __device__ static constexpr int stages_for(bool x3, int ctas) {
-        const int s = (int)((SMEM_MAX / ctas - 1024 - (int)fixed_bytes(x3)) / (A_STAGE * (x3 ? 2 : 1)));
+    // (the split mode also needs `lo` residual buffers of one stage each)
+    __host__ __device__ static constexpr int stages_for(bool x3, int ctas, int lo = 1) {
+        const int s = (int)((SMEM_MAX / ctas - 1024 - (int)fixed_bytes(x3) - (x3 ? lo * A_STAGE : 0)) / A_STAGE);
         return s > 8 ? 8 : s;
     }
-    __host__ __device__ static constexpr size_t smem_bytes(bool x3, int S) { return fixed_bytes(x3) + (size_t)S * A_STAGE * (x3 ? 2 : 1); }
+    __host__ __device__ static constexpr size_t smem_bytes(bool x3, int S, int L) {
+        return fixed_bytes(x3) + (size_t)S * A_STAGE + (x3 ? (size_t)L * A_STAGE : 0);
+    }
 };
 
 template <int K, int Q, bool RELU, bool X3>
@@ -26,32 +29,34 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_ou
                                                                                          const float *__restrict__ W1,
                                                                                          const float *__restrict__ Q_col,
                                                                                          const float *__restrict__ Q_row, int64_t c, int M,
-                                                                                         float *__restrict__ out, const int S) {
+                                                                                         float *__restrict__ out, const int S, const int L) {
     using Cfg = GltFwdCfg<K, Q>;
     using TA = typename Cfg::TA;
     constexpr int QS = Cfg::QS;
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
-    unsigned char *As = base;                                      // [S][A_STAGE]   raw -> hi
-    unsigned char *Al = As + S * Cfg::A_STAGE;                     // [S][A_STAGE]   lo (X3 only)
-    unsigned char *Bh = Al + (X3 ? S * Cfg::A_STAGE : 0);          // [B_BYTES]
+    unsigned char *As = base;                                      // [S][A_STAGE]   landed tiles (= the hi operand)
+    unsigned char *Al = As + S * Cfg::A_STAGE;                     // [L][A_STAGE]   residuals lo (X3 only)
+    unsigned char *Bh = Al + (X3 ? L * Cfg::A_STAGE : 0);          // [B_BYTES]
     unsigned char *Bl = Bh + Cfg::B_BYTES;                         // [B_BYTES]      (X3 only)
     float *Os = reinterpret_cast<float *>(Bh + Cfg::B_BYTES * (X3 ? 2 : 1));   // [128][QS]
     uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + Cfg::OS_BYTES);
-    // barriers: full[S] | empty[S] | conv[S] | tmem_full[2] | tmem_empty[2]
+    // barriers: full[S] | empty[S] | conv[L] | lofree[L] | tmem_full[2] | tmem_empty[2]   (S, L <= 8)
     const uint32_t bar0 = glt_smem_u32(bars);
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
-    auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };
-    auto TFULL = [&](int a) { return bar0 + 8u * (3 * S + a); };
-    auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * S + 2 + a); };
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + 4);
+    auto CONV = [&](int l) { return bar0 + 8u * (2 * S + l); };
+    auto LOFREE = [&](int l) { return bar0 + 8u * (2 * S + L + l); };
+    auto TFULL = [&](int a) { return bar0 + 8u * (2 * S + 2 * L + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (2 * S + 2 * L + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * S + 2 * L + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (int)((c + GLT_TILE - 1) / GLT_TILE), G = gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); }
+        for (int l = 0; l < L; ++l) { glt_mbar_init(CONV(l), 4); glt_mbar_init(LOFREE(l), 1); }
         for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
         glt_fence_barrier_init();
         glt_prefetch_tmap(&tmH);
@@ -81,13 +86,14 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_ou
     } else if (warp == 1) {
         if (lane == 0) {   // ---------------- MMA issuer
             constexpr uint32_t idesc = glt_idesc_tf32(GLT_TILE, Q, 0, 0);
-            int s = 0, ph = 0, a = 0, aph = 0;
+            int s = 0, ph = 0, a = 0, aph = 0, l = 0, lph = 0;
             for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(TEMPTY(a), aph ^ 1);
-                glt_mbar_wait(X3 ? CONV(s) : FULL(s), ph);
+                if constexpr (X3) glt_mbar_wait(CONV(l), lph);   // the residual is ready (its producer had waited for FULL(s))
+                else glt_mbar_wait(FULL(s), ph);
                 glt_tc_fence_after();
                 const uint32_t d = tmem_base + a * Q;
-                const uint32_t a_hi = glt_smem_u32(As + s * Cfg::A_STAGE), a_lo = glt_smem_u32(Al + s * Cfg::A_STAGE);
+                const uint32_t a_hi = glt_smem_u32(As + s * Cfg::A_STAGE), a_lo = glt_smem_u32(Al + l * Cfg::A_STAGE);
                 const uint32_t b_hi = glt_smem_u32(Bh), b_lo = glt_smem_u32(Bl);
                 uint32_t acc = 0;
 #pragma unroll
@@ -104,9 +110,11 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_ou
                         }
                 }
                 glt_tc_commit(EMPTY(s));    // the stage may be refilled once these MMAs have read it
+                if constexpr (X3) glt_tc_commit(LOFREE(l));
                 glt_tc_commit(TFULL(a));    // accumulator ready for the epilogue
                 if (++s == S) { s = 0; ph ^= 1; }
                 if (++a == 2) { a = 0; aph ^= 1; }
+                if (++l == L) { l = 0; lph ^= 1; }
             }
         }
     } else if (warp < 6) {
@@ -120,14 +128,26 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_ou
             const int64_t e = (int64_t)t * GLT_TILE + row;
             return (t < ntiles && e < c) ? __ldg(&col[e]) : -1;
         };
-        auto gather = [&](int t, int cidx, float *dst) {
+        // raw Q_col[col] rows of the NEXT tile are kept in registers un-added (an add would wait for the loads right
+        // away); the Q_row[e / M] rows are shared by M consecutive edges and are re-read at use time (L1 hits)
+        auto gather_col = [&](int cidx, float *dst) {
             if (cidx >= 0) {
-                const int64_t e = (int64_t)t * GLT_TILE + row;
-                const float *qc = Q_col + (int64_t)cidx * Q, *qr = Q_row + edge_row(e) * Q;
+                const float *qc = Q_col + (int64_t)cidx * Q;
 #pragma unroll
                 for (int j = 0; j < Q / 4; ++j) {
-                    const float4 x = glf_ldg4(qc + 4 * j), y = glf_ldg4(qr + 4 * j);
-                    dst[4 * j] = x.x + y.x; dst[4 * j + 1] = x.y + y.y; dst[4 * j + 2] = x.z + y.z; dst[4 * j + 3] = x.w + y.w;
+                    const float4 x = glf_ldg4(qc + 4 * j);
+                    dst[4 * j] = x.x; dst[4 * j + 1] = x.y; dst[4 * j + 2] = x.z; dst[4 * j + 3] = x.w;
+                }
+            }
+        };
+        auto add_row = [&](int t, float *dst) {
+            const int64_t e = (int64_t)t * GLT_TILE + row;
+            if (e < c) {
+                const float *qr = Q_row + edge_row(e) * Q;
+#pragma unroll
+                for (int j = 0; j < Q / 4; ++j) {
+                    const float4 y = glf_ldg4(qr + 4 * j);
+                    dst[4 * j] += y.x; dst[4 * j + 1] += y.y; dst[4 * j + 2] += y.z; dst[4 * j + 3] += y.w;
                 }
             }
         };
@@ -136,11 +156,12 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_ou
         float cur[Q], nxt[Q];
 #pragma unroll
         for (int j = 0; j < Q; ++j) cur[j] = nxt[j] = 0.f;
-        gather(t, load_col(t), cur);
+        gather_col(load_col(t), cur);
         int c_next = load_col(t + G);
         for (; t < ntiles; t += G) {
-            gather(t + G, c_next, nxt);
+            gather_col(c_next, nxt);
             c_next = load_col(t + 2 * G);
+            add_row(t, cur);
             const int64_t e0 = (int64_t)t * GLT_TILE;
             glt_mbar_wait(TFULL(a), aph);
             glt_tc_fence_after();
@@ -171,15 +192,17 @@ __global__ void __launch_bounds__(X3 ? GLT_THREADS_X3 : GLT_THREADS) glt_edge_ou
         // ---------------- converter warps (X3 only): split the landed tile into TF32 hi / lo in place
         if constexpr (X3) {
             const int wtid = tid - 192;
-            int s = 0, ph = 0;
+            int s = 0, ph = 0, l = 0, lph = 0;
             for (int t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(FULL(s), ph);
-                glt_split_inplace(reinterpret_cast<float *>(As + s * Cfg::A_STAGE), reinterpret_cast<float *>(Al + s * Cfg::A_STAGE),
-                                  Cfg::A_STAGE / 4, wtid, 128);
+                glt_mbar_wait(LOFREE(l), lph ^ 1);
+                glt_split_inplace<Cfg::A_STAGE / 4>(reinterpret_cast<const float *>(As + s * Cfg::A_STAGE),
+                                                    reinterpret_cast<float *>(Al + l * Cfg::A_STAGE), wtid);
                 glt_fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) glt_mbar_arrive(CONV(s));
+                if (lane == 0) glt_mbar_arrive(CONV(l));
                 if (++s == S) { s = 0; ph ^= 1; }
+                if (++l == L) { l = 0; lph ^= 1; }
             }
         }
     }
@@ -204,23 +227,23 @@ static int glt_launch_edge_out_t(const float *H, const int32_t *col, const float
     // CTAs per SM / ring depth: as many CTAs (<= 4) as keep a 2-deep ring: each CTA is an independent
     // load -> MMA -> epilogue pipeline, so co-resident CTAs hide each other's latencies (measured on B200, k=32 q=16, 3.67 M
     // edges: 1 CTA x 4 stages 272 us, 2 x 4 170 us, 3 x 3 150 us, 4 x 2 148 us).  NBPC_GLT_FWD="ctas,stages" overrides.
-    static int grid_cache = 0, S = 0;
+    static int grid_cache = 0, S = 0, L = 1;
     if (!grid_cache) {
         int ctas = 1;
         for (int t = 4; t >= 1; --t)
             if (Cfg::stages_for(X3, t) >= 2 && t * Cfg::TMEM_COLS <= 512) { ctas = t; break; }
         S = Cfg::stages_for(X3, ctas);
         S = S > 4 ? 4 : S;
-        glt_env_cfg("NBPC_GLT_FWD", &ctas, &S);
-        if (S < 1 || S > Cfg::stages_for(X3, 1)) return 1;
-        grid_cache = glt_grid(kern, threads, Cfg::smem_bytes(X3, S), ctas);
+        glt_env_cfg("NBPC_GLT_FWD", &ctas, &S, &L);
+        if (S < 1 || S > 8 || L < 1 || L > 8 || Cfg::smem_bytes(X3, S, L) > (size_t)Cfg::SMEM_MAX) return 1;
+        grid_cache = glt_grid(kern, threads, Cfg::smem_bytes(X3, S, L), ctas);
     }
-    const size_t smem = Cfg::smem_bytes(X3, S);
+    const size_t smem = Cfg::smem_bytes(X3, S, L);
     if (grid_cache < 0) return 1;
     const int64_t ntiles = (c + GLT_TILE - 1) / GLT_TILE;
     const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
     NBPC_LAUNCH_N(NbpcKName(X3 ? "glt_edge_out_tf32x3" : "glt_edge_out_tf32", K, Q).c_str(), kern, grid, threads, smem, stream, tm, col, W1, Qc,
-                  Qr, c, M, out, S);
+                  Qr, c, M, out, S, L);
     return 0;
     }
 }

@@ -428,7 +428,13 @@ def test_graph_layer_shapes_vs_oracle(nb, k, q, is_last, relu):
     Bc = torch.tensor(Bv, dtype=torch.float64, requires_grad=True)
     oc = ref_layers.shift_inv_layer(Hc, coo_np, (b, N), (Wc, Bc), is_last=is_last)
     if relu:
-        oc = torch.relu(oc)
+        # ReLU'(z) is discontinuous at 0: a pre-activation within rounding noise of zero may legitimately land on the
+        # other side, and ONE flipped mask bit moves every gradient of its sample through the cube pool.  The oracle
+        # therefore uses the device's mask, after checking that it differs from its own only at such |z| < 2e-5.
+        mask_dev = torch.tensor(o.detach().cpu().numpy() > 0)
+        flips = mask_dev != (oc.detach() > 0)
+        assert int(flips.sum()) <= 4 and (not flips.any() or float(oc.detach().abs()[flips].max()) < 2e-5)
+        oc = oc * mask_dev.double()
     (oc * torch.tensor(gout, dtype=torch.float64)).sum().backward()
 
     np.testing.assert_allclose(o.detach().cpu().numpy(), oc.detach().numpy(), rtol=2e-5, atol=2e-5)

@@ -12,6 +12,7 @@ ap.add_argument("--b", type=int, default=8)
 ap.add_argument("--m", type=int, default=14)
 ap.add_argument("--shape", default="32,16")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--nomask", action="store_true")
 a = ap.parse_args()
 dev = "cuda"
 torch.manual_seed(0)
@@ -30,7 +31,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def run():
     Z, Pc, Pr, Pq = ops.graph_layer_fwd(H, col, csrT_ptr, csrT_edge, W, bias, B, N, M, False, True)
     flush.zero_()
-    ops.graph_layer_bwd(g, H, Z, col, csrT_ptr, csrT_edge, W, Pc, Pr, Pq, B, N, M, False, False, True, True)
+    ops.graph_layer_bwd(g, H, Z, col, csrT_ptr, csrT_edge, W, Pc, Pr, Pq, B, N, M, False, False, not a.nomask, True)
     flush.zero_()
 for _ in range(3):
     run()
