@@ -364,6 +364,165 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
         if (m >= K - P.k) P.idx_out[out + (m - (K - P.k))] = top.id[m];
 }
 
+// ------------------------------------------------------------------ 3b. query, warp-uniform control flow
+// Same traversal, same pruning and the same total order as knn_query, but every loop has a warp-uniform trip count (the
+// shell radius runs until the LAST lane of the warp is done, a row segment is walked for the longest lane's length,
+// shorter or pruned lanes are predicated off), so the warp stays converged and the expensive sorted insertion can be
+// DEFERRED: a candidate that beats the lane's (possibly stale) k-th best is parked in a 4-deep per-lane queue in
+// shared memory, and the queues are drained by all lanes together when some lane's queue is full or a shell ends.
+// In knn_query the insertion (~120 predicated instructions) ran whenever ANY lane accepted a candidate - on nearly
+// every candidate with one or two lanes active (ncu: 10 of 32 lanes active per instruction on average).
+#ifndef NBPC_HOST_EMU
+template <int K, bool PERIODIC>
+__global__ void __launch_bounds__(KNN_THREADS) knn_query_uniform(KnnQueryParams P) {
+    constexpr unsigned FULLM = 0xffffffffu;
+    __shared__ double pend_d_s[KNN_PEND * KNN_THREADS];
+    __shared__ int pend_i_s[KNN_PEND * KNN_THREADS];
+    double *pend_d = pend_d_s + threadIdx.x;
+    int *pend_i = pend_i_s + threadIdx.x;
+    int npend = 0;
+
+    const int64_t total = (int64_t)P.B * P.N;
+    const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s_raw < total;
+    const int64_t s = valid ? s_raw : total - 1;       // tail lanes shadow the last query and never write
+    const int b = (int)(s / P.N);
+    const int G = P.G;
+    const KnnGridInfo gi = P.info[b];
+    const float4 me = P.sorted[s];
+    const int my_id = __float_as_int(me.w) & KNN_IDX_MASK;
+    const double px = (double)me.x, py = (double)me.y, pz = (double)me.z;
+    const int cx = knn_cell_coord(me.x, gi.lo[0], gi.inv_h, G);
+    const int cy = knn_cell_coord(me.y, gi.lo[1], gi.inv_h, G);
+    const int cz = knn_cell_coord(me.z, gi.lo[2], gi.inv_h, G);
+    const float frx = fminf(fmaxf((me.x - gi.lo[0]) * gi.inv_h - (float)cx, 0.f), 1.f);
+    const float fry = fminf(fmaxf((me.y - gi.lo[1]) * gi.inv_h - (float)cy, 0.f), 1.f);
+    const float frz = fminf(fmaxf((me.z - gi.lo[2]) * gi.inv_h - (float)cz, 0.f), 1.f);
+    const float margin = fminf(fminf(fminf(frx, 1.f - frx), fminf(fry, 1.f - fry)), fminf(frz, 1.f - frz));
+    const float inv_h2 = gi.inv_h * gi.inv_h * 1.0001f;
+    const int tmin = PERIODIC ? -G : 0, tmax = PERIODIC ? 2 * G - 1 : G - 1;
+    const int Rmax = nbpc_max(nbpc_max(cx - tmin, tmax - cx), nbpc_max(nbpc_max(cy - tmin, tmax - cy), nbpc_max(cz - tmin, tmax - cz)));
+    const int64_t cellbase = (int64_t)b * G * G * G;
+    const bool skip_self = !P.include_self;
+
+    KnnTopK<K> top;
+    top.init(P.k);
+    auto flush = [&]() {
+#pragma unroll
+        for (int f = 0; f < KNN_PEND; ++f) {
+            if (f < npend) {
+                const double fd = pend_d[f * KNN_THREADS];
+                const int fi = pend_i[f * KNN_THREADS];
+                if (top.accepts(fd, fi)) top.insert(fd, fi);
+            }
+        }
+        npend = 0;
+    };
+
+    bool done = !valid;
+    for (int R = 0;; ++R) {
+        const bool act = !done && R <= Rmax;
+        if (!__any_sync(FULLM, act)) break;
+        for (int dz = -R; dz <= R; ++dz) {
+            int tz = cz + dz;
+            bool plane_ok = act && tz >= tmin && tz <= tmax;
+            int sz = 0;
+            if (PERIODIC) {
+                if (tz < 0) { tz += G; sz = -1; } else if (tz >= G) { tz -= G; sz = 1; }
+            }
+            const bool zface = (dz == -R || dz == R);
+            const float gz = KNN_GAP(dz, frz);
+            plane_ok = plane_ok && !(gz * gz > (float)top.d[K - 1] * inv_h2);
+            if (!__any_sync(FULLM, plane_ok)) continue;
+            for (int dy = -R; dy <= R; ++dy) {
+                int ty = cy + dy;
+                bool row_ok = plane_ok && ty >= tmin && ty <= tmax;
+                const float gy = KNN_GAP(dy, fry);
+                const float rem = (float)top.d[K - 1] * inv_h2 - (gz * gz + gy * gy);
+                row_ok = row_ok && !(rem < 0.f);
+                if (!__any_sync(FULLM, row_ok)) continue;
+                const float xr = fminf(sqrtf(fmaxf(rem, 0.f)) + 1e-3f, 8192.f);
+                const int x_lo = (int)floorf((float)cx + frx - xr), x_hi = (int)floorf((float)cx + frx + xr);
+                int sy = 0;
+                if (PERIODIC) {
+                    if (ty < 0) { ty += G; sy = -1; } else if (ty >= G) { ty -= G; sy = 1; }
+                }
+                const bool full_row = zface || dy == -R || dy == R;   // warp-uniform
+                const int64_t rowbase = cellbase + ((int64_t)tz * G + ty) * G;
+                const int nparts = full_row ? 1 : 2;
+                for (int part = 0; part < nparts; ++part) {
+                    int x0 = full_row ? cx - R : (part == 0 ? cx - R : cx + R);
+                    int x1 = full_row ? cx + R : x0;
+                    bool part_ok = row_ok;
+                    if (full_row) {
+                        x0 = nbpc_max(x0, nbpc_max(tmin, x_lo));
+                        x1 = nbpc_min(x1, nbpc_min(tmax, x_hi));
+                    } else if (x0 < tmin || x0 > tmax || x0 < x_lo || x0 > x_hi) {
+                        part_ok = false;
+                    }
+                    const int nseg = PERIODIC ? 3 : 1;
+                    for (int seg = 0; seg < nseg; ++seg) {
+                        const int sx = PERIODIC ? seg - 1 : 0;
+                        const int lo = nbpc_max(x0, sx * G), hi = nbpc_min(x1, sx * G + G - 1);
+                        int jb = 0, je = 0;
+                        if (part_ok && lo <= hi) {
+                            jb = __ldg(&P.cell_start[rowbase + (lo - sx * G)]);
+                            je = __ldg(&P.cell_start[rowbase + (hi - sx * G) + 1]);
+                        }
+                        const int len = je - jb;
+                        const int maxlen = __reduce_max_sync(FULLM, len);
+                        if (maxlen <= 0) continue;
+                        int req = 0, reqmask = 0;
+                        if (PERIODIC) {
+                            if (sx) { reqmask |= 3; req |= (sx > 0 ? 1 : 2); }
+                            if (sy) { reqmask |= 3 << 2; req |= (sy > 0 ? 1 : 2) << 2; }
+                            if (sz) { reqmask |= 3 << 4; req |= (sz > 0 ? 1 : 2) << 4; }
+                        }
+                        const bool unshifted = (sx | sy | sz) == 0;
+                        const double ox = (double)sx, oy = (double)sy, oz = (double)sz;
+                        for (int i = 0; i < maxlen; ++i) {
+                            if (i < len) {
+                                const float4 c = __ldg(&P.sorted[jb + i]);
+                                const int w = __float_as_int(c.w);
+                                const int cid = w & KNN_IDX_MASK;
+                                bool take = !(PERIODIC && (((w >> KNN_FLAG_SHIFT) & reqmask) != req));
+                                take = take && !(skip_self && unshifted && cid == my_id);
+                                const double tx = __dsub_rn(px, __dadd_rn((double)c.x, ox));
+                                const double ty2 = __dsub_rn(py, __dadd_rn((double)c.y, oy));
+                                const double tz2 = __dsub_rn(pz, __dadd_rn((double)c.z, oz));
+                                const double dd = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty2, ty2)), __dmul_rn(tz2, tz2));
+                                if (take && top.accepts(dd, cid)) {
+                                    pend_d[npend * KNN_THREADS] = dd;
+                                    pend_i[npend * KNN_THREADS] = cid;
+                                    ++npend;
+                                }
+                            }
+                            if (__any_sync(FULLM, npend == KNN_PEND)) flush();
+                        }
+                    }
+                }
+            }
+        }
+        if (__any_sync(FULLM, npend > 0)) flush();   // the termination test needs the true k-th best
+        const double g = ((double)R + (double)margin - 1e-3) * gi.h;
+        if (act && g > 0.0 && top.d[K - 1] < g * g) done = true;
+        if (R >= Rmax) done = true;
+    }
+
+    if (!valid) return;
+    const int64_t out = ((int64_t)b * P.N + my_id) * P.k;
+    if (P.d2_out) {
+#pragma unroll
+        for (int m = 0; m < K; ++m)
+            if (m >= K - P.k) P.d2_out[out + (m - (K - P.k))] = top.d[m];
+    }
+    if (P.order == NBPC_ORDER_INDEX) top.sort_ids_ascending();
+#pragma unroll
+    for (int m = 0; m < K; ++m)
+        if (m >= K - P.k) P.idx_out[out + (m - (K - P.k))] = top.id[m];
+}
+#endif
+
 // ------------------------------------------------------------------ host side
 static int knn_grid_cells(int N) {
     // ~1 particle per cell by default (NBPC_KNN_RHO overrides): with the per-row pruning above a query
@@ -409,6 +568,19 @@ static KnnWorkspace knn_carve(void *ws, size_t ws_bytes, int B, int N, int G) {
 template <int K>
 static void knn_launch_query(const KnnQueryParams &P, int periodic, cudaStream_t stream) {
     const int grid = nbpc_cdiv((int64_t)P.B * P.N, KNN_THREADS);
+#ifndef NBPC_HOST_EMU
+    // warp-uniform kernel with deferred insertion by default; NBPC_KNN_V=1 selects the per-thread traversal
+    static int version = 0;
+    if (!version) {
+        const char *e = getenv("NBPC_KNN_V");
+        version = (e && atoi(e) == 1) ? 1 : 2;
+    }
+    if (version == 2) {
+        void (*kern2)(KnnQueryParams) = periodic ? knn_query_uniform<K, true> : knn_query_uniform<K, false>;
+        NBPC_LAUNCH_N("knn_query", kern2, grid, KNN_THREADS, 0, stream, P);
+        return;
+    }
+#endif
     void (*kern)(KnnQueryParams) = periodic ? knn_query<K, true> : knn_query<K, false>;
     NBPC_LAUNCH_N("knn_query", kern, grid, KNN_THREADS, 0, stream, P);
 }
