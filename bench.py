@@ -202,25 +202,33 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
     relu = 2 if (k, q) in relu_by_layer and relu_by_layer[(k, q)] else 1   # masked dZ also reads H_out
     if base == "knn_query":
         return n * (12 + 4 * M)                      # xyz in, int32 idx out
-    if base in ("gl_pool_kernel", "glf_pool_kernel"):          # H read for the row pool + gathered for the col pool
-        return c * (2 * 4 * k + 4) + n * (4 + 2 * 4 * k)
-    if base in ("gl_edge_out_kernel", "glf_edge_out_kernel"):  # H in, col in, H_out out (+ node tables)
-        return c * (4 * k + 4 + 4 * q) + n * 2 * 4 * q
+    if base in ("gl_pool_kernel", "glf_pool_kernel", "gln_pool_kernel", "gln_pool_generic_kernel"):
+        return c * (2 * 4 * k + 4) + n * (4 + 2 * 4 * k)       # H read for the row pool + gathered for the col pool
+    if base in ("gl_edge_out_kernel", "glf_edge_out_kernel", "glk3_edge_out_kernel", "glt_edge_out_tf32", "glt_edge_out_tf32x3"):
+        return c * (4 * k + 4 + 4 * q) + n * 2 * 4 * q         # H in, col in, H_out out (+ node tables)
     if base == "gl_last_out_kernel":
         return c * (4 * k + 4) + n * 3 * 4 * q
     if base == "glf_last_out_kernel":
         return c * 4 + n * (4 * k + 3 * 4 * q)
-    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel"):     # dZ read twice (row sums + gathered); the network
-        return c * (2 * 4 * q + 4) + n * (4 + 2 * 4 * q)       # path delivers dZ pre-masked (no H_out read)
+    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel", "gln_bwd_pool_kernel"):   # dZ read twice (row sums + gathered);
+        return c * (2 * 4 * q + 4) + n * (4 + 2 * 4 * q)       # the network path delivers dZ pre-masked (no H_out read)
     if base == "xty_partial_dW1":
         return c * (4 * k + 4 * q * relu)
     if base == "glb_edge_in_kernel":
         return c * (4 * q * relu + 4 + 4 * k) + n * 2 * 4 * k
-    if base == "glf_edge_bwd_kernel":                          # dZ + H in, dH out (not for the first layer), col
+    if base in ("glf_edge_bwd_kernel", "glt_edge_bwd_tf32", "glt_edge_bwd_tf32x3"):   # dZ + H in, dH out (not for layer 1), col
         first = (k == 3)
         return c * (4 * q + 4 * k + (0 if first else 4 * k + 4)) + (0 if first else n * 2 * 4 * k)
+    if base == "glk3_edge_dw_kernel":                          # first layer: E (c,3) and dZ in, dW1 out
+        return c * (12 + 4 * q)
     if base == "glf_last_edge_in_kernel":                      # col in, H (mask) in, dH out
         return c * (4 + 2 * 4 * k) + n * 2 * 4 * k
+    if base == "gln_node_project_kernel":                      # P_col, P_row in; Q_col, Q_row out
+        return n * (2 * 4 * k + 2 * 4 * q)
+    if base == "gln_node_grad_kernel":                         # dQ_col, dQ_row, in-degree in; G_col, G_row out
+        return n * (2 * 4 * q + 2 * 4 * k + 4)
+    if base in ("glf_node_xty_dW2", "glf_node_xty_dW3"):       # node tensors X (n,k) and Y (n,q), once per layer
+        return None
     if base == "edge_features_kernel":
         return c * (4 + 12) + n * 12
     if base in ("adj_coo_kernel",):
