@@ -464,6 +464,38 @@ def main():
             extras[f"knn_128^3_{kind}_roofline_frac"] = ab / (t_ms * 1e-3) / 1e9 / peak
             del xb
 
+        # BASELINE config 5: 128^3-particle multi-redshift rollout INFERENCE, periodic kNN graph rebuilt every step
+        # (graph.rollout_shift_inv: pbc kNN -> 9-channel edges -> [9,32,16,6] graph net -> scaled residual -> readout)
+        try:
+            n5 = 128 ** 3
+            rng = np.random.default_rng(5)
+            X5 = np.concatenate([syn.make_box("uniform", 1, n5, 0), 0.01 * rng.standard_normal((1, n5, 3)).astype(np.float32)], axis=-1)
+            X5 = torch.from_numpy(np.ascontiguousarray(X5, dtype=np.float32)).to(dev)
+            ch5 = [9, 32, 16, 6]
+            st5 = tu.ParamStore(ch5, device=dev)
+            st5.load_numpy(syn.glorot_params(ch5))
+            mv5 = types.SimpleNamespace(channels=ch5, var_scope="params", get_layer_vars=st5.get_layer_vars,
+                                        get_scalars=lambda: (0.01, 0.01))
+            with torch.no_grad():
+                Xc = X5
+                for _ in range(2):
+                    Xc = graph.rollout_shift_inv(Xc, mv5, 14, 0.05)
+                torch.cuda.synchronize()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+                reps = 5
+                for _ in range(reps):
+                    Xc = graph.rollout_shift_inv(Xc, mv5, 14, 0.05)
+                ev[1].record()
+                torch.cuda.synchronize()
+            t5 = ev[0].elapsed_time(ev[1]) / reps
+            extras["rollout_128^3"] = {"ms_per_rollout_step": t5, "particles_per_s": n5 / (t5 * 1e-3), "channels": ch5, "k": 14,
+                                       "boundary_threshold": 0.05, "finite": bool(torch.isfinite(Xc).all()),
+                                       "what": "inference, periodic kNN rebuilt every step, FP64 kNN distances, tf32x3/fp32 layers"}
+            del X5, Xc
+        except Exception as exc:   # the headline line must survive a failure of this extra
+            extras["rollout_128^3"] = {"error": repr(exc)[:300]}
+
     # ---- the reference's CPU path on this box's host cores (bounded sample)
     cpu = None
     if not a.no_cpu_baseline and world == 1:

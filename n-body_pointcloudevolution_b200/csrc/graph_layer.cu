@@ -449,35 +449,36 @@ static int glf_node_xty(const char *name, const float *X, const float *Y, int64_
 #include "graph_layer_k3.cuh"
 
 #ifndef NBPC_HOST_EMU
-// ---- first-layer (k = 3) streaming kernels
-static bool glk3_shape_ok(int k, int q) { return k == 3 && (q == 16 || q == 32 || q == 64); }
-static void glk3_launch_edge_out(int q, const float *E, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c,
-                                 int M, int relu, float *out, cudaStream_t stream) {
+// ---- first-layer (k = 3 / 9 / 10) streaming kernels
+static bool glk3_shape_ok(int k, int q) { return (k == 3 || k == 9 || k == 10) && (q == 16 || q == 32 || q == 64); }
+#define GLK3_FOR_KQ(X) X(3, 16) X(3, 32) X(3, 64) X(9, 16) X(9, 32) X(9, 64) X(10, 16) X(10, 32) X(10, 64)
+static void glk3_launch_edge_out(int k, int q, const float *E, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
+                                 int64_t c, int M, int relu, float *out, cudaStream_t stream) {
     const uint32_t magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)M);
-#define X(Q_)                                                                                                              \
-    if (q == Q_) {                                                                                                        \
-        const int epb = GLK3_THREADS / (Q_ / 4) * GLK3_UNROLL;                                                            \
+#define X(K_, Q_)                                                                                                          \
+    if (k == K_ && q == Q_) {                                                                                             \
+        const int epb = GLK3_THREADS / (Q_ / 4) * glk3_unroll(K_);                                                        \
         const int grid = (int)((c + epb - 1) / epb);                                                                      \
-        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_kernel", 3, q).c_str(), (glk3_edge_out_kernel<Q_, true>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)c, (uint32_t)M, magic, out); \
-        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_kernel", 3, q).c_str(), (glk3_edge_out_kernel<Q_, false>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)c, (uint32_t)M, magic, out); \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_kernel", k, q).c_str(), (glk3_edge_out_kernel<K_, Q_, true>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)c, (uint32_t)M, magic, out); \
+        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_kernel", k, q).c_str(), (glk3_edge_out_kernel<K_, Q_, false>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)c, (uint32_t)M, magic, out); \
     }
-    X(16) X(32) X(64)
+    GLK3_FOR_KQ(X)
 #undef X
 }
 // dW1 = E^T dZ; returns the number of per-block partials
-static int glk3_launch_edge_dw(int q, const float *E, const float *dOut, const float *Hout, int64_t c, int relu, float *partial,
+static int glk3_launch_edge_dw(int k, int q, const float *E, const float *dOut, const float *Hout, int64_t c, int relu, float *partial,
                                cudaStream_t stream) {
     int nb = 0;
-#define X(Q_)                                                                                                              \
-    if (q == Q_) {                                                                                                        \
-        const int64_t unit = GLK3_THREADS / (Q_ / 4) * GLK3_UNROLL;                                                       \
+#define X(K_, Q_)                                                                                                          \
+    if (k == K_ && q == Q_) {                                                                                             \
+        const int64_t unit = GLK3_THREADS / (Q_ / 4) * glk3_unroll(K_);                                                   \
         int64_t epb = (c + gl_num_sms() * 8 - 1) / (gl_num_sms() * 8);                                                    \
         epb = (epb + unit - 1) / unit * unit;                                                                             \
         nb = (int)((c + epb - 1) / epb);                                                                                  \
-        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_dw_kernel", 3, q).c_str(), (glk3_edge_dw_kernel<Q_, true>), nb, GLK3_THREADS, 0, stream, E, dOut, Hout, (uint32_t)c, (uint32_t)epb, partial); \
-        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_dw_kernel", 3, q).c_str(), (glk3_edge_dw_kernel<Q_, false>), nb, GLK3_THREADS, 0, stream, E, dOut, Hout, (uint32_t)c, (uint32_t)epb, partial); \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_dw_kernel", k, q).c_str(), (glk3_edge_dw_kernel<K_, Q_, true>), nb, GLK3_THREADS, 0, stream, E, dOut, Hout, (uint32_t)c, (uint32_t)epb, partial); \
+        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_dw_kernel", k, q).c_str(), (glk3_edge_dw_kernel<K_, Q_, false>), nb, GLK3_THREADS, 0, stream, E, dOut, Hout, (uint32_t)c, (uint32_t)epb, partial); \
     }
-    X(16) X(32) X(64)
+    GLK3_FOR_KQ(X)
 #undef X
     return nb;
 }
@@ -504,8 +505,8 @@ static void gl_colsum(const float *X, int ch, int N, int B, int nblk, float divi
 #ifndef NBPC_HOST_EMU
 // ================================================================== fused node-level pipeline (graph_layer_node.cuh)
 #define GLN_FOR_KQ(X)                                                                                                   \
-    X(3, 16) X(3, 32) X(3, 64) X(16, 3) X(16, 16) X(16, 32) X(16, 64) X(32, 3) X(32, 16) X(32, 32) X(32, 64) X(64, 3) X(64, 16) \
-    X(64, 32) X(64, 64)
+    X(3, 16) X(3, 32) X(3, 64) X(9, 16) X(9, 32) X(9, 64) X(10, 16) X(10, 32) X(10, 64) X(16, 3) X(16, 6) X(16, 16) X(16, 32) X(16, 64) \
+    X(32, 3) X(32, 6) X(32, 16) X(32, 32) X(32, 64) X(64, 3) X(64, 6) X(64, 16) X(64, 32) X(64, 64)
 static bool gln_shape_ok(int k, int q) {
 #define X(K_, Q_) if (k == K_ && q == Q_) return true;
     GLN_FOR_KQ(X)
@@ -562,7 +563,7 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (glk3_shape_ok(k, q)) {
-        glk3_launch_edge_out(q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+        glk3_launch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     int rc = 1;
@@ -580,7 +581,7 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
 static bool gl_fused_ok(int k, int q, int is_last) {
     if (!gln_shape_ok(k, q)) return false;
     if (is_last) return true;                       // node-level output
-    return glf_edge_shape_ok(k, q);                 // q in {16,32,64}
+    return glf_edge_shape_ok(k, q) || glk3_shape_ok(k, q);
 }
 
 static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out, const int32_t *col, const int32_t *csrT_ptr,
@@ -647,7 +648,7 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
         fa.part[0] = w.xty_partial; fa.n[0] = nb;
     } else if (!dH_in && glk3_shape_ok(k, q)) {
         fa.part[0] = w.xty_partial;
-        fa.n[0] = glk3_launch_edge_dw(q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
+        fa.n[0] = glk3_launch_edge_dw(k, q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
     } else {
         int rc = 1, nb = 0;
 #define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, nullptr, stream, &nb);
@@ -811,7 +812,7 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (fast && glk3_shape_ok(k, q)) {
-        glk3_launch_edge_out(q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+        glk3_launch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (fast && glf_edge_shape_ok(k, q)) {
@@ -961,7 +962,7 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
         return nbpc_check_launch("nbpc_graph_layer_bwd");
     }
     if (fast && !is_last && !dH_in && glk3_shape_ok(k, q)) {
-        const int nb = glk3_launch_edge_dw(q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
+        const int nb = glk3_launch_edge_dw(k, q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
         glf_reduce_partials(w.xty_partial, nb, k, q, 0, dW, stream);
         return nbpc_check_launch("nbpc_graph_layer_bwd");
     }

@@ -25,6 +25,7 @@ __all__ = [
     "get_indices_from_list_CSR", "to_coo_batch_ZA_diag", "to_coo_batch", "confirm_CSR_to_COO_index_integrity",
     "include_node_features", "get_input_features_shift_inv_ZA", "get_input_features_shift_inv",
     "shift_inv_conv", "shift_inv_layer", "network_func_shift_inv_za", "model_func_shift_inv_za",
+    "network_func_shift_inv", "model_func_shift_inv", "rollout_shift_inv",
 ]
 
 
@@ -293,15 +294,14 @@ def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
     return _layer(_to_cuda(H_in, torch.float32), COO_feats, bN, layer_vars, is_last, False)
 
 
-def network_func_shift_inv_za(edges, coo, num_layers, dims, activation, model_vars):
-    """graph.py:463-476.  A ReLU activation is fused into the layer kernel; any other callable is
-    applied to the un-activated layer output."""
+def _network(H0, coo, num_layers, dims, activation, model_vars):
+    """Layer loop shared by the network functions.  A ReLU activation is fused into the layer kernel; any other
+    callable is applied to the un-activated layer output."""
     fuse = _is_relu(activation)
     # inside this function every hidden tensor has exactly one consumer (the next layer), so the ReLU
     # backward of layer l is applied by layer l+1's edge kernel (input_relu) and layer l skips its own mask
     chain = fuse and num_layers > 1
-    H = _layer(_to_cuda(edges, torch.float32), coo, dims, model_vars.get_layer_vars(0), False, fuse,
-               input_relu=False, grad_premasked=chain)
+    H = _layer(H0, coo, dims, model_vars.get_layer_vars(0), False, fuse, input_relu=False, grad_premasked=chain)
     if not fuse:
         H = activation(H)
     for layer_idx in range(1, num_layers):
@@ -311,6 +311,59 @@ def network_func_shift_inv_za(edges, coo, num_layers, dims, activation, model_va
         if not is_last and not fuse:
             H = activation(H)
     return H
+
+
+def network_func_shift_inv_za(edges, coo, num_layers, dims, activation, model_vars):
+    """graph.py:463-476."""
+    return _network(_to_cuda(edges, torch.float32), coo, num_layers, dims, activation, model_vars)
+
+
+def network_func_shift_inv(X_in_edges, X_in_nodes, COO_feats, num_layers, dims, activation, model_vars, redshift=None):
+    """graph.py:517-533 (the multi-redshift network; kept in a commented-out block by the reference): the input layer
+    sees [relative position, velocity of the row node, velocity of the column node (, redshift)] = 9 | 10 channels."""
+    H_in = include_node_features(X_in_edges, X_in_nodes, COO_feats, redshift=redshift)
+    return _network(H_in, COO_feats, num_layers, dims, activation, model_vars)
+
+
+def model_func_shift_inv(X_in, COO_feats, model_vars, dims, activation=torch.relu, redshift=None):
+    """graph.py:536-567 (commented-out block): X_in (b,N,6) = [position, velocity] at one redshift -> the prediction
+    at the next one, (b,N,6) (or (b,N,3) for a 3-channel network): loc' = net[:3]*loc_scalar + loc + vel*vel_scalar,
+    vel' = net[3:]*vel_scalar + vel, with (loc_scalar, vel_scalar) = model_vars.get_scalars()."""
+    num_layers = len(model_vars.channels) - 1
+    X = _to_cuda(X_in, torch.float32)
+    edges, nodes = get_input_features_shift_inv(X, COO_feats, dims)
+    net_out = network_func_shift_inv(edges, nodes, COO_feats, num_layers, dims[:-1], activation, model_vars, redshift)
+    loc_scalar, vel_scalar = model_vars.get_scalars()
+    loc, vel = X[..., :3], X[..., 3:]
+    H_out = net_out[..., :3] * loc_scalar + loc + vel * vel_scalar
+    if net_out.shape[-1] > 3:
+        H_out = torch.cat([H_out, net_out[..., 3:] * vel_scalar + vel], dim=-1)
+    return H_out
+
+
+def rollout_shift_inv(X0, model_vars_per_step, K, boundary_threshold, redshifts=None, activation=torch.relu,
+                      include_self=False, trajectory=False):
+    """Multi-redshift rollout (BASELINE config 5): for every step the periodic kNN graph is REBUILT on the
+    current positions (get_pbc_kneighbors_csr, graph.py:896-917), the network predicts the next [position, velocity]
+    (model_func_shift_inv) and nn.get_readout (nn.py:107-119) wraps the positions back into the unit box.
+    model_vars_per_step: one model_vars per step (or a single one used for every step); redshifts: optional sequence
+    of scalars appended as a 10th input channel.  Returns the final state (b,N,6), or all states if trajectory."""
+    from . import nn as _nn
+    X = _to_cuda(X0, torch.float32)
+    b, N = X.shape[0], X.shape[1]
+    steps = len(model_vars_per_step) if isinstance(model_vars_per_step, (list, tuple)) else (len(redshifts) if redshifts is not None else 1)
+    states = []
+    for i in range(steps):
+        mv = model_vars_per_step[i] if isinstance(model_vars_per_step, (list, tuple)) else model_vars_per_step
+        A = get_pbc_kneighbors_csr(X, K, boundary_threshold, include_self=include_self)
+        coo = to_coo_batch(A)
+        rs = None
+        if redshifts is not None:
+            rs = torch.full((b * N * K, 1), float(redshifts[i]), dtype=torch.float32, device=X.device)
+        X = _nn.get_readout(model_func_shift_inv(X, coo, mv, (b, N, K), activation, rs))
+        if trajectory:
+            states.append(X)
+    return states if trajectory else X
 
 
 def model_func_shift_inv_za(init_pos, COO_feats, ZA_displacement, ZA_diagonal, model_vars, dims,

@@ -116,6 +116,35 @@ def model_func_shift_inv_za(init_pos, COO_feats, ZA_displacement, ZA_diagonal, m
     return network_func_shift_inv_za(edges, COO_feats, num_layers, dims[:-1], activation, model_vars)
 
 
+def network_func_shift_inv(X_in_edges, X_in_nodes, COO_feats, num_layers, dims, activation, model_vars, redshift=None):
+    """graph.py:517-533 - the multi-redshift network.  The reference keeps this function inside a commented-out block
+    (graph.py:516-567); it is restated from that text, on top of the live include_node_features (graph.py:245-275)
+    and shift_inv_layer (graph.py:394-456)."""
+    H_in = include_node_features(X_in_edges, X_in_nodes, COO_feats, redshift=redshift)
+    H = activation(shift_inv_layer(H_in, COO_feats, dims, model_vars.get_layer_vars(0)))
+    for layer_idx in range(1, num_layers):
+        is_last = layer_idx == num_layers - 1
+        H = shift_inv_layer(H, COO_feats, dims, model_vars.get_layer_vars(layer_idx), is_last=is_last)
+        if not is_last:
+            H = activation(H)
+    return H
+
+
+def model_func_shift_inv(X_in, COO_feats, model_vars, dims, activation=torch.relu, redshift=None):
+    """graph.py:536-567 (commented-out block, see network_func_shift_inv): X_in (b,N,6) = [position, velocity] ->
+    (b,N,6|3): loc' = net[:3]*loc_scalar + loc + vel*vel_scalar, vel' = net[3:]*vel_scalar + vel."""
+    num_layers = len(model_vars.channels) - 1
+    edges, nodes = get_input_features_shift_inv(X_in, COO_feats, dims)
+    X_in_loc, X_in_vel = X_in[..., :3], X_in[..., 3:]
+    net_out = network_func_shift_inv(edges, nodes, COO_feats, num_layers, dims[:-1], activation, model_vars, redshift)
+    loc_scalar, vel_scalar = model_vars.get_scalars()
+    H_out = net_out[..., :3] * loc_scalar + X_in_loc + X_in_vel * vel_scalar
+    if net_out.shape[-1] > 3:
+        H_vel = net_out[..., 3:] * vel_scalar + X_in_vel
+        H_out = torch.cat([H_out, H_vel], dim=-1)
+    return H_out
+
+
 # ------------------------------------------------------------------ set layer
 def set_layer(h_in, layer_vars):
     """nn.py:10-28 (only W[0] of the layer's weights is used, nn.py:22)"""

@@ -591,3 +591,69 @@ def test_tensor_core_model_c1_golden(nb, syn, math_mode, mode):
                 np.testing.assert_allclose(W.grad[wi].cpu().numpy(), ref, rtol=2e-4, atol=1e-7)
             else:
                 assert np.abs(W.grad[wi].cpu().numpy() - ref).max() <= 5e-3 * float(np.abs(ref).max()) + 1e-9, (li, wi)
+
+
+# =============================================================================== multi-redshift rollout
+@pytest.mark.parametrize("with_redshift", [False, True])
+def test_rollout_shift_inv_vs_oracle(nb, with_redshift):
+    """model_func_shift_inv / rollout_shift_inv (graph.py:517-567, legacy multi-redshift path): periodic kNN rebuilt every
+    step, 9|10-channel input edges, scaled residual update, readout wrap.  Every step is compared with the float64
+    oracle fed with the device's state of the previous step (teacher forcing: the kNN of a drifted copy could differ)."""
+    b, N, K, thr = 2, 512, 8, 0.25
+    rng = np.random.default_rng(11)
+    X0 = np.concatenate([rng.random((b, N, 3)), 0.02 * rng.standard_normal((b, N, 3))], axis=-1).astype(np.float32)
+    ch = [10 if with_redshift else 9, 16, 16, 6]
+    redshifts = [0.9, 0.4, 0.1] if with_redshift else None   # small: one readout wrap must bring positions back
+    steps = 3
+    params = []
+    for _ in range(steps):
+        layers = []
+        for kk, qq in zip(ch[:-1], ch[1:]):
+            layers.append(([(rng.standard_normal((kk, qq)) * np.sqrt(2.0 / (kk + qq))).astype(np.float32) for _ in range(4)],
+                           (0.01 * rng.standard_normal(qq)).astype(np.float32)))
+        params.append(layers)
+    scalars = (0.05, 0.02)
+
+    def mv_dev(i):
+        tp = [([torch.tensor(w, device=DEV) for w in Ws], torch.tensor(B, device=DEV)) for Ws, B in params[i]]
+        return types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda j: tp[j], get_scalars=lambda: scalars)
+
+    def mv_ref(i):
+        tp = [([torch.tensor(w, dtype=torch.float64) for w in Ws], torch.tensor(B, dtype=torch.float64)) for Ws, B in params[i]]
+        return types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda j: tp[j], get_scalars=lambda: scalars)
+
+    states = nb.graph.rollout_shift_inv(X0, [mv_dev(i) for i in range(steps)], K, thr, redshifts=redshifts, trajectory=True)
+    assert len(states) == steps and tuple(states[-1].shape) == (b, N, 6)
+    prev = X0
+    for i in range(steps):
+        A = ref_graph.get_pbc_kneighbors_csr(prev, K, thr)
+        dev_idx = idx_of(nb.graph.get_pbc_kneighbors_csr(prev, K, thr))
+        assert np.array_equal(dev_idx, np.stack([a.indices.reshape(N, K) for a in A]))
+        coo = ref_graph.to_coo_batch(A)
+        rs = None if redshifts is None else torch.full((b * N * K, 1), redshifts[i], dtype=torch.float64)
+        out = ref_layers.model_func_shift_inv(torch.tensor(prev, dtype=torch.float64), coo, mv_ref(i), (b, N, K), torch.relu, rs)
+        ref = ref_layers.get_readout(out).numpy()
+        got = states[i].cpu().numpy()
+        assert got[..., :3].min() >= 0.0 and got[..., :3].max() <= 1.0
+        d = np.abs(got - ref)
+        d[..., :3] = np.minimum(d[..., :3], 1.0 - d[..., :3])      # positions live on the unit torus
+        assert d.max() < 2e-5, (i, d.max())
+        prev = got
+
+
+@pytest.mark.parametrize("tag", ["v9", "v10"])
+def test_legacy_multi_redshift_model_golden(nb, tag):
+    """graph.model_func_shift_inv against the reference's own legacy block (tests/golden/rollout_small.npz)."""
+    g = load_golden("rollout_small.npz")
+    X, coo = g[f"{tag}_X"], g[f"{tag}_coo"]
+    b, N = X.shape[0], X.shape[1]
+    K = coo.shape[1] // (b * N)
+    ch = [int(v) for v in g[f"{tag}_channels"]]
+    tp = [([torch.tensor(g[f"{tag}_W{li}_{wi}"], device=DEV) for wi in range(4)], torch.tensor(g[f"{tag}_B{li}"], device=DEV))
+          for li in range(len(ch) - 1)]
+    scalars = tuple(float(v) for v in g[f"{tag}_scalars"])
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda j: tp[j], get_scalars=lambda: scalars)
+    rs = torch.full((b * N * K, 1), 2.5, device=DEV) if ch[0] == 10 else None
+    y = nb.graph.model_func_shift_inv(X, torch.tensor(coo, device=DEV), mv, (b, N, K), torch.relu, rs)
+    np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}_f32_out"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}_f64_out"], rtol=2e-5, atol=2e-6)

@@ -178,3 +178,30 @@ def test_losses_readout():
         l2 = ref_layers.loss_ZA(p2, t[..., :3]); l2.backward()
         np.testing.assert_allclose(l2.item(), g[f"{tag}_loss_za"], rtol=1e-5)
         np.testing.assert_allclose(p2.grad.numpy(), g[f"{tag}_loss_za_gpred"], rtol=1e-5, atol=1e-9)
+
+
+def _rollout_case(g, tag, dtype):
+    import types
+    ch = [int(v) for v in g[f"{tag}_channels"]]
+    tp = []
+    for li in range(len(ch) - 1):
+        tp.append(([torch.tensor(g[f"{tag}_W{li}_{wi}"], dtype=dtype) for wi in range(4)], torch.tensor(g[f"{tag}_B{li}"], dtype=dtype)))
+    scalars = tuple(float(v) for v in g[f"{tag}_scalars"])
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda j: tp[j], get_scalars=lambda: scalars)
+    return ch, mv
+
+
+@pytest.mark.parametrize("tag", ["v9", "v10"])
+def test_legacy_multi_redshift_model_restatement(tag):
+    """oracle.ref_layers.model_func_shift_inv vs the reference's own (commented-out) graph.py:517-567 block, executed
+    unmodified by oracle/make_golden_rollout.py."""
+    from oracle import ref_layers
+    g = load_golden("rollout_small.npz")
+    X, coo = g[f"{tag}_X"], g[f"{tag}_coo"]
+    b, N = X.shape[0], X.shape[1]
+    K = coo.shape[1] // (b * N)
+    for dtype, name, tol in ((torch.float32, "f32", 1e-6), (torch.float64, "f64", 1e-12)):
+        ch, mv = _rollout_case(g, tag, dtype)
+        rs = torch.full((b * N * K, 1), 2.5, dtype=dtype) if ch[0] == 10 else None
+        y = ref_layers.model_func_shift_inv(torch.tensor(X, dtype=dtype), coo, mv, (b, N, K), torch.relu, rs)
+        np.testing.assert_allclose(y.numpy(), g[f"{tag}_{name}_out"], rtol=tol, atol=tol)
