@@ -657,3 +657,17 @@ def test_legacy_multi_redshift_model_golden(nb, tag):
     y = nb.graph.model_func_shift_inv(X, torch.tensor(coo, device=DEV), mv, (b, N, K), torch.relu, rs)
     np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}_f32_out"], rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(y.cpu().numpy(), g[f"{tag}_f64_out"], rtol=2e-5, atol=2e-6)
+
+
+# =============================================================================== drop-in train.py
+@pytest.mark.parametrize("argv", [["-k", "8", "-c", "3", "16", "3"], ["-k", "-1", "-c", "6", "16", "8", "3"]])
+def test_train_entry_point_runs(tmp_path, argv):
+    """train.py with the reference's flags (utils.py:242-271): graph model (-k 8) and set model (-k -1) on the synthetic
+    data set, checkpoints written, evaluation loop returns finite errors, and training reduces the loss."""
+    import train
+    common = ["-i", "40", "-b", "2", "-t", "4", "-l", "0.01", "--side", "8", "--checkpoint", "20", "--out_dir", str(tmp_path), "-n", "t"]
+    err = train.main(argv + common)
+    assert err is not None and err.shape == (2,) and np.isfinite(err).all()
+    assert (tmp_path / "t" / "Session" / "chkpt-40.pt").is_file() and (tmp_path / "t" / "Results" / "error_test.npy").is_file()
+    err0 = train.main(argv + ["-i", "0"] + common[2:])          # untrained parameters, same test set
+    assert err.mean() < err0.mean()
