@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--channels", type=int, nargs="+", default=[3, 32, 16, 3])
     ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the 128^3 kNN build timing")
     return ap.parse_args()
 
@@ -297,7 +298,7 @@ def main():
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
 
-    def train_step(x, za, tgt, comm=True):
+    def train_step(x, za, tgt, comm=True, dev_step=False):
         A = graph.get_kneighbor_list(x, k)                           # kNN rebuilt every step
         coo, diag = graph.to_coo_batch_ZA_diag(A)
         pred = graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
@@ -306,8 +307,25 @@ def main():
         loss.backward()
         if comm:
             tu.allreduce_gradients(store, world)
-        adam.step(grad_scale=1.0 / world)
+        if dev_step:
+            adam.step_dev(grad_scale=1.0 / world)                    # step count in device memory: graph capturable
+        else:
+            adam.step(grad_scale=1.0 / world)
         return loss
+
+    # The whole step (kNN build, adjacency, forward, backward, all-reduce, Adam: ~58 launches) is captured once in a
+    # CUDA graph and replayed, so the timed region is not limited by the host's launch rate; --no-graph launches eagerly.
+    graphed, graph_note = None, "eager launches (--no-graph)"
+    if not a.no_graph:
+        try:
+            graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), resident[0])
+            graph_note = "one CUDA graph replay per step (whole step captured once)"
+        except Exception as exc:
+            graphed, graph_note = None, f"eager launches (graph capture failed: {repr(exc)[:200]})"
+            torch.cuda.synchronize()
+
+    def run_step(x, za, tgt):
+        return graphed(x, za, tgt) if graphed is not None else train_step(x, za, tgt)
 
     def barrier():
         if world > 1:
@@ -338,7 +356,7 @@ def main():
         return float(ms.item())
 
     def step_resident(i):
-        train_step(*resident[i % n_pool])
+        run_step(*resident[i % n_pool])
 
     # End to end: every step's inputs start in pinned HOST memory and every step's loss ends in pinned host memory.
     # Like a production input pipeline the copies are asynchronous: step i+1's H2D runs on a copy stream while step i
@@ -366,7 +384,7 @@ def main():
             prefetch(0)
         torch.cuda.current_stream().wait_event(ready[sl])
         prefetch(i + 1)
-        loss = train_step(*slots[sl])
+        loss = run_step(*slots[sl])
         consumed[sl].record()
         used[sl] = True
         loss_host[i % loss_host.numel()].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H read of the loss
@@ -382,6 +400,8 @@ def main():
     l0 = lib.launch_count()
     ms = timed(step_resident, a.steps, "resident")
     launches = lib.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.kernels_per_replay * a.steps             # kernels are launched by the graph replays
     clocks = sampler.stop(skip) if sampler else {}
     particles = world * b * N
     value = particles * a.steps / (ms * 1e-3)
@@ -512,7 +532,7 @@ def main():
         "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 TF32x3 error-compensated, FP32-class accuracy)",
                   "tf32": "tf32 (tcgen05 single pass, FP32 accumulate)"}[lib.get_math_mode()],
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "math_mode": lib.get_math_mode(), "particles_per_step": particles, "edges_per_step": particles * k,
+        "config": {"workload": workload_name(a), "math_mode": lib.get_math_mode(), "launch": graph_note, "particles_per_step": particles, "edges_per_step": particles * k,
                    "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)",
                    "l2": "step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"},
         "clocks": clocks,

@@ -204,6 +204,12 @@ int nbpc_readout(const float *h, int64_t rows, int C, float *out, void *stream);
 int nbpc_adam_tf(float *param, const float *grad, float *m, float *v, int64_t n, float lr,
                  float beta1, float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
+/* Same step with the step count t kept in device memory (*step_counter is incremented first, then used): every launch
+ * parameter is then identical from step to step, so a whole training step can be captured in a CUDA graph and
+ * replayed. */
+int nbpc_adam_tf_dev(float *param, const float *grad, float *m, float *v, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int64_t *step_counter, float grad_scale, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,6 +127,25 @@ __global__ void adam_tf_kernel(float *__restrict__ p, const float *__restrict__ 
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+// same update with the step counter in device memory (incremented by thread 0 AFTER every thread has read it is not
+// possible in one launch, so the counter is advanced by a 1-thread kernel first): the launch parameters are then
+// identical every step, which is what a CUDA-graph replay needs
+__global__ void adam_tick_kernel(int64_t *step) { *step += 1; }
+__global__ void adam_tf_dev_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                   float *__restrict__ v, int64_t n, const int64_t *__restrict__ step, float lr, float b1,
+                                   float b2, float eps, float gscale) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double t = (double)*step;
+    const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+}
+
 template <int PBC>
 static int loss_fwd_impl(const float *pred, int ldp, const float *truth, int ldt, int64_t rows, float scale,
                          float *loss_out, void *workspace, size_t ws_bytes, cudaStream_t stream, const char *name) {
@@ -222,6 +241,18 @@ int nbpc_adam_tf(float *param, const float *grad, float *m, float *v, int64_t n,
     NBPC_LAUNCH(adam_tf_kernel, nbpc_cdiv(n, LOSS_THREADS), LOSS_THREADS, 0, stream, param, grad, m, v, n, (float)lr_t,
                 beta1, beta2, eps, grad_scale);
     return nbpc_check_launch("nbpc_adam_tf");
+}
+
+int nbpc_adam_tf_dev(float *param, const float *grad, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, int64_t *step_counter, float grad_scale, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(param && grad && m && v && step_counter, "null pointer");
+    NBPC_ARG(n >= 1, "bad sizes");
+    NBPC_LAUNCH(adam_tick_kernel, 1, 1, 0, stream, step_counter);
+    NBPC_LAUNCH(adam_tf_dev_kernel, nbpc_cdiv(n, LOSS_THREADS), LOSS_THREADS, 0, stream, param, grad, m, v, n, step_counter, lr,
+                beta1, beta2, eps, grad_scale);
+    return nbpc_check_launch("nbpc_adam_tf_dev");
 }
 
 }  // extern "C"

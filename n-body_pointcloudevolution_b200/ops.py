@@ -455,6 +455,22 @@ def adam_tf_(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.
     _lib.check(rc, "nbpc_adam_tf")
 
 
+def adam_tf_dev_(param: torch.Tensor, grad: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step_counter: torch.Tensor,
+                 lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8, grad_scale: float = 1.0) -> None:
+    """adam_tf_ with the step count in a device int64 tensor (incremented by the call): CUDA-graph capturable."""
+    _need_cuda(param, grad, m, v, step_counter)
+    L = _lib.load()
+    for t in (param, grad, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("adam_tf_dev_: buffers must be contiguous float32")
+    if step_counter.dtype != torch.int64 or step_counter.numel() != 1:
+        raise RuntimeError("adam_tf_dev_: step_counter must be one int64")
+    with torch.cuda.device(param.device):
+        rc = L.nbpc_adam_tf_dev(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), lr, beta1, beta2, eps,
+                                _ptr(step_counter), grad_scale, _stream())
+    _lib.check(rc, "nbpc_adam_tf_dev")
+
+
 def device_check() -> None:
     """Raise unless the current CUDA device is an sm_100 part."""
     _lib.check(_lib.load().nbpc_device_check(), "nbpc_device_check")

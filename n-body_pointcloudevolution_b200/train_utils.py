@@ -7,7 +7,7 @@ from collections import namedtuple
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from .synthetic import PARAMS_SEED
 
 ModelVars = namedtuple("ModelVars", ["num_layers", "get_layer_vars", "activation"])  # utils.py:199-202
@@ -48,7 +48,8 @@ class ParamStore:
             self._B.append(Bv)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
-        self.step_count = 0
+        self.step_count = 0                                  # AdamTF.step(): count kept on the host
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)   # AdamTF.step_dev(): count in device memory
 
     def get_layer_vars(self, i):
         """([W_0..W_{n_w-1}] as one (n_w,k,q) tensor - indexable like the reference's list -, B)."""
@@ -82,6 +83,41 @@ class AdamTF:
         s = self.store
         s.step_count += 1
         ops.adam_tf_(s.flat, s.flat_grad, s.m, s.v, s.step_count, self.lr, self.beta1, self.beta2, self.eps, grad_scale)
+
+    def step_dev(self, grad_scale=1.0):
+        """Same update with the step count in device memory (CUDA-graph capturable; do not mix with step())."""
+        s = self.store
+        ops.adam_tf_dev_(s.flat, s.flat_grad, s.m, s.v, s.step_dev, self.lr, self.beta1, self.beta2, self.eps, grad_scale)
+
+
+class GraphedStep:
+    """One whole training step (kNN graph build, forward, backward, gradient all-reduce, Adam) captured ONCE in a CUDA
+    graph and replayed: ~60 kernel launches become one graph launch, so the step is not limited by the host's launch
+    rate.  `step_fn(*static_inputs) -> loss` must be shape-static, sync-free and use AdamTF.step_dev (the reference's
+    loop is: same shapes every iteration, train.py:87-120).  Inputs are copied into the static tensors before a replay.
+        gs = GraphedStep(step_fn, example_inputs);  loss = gs(x, za, target)      # loss: static 0-d tensor"""
+
+    def __init__(self, step_fn, example_inputs, warmup=3):
+        self.static_in = tuple(torch.empty_like(t).copy_(t) for t in example_inputs)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # lazy initialisations must not happen inside the capture
+            for _ in range(warmup):
+                step_fn(*self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = step_fn(*self.static_in)
+        self.kernels_per_replay = _lib.launch_count() - n0     # libnbpc kernels inside one replay
+
+    def __call__(self, *inputs):
+        for d, s in zip(self.static_in, inputs):
+            if d.data_ptr() != s.data_ptr():
+                d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.loss
 
 
 def allreduce_gradients(store, world_size):

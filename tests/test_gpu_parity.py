@@ -660,7 +660,8 @@ def test_legacy_multi_redshift_model_golden(nb, tag):
 
 
 # =============================================================================== drop-in train.py
-@pytest.mark.parametrize("argv", [["-k", "8", "-c", "3", "16", "3"], ["-k", "-1", "-c", "6", "16", "8", "3"]])
+@pytest.mark.parametrize("argv", [["-k", "8", "-c", "3", "16", "3"], ["-k", "-1", "-c", "6", "16", "8", "3"],
+                                  ["-k", "8", "-c", "3", "16", "3", "--graph"]])
 def test_train_entry_point_runs(tmp_path, argv):
     """train.py with the reference's flags (utils.py:242-271): graph model (-k 8) and set model (-k -1) on the synthetic
     data set, checkpoints written, evaluation loop returns finite errors, and training reduces the loss."""
@@ -669,5 +670,42 @@ def test_train_entry_point_runs(tmp_path, argv):
     err = train.main(argv + common)
     assert err is not None and err.shape == (2,) and np.isfinite(err).all()
     assert (tmp_path / "t" / "Session" / "chkpt-40.pt").is_file() and (tmp_path / "t" / "Results" / "error_test.npy").is_file()
-    err0 = train.main(argv + ["-i", "0"] + common[2:])          # untrained parameters, same test set
+    err0 = train.main([v for v in argv if v != "--graph"] + ["-i", "0"] + common[2:])          # untrained parameters, same test set
     assert err.mean() < err0.mean()
+
+
+def test_graphed_step_matches_eager(nb, syn):
+    """train_utils.GraphedStep (whole training step captured in one CUDA graph, Adam step count in device memory) must
+    reproduce the eager loop bit for bit: same losses, same parameters after 6 steps on changing inputs."""
+    tu, graph, nn_ = nb.train_utils, nb.graph, nb.nn
+    ch, b, N, k = [3, 32, 16, 3], 2, 1000, 8
+    batches = []
+    for i in range(3):
+        x = torch.tensor(syn.make_box("clustered", b, N, 20 + i), device=DEV)
+        za, tgt = (torch.tensor(t, device=DEV) for t in syn.za_features(b, N, 20 + i))
+        batches.append((x, za, tgt))
+
+    def make():
+        store = tu.ParamStore(ch, device=DEV)
+        store.load_numpy(syn.glorot_params(ch))
+        adam = tu.AdamTF(store, lr=0.01)
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+
+        def step(x, za, tgt, dev_step):
+            coo, diag = graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(x, k))
+            loss = nn_.loss_ZA(graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k)), tgt)
+            store.zero_grad()
+            loss.backward()
+            adam.step_dev() if dev_step else adam.step()
+            return loss
+        return store, step
+
+    store_e, step_e = make()
+    eager = [float(step_e(*batches[i % 3], False).detach()) for i in range(6)]
+    store_g, step_g = make()
+    gs = tu.GraphedStep(lambda x, za, tgt: step_g(x, za, tgt, True), batches[0], warmup=0)
+    assert gs.kernels_per_replay > 20
+    graphed = [float(gs(*batches[i % 3]).detach()) for i in range(6)]
+    assert graphed == eager
+    assert torch.equal(store_g.flat, store_e.flat) and int(store_g.step_dev.item()) == 6
+    assert eager[-1] < eager[0]

@@ -48,6 +48,7 @@ def parser():
     adg("--side", type=int, default=32, help="particles per axis of the synthetic data set")
     adg("--num_samples", type=int, default=0, help="synthetic samples (default: num_test + 100 + 4 * batch_size)")
     adg("--checkpoint", type=int, default=250, help="steps between checkpoints (train.py:29)")
+    adg("--graph", action="store_true", help="capture the training step once in a CUDA graph and replay it every iteration")
     return ap
 
 
@@ -104,7 +105,7 @@ def build_step(args, store, dev):
     K = args.kneighbors
 
     def forward(batch):
-        x = torch.from_numpy(batch).to(dev, non_blocking=True)
+        x = batch if isinstance(batch, torch.Tensor) else torch.from_numpy(batch).to(dev, non_blocking=True)
         true_error = x[..., 6:].contiguous()
         if K == -1:
             pred = nn.model_func_set(x[..., :6].contiguous(), mv)                       # train.py:66
@@ -146,15 +147,30 @@ def main(argv=None):
             torch.save({"step": step, "params": store.flat.cpu(), "m": store.m.cpu(), "v": store.v.cpu(), "channels": args.channels},
                        os.path.join(out_dir, "Session", f"chkpt-{step}.pt"))
 
+    def train_step(x, dev_step=False):
+        pred, loss = forward(x)
+        store.zero_grad()
+        loss.backward()
+        nbpc.train_utils.allreduce_gradients(store, world)
+        adam.step_dev(grad_scale=1.0 / world) if dev_step else adam.step(grad_scale=1.0 / world)
+        return loss
+
+    graphed = None
+    if args.graph and args.num_iters > 0:
+        # GraphedStep's warm-up steps would train on the example batch: snapshot and restore the optimiser state
+        example = torch.from_numpy(dataset.get_minibatch(args.batch_size)).to(dev)
+        state = [t.clone() for t in (store.flat, store.m, store.v, store.step_dev)]
+        graphed = nbpc.train_utils.GraphedStep(lambda x: train_step(x, dev_step=True), (example,), warmup=2)
+        with torch.no_grad():
+            for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
+                t.copy_(s0)
+
     tstart = time.time()
     if rank == 0:
         print(f"\nTraining:\n{'=' * 78}")
     for step in range(args.num_iters):
-        pred, loss = forward(dataset.get_minibatch(args.batch_size))
-        store.zero_grad()
-        loss.backward()
-        nbpc.train_utils.allreduce_gradients(store, world)
-        adam.step(grad_scale=1.0 / world)
+        batch = dataset.get_minibatch(args.batch_size)
+        loss = graphed(torch.from_numpy(batch).to(dev, non_blocking=True)) if graphed is not None else train_step(batch)
         if (step + 1) % args.checkpoint == 0:                                          # train.py:117-120
             save(step)
             if rank == 0:
