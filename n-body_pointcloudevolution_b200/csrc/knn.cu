@@ -487,9 +487,12 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_uniform(KnnQueryParams 
                         }
                         const bool unshifted = (sx | sy | sz) == 0;
                         const double ox = (double)sx, oy = (double)sy, oz = (double)sz;
+                        float4 c_pre = make_float4(0.f, 0.f, 0.f, 0.f);   // candidate i + 1 is loaded while candidate i is evaluated
+                        if (len > 0) c_pre = __ldg(&P.sorted[jb]);
                         for (int i = 0; i < maxlen; ++i) {
+                            const float4 c = c_pre;
+                            if (i + 1 < len) c_pre = __ldg(&P.sorted[jb + i + 1]);
                             if (i < len) {
-                                const float4 c = __ldg(&P.sorted[jb + i]);
                                 const int w = __float_as_int(c.w);
                                 const int cid = w & KNN_IDX_MASK;
                                 bool take = !(PERIODIC && (((w >> KNN_FLAG_SHIFT) & reqmask) != req));
