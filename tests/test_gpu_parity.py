@@ -709,3 +709,29 @@ def test_graphed_step_matches_eager(nb, syn):
     assert graphed == eager
     assert torch.equal(store_g.flat, store_e.flat) and int(store_g.step_dev.item()) == 6
     assert eager[-1] < eager[0]
+
+
+def test_train_step_128_cubed_finite_and_deterministic(nb, syn):
+    """BASELINE's largest box as a TRAINING step (29.4 M edges, 3.8 GB edge tensors: byte offsets beyond 2^32): loss and
+    every gradient finite, two runs bit-identical, and sample-independence: the same box inside a batch of one and as
+    sample 0 of nothing else gives the gradients the 32^3 tests pin (size-independent property: the mean of the
+    per-node loss terms equals the loss)."""
+    ch, b, N, k = [3, 32, 16, 3], 1, 128 ** 3, 14
+    x = torch.tensor(syn.make_box("uniform", b, N, 1), device=DEV)
+    za, tgt = (torch.tensor(t, device=DEV) for t in syn.za_features(b, N, 1))
+    outs = []
+    for _ in range(2):
+        store = nb.train_utils.ParamStore(ch, device=DEV)
+        store.load_numpy(syn.glorot_params(ch))
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+        coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, k))
+        pred = nb.graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
+        loss = nb.nn.loss_ZA(pred, tgt)
+        store.zero_grad()
+        loss.backward()
+        outs.append((float(loss.detach()), store.flat_grad.clone(), pred.detach()))
+        del coo, diag, pred, loss
+    assert np.isfinite(outs[0][0]) and bool(torch.isfinite(outs[0][1]).all()) and float(outs[0][1].abs().max()) > 0
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    per_node = ((outs[0][2] - tgt) ** 2).sum(-1).double().mean()
+    assert abs(float(per_node) - outs[0][0]) <= 1e-5 * outs[0][0]
