@@ -298,7 +298,7 @@ def main():
     resident = [tuple(t.to(dev) for t in hb) for hb in host]
     staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
 
-    def train_step(x, za, tgt, comm=True, dev_step=False):
+    def train_step(x, za, tgt, comm=True, dev_step=False, update=True):
         A = graph.get_kneighbor_list(x, k)                           # kNN rebuilt every step
         coo, diag = graph.to_coo_batch_ZA_diag(A)
         pred = graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
@@ -307,6 +307,8 @@ def main():
         loss.backward()
         if comm:
             tu.allreduce_gradients(store, world)
+        if not update:
+            return loss
         if dev_step:
             adam.step_dev(grad_scale=1.0 / world)                    # step count in device memory: graph capturable
         else:
@@ -318,14 +320,26 @@ def main():
     graphed, graph_note = None, "eager launches (--no-graph)"
     if not a.no_graph:
         try:
-            graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), resident[0])
-            graph_note = "one CUDA graph replay per step (whole step captured once)"
+            if world == 1:
+                graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), resident[0])
+                graph_note = "one CUDA graph replay per step (whole step captured once)"
+            else:
+                # the NCCL all-reduce stays outside the capture (capturing it hung with the NCCL watchdog thread alive):
+                # graph = kNN build + forward + backward; all-reduce and Adam are launched eagerly behind it
+                graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, comm=False, update=False), resident[0])
+                graph_note = "one CUDA graph replay per step (kNN + forward + backward), NCCL all-reduce and Adam launched eagerly"
         except Exception as exc:
             graphed, graph_note = None, f"eager launches (graph capture failed: {repr(exc)[:200]})"
             torch.cuda.synchronize()
 
     def run_step(x, za, tgt):
-        return graphed(x, za, tgt) if graphed is not None else train_step(x, za, tgt)
+        if graphed is None:
+            return train_step(x, za, tgt)
+        loss = graphed(x, za, tgt)
+        if world > 1:
+            tu.allreduce_gradients(store, world)
+            adam.step(grad_scale=1.0 / world)
+        return loss
 
     def barrier():
         if world > 1:
@@ -400,8 +414,8 @@ def main():
     l0 = lib.launch_count()
     ms = timed(step_resident, a.steps, "resident")
     launches = lib.launch_count() - l0
-    if graphed is not None:
-        launches = graphed.kernels_per_replay * a.steps             # kernels are launched by the graph replays
+    if graphed is not None:                                          # kernels are launched by the graph replays
+        launches = (graphed.kernels_per_replay + (1 if world > 1 else 0)) * a.steps
     clocks = sampler.stop(skip) if sampler else {}
     particles = world * b * N
     value = particles * a.steps / (ms * 1e-3)
