@@ -168,18 +168,22 @@ struct KnnTopK {
     // precondition: accepts(dd, ii).  Fully predicated (no early exit): an early-exit loop makes the
     // compiler index the arrays dynamically, which moves them from registers to local memory.
     __device__ __forceinline__ void insert(double dd, int ii) {
-        bool below_m = true;  // new entry sorts before slot m (true for m = K-1 by the precondition)
+        // the list is sorted, so "new sorts before slot m-1" implies "new sorts before slot m": with the precondition
+        // (new sorts before slot K-1) slot m becomes  below[m-1] ? old[m-1] : (below[m] ? new : old[m]).
+        // Bitwise | and & (no short-circuit) keep the comparison straight-line: 2 DSETP + 1 ISETP + 1 LOP per slot.
+        bool below[K];
+#pragma unroll
+        for (int m = 0; m < K - 1; ++m) below[m] = (dd < d[m]) | ((dd == d[m]) & (ii < id[m]));
+        below[K - 1] = true;
 #pragma unroll
         for (int m = K - 1; m > 0; --m) {
-            const bool below_m1 = dd < d[m - 1] || (dd == d[m - 1] && ii < id[m - 1]);
-            d[m] = below_m1 ? d[m - 1] : (below_m ? dd : d[m]);
-            id[m] = below_m1 ? id[m - 1] : (below_m ? ii : id[m]);
-            below_m = below_m1;
+            const double dn = below[m] ? dd : d[m];
+            const int in = below[m] ? ii : id[m];
+            d[m] = below[m - 1] ? d[m - 1] : dn;
+            id[m] = below[m - 1] ? id[m - 1] : in;
         }
-        if (below_m) {
-            d[0] = dd;
-            id[0] = ii;
-        }
+        d[0] = below[0] ? dd : d[0];
+        id[0] = below[0] ? ii : id[0];
     }
     __device__ __forceinline__ void sort_ids_ascending() {  // bitonic network on the ids padded to a power of two
         constexpr int KP = K <= 8 ? 8 : (K <= 16 ? 16 : (K <= 32 ? 32 : 64));
