@@ -132,7 +132,7 @@ class ClockSampler:
     nvidia-smi child process polling next to the benchmark stalled the launching thread by milliseconds per query)."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index, period_s=0.05):
+    def __init__(self, gpu_index, period_s=0.02):
         import threading
         self.samples, self.period, self._stop, self.thread, self.h = [], period_s, threading.Event(), None, None
         try:
@@ -184,10 +184,13 @@ class ClockSampler:
         self._stop.set()
         self.thread.join(timeout=2)
         rows = [r for r in self.samples if r[0] >= since]
+        if not rows and self.samples:        # timed region shorter than the sampling period: nearest sample (warm-up load)
+            rows = [min(self.samples, key=lambda r: abs(r[0] - since))]
+            out["note"] = "timed region shorter than the 20 ms sampling period: nearest sample, taken under the warm-up load"
         if rows:
             reasons = sorted({name for _, _, mask, _ in rows for name, bit in self.REASONS if mask & bit})
             out.update(sm_mhz=float(np.median([r[1] for r in rows])), sm_max_mhz=self.max_sm, reasons=reasons,
-                       samples=len(rows), power_w_max=float(np.nanmax([r[3] for r in rows])), source="NVML thread, 50 ms period")
+                       samples=len(rows), power_w_max=float(np.nanmax([r[3] for r in rows])), source="NVML thread, 20 ms period")
         return out
 
 
