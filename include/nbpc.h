@@ -141,6 +141,16 @@ int nbpc_segment_reduce(const float *h, int k, const int32_t *seg_ptr, const int
 int nbpc_gather_rows(const float *src, int k, const int32_t *ids, int64_t n_ids,
                      const int32_t *seg_ptr, float *out, void *stream);
 
+/* ---------------------------------------------------------------- dense projection (15-weight layer, graph.py:20-200)
+ * nbpc_linear: Y (n,q) = X (n,k) W [+ bias]; W is (k,q), or (q,k) with transpose_w (Y = X W^T, the input gradient);
+ *              accumulate adds into Y.  nbpc_xty: out (k,q) = X^T Y over n rows, fixed summation order (the weight
+ *              gradient); workspace from nbpc_xty_workspace_bytes. */
+int nbpc_linear(const float *X, const float *W, const float *bias, int64_t n, int k, int q, int transpose_w,
+                int accumulate, float *Y, void *stream);
+size_t nbpc_xty_workspace_bytes(int64_t n, int k, int q);
+int nbpc_xty(const float *X, const float *Y, int64_t n, int k, int q, float *out, void *workspace, size_t ws_bytes,
+             void *stream);
+
 /* ---------------------------------------------------------------- shift-invariant graph layer
  * graph.shift_inv_layer (graph.py:394-456):
  *   Z = H W1 + pool_col(H) W2 + pool_row(H) W3 + pool_cube(H) W4 + B        (c, q)

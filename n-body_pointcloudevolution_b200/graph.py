@@ -26,6 +26,7 @@ __all__ = [
     "include_node_features", "get_input_features_shift_inv_ZA", "get_input_features_shift_inv",
     "shift_inv_conv", "shift_inv_layer", "network_func_shift_inv_za", "model_func_shift_inv_za",
     "network_func_shift_inv", "model_func_shift_inv", "rollout_shift_inv",
+    "get_symmetrized_adjacency", "shift_inv_15op_layer", "network_func_15op_shift_inv_za", "model_func_15op_shift_inv_za",
 ]
 
 
@@ -339,6 +340,123 @@ def model_func_shift_inv(X_in, COO_feats, model_vars, dims, activation=torch.rel
     if net_out.shape[-1] > 3:
         H_out = torch.cat([H_out, net_out[..., 3:] * vel_scalar + vel], dim=-1)
     return H_out
+
+
+# =============================================================================== 15-weight layer (graph.py:20-229)
+class SymAdjacency(dict):
+    """The `adj` dict of shift_inv_15op_layer (graph.py:46-59): row / col / all / tra (S,), dia / dal (b*N,) as int32
+    device tensors, plus the CSR of every index list (built once, on demand) that makes the pooling forward and the
+    gather backward deterministic segment sums."""
+
+    def __init__(self, fields, b, N):
+        super().__init__(fields)
+        self.b, self.N = b, N
+        self._csr = {}
+
+    def csr(self, name, num_segs):
+        key = (name, num_segs)
+        if key not in self._csr:
+            ptr, members, status = ops.segment_csr(self[name], int(num_segs))
+            self._csr[key] = (ptr, members)
+        return self._csr[key]
+
+
+def get_symmetrized_adjacency(A):
+    """The adjacency the 15-weight layer expects and for which the reference ships no builder: the
+    SYMMETRISED kNN graph A u A^T of every sample, edges in row-major (row, col) order, with
+      row, col : node ids of every edge (shifted by i*N across the batch),  all : sample id of every edge,
+      tra      : position of the transposed edge (col, row),                dia : position of the self edge of every node,
+      dal      : sample id of every node.
+    The kNN lists must include the self edge (include_self=True).  Index bookkeeping uses torch's device sort/unique
+    (library calls: this is graph preprocessing, not the layer arithmetic)."""
+    idx = _as_batch(A)
+    b, N, M = idx.shape
+    BN = b * N
+    dev = idx.device
+    off = (torch.arange(b, device=dev, dtype=torch.int64) * N).view(b, 1, 1)
+    cols = (idx.to(torch.int64) + off).reshape(-1)
+    rows = torch.arange(BN, device=dev, dtype=torch.int64).repeat_interleave(M)
+    keys = torch.unique(torch.cat([rows * BN + cols, cols * BN + rows]))          # sorted: row-major edge order
+    row, col = keys // BN, keys % BN
+    tra = torch.searchsorted(keys, col * BN + row)
+    nodes = torch.arange(BN, device=dev, dtype=torch.int64)
+    dia = torch.searchsorted(keys, nodes * BN + nodes)
+    if not bool((keys[dia.clamp(max=keys.numel() - 1)] == nodes * BN + nodes).all()):
+        raise ValueError("get_symmetrized_adjacency: every node needs its self edge (build the kNN graph with include_self=True)")
+    i32 = lambda t: t.to(torch.int32).contiguous()
+    return SymAdjacency({"row": i32(row), "col": i32(col), "all": i32(row // N), "tra": i32(tra), "dia": i32(dia),
+                         "dal": i32(nodes // N)}, b, N)
+
+
+def _as_sym(adj, b, N):
+    if isinstance(adj, SymAdjacency):
+        return adj
+    return SymAdjacency({k: _to_cuda(v, torch.int32).contiguous().reshape(-1) for k, v in adj.items()}, b, N)
+
+
+def shift_inv_15op_layer(H_in, adj, bN, layer_vars, is_last=False):
+    """graph.py:20-200: the 15-weight permutation-equivariant basis on a symmetrised adjacency.  W (15, k, q), B (2, q);
+    H_in (S, k) -> (S, q), or (b, N, q) if is_last (pooled over adj["row"]).
+    Same sums as the reference, associated at node level: every pooled operand is projected once per NODE and then
+    gathered to the edges (the reference projects after broadcasting), i.e.
+        out[e] = H[e] W0 + H[tra[e]] W1 + T_col[col[e]] + T_row[row[e]] + T_all[all[e]] + [e is diagonal] T_dia[node]
+        T_col = Hr W3 + Hc W7 + Hd W13          T_row = Hr W4 + Hc W6 + Hd W14          T_all = Ha W9 + Hp W11 + B[1]
+        T_dia = Hd W2 + Hr W5 + Hc W8 + (Ha W10 + Hp W12)[dal] + B[0]
+    with Hr / Hc / Ha = segment means of H over col / row / all, Hd = H[dia], Hp = segment mean of Hd over dal."""
+    b, N = bN
+    BN = b * N
+    W, B = layer_vars
+    W = W if isinstance(W, torch.Tensor) and W.dim() == 3 else torch.stack(list(W))
+    B = B if isinstance(B, torch.Tensor) else torch.stack(list(B))
+    H = _to_cuda(H_in, torch.float32)
+    adj = _as_sym(adj, b, N)
+    S = H.shape[0]
+    lin = ops.Linear.apply
+
+    def pool(h, name, nseg):
+        ptr, mem = adj.csr(name, nseg)
+        return ops.SegmentPool.apply(h, adj[name], ptr, mem, False)
+
+    def gather(src, name):
+        ptr, mem = adj.csr(name, src.shape[0])
+        return ops.GatherRows.apply(src, adj[name], ptr, mem)
+
+    Hr, Hc, Ha = pool(H, "col", BN), pool(H, "row", BN), pool(H, "all", b)
+    Hd = gather(H, "dia")
+    Hp = pool(Hd, "dal", b)
+    T_col = lin(Hr, W[3]) + lin(Hc, W[7]) + lin(Hd, W[13])
+    T_row = lin(Hr, W[4]) + lin(Hc, W[6]) + lin(Hd, W[14])
+    T_all = lin(Ha, W[9]) + lin(Hp, W[11]) + B[1]
+    T_dia = lin(Hd, W[2]) + lin(Hr, W[5]) + lin(Hc, W[8]) + gather(lin(Ha, W[10]) + lin(Hp, W[12]), "dal") + B[0]
+    out = lin(H, W[0]) + lin(gather(H, "tra"), W[1]) + gather(T_col, "col") + gather(T_row, "row") + gather(T_all, "all")
+    # broadcast to the diagonal (tf.scatter_nd, graph.py:106): edge e receives T_dia[i] iff e == dia[i]
+    inv = torch.full((S,), BN, dtype=torch.int32, device=H.device)
+    inv[adj["dia"].long()] = torch.arange(BN, dtype=torch.int32, device=H.device)
+    key = ("_inv_dia", BN + 1)
+    if key not in adj._csr:
+        adj["_inv_dia"] = inv
+        adj.csr("_inv_dia", BN + 1)
+    out = out + gather(torch.cat([T_dia, torch.zeros_like(T_dia[:1])]), "_inv_dia")
+    if is_last:
+        return pool(out, "row", BN).reshape(b, N, -1)
+    return out
+
+
+def network_func_15op_shift_inv_za(edges, adj, num_layers, dims, activation, sess_mgr):
+    """graph.py:202-216"""
+    H = activation(shift_inv_15op_layer(edges, adj, dims, sess_mgr.get_layer_vars(0)))
+    for layer_idx in range(1, num_layers):
+        is_last = layer_idx == num_layers - 1
+        H = shift_inv_15op_layer(H, adj, dims, sess_mgr.get_layer_vars(layer_idx), is_last=is_last)
+        if not is_last:
+            H = activation(H)
+    return H
+
+
+def model_func_15op_shift_inv_za(edges, adj_map, sess_mgr, dims, activation=torch.relu):
+    """graph.py:219-229"""
+    num_layers = len(sess_mgr.channels) - 1
+    return network_func_15op_shift_inv_za(edges, adj_map, num_layers, dims[:-1], activation, sess_mgr)
 
 
 def rollout_shift_inv(X0, model_vars_per_step, K, boundary_threshold, redshifts=None, activation=torch.relu,

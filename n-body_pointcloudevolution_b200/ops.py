@@ -202,6 +202,75 @@ class SegmentPool(torch.autograd.Function):
         return gather_rows(g, ids, seg_ptr), None, None, None, None
 
 
+class GatherRows(torch.autograd.Function):
+    """y = src[ids] (tf.gather / tf.gather_nd on rows).  Backward = deterministic segment sum over the CSR of ids
+    (members of a row in ascending order), not an atomic scatter."""
+
+    @staticmethod
+    def forward(ctx, src, ids, seg_ptr, seg_members):
+        ctx.save_for_backward(seg_ptr, seg_members)
+        return gather_rows(src, ids, None)
+
+    @staticmethod
+    def backward(ctx, g):
+        seg_ptr, seg_members = ctx.saved_tensors
+        return segment_reduce(g.contiguous(), seg_ptr, seg_members, False), None, None, None
+
+
+# ================================================================== dense projection (15-weight layer)
+@torch.library.custom_op("nbpc::linear", mutates_args=())
+def linear(X: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], transpose_w: bool) -> torch.Tensor:
+    """Y = X W (+ bias), W (k,q); with transpose_w W is (q,k) and Y = X W^T."""
+    _need_cuda(X, W, bias)
+    L = _lib.load()
+    X, W = _f32c(X), _f32c(W)
+    n, k = X.shape
+    q = W.shape[0] if transpose_w else W.shape[1]
+    if (W.shape[1] if transpose_w else W.shape[0]) != k:
+        raise RuntimeError(f"linear: X is {tuple(X.shape)} but W is {tuple(W.shape)} (transpose_w={transpose_w})")
+    Y = torch.empty((n, q), dtype=torch.float32, device=X.device)
+    b = None if bias is None else _f32c(bias)
+    with torch.cuda.device(X.device):
+        rc = L.nbpc_linear(_ptr(X), _ptr(W), _ptr(b), n, k, q, int(transpose_w), 0, _ptr(Y), _stream())
+    _lib.check(rc, "nbpc_linear")
+    return Y
+
+
+@torch.library.custom_op("nbpc::xty", mutates_args=())
+def xty(X: torch.Tensor, Y: torch.Tensor) -> torch.Tensor:
+    """X^T Y over the rows, fixed summation order (bit-reproducible)."""
+    _need_cuda(X, Y)
+    L = _lib.load()
+    X, Y = _f32c(X), _f32c(Y)
+    n, k = X.shape
+    q = Y.shape[1]
+    out = torch.zeros((k, q), dtype=torch.float32, device=X.device)
+    if n == 0:
+        return out
+    ws = _workspace(L.nbpc_xty_workspace_bytes(n, k, q), X.device)
+    with torch.cuda.device(X.device):
+        rc = L.nbpc_xty(_ptr(X), _ptr(Y), n, k, q, _ptr(out), _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_xty")
+    return out
+
+
+class Linear(torch.autograd.Function):
+    """tf.matmul(X, W) (graph.py:147-189) with dX = dY W^T and the deterministic dW = X^T dY."""
+
+    @staticmethod
+    def forward(ctx, X, W):
+        ctx.save_for_backward(X, W)
+        return linear(X, W, None, False)
+
+    @staticmethod
+    def backward(ctx, g):
+        X, W = ctx.saved_tensors
+        g = g.contiguous()
+        dX = linear(g, W, None, True) if ctx.needs_input_grad[0] else None
+        dW = xty(X, g) if ctx.needs_input_grad[1] else None
+        return dX, dW
+
+
 # ================================================================== graph layer
 @torch.library.custom_op("nbpc::graph_layer_fwd", mutates_args=())
 def graph_layer_fwd(H_in: torch.Tensor, col: torch.Tensor, csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor,

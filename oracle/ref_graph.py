@@ -171,3 +171,26 @@ def to_coo_batch_ZA_diag(A):
 def to_coo_batch(A):
     """graph.py:664-697"""
     return to_coo_batch_ZA_diag(A)[0]
+
+
+def get_symmetrized_adjacency(A):
+    """The `adj` dict shift_inv_15op_layer documents (graph.py:46-59); the reference ships no builder for it.
+    Symmetrised kNN graph A u A^T per sample, edges in row-major (row, col) order, ids shifted by i*N."""
+    b = len(A)
+    N = A[0].shape[0]
+    M = A[0].indices.shape[0] // N
+    BN = b * N
+    rows, cols = [], []
+    for i, a in enumerate(A):
+        r = np.repeat(np.arange(N, dtype=np.int64), M) + i * N
+        c = a.indices.astype(np.int64) + i * N
+        rows += [r, c]
+        cols += [c, r]
+    keys = np.unique(np.concatenate(rows) * BN + np.concatenate(cols))
+    row, col = keys // BN, keys % BN
+    nodes = np.arange(BN, dtype=np.int64)
+    tra = np.searchsorted(keys, col * BN + row)
+    dia = np.searchsorted(keys, nodes * BN + nodes)
+    assert np.array_equal(keys[dia], nodes * BN + nodes), "self edges required (include_self=True)"
+    i32 = lambda t: t.astype(np.int32)
+    return {"row": i32(row), "col": i32(col), "all": i32(row // N), "tra": i32(tra), "dia": i32(dia), "dal": i32(nodes // N)}

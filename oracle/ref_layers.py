@@ -145,6 +145,49 @@ def model_func_shift_inv(X_in, COO_feats, model_vars, dims, activation=torch.rel
     return H_out
 
 
+def shift_inv_15op_layer(H_in, adj, bN, layer_vars, is_last=False):
+    """graph.py:20-200, op for op (15 projections after broadcasting, two biases)."""
+    b, N = bN
+    W, B = layer_vars
+    S, q = H_in.shape[0], W[0].shape[-1]
+    idx = {k: _t(np.asarray(v)).long() for k, v in adj.items()}
+
+    def pool(h, name, nseg):
+        return _segment_mean(h, idx[name], nseg)
+
+    def to_diag(h):                                          # tf.scatter_nd (graph.py:106)
+        return torch.zeros((S, q), dtype=h.dtype).index_add(0, idx["dia"], h)
+
+    H_all = [H_in @ W[0], H_in[idx["tra"]] @ W[1]]
+    Hd = H_in[idx["dia"]]
+    H_all.append(to_diag(Hd @ W[2]))
+    Hr = pool(H_in, "col", b * N)
+    H_all += [(Hr @ W[3])[idx["col"]], (Hr @ W[4])[idx["row"]], to_diag(Hr @ W[5])]
+    Hc = pool(H_in, "row", b * N)
+    H_all += [(Hc @ W[6])[idx["row"]], (Hc @ W[7])[idx["col"]], to_diag(Hc @ W[8])]
+    Ha = pool(H_in, "all", b)
+    H_all += [(Ha @ W[9])[idx["all"]], to_diag((Ha @ W[10])[idx["dal"]])]
+    Hp = _segment_mean(Hd, idx["dal"], b)
+    H_all += [(Hp @ W[11])[idx["all"]], to_diag((Hp @ W[12])[idx["dal"]])]
+    H_all += [(Hd @ W[13])[idx["col"]], (Hd @ W[14])[idx["row"]]]
+    B_diag = to_diag(B[0].expand(b * N, q))
+    H = sum(H_all) + B_diag + B[1]
+    if is_last:
+        return pool(H, "row", b * N).reshape(b, N, -1)
+    return H
+
+
+def network_func_15op_shift_inv_za(edges, adj, num_layers, dims, activation, sess_mgr):
+    """graph.py:202-216"""
+    H = activation(shift_inv_15op_layer(edges, adj, dims, sess_mgr.get_layer_vars(0)))
+    for layer_idx in range(1, num_layers):
+        is_last = layer_idx == num_layers - 1
+        H = shift_inv_15op_layer(H, adj, dims, sess_mgr.get_layer_vars(layer_idx), is_last=is_last)
+        if not is_last:
+            H = activation(H)
+    return H
+
+
 # ------------------------------------------------------------------ set layer
 def set_layer(h_in, layer_vars):
     """nn.py:10-28 (only W[0] of the layer's weights is used, nn.py:22)"""

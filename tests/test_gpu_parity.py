@@ -735,3 +735,36 @@ def test_train_step_128_cubed_finite_and_deterministic(nb, syn):
     assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
     per_node = ((outs[0][2] - tgt) ** 2).sum(-1).double().mean()
     assert abs(float(per_node) - outs[0][0]) <= 1e-5 * outs[0][0]
+
+
+# =============================================================================== 15-weight layer
+def test_15op_layer_golden(nb):
+    """graph.get_symmetrized_adjacency / shift_inv_15op_layer / network_func_15op_shift_inv_za (graph.py:20-216) against
+    the unmodified reference run (tests/golden/layer15_small.npz): adjacency bit-exact, outputs rtol 2e-5 vs the float32
+    run, gradients rtol 2e-4 vs the float64 run."""
+    g = load_golden("layer15_small.npz")
+    ch = [int(v) for v in g["channels"]]
+    x = g["x"]
+    b, N, K = x.shape[0], x.shape[1], int(g["K"])
+    adj = nb.graph.get_symmetrized_adjacency(nb.graph.get_kneighbor_list(x, K))
+    for name in ("row", "col", "all", "tra", "dia", "dal"):
+        assert np.array_equal(adj[name].cpu().numpy(), g[f"adj_{name}"]), name
+    tp = [(torch.tensor(g[f"W{li}"], device=DEV, requires_grad=True), torch.tensor(g[f"B{li}"], device=DEV, requires_grad=True))
+          for li in range(len(ch) - 1)]
+    H = torch.tensor(g["H"], device=DEV, requires_grad=True)
+    mgr = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda j: tp[j])
+    lay0 = nb.graph.shift_inv_15op_layer(H, adj, (b, N), tp[0])
+    # a plain dict of arrays (what a reference caller would pass) must work too
+    lay0_d = nb.graph.shift_inv_15op_layer(H, {k: g[f"adj_{k}"] for k in ("row", "col", "all", "tra", "dia", "dal")}, (b, N), tp[0])
+    net = nb.graph.model_func_15op_shift_inv_za(H, adj, mgr, (b, N, K))
+    loss = ((net - torch.tensor(g["tgt"], device=DEV)) ** 2).sum(-1).mean()
+    loss.backward()
+    np.testing.assert_allclose(lay0.detach().cpu().numpy(), g["f32_layer0"], rtol=2e-5, atol=2e-5)
+    assert torch.equal(lay0, lay0_d)
+    np.testing.assert_allclose(net.detach().cpu().numpy(), g["f32_net"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(loss.item(), float(g["f64_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(H.grad.cpu().numpy(), g["f64_gH"], rtol=2e-4, atol=2e-6)
+    for li, (W, B) in enumerate(tp):
+        scale = float(np.abs(g[f"f64_gW{li}"]).max())
+        np.testing.assert_allclose(W.grad.cpu().numpy(), g[f"f64_gW{li}"], rtol=2e-4, atol=2e-5 * scale)
+        np.testing.assert_allclose(B.grad.cpu().numpy(), g[f"f64_gB{li}"], rtol=2e-4, atol=2e-6)

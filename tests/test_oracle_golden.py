@@ -205,3 +205,37 @@ def test_legacy_multi_redshift_model_restatement(tag):
         rs = torch.full((b * N * K, 1), 2.5, dtype=dtype) if ch[0] == 10 else None
         y = ref_layers.model_func_shift_inv(torch.tensor(X, dtype=dtype), coo, mv, (b, N, K), torch.relu, rs)
         np.testing.assert_allclose(y.numpy(), g[f"{tag}_{name}_out"], rtol=tol, atol=tol)
+
+
+def test_15op_layer_restatement_and_adjacency():
+    """oracle.ref_layers.shift_inv_15op_layer / network_func_15op_shift_inv_za vs the UNMODIFIED reference
+    (graph.py:20-216, oracle/make_golden_15op.py), and the properties of the symmetrised-adjacency builder."""
+    import types
+    from oracle import ref_layers
+    g = load_golden("layer15_small.npz")
+    ch = [int(v) for v in g["channels"]]
+    x = g["x"]
+    b, N, K = x.shape[0], x.shape[1], int(g["K"])
+    adj = ref_graph.get_symmetrized_adjacency(ref_graph.get_kneighbor_list(x, K))
+    for name in ("row", "col", "all", "tra", "dia", "dal"):
+        assert np.array_equal(adj[name], g[f"adj_{name}"]), name
+    S = adj["row"].shape[0]
+    assert np.array_equal(adj["tra"][adj["tra"]], np.arange(S))                       # transposition is an involution
+    assert np.array_equal(adj["row"][adj["tra"]], adj["col"]) and np.array_equal(adj["col"][adj["tra"]], adj["row"])
+    assert np.array_equal(adj["row"][adj["dia"]], np.arange(b * N)) and np.array_equal(adj["col"][adj["dia"]], np.arange(b * N))
+    assert np.all(np.diff(adj["row"].astype(np.int64) * b * N + adj["col"]) > 0)      # row-major, no duplicates
+    for dt, name, tol in ((torch.float32, "f32", 2e-5), (torch.float64, "f64", 1e-11)):
+        tp = [(torch.tensor(g[f"W{li}"], dtype=dt, requires_grad=True), torch.tensor(g[f"B{li}"], dtype=dt, requires_grad=True))
+              for li in range(len(ch) - 1)]
+        H = torch.tensor(g["H"], dtype=dt, requires_grad=True)
+        mgr = types.SimpleNamespace(channels=ch, get_layer_vars=lambda j: tp[j])
+        lay0 = ref_layers.shift_inv_15op_layer(H, adj, (b, N), tp[0])
+        net = ref_layers.network_func_15op_shift_inv_za(H, adj, len(ch) - 1, (b, N), torch.relu, mgr)
+        loss = ((net - torch.tensor(g["tgt"], dtype=dt)) ** 2).sum(-1).mean()
+        loss.backward()
+        np.testing.assert_allclose(lay0.detach().numpy(), g[f"{name}_layer0"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(net.detach().numpy(), g[f"{name}_net"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(H.grad.numpy(), g[f"{name}_gH"], rtol=tol * 10, atol=tol)
+        for li, (W, B) in enumerate(tp):
+            np.testing.assert_allclose(W.grad.numpy(), g[f"{name}_gW{li}"], rtol=tol * 10, atol=tol)
+            np.testing.assert_allclose(B.grad.numpy(), g[f"{name}_gB{li}"], rtol=tol * 10, atol=tol)
