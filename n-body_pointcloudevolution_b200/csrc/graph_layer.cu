@@ -484,6 +484,46 @@ static int glk3_launch_edge_dw(int k, int q, const float *E, const float *dOut, 
 }
 #endif
 
+#ifndef NBPC_HOST_EMU
+// whole backward of a first (k = 3) layer in one pass over dZ; returns the blocks per sample (<= 0 on error)
+template <int Q, bool RELU>
+static int glk3_launch_first_layer_bwd_t(const float *E, const float *dOut, const float *Hout, const int32_t *col, const float *P_col,
+                                         const float *P_row, int B, int64_t edges_per_sample, int M, int max_blocks_per_sample,
+                                         float *part1, float *part2, float *part3, float *colsum_partial, cudaStream_t stream) {
+    auto kern = glk3_first_layer_bwd_kernel<Q, RELU>;
+    const size_t smem = Glk3FbCfg<Q, RELU>::SMEM;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        configured = true;
+    }
+    const uint32_t magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)M);
+    const int64_t ntiles = (edges_per_sample + GLK3_FB_TILE - 1) / GLK3_FB_TILE;
+    const int64_t want = nbpc_max((int64_t)1, nbpc_min((int64_t)gl_num_sms() * 8 / B, (int64_t)max_blocks_per_sample));
+    const int64_t tpb = (ntiles + want - 1) / want;
+    const int nblk = (int)((ntiles + tpb - 1) / tpb);
+    NBPC_LAUNCH_N(NbpcKName("glk3_first_layer_bwd_kernel", 3, Q).c_str(), kern, dim3(nblk, B), GLK3_THREADS, smem, stream, E, dOut, Hout, col,
+                  P_col, P_row, (uint32_t)edges_per_sample, (uint32_t)tpb, (uint32_t)M, magic, part1, part2, part3, colsum_partial);
+    return nblk;
+}
+static int glk3_launch_first_layer_bwd(int q, const float *E, const float *dOut, const float *Hout, const int32_t *col,
+                                       const float *P_col, const float *P_row, int B, int64_t edges_per_sample, int M, int relu,
+                                       int max_blocks_per_sample, float *part1, float *part2, float *part3, float *colsum_partial,
+                                       cudaStream_t stream) {
+#define X(Q_)                                                                                                              \
+    if (q == Q_)                                                                                                          \
+        return relu ? glk3_launch_first_layer_bwd_t<Q_, true>(E, dOut, Hout, col, P_col, P_row, B, edges_per_sample, M, max_blocks_per_sample, part1, part2, part3, colsum_partial, stream) \
+                    : glk3_launch_first_layer_bwd_t<Q_, false>(E, dOut, Hout, col, P_col, P_row, B, edges_per_sample, M, max_blocks_per_sample, part1, part2, part3, colsum_partial, stream);
+    X(16) X(32) X(64)
+#undef X
+    return -1;
+}
+#endif
+
 // per-sample column sums of a node tensor X (B*N, ch): out[s] = sum_n X[s,n] / divisor
 static void gl_colsum(const float *X, int ch, int N, int B, int nblk, float divisor, float *partial, float *out, bool fast,
                       cudaStream_t stream) {
@@ -590,6 +630,23 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
                         float *dB, GlWorkspace &w, cudaStream_t stream) {
     const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
     float *dQ_col = w.Qc, *dQ_row = w.Qr;
+    if (!is_last && !dH_in && k == 3 && glk3_shape_ok(k, q) && B <= gl_max_partial_blocks() && !getenv("NBPC_NO_FIRST_LAYER_FUSION")) {
+        // first layer: every gradient from ONE pass over dZ (graph_layer_k3.cuh).  Blocks per sample are bounded by the
+        // partial buffers: B * nb <= gl_max_partial_blocks() rows of (k,q) and nb <= ceil(N / 16) rows of the column sums
+        const int nb = glk3_launch_first_layer_bwd(q, H_in, dOut, H_out, col, P_col, P_row, B, (int64_t)N * M, M, relu,
+                                                   nbpc_min(gl_max_partial_blocks() / B, nbpc_cdiv(N, 16)), w.xty_partial,
+                                                   w.xty_partial2, w.xty_partial3, w.cube_partial, stream);
+        if (nb <= 0) {
+            nbpc_set_error("nbpc_graph_layer_bwd: could not configure shared memory");
+            return NBPC_ELAUNCH;
+        }
+        NBPC_LAUNCH(gln_cube_bwd_kernel, B, GLN_TINY_THREADS, 0, stream, w.cube_partial, nb, N, M, k, q, W + 3 * kq, w.dCq, (float *)nullptr);
+        GlnFinalArgs fa;
+        for (int i = 0; i < 3; ++i) { fa.n[i] = nb * B; fa.tr[i] = 0; }
+        fa.part[0] = w.xty_partial; fa.part[1] = w.xty_partial2; fa.part[2] = w.xty_partial3;
+        NBPC_LAUNCH(gln_final_kernel, dim3(nbpc_cdiv(kq, 32), 4), 1024, 0, stream, fa, P_cube, w.dCq, B, k, q, dW, dB);
+        return nbpc_check_launch("nbpc_graph_layer_bwd");
+    }
     // ---- dQ_row, dQ_col (+ column sums of dQ_row)
     int nblk = 0;
     if (is_last) {

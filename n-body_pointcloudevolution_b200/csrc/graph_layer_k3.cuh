@@ -131,4 +131,156 @@ __global__ void __launch_bounds__(GLK3_THREADS) glk3_edge_dw_kernel(const float 
         __syncthreads();
     }
 }
+
+// ------------------------------------------------------------------ first layer, whole backward in ONE pass over dZ
+// The first layer needs no input gradient, so its node-level gradients can be folded into the edge stream:
+//   dW1 = sum_e E[e]^T dZ[e]           dW2 = P_col^T dQ_col = sum_e P_col[col[e]]^T dZ[e]
+//   dW3 = P_row^T dQ_row = sum_e P_row[e / M]^T dZ[e]        dCq[s] = sum_{e in s} dZ[e]  (-> dW4, dB)
+// i.e. dZ (c,Q) is read once instead of three times (the backward pooling read it twice more) and the pooling, the node
+// X^T Y kernels and their partial reductions disappear.  K = 3 only.  The 40 accumulator registers per thread leave too
+// few loads in flight for a register-only stream (measured 2 TB/s), so the dZ / E / col tiles are staged through a
+// 3-deep cp.async ring in shared memory: bytes in flight no longer depend on the register budget.
+// grid (blocks per sample, B): a block's tiles belong to one sample, so its column sum is a partial of dCq[sample].
+#define GLK3_FB_TILE 128
+#define GLK3_FB_STAGES 3
+__device__ __forceinline__ void glk3_cp_async4(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void glk3_cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+template <int Q, bool RELU>
+struct Glk3FbCfg {
+    static constexpr int ZF = GLK3_FB_TILE * Q;                                   // floats of one dZ tile
+    static constexpr int STAGE_F = ZF * (RELU ? 2 : 1) + GLK3_FB_TILE * 3 + GLK3_FB_TILE;   // dZ | (H_out) | E | col
+    static constexpr size_t SMEM = sizeof(float) * (size_t)STAGE_F * GLK3_FB_STAGES;
+};
+template <int Q, bool RELU>
+__global__ void __launch_bounds__(GLK3_THREADS) glk3_first_layer_bwd_kernel(
+    const float *__restrict__ E, const float *__restrict__ dOut, const float *__restrict__ Hout, const int32_t *__restrict__ col,
+    const float *__restrict__ P_col, const float *__restrict__ P_row, uint32_t edges_per_sample, uint32_t tiles_per_block, uint32_t M,
+    uint32_t magic, float *__restrict__ part1, float *__restrict__ part2, float *__restrict__ part3, float *__restrict__ colsum_partial) {
+    using Cfg = Glk3FbCfg<Q, RELU>;
+    constexpr int K = 3, G = Q / 4, SLOTS = GLK3_THREADS / G, TILE = GLK3_FB_TILE, S = GLK3_FB_STAGES;
+    extern __shared__ __align__(16) float glk3_smem[];
+    const int tid = threadIdx.x, g = tid % G, slot = tid / G;
+    const uint32_t s = blockIdx.y;
+    const uint32_t e_sample = s * edges_per_sample, e_sample_end = e_sample + edges_per_sample;
+    const uint32_t ntiles_sample = (edges_per_sample + TILE - 1) / TILE;
+    const uint32_t t_begin = blockIdx.x * tiles_per_block, t_end = nbpc_min(t_begin + tiles_per_block, ntiles_sample);
+
+    auto issue = [&](uint32_t t, int st) {
+        float *Zs = glk3_smem + (size_t)st * Cfg::STAGE_F, *Hs = Zs + Cfg::ZF;
+        float *Es = Zs + Cfg::ZF * (RELU ? 2 : 1);
+        int *Cs = reinterpret_cast<int *>(Es + TILE * 3);
+        const uint32_t e0 = e_sample + t * TILE;
+        for (int i = tid; i < TILE * G; i += GLK3_THREADS) {
+            const int r = i / G, ch = i % G;
+            const uint32_t e = e0 + r;
+            if (e < e_sample_end) {
+                glk3_cp_async16(Zs + r * Q + 4 * ch, dOut + (size_t)e * Q + 4 * ch);
+                if (RELU) glk3_cp_async16(Hs + r * Q + 4 * ch, Hout + (size_t)e * Q + 4 * ch);
+            } else {
+                *reinterpret_cast<float4 *>(Zs + r * Q + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (RELU) *reinterpret_cast<float4 *>(Hs + r * Q + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        for (int i = tid; i < TILE * 4; i += GLK3_THREADS) {   // 3 floats of E and the column index per row
+            const int r = i >> 2, w = i & 3;
+            const uint32_t e = e0 + r;
+            if (e < e_sample_end) {
+                if (w < 3) glk3_cp_async4(Es + r * 3 + w, E + (size_t)e * 3 + w);
+                else glk3_cp_async4(Cs + r, col + e);
+            } else {
+                if (w < 3) Es[r * 3 + w] = 0.f;
+                else Cs[r] = (int)(s * (edges_per_sample / M));   // any valid node id of this sample
+            }
+        }
+    };
+
+    float4 a1[K], a2[K], a3[K], cs = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) a1[kk] = a2[kk] = a3[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll
+    for (int p = 0; p < S - 1; ++p) {
+        if (t_begin + p < t_end) issue(t_begin + p, p);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    int st = 0;
+    for (uint32_t t = t_begin; t < t_end; ++t) {
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(S - 2) : "memory");
+        __syncthreads();                       // tile t landed for everybody; the stage refilled below is no longer read
+        if (t + S - 1 < t_end) issue(t + S - 1, (st + S - 1) % S);
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        const float *Zs = glk3_smem + (size_t)st * Cfg::STAGE_F, *Hs = Zs + Cfg::ZF;
+        const float *Es = Zs + Cfg::ZF * (RELU ? 2 : 1);
+        const int *Cs = reinterpret_cast<const int *>(Es + TILE * 3);
+        const uint32_t e0 = e_sample + t * TILE;
+#pragma unroll 2
+        for (int r = slot; r < TILE; r += SLOTS) {
+            const int cidx = Cs[r];
+            const uint32_t e = nbpc_min(e0 + r, e_sample_end - 1);
+            const uint32_t ridx = glk3_div(e, M, magic);
+            float pc[K], pr[K], x[K];
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                pc[kk] = __ldg(&P_col[K * (size_t)cidx + kk]);
+                pr[kk] = __ldg(&P_row[K * (size_t)ridx + kk]);
+                x[kk] = Es[r * 3 + kk];
+            }
+            float4 v = *reinterpret_cast<const float4 *>(Zs + r * Q + 4 * g);
+            if (RELU) {
+                const float4 h = *reinterpret_cast<const float4 *>(Hs + r * Q + 4 * g);
+                v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+            }
+            cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) {
+                a1[kk].x = fmaf(x[kk], v.x, a1[kk].x); a1[kk].y = fmaf(x[kk], v.y, a1[kk].y);
+                a1[kk].z = fmaf(x[kk], v.z, a1[kk].z); a1[kk].w = fmaf(x[kk], v.w, a1[kk].w);
+                a2[kk].x = fmaf(pc[kk], v.x, a2[kk].x); a2[kk].y = fmaf(pc[kk], v.y, a2[kk].y);
+                a2[kk].z = fmaf(pc[kk], v.z, a2[kk].z); a2[kk].w = fmaf(pc[kk], v.w, a2[kk].w);
+                a3[kk].x = fmaf(pr[kk], v.x, a3[kk].x); a3[kk].y = fmaf(pr[kk], v.y, a3[kk].y);
+                a3[kk].z = fmaf(pr[kk], v.z, a3[kk].z); a3[kk].w = fmaf(pr[kk], v.w, a3[kk].w);
+            }
+        }
+        st = (st + 1) % S;
+    }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();
+    float4 *red = reinterpret_cast<float4 *>(glk3_smem);
+    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    // 10 rows (3 x dW1, 3 x dW2, 3 x dW3, column sum) through the same fixed tree over the slots, one at a time
+#pragma unroll 1
+    for (int r = 0; r < 3 * K + 1; ++r) {
+        float4 mine = cs;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (r == j) mine = a1[j];
+            if (r == K + j) mine = a2[j];
+            if (r == 2 * K + j) mine = a3[j];
+        }
+        red[tid] = mine;
+        __syncthreads();
+        for (int stride = SLOTS / 2; stride >= 1; stride >>= 1) {
+            if (slot < stride) {
+                float4 a = red[tid];
+                const float4 b = red[tid + stride * G];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+                red[tid] = a;
+            }
+            __syncthreads();
+        }
+        if (slot == 0) {
+            float *dst = r < K ? part1 + (blk * K + r) * Q
+                               : (r < 2 * K ? part2 + (blk * K + (r - K)) * Q
+                                            : (r < 3 * K ? part3 + (blk * K + (r - 2 * K)) * Q : colsum_partial + blk * Q));
+            *reinterpret_cast<float4 *>(dst + 4 * g) = red[tid];
+        }
+        __syncthreads();
+    }
+}
 #endif  // !NBPC_HOST_EMU
