@@ -671,7 +671,7 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
 #define X(K_, Q_)                                                                                                       \
     if (k == K_ && q == Q_)                                                                                            \
         NBPC_LAUNCH_N(NbpcKName("gln_node_grad_kernel", k, q).c_str(), (gln_node_grad_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, 0,  \
-                      stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, w.Gc, w.Gr);
+                      stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr);
         GLN_FOR_KQ(X)
 #undef X
     }
@@ -689,12 +689,9 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
     if (is_last) {
         // row-mean output: dZ[e] = dOutM[e/M]/M  =>  dW1 = P_row^T dOutM (= dW3), dH[e] = R[e/M] + G_col[col[e]]
         fa.part[0] = fa.part[2]; fa.n[0] = fa.n[2]; fa.tr[0] = fa.tr[2];
-        if (dH_in) {
-            NBPC_LAUNCH_N(NbpcKName("glf_last_rowterm_kernel", k, q).c_str(), glf_last_rowterm_kernel, nbpc_cdiv(BN * k, 256), 256, 0, stream,
-                          dQ_row, W, (int)BN, M, k, q, w.Gr);
+        if (dH_in)   // the row term (dOutM W1^T) / M is already in G_row (gln_node_grad_kernel, add_w1)
             NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256, 0,
                           stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, c, M, k, dH_in);
-        }
     } else if (!relu && dH_in && g_nbpc_math_mode != NBPC_MATH_FP32 && glt_bwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3, c)) {
         const int nb = glt_edge_bwd(k, q, dOut, H_in, col, W, w.Gc, w.Gr, c, M, mask_input, g_nbpc_math_mode == NBPC_MATH_TF32X3, dH_in,
                                     w.xty_partial, stream);

@@ -317,17 +317,19 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_node_project_kernel(const flo
 }
 
 // G_col = (dQ_col W2^T) / max(indeg, 1);  G_row = (dQ_row W3^T) / M + Gq[sample]
+// add_w1 (last layer, whose output is the row mean of Z): G_row additionally carries the row term of dH,
+// (dQ_row W1^T) / M, i.e. dQ_row is projected with (W3 + W1)^T
 template <int K, int Q>
 __global__ void __launch_bounds__(GLN_THREADS) gln_node_grad_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
                                                                      const float *__restrict__ Gq, const float *__restrict__ W,
                                                                      const int32_t *__restrict__ csrT_ptr, int BN, int N, int M,
-                                                                     float *__restrict__ G_col, float *__restrict__ G_row) {
+                                                                     int add_w1, float *__restrict__ G_col, float *__restrict__ G_row) {
     constexpr int KP = (K + 3) / 4 * 4;
     __shared__ __align__(16) float W2t[Q * KP], W3t[Q * KP];   // transposed: [q][k]
     for (int i = threadIdx.x; i < Q * KP; i += GLN_THREADS) {
         const int qo = i / KP, kk = i % KP;
         W2t[i] = kk < K ? __ldg(&W[(int64_t)K * Q + kk * Q + qo]) : 0.f;
-        W3t[i] = kk < K ? __ldg(&W[2 * (int64_t)K * Q + kk * Q + qo]) : 0.f;
+        W3t[i] = kk < K ? __ldg(&W[2 * (int64_t)K * Q + kk * Q + qo]) + (add_w1 ? __ldg(&W[kk * Q + qo]) : 0.f) : 0.f;
     }
     __syncthreads();
     const float rm = 1.f / (float)M;
