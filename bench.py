@@ -225,6 +225,8 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
         return c * (4 * q + 4 * k + (0 if first else 4 * k + 4)) + (0 if first else n * 2 * 4 * k)
     if base == "glk3_edge_dw_kernel":                          # first layer: E (c,3) and dZ in, dW1 out
         return c * (12 + 4 * q)
+    if base == "glk3_first_layer_bwd_kernel":                  # first layer, all gradients: E, col and dZ in (once)
+        return c * (12 + 4 + 4 * q) + n * 2 * 12
     if base == "glf_last_edge_in_kernel":                      # col in, H (mask) in, dH out
         return c * (4 + 2 * 4 * k) + n * 2 * 4 * k
     if base == "gln_node_project_kernel":                      # P_col, P_row in; Q_col, Q_row out
