@@ -768,3 +768,43 @@ def test_15op_layer_golden(nb):
         scale = float(np.abs(g[f"f64_gW{li}"]).max())
         np.testing.assert_allclose(W.grad.cpu().numpy(), g[f"f64_gW{li}"], rtol=2e-4, atol=2e-5 * scale)
         np.testing.assert_allclose(B.grad.cpu().numpy(), g[f"f64_gB{li}"], rtol=2e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("b,N,M,ch", [(3, 601, 10, [3, 32, 16, 3]), (1, 257, 5, [3, 16, 32, 3]), (2, 1000, 32, [3, 64, 16, 3]),
+                                      (5, 130, 7, [3, 32, 3])])
+def test_graph_model_odd_shapes_vs_oracle(nb, b, N, M, ch):
+    """Whole model (default math mode) on shapes where nothing divides anything: edges per sample not a multiple of the
+    128-edge tile (the one-pass first-layer backward walks per-sample tiles), odd batch sizes, k = 5 / 7 / 32, two- and
+    three-layer nets - forward, loss and every gradient against the float64 oracle."""
+    rng = np.random.default_rng(b * 1000 + N)
+    x = rng.random((b, N, 3)).astype(np.float32)
+    za = (0.01 * rng.standard_normal((b, N, 3))).astype(np.float32)
+    tgt = (0.01 * rng.standard_normal((b, N, 3))).astype(np.float32)
+    params = [([(rng.standard_normal((kk, qq)) * np.sqrt(2.0 / (kk + qq))).astype(np.float32) for _ in range(4)],
+               (0.01 * rng.standard_normal(qq)).astype(np.float32)) for kk, qq in zip(ch[:-1], ch[1:])]
+    tp = [([torch.tensor(w, device=DEV, requires_grad=True) for w in Ws], torch.tensor(B, device=DEV, requires_grad=True)) for Ws, B in params]
+    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda i: tp[i])
+    xt = torch.tensor(x, device=DEV)
+    coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(xt, M))
+    pred = nb.graph.model_func_shift_inv_za(xt, coo, torch.tensor(za, device=DEV), diag, mv, (b, N, M))
+    loss = nb.nn.loss_ZA(pred, torch.tensor(tgt, device=DEV))
+    loss.backward()
+
+    rA = ref_graph.get_kneighbor_list(x, M, backend="exact")
+    rcoo, rdiag = ref_graph.to_coo_batch_ZA_diag(rA)
+    assert np.array_equal(coo.cpu().numpy(), rcoo) and np.array_equal(diag.cpu().numpy(), rdiag)
+    rp = [([torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in Ws], torch.tensor(B, dtype=torch.float64, requires_grad=True))
+          for Ws, B in params]
+    rmv = types.SimpleNamespace(channels=ch, get_layer_vars=lambda i: rp[i])
+    rpred = ref_layers.model_func_shift_inv_za(torch.tensor(x, dtype=torch.float64), rcoo, torch.tensor(za, dtype=torch.float64), rdiag,
+                                               rmv, (b, N, M))
+    rloss = ref_layers.loss_ZA(rpred, torch.tensor(tgt, dtype=torch.float64))
+    rloss.backward()
+    np.testing.assert_allclose(pred.detach().cpu().numpy(), rpred.detach().numpy(), rtol=5e-5, atol=5e-6)
+    np.testing.assert_allclose(loss.item(), rloss.item(), rtol=2e-5)
+    for li in range(len(ch) - 1):
+        for wi in range(4):
+            ref = rp[li][0][wi].grad.numpy()
+            np.testing.assert_allclose(tp[li][0][wi].grad.cpu().numpy(), ref, rtol=5e-4, atol=5e-5 * float(np.abs(ref).max()))
+        ref = rp[li][1].grad.numpy()
+        np.testing.assert_allclose(tp[li][1].grad.cpu().numpy(), ref, rtol=5e-4, atol=5e-5 * float(np.abs(ref).max()) + 1e-12)
