@@ -308,142 +308,7 @@ static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int 
     return w;
 }
 
-#ifndef NBPC_HOST_EMU
-// ---- template dispatch over the compiled (K, Q) shapes of the edge-level kernels
-#define GLF_FOR_KQ(X)  X(3, 16) X(3, 32) X(3, 64) X(16, 16) X(16, 32) X(16, 64) X(32, 16) X(32, 32) X(32, 64) X(64, 16) X(64, 32) X(64, 64)
-
-static bool glf_edge_shape_ok(int k, int q) {
-#define X(K_, Q_) if (k == K_ && q == Q_) return true;
-    GLF_FOR_KQ(X)
-#undef X
-    return false;
-}
-
-// persistent grid: blocks/SM from the occupancy calculator (cached per kernel instance)
-template <class F>
-static int glf_persistent_grid(F kern, int threads, size_t smem) {
-    if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-            cudaGetLastError();
-            return -1;
-        }
-    }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
-        cudaGetLastError();
-        return -1;
-    }
-    if (occ > 8) occ = 8;
-    return gl_num_sms() * occ;
-}
-
-template <int K, int Q, bool RELU>
-static int glf_launch_edge_out_t(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
-                                 int64_t c, int M, float *out, cudaStream_t stream) {
-    constexpr int KS = (K == 3) ? 0 : glf_stride(K), QS = glf_stride(Q);
-    const size_t smem = sizeof(float) * (size_t)(((K * Q + 3) / 4) * 4 + GLF_TE * QS + 2 * GLF_TE * KS);
-    auto kern = glf_edge_out_kernel<K, Q, RELU>;
-    static int grid_cache = 0;
-    const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;
-    if (!grid_cache) grid_cache = glf_persistent_grid(kern, GLF_THREADS, smem);
-    if (grid_cache < 0) return 1;
-    const int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
-    NBPC_LAUNCH_N(NbpcKName("glf_edge_out_kernel", K, Q).c_str(), kern, grid, GLF_THREADS, smem, stream, H, col, W1, Qc, Qr, c, M, out);
-    return 0;
-}
-template <int K, int Q>
-static int glf_launch_edge_out(const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
-                               int64_t c, int M, int relu, float *out, cudaStream_t stream) {
-    return relu ? glf_launch_edge_out_t<K, Q, true>(H, col, W1, Qc, Qr, c, M, out, stream)
-                : glf_launch_edge_out_t<K, Q, false>(H, col, W1, Qc, Qr, c, M, out, stream);
-}
-
-// launches the edge backward kernel; returns the number of per-block partials written (<= 0 on error)
-template <int K, int Q, bool RELU, bool HAS_DH, bool MASK_IN>
-static int glf_launch_edge_bwd_t(const char *name, const float *dOut, const float *Hout, const float *H, const int32_t *col,
-                                 const float *W1, const float *Gc, const float *Gr, int64_t c, int M, float *dH,
-                                 float *partial, cudaStream_t stream) {
-    constexpr int KP = (K == 3) ? 4 : K;
-    constexpr int KS = glf_stride(KP), QS = glf_stride(Q);
-    constexpr int TILE = GLF_TE * (KS + QS + (RELU ? QS : 0));
-    const size_t smem = sizeof(float) * (size_t)(Q * KP + 2 * TILE);
-    auto kern = glf_edge_bwd_kernel<K, Q, RELU, HAS_DH, MASK_IN>;
-    static int grid_cache = 0;
-    if (!grid_cache) grid_cache = glf_persistent_grid(kern, GLF_THREADS, smem);
-    if (grid_cache < 0) return -1;
-    const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;
-    int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
-    const int tpb = (int)((ntiles + grid - 1) / grid);
-    grid = (int)((ntiles + tpb - 1) / tpb);
-    NBPC_LAUNCH_N(name, kern, grid, GLF_THREADS, smem, stream, dOut, Hout, H, col, W1, Gc, Gr, c, M, tpb, dH, partial);
-    return grid;
-}
-
-static void glf_reduce_partials(const float *partial, int nblocks, int rows, int cols, int transpose, float *out,
-                                cudaStream_t stream) {
-    NBPC_LAUNCH(glf_partial_reduce_kernel, nbpc_cdiv(rows * cols, 32), 1024, 0, stream, partial, nblocks, rows, cols, transpose, out);
-}
-
-// dW1 == nullptr: leave the nb per-block partials for the caller to reduce (*nb_out)
-template <int K, int Q>
-static int glf_launch_edge_bwd(const float *dOut, const float *Hout, const float *H, const int32_t *col, const float *W1,
-                               const float *Gc, const float *Gr, int64_t c, int M, int relu, int mask_in, float *dH,
-                               float *partial, float *dW1, cudaStream_t stream, int *nb_out = nullptr) {
-    int nb = -1;
-    const NbpcKName nm("glf_edge_bwd_kernel", K, Q);
-    const char *n = nm.c_str();
-    if constexpr (K % 4 == 0) {
-        if (dH) {
-            if (relu && mask_in) nb = glf_launch_edge_bwd_t<K, Q, true, true, true>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-            else if (relu) nb = glf_launch_edge_bwd_t<K, Q, true, true, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-            else if (mask_in) nb = glf_launch_edge_bwd_t<K, Q, false, true, true>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-            else nb = glf_launch_edge_bwd_t<K, Q, false, true, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-        }
-    }
-    if (!dH) {
-        nb = relu ? glf_launch_edge_bwd_t<K, Q, true, false, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream)
-                  : glf_launch_edge_bwd_t<K, Q, false, false, false>(n, dOut, Hout, H, col, W1, Gc, Gr, c, M, dH, partial, stream);
-    }
-    if (nb <= 0) return 1;
-    if (nb_out) *nb_out = nb;
-    if (dW1) glf_reduce_partials(partial, nb, K, Q, 0, dW1, stream);
-    return 0;
-}
-
-// X^T Y over n node rows -> out (k,q); deterministic.  Uses the micro-tile kernel when (k,q) or (q,k)
-// is a compiled shape, else the generic kernel.
-// out == nullptr: leave the partials (count -> *nb_out, layout (q,k) instead of (k,q) -> *transposed) for the caller
-static int glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, int k, int q, float *partial,
-                        float *out, cudaStream_t stream, int *nb_out = nullptr, int *transposed = nullptr) {
-    int nb = 0;
-    if (transposed) *transposed = 0;
-#define XN(K_, Q_)                                                                                                    \
-    if (!nb && k == K_ && q == Q_) {                                                                                 \
-        nb = glf_launch_edge_bwd_t<K_, Q_, false, false, false>(name, Y, nullptr, X, nullptr, nullptr, nullptr, nullptr, n, 1, \
-                                                                nullptr, partial, stream);                          \
-        if (nb > 0 && out) glf_reduce_partials(partial, nb, k, q, 0, out, stream);                                   \
-    }                                                                                                                \
-    if (!nb && k == Q_ && q == K_ && K_ != Q_) {                                                                     \
-        nb = glf_launch_edge_bwd_t<K_, Q_, false, false, false>(name, X, nullptr, Y, nullptr, nullptr, nullptr, nullptr, n, 1, \
-                                                                nullptr, partial, stream);                          \
-        if (nb > 0 && out) glf_reduce_partials(partial, nb, q, k, 1, out, stream);                                   \
-        if (nb > 0 && transposed) *transposed = 1;                                                                   \
-    }
-    GLF_FOR_KQ(XN)
-#undef XN
-    if (nb < 0) return 1;
-    if (nb > 0) {
-        if (nb_out) *nb_out = nb;
-        return 0;
-    }
-    const int rpb = gl_node_xty_rows_per_block(n), grid = gl_node_xty_grid(n);
-    const size_t smem = sizeof(float) * (size_t)GLF_XTY_ROWS * (k + q);
-    NBPC_LAUNCH_N(name, glf_node_xty_kernel, grid, 256, smem, stream, X, Y, n, rpb, k, q, partial);
-    if (out) glf_reduce_partials(partial, grid, k, q, 0, out, stream);
-    if (nb_out) *nb_out = grid;
-    return 0;
-}
-#endif  // !NBPC_HOST_EMU
+#include "graph_layer_glf.h"
 
 #include "graph_layer_tc.h"
 #include "graph_layer_k3.cuh"
@@ -606,10 +471,7 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
         glk3_launch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
-    int rc = 1;
-#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_out<K_, Q_>(H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
-    GLF_FOR_KQ(X)
-#undef X
+    const int rc = glf_dispatch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
     if (rc) {
         nbpc_set_error("nbpc_graph_layer_fwd: could not configure shared memory");
         return NBPC_ELAUNCH;
@@ -704,10 +566,8 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
         fa.part[0] = w.xty_partial;
         fa.n[0] = glk3_launch_edge_dw(k, q, H_in, dOut, H_out, c, relu, w.xty_partial, stream);
     } else {
-        int rc = 1, nb = 0;
-#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, nullptr, stream, &nb);
-        GLF_FOR_KQ(X)
-#undef X
+        int nb = 0;
+        const int rc = glf_dispatch_edge_bwd(k, q, dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, nullptr, stream, &nb);
         if (rc) {
             nbpc_set_error("nbpc_graph_layer_bwd: could not configure shared memory");
             return NBPC_ELAUNCH;
@@ -870,10 +730,7 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (fast && glf_edge_shape_ok(k, q)) {
-        int rc = 1;
-#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_out<K_, Q_>(H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
-        GLF_FOR_KQ(X)
-#undef X
+        const int rc = glf_dispatch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
         if (rc) {
             nbpc_set_error("nbpc_graph_layer_fwd: could not configure shared memory");
             return NBPC_ELAUNCH;
@@ -1021,10 +878,7 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
         return nbpc_check_launch("nbpc_graph_layer_bwd");
     }
     if (fast && !is_last && glf_edge_shape_ok(k, q) && (!dH_in || k % 4 == 0)) {
-        int rc = 1;
-#define X(K_, Q_) if (k == K_ && q == Q_) rc = glf_launch_edge_bwd<K_, Q_>(dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, dW, stream);
-        GLF_FOR_KQ(X)
-#undef X
+        const int rc = glf_dispatch_edge_bwd(k, q, dOut, H_out, H_in, col, W, w.Gc, w.Gr, c, M, relu, mask_input, dH_in, w.xty_partial, dW, stream, nullptr);
         if (rc) {
             nbpc_set_error("nbpc_graph_layer_bwd: could not configure shared memory");
             return NBPC_ELAUNCH;

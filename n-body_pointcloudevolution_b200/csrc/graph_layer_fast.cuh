@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *
 
 // out = sum over blocks of partial[b] (rows x cols), fixed order; transpose: out is (cols x rows).
 // block = 32 lanes x 32 warps: 32 consecutive outputs, warp w sums blocks b = w, w+32, ...
-__global__ void __launch_bounds__(1024) glf_partial_reduce_kernel(const float *__restrict__ partial, int nblocks, int rows,
+static __global__ void __launch_bounds__(1024) glf_partial_reduce_kernel(const float *__restrict__ partial, int nblocks, int rows,
                                                                    int cols, int transpose, float *__restrict__ out) {
     __shared__ float red[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -437,7 +437,7 @@ __global__ void __launch_bounds__(1024) glf_partial_reduce_kernel(const float *_
     }
 }
 
-__global__ void glf_copy_kernel(const float *__restrict__ src, float *__restrict__ dst, int n) {
+static __global__ void glf_copy_kernel(const float *__restrict__ src, float *__restrict__ dst, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
@@ -445,7 +445,7 @@ __global__ void glf_copy_kernel(const float *__restrict__ src, float *__restrict
 // ------------------------------------------------------------------ node-level kernels (runtime k, q)
 // persistent grid-stride blocks: the weights are staged in shared memory once per block
 // Q_col = P_col W2;  Q_row = P_row W3 + (P_cube W4 + B)
-__global__ void __launch_bounds__(256) glf_node_project_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
+static __global__ void __launch_bounds__(256) glf_node_project_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
                                                                 const float *__restrict__ P_cube, const float *__restrict__ W,
                                                                 const float *__restrict__ bias, int BN, int N, int k, int q,
                                                                 float *__restrict__ Q_col, float *__restrict__ Q_row) {
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(256) glf_node_project_kernel(const float *__re
 }
 
 // G_col = (dQ_col W2^T)/max(indeg,1);  G_row = (dQ_row W3^T)/M + (dCq W4^T)/(N M)
-__global__ void __launch_bounds__(256) glf_node_grad_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
+static __global__ void __launch_bounds__(256) glf_node_grad_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
                                                              const float *__restrict__ dCq, const float *__restrict__ W,
                                                              const int32_t *__restrict__ csrT_ptr, int BN, int N, int M,
                                                              int k, int q, float *__restrict__ G_col, float *__restrict__ G_row) {
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(256) glf_node_grad_kernel(const float *__restr
 
 // ---- 4-wide node kernels (k % 4 == 0 and q % 4 == 0): float4 row loads, LDS.128 weights, 4 outputs / thread
 // per-sample constants are hoisted into tiny kernels:  Cq[s] = P_cube[s] W4 + bias,  Gq[s] = dCq[s] W4^T / (N M)
-__global__ void glf_cube_project_kernel(const float *__restrict__ P_cube, const float *__restrict__ W4,
+static __global__ void glf_cube_project_kernel(const float *__restrict__ P_cube, const float *__restrict__ W4,
                                         const float *__restrict__ bias, int B, int k, int q, float *__restrict__ Cq) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * q) return;
@@ -511,7 +511,7 @@ __global__ void glf_cube_project_kernel(const float *__restrict__ P_cube, const 
     for (int kk = 0; kk < k; ++kk) a += P_cube[s * k + kk] * W4[kk * q + qo];
     Cq[t] = a + bias[qo];
 }
-__global__ void glf_cube_grad_kernel(const float *__restrict__ dCq, const float *__restrict__ W4, int B, int N, int M, int k,
+static __global__ void glf_cube_grad_kernel(const float *__restrict__ dCq, const float *__restrict__ W4, int B, int N, int M, int k,
                                      int q, float *__restrict__ Gq) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= B * k) return;
@@ -521,7 +521,7 @@ __global__ void glf_cube_grad_kernel(const float *__restrict__ dCq, const float 
     Gq[t] = a / ((float)N * (float)M);
 }
 
-__global__ void __launch_bounds__(256) glf_node_project4_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
+static __global__ void __launch_bounds__(256) glf_node_project4_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
                                                                  const float *__restrict__ Cq, const float *__restrict__ W,
                                                                  int BN, int N, int k, int q, float *__restrict__ Q_col,
                                                                  float *__restrict__ Q_row) {
@@ -552,7 +552,7 @@ __global__ void __launch_bounds__(256) glf_node_project4_kernel(const float *__r
     }
 }
 
-__global__ void __launch_bounds__(256) glf_node_grad4_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
+static __global__ void __launch_bounds__(256) glf_node_grad4_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
                                                               const float *__restrict__ Gq, const float *__restrict__ W,
                                                               const int32_t *__restrict__ csrT_ptr, int BN, int N, int M,
                                                               int k, int q, float *__restrict__ G_col, float *__restrict__ G_row) {
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(256) glf_node_grad4_kernel(const float *__rest
 
 // ---- per-sample column sums (cube pool / dCq): block = 32 lanes (channels) x 8 warps (row slices)
 // partial[s][blk][ch] = sum of rows [blk*rpb, (blk+1)*rpb) of sample s;   grid (nblk, B)
-__global__ void __launch_bounds__(256) glf_colsum_partial_kernel(const float *__restrict__ X, int ch, int N, int rpb,
+static __global__ void __launch_bounds__(256) glf_colsum_partial_kernel(const float *__restrict__ X, int ch, int N, int rpb,
                                                                   float *__restrict__ partial) {
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(256) glf_colsum_partial_kernel(const float *__
     }
 }
 // out[s][ch] = (sum_blk partial[s][blk][ch]) / divisor;   grid (B)
-__global__ void __launch_bounds__(256) glf_colsum_final_kernel(const float *__restrict__ partial, int ch, int nblk, float divisor,
+static __global__ void __launch_bounds__(256) glf_colsum_final_kernel(const float *__restrict__ partial, int ch, int nblk, float divisor,
                                                                 float *__restrict__ out) {
     __shared__ float red[8][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(256) glf_colsum_final_kernel(const float *__re
 
 // generic X^T Y over n node rows (runtime k, q; used when no micro-tile instance fits)
 #define GLF_XTY_ROWS 32
-__global__ void __launch_bounds__(256) glf_node_xty_kernel(const float *__restrict__ X, const float *__restrict__ Y, int64_t n,
+static __global__ void __launch_bounds__(256) glf_node_xty_kernel(const float *__restrict__ X, const float *__restrict__ Y, int64_t n,
                                                             int rows_per_block, int k, int q, float *__restrict__ partial) {
     extern __shared__ __align__(16) float smem[];   // Xs [ROWS][k], Ys [ROWS][q]
     float *Xs = smem, *Ys = smem + GLF_XTY_ROWS * k;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(256) glf_node_xty_kernel(const float *__restri
 
 // ------------------------------------------------------------------ last layer, node level
 // out[i] = act( P_row[i] W1 + (1/M) sum_m Q_col[col[iM+m]] + Q_row[i] )  ==  row-mean of Z (graph.py:455)
-__global__ void __launch_bounds__(256) glf_last_out_kernel(const float *__restrict__ P_row, const int32_t *__restrict__ col,
+static __global__ void __launch_bounds__(256) glf_last_out_kernel(const float *__restrict__ P_row, const int32_t *__restrict__ col,
                                                             const float *__restrict__ W1, const float *__restrict__ Q_col,
                                                             const float *__restrict__ Q_row, int BN, int M, int k, int q,
                                                             int relu, float *__restrict__ out) {
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(256) glf_last_out_kernel(const float *__restri
 
 // last-layer backward, node level.  dOutM = dOut * [out > 0] (relu).
 //   dQ_row[i] = dOutM[i];  dQ_col[j] = (1/M) sum_{e in csrT[j]} dOutM[e / M]
-__global__ void __launch_bounds__(256) glf_last_bwd_pool_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout,
+static __global__ void __launch_bounds__(256) glf_last_bwd_pool_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout,
                                                                  int relu, int BN, int M, int q,
                                                                  const int32_t *__restrict__ csrT_ptr,
                                                                  const int32_t *__restrict__ csrT_edge,
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(256) glf_last_bwd_pool_kernel(const float *__r
 }
 
 // R[i] = (dOutM[i] W1^T)/M + G_row[i]   (in place on G_row)
-__global__ void __launch_bounds__(256) glf_last_rowterm_kernel(const float *__restrict__ dQ_row, const float *__restrict__ W1,
+static __global__ void __launch_bounds__(256) glf_last_rowterm_kernel(const float *__restrict__ dQ_row, const float *__restrict__ W1,
                                                                 int BN, int M, int k, int q, float *__restrict__ G_row) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)BN * k) return;
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(256) glf_last_rowterm_kernel(const float *__re
 }
 
 // dH[e] = (R[e / M] + G_col[col[e]]) [* (H[e] > 0) if Hmask]     thread per (edge, 4-channel group); k % 4 == 0
-__global__ void __launch_bounds__(256) glf_last_edge_in_kernel(const int32_t *__restrict__ col, const float *__restrict__ R,
+static __global__ void __launch_bounds__(256) glf_last_edge_in_kernel(const int32_t *__restrict__ col, const float *__restrict__ R,
                                                                 const float *__restrict__ G_col,
                                                                 const float *__restrict__ Hmask, int64_t c, int M, int k,
                                                                 float *__restrict__ dH) {
