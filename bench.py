@@ -47,11 +47,18 @@ def parse():
     ap.add_argument("--k", type=int, default=14)
     ap.add_argument("--kind", default="uniform", choices=["uniform", "clustered"])
     ap.add_argument("--channels", type=int, nargs="+", default=[3, 32, 16, 3])
-    ap.add_argument("--cpu-batch", type=int, default=2, help="samples in the bounded CPU sample")
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="samples per CPU step (default: the full batch for --impl reference, 2 for the cpu_baseline leg)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the 128^3 kNN build timing")
     return ap.parse_args()
+
+
+def common_config(a, world):
+    """The keys both arms print identically (the driver compares the arms' configs)."""
+    N = a.n_side ** 3
+    return {"workload": workload_name(a), "particles_per_step_per_gpu": a.batch * N, "edges_per_step_per_gpu": a.batch * N * a.k}
 
 
 def workload_name(a):
@@ -80,9 +87,18 @@ def cpu_reference_step(x, za, tgt, k, channels, params):
     return {"knn": t1 - t0, "coo": t2 - t1, "fwd": t3 - t2, "bwd": t4 - t3, "total": t4 - t0, "loss": float(loss.detach())}
 
 
-def cpu_sample(a, syn, steps, warmup):
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host core it can."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
+def cpu_sample(a, syn, steps, warmup, b):
     N = a.n_side ** 3
-    b = a.cpu_batch
     params = syn.glorot_params(a.channels)
     x = syn.make_box(a.kind, b, N, 0)
     za, tgt = syn.za_features(b, N, 0)
@@ -103,15 +119,17 @@ def run_reference(a):
     if rank != 0:
         return
     syn = importlib.import_module("n-body_pointcloudevolution_b200.synthetic")
-    value, dt, stage = cpu_sample(a, syn, a.steps, min(a.warmup, 1))
-    cores = torch.get_num_threads()
-    sample = (f"{a.cpu_batch} samples of the {a.n_side}^3 workload per step "
-              f"(kNN sklearn 1 thread, layers torch-CPU {cores} threads)")
+    cores = use_all_host_threads()
+    b = a.cpu_batch or a.batch                     # the full batch of the GPU arm: same config
+    value, dt, stage = cpu_sample(a, syn, a.steps, min(a.warmup, 1), b)
+    sample = (f"{b} samples of the {a.n_side}^3 workload per step "
+              f"(kNN sklearn 1 thread as shipped, layers torch-CPU {cores} threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "reference_sample": sample},
+        "config": common_config(a, 1),
+        "arm": {"reference_sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count(), "stage_s": stage},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -207,15 +225,15 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
     if base == "knn_query":
         return n * (12 + 4 * M)                      # xyz in, int32 idx out
     if base in ("gl_pool_kernel", "glf_pool_kernel", "gln_pool_kernel", "gln_pool_generic_kernel"):
-        return c * (2 * 4 * k + 4) + n * (4 + 2 * 4 * k)       # H read for the row pool + gathered for the col pool
+        return c * (4 * k + 4) + n * (4 + 2 * 4 * k)           # contract: the pool pass reads H ONCE
     if base in ("gl_edge_out_kernel", "glf_edge_out_kernel", "glk3_edge_out_kernel", "glt_edge_out_tf32", "glt_edge_out_tf32x3"):
         return c * (4 * k + 4 + 4 * q) + n * 2 * 4 * q         # H in, col in, H_out out (+ node tables)
     if base == "gl_last_out_kernel":
         return c * (4 * k + 4) + n * 3 * 4 * q
     if base == "glf_last_out_kernel":
         return c * 4 + n * (4 * k + 3 * 4 * q)
-    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel", "gln_bwd_pool_kernel"):   # dZ read twice (row sums + gathered);
-        return c * (2 * 4 * q + 4) + n * (4 + 2 * 4 * q)       # the network path delivers dZ pre-masked (no H_out read)
+    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel", "gln_bwd_pool_kernel"):   # contract: dZ read ONCE by the pool pass;
+        return c * (4 * q + 4) + n * (4 + 2 * 4 * q)           # the network path delivers dZ pre-masked (no H_out read)
     if base == "xty_partial_dW1":
         return c * (4 * k + 4 * q * relu)
     if base == "glb_edge_in_kernel":
@@ -266,6 +284,153 @@ def ncu_traffic(name):
 
 
 # ----------------------------------------------------------------------------- our arm
+class Workload:
+    """One training workload on this rank: a pool of distinct batches resident in HBM (and their pinned host copies), the
+    parameter store, and the step function - eager or replayed from one CUDA graph."""
+
+    def __init__(self, nb, dev, rank, world, n_side, b, k, ch, kind, use_graph, n_pool=4, host_copies=True):
+        syn, graph, nn_, tu = nb.synthetic, nb.graph, nb.nn, nb.train_utils
+        self.nb, self.dev, self.world, self.b, self.N, self.k, self.ch = nb, dev, world, b, n_side ** 3, k, ch
+        N = self.N
+        self.store = store = tu.ParamStore(ch, device=dev)
+        store.load_numpy(syn.glorot_params(ch))
+        self.adam = adam = tu.AdamTF(store, lr=0.01)
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+        self.n_pool = n_pool
+        self.host = []
+        for i in range(n_pool):                                      # different boxes every step; every rank owns its samples
+            seed = 1000 * rank + i
+            x = syn.make_box(kind, b, N, seed)
+            za, tgt = syn.za_features(b, N, seed)
+            ts = tuple(torch.from_numpy(t) for t in (x, za, tgt))
+            self.host.append(tuple(t.pin_memory() for t in ts) if host_copies else ts)
+        self.resident = [tuple(t.to(dev) for t in hb) for hb in self.host]
+        if not host_copies:
+            self.host = None
+
+        def train_step(x, za, tgt, comm=True, dev_step=False, update=True):
+            A = graph.get_kneighbor_list(x, k)                       # kNN rebuilt every step
+            coo, diag = graph.to_coo_batch_ZA_diag(A)
+            pred = graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
+            loss = nn_.loss_ZA(pred, tgt)
+            store.zero_grad()
+            loss.backward()
+            if comm:
+                tu.allreduce_gradients(store, world)
+            if not update:
+                return loss
+            if dev_step:
+                adam.step_dev(grad_scale=1.0 / world)                # step count in device memory: graph capturable
+            else:
+                adam.step(grad_scale=1.0 / world)
+            return loss
+        self.train_step = train_step
+
+        # The whole step (kNN build, adjacency, forward, backward, Adam) is captured once in a CUDA graph and replayed, so
+        # the timed region is not limited by the host's launch rate; --no-graph launches eagerly.
+        self.graphed, self.graph_note = None, "eager launches (--no-graph)"
+        if use_graph:
+            try:
+                if world == 1:
+                    self.graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), self.resident[0])
+                    self.graph_note = "one CUDA graph replay per step (whole step captured once)"
+                else:
+                    # the NCCL all-reduce stays outside the capture (capturing it hung with the NCCL watchdog thread alive):
+                    # graph = kNN build + forward + backward; all-reduce and Adam are launched eagerly behind it
+                    self.graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, comm=False, update=False), self.resident[0])
+                    self.graph_note = "one CUDA graph replay per step (kNN + forward + backward), NCCL all-reduce and Adam launched eagerly"
+            except Exception as exc:
+                self.graphed, self.graph_note = None, f"eager launches (graph capture failed: {repr(exc)[:200]})"
+                torch.cuda.synchronize()
+
+    def run_step(self, x, za, tgt):
+        if self.graphed is None:
+            return self.train_step(x, za, tgt)
+        loss = self.graphed(x, za, tgt)
+        if self.world > 1:
+            self.nb.train_utils.allreduce_gradients(self.store, self.world)
+            self.adam.step(grad_scale=1.0 / self.world)
+        return loss
+
+    def step_resident(self, i):
+        return self.run_step(*self.resident[i % self.n_pool])
+
+
+def barrier(world):
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps, world, dev, stats=None, tag=None):
+    """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides; CUDA-event time, max over ranks (ms)."""
+    barrier(world)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    host = []
+    ev[0].record()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        fn(i)
+        ev[i + 1].record()
+        host.append(time.perf_counter() - t0)
+    barrier(world)
+    if stats is not None:
+        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
+        hd = np.diff(np.array([0.0] + host)) * 1e3
+        stats[tag] = {"device_ms_median": float(np.median(per)), "device_ms_max": float(per.max()),
+                      "device_ms_min": float(per.min()), "host_enqueue_ms_median": float(np.median(hd)),
+                      "host_enqueue_ms_max": float(hd.max()), "argmax": int(per.argmax())}
+    ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def event_ms(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(reps):
+        fn()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / reps
+
+
+def knn_sweep(nb, dev, peak, with_sklearn):
+    """BASELINE config 3: kNN graph construction, N in {8 x 32^3, 64^3, 128^3}, k in {8, 14, 32}, uniform and clustered
+    boxes, open box (graph.get_kneighbor_list, index order) and periodic box (graph.get_pbc_kneighbors_csr, thr 0.05,
+    distance order).  Algorithmic bytes = particles * (12 + 4 k).  sklearn (the reference's kneighbors_graph
+    call, one thread as shipped) is timed beside it on one sample where that takes seconds, not minutes."""
+    syn, graph = nb.synthetic, nb.graph
+    rows = []
+    for side, b in ((32, 8), (64, 1), (128, 1)):
+        N = side ** 3
+        for kind in ("uniform", "clustered"):
+            xh = syn.make_box(kind, b, N, 0)
+            x = torch.from_numpy(xh).to(dev)
+            for k in (8, 14, 32):
+                reps = 10 if side < 128 else 5
+                t_open = event_ms(lambda: graph.get_kneighbor_list(x, k), reps)
+                t_pbc = event_ms(lambda: graph.get_pbc_kneighbors_csr(x, k, 0.05, include_self=True), reps)
+                ab = b * N * (12 + 4 * k)
+                row = {"particles": f"{b}x{side}^3", "kind": kind, "k": k, "open_ms": round(t_open, 4), "periodic_ms": round(t_pbc, 4),
+                       "algorithmic_bytes": ab, "open_roofline_frac": ab / (t_open * 1e-3) / 1e9 / peak,
+                       "periodic_roofline_frac": ab / (t_pbc * 1e-3) / 1e9 / peak,
+                       "open_particles_per_s": b * N / (t_open * 1e-3)}
+                if with_sklearn and (side == 32 or (side == 64 and k == 14)):
+                    from oracle import ref_graph                      # CPU leg (checker code timed as the baseline)
+                    t0 = time.perf_counter()
+                    ref_graph.get_kneighbor_list(xh[:1], k)
+                    row["sklearn_open_ms_per_sample"] = round((time.perf_counter() - t0) * 1e3, 1)
+                    row["sklearn_note"] = "kneighbors_graph (KD-tree, 1 thread as shipped, graph.py:709) on ONE sample"
+                rows.append(row)
+            del x
+    return rows
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -283,106 +448,20 @@ def main():
         torch.distributed.init_process_group("nccl", device_id=dev)
 
     nb = importlib.import_module("n-body_pointcloudevolution_b200")
-    syn, graph, nn_, tu, lib = nb.synthetic, nb.graph, nb.nn, nb.train_utils, nb._lib
+    syn, graph, tu, lib = nb.synthetic, nb.graph, nb.train_utils, nb._lib
     nb.ops.device_check()
 
     N, b, k, ch = a.n_side ** 3, a.batch, a.k, a.channels
-    store = tu.ParamStore(ch, device=dev)
-    store.load_numpy(syn.glorot_params(ch))
-    adam = tu.AdamTF(store, lr=0.01)
-    mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
-
-    # a pool of distinct batches (different boxes every step; every rank owns its own samples)
-    n_pool = 4
-    host = []
-    for i in range(n_pool):
-        seed = 1000 * rank + i
-        x = syn.make_box(a.kind, b, N, seed)
-        za, tgt = syn.za_features(b, N, seed)
-        host.append(tuple(torch.from_numpy(t).pin_memory() for t in (x, za, tgt)))
-    resident = [tuple(t.to(dev) for t in hb) for hb in host]
-    staging = tuple(torch.empty_like(t, device=dev) for t in host[0])
-
-    def train_step(x, za, tgt, comm=True, dev_step=False, update=True):
-        A = graph.get_kneighbor_list(x, k)                           # kNN rebuilt every step
-        coo, diag = graph.to_coo_batch_ZA_diag(A)
-        pred = graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k))
-        loss = nn_.loss_ZA(pred, tgt)
-        store.zero_grad()
-        loss.backward()
-        if comm:
-            tu.allreduce_gradients(store, world)
-        if not update:
-            return loss
-        if dev_step:
-            adam.step_dev(grad_scale=1.0 / world)                    # step count in device memory: graph capturable
-        else:
-            adam.step(grad_scale=1.0 / world)
-        return loss
-
-    # The whole step (kNN build, adjacency, forward, backward, all-reduce, Adam: ~58 launches) is captured once in a
-    # CUDA graph and replayed, so the timed region is not limited by the host's launch rate; --no-graph launches eagerly.
-    graphed, graph_note = None, "eager launches (--no-graph)"
-    if not a.no_graph:
-        try:
-            if world == 1:
-                graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), resident[0])
-                graph_note = "one CUDA graph replay per step (whole step captured once)"
-            else:
-                # the NCCL all-reduce stays outside the capture (capturing it hung with the NCCL watchdog thread alive):
-                # graph = kNN build + forward + backward; all-reduce and Adam are launched eagerly behind it
-                graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, comm=False, update=False), resident[0])
-                graph_note = "one CUDA graph replay per step (kNN + forward + backward), NCCL all-reduce and Adam launched eagerly"
-        except Exception as exc:
-            graphed, graph_note = None, f"eager launches (graph capture failed: {repr(exc)[:200]})"
-            torch.cuda.synchronize()
-
-    def run_step(x, za, tgt):
-        if graphed is None:
-            return train_step(x, za, tgt)
-        loss = graphed(x, za, tgt)
-        if world > 1:
-            tu.allreduce_gradients(store, world)
-            adam.step(grad_scale=1.0 / world)
-        return loss
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
-
+    wl = Workload(nb, dev, rank, world, a.n_side, b, k, ch, a.kind, not a.no_graph)
+    store, host, n_pool, graph_note = wl.store, wl.host, wl.n_pool, wl.graph_note
     step_stats = {}
-
-    def timed(fn, steps, tag):
-        barrier()
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-        host = []
-        ev[0].record()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            fn(i)
-            ev[i + 1].record()
-            host.append(time.perf_counter() - t0)
-        barrier()
-        per = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)])
-        hd = np.diff(np.array([0.0] + host)) * 1e3
-        step_stats[tag] = {"device_ms_median": float(np.median(per)), "device_ms_max": float(per.max()),
-                           "device_ms_min": float(per.min()), "host_enqueue_ms_median": float(np.median(hd)),
-                           "host_enqueue_ms_max": float(hd.max()), "argmax": int(per.argmax())}
-        ms = torch.tensor([ev[0].elapsed_time(ev[steps])], device=dev)
-        if world > 1:
-            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
-        return float(ms.item())
-
-    def step_resident(i):
-        run_step(*resident[i % n_pool])
 
     # End to end: every step's inputs start in pinned HOST memory and every step's loss ends in pinned host memory.
     # Like a production input pipeline the copies are asynchronous: step i+1's H2D runs on a copy stream while step i
     # computes (two device staging slots, event-ordered), and the loss is read back with a non-blocking D2H copy; all
     # copies complete inside the timed region (it ends with a device-wide synchronize).
     copy_stream = torch.cuda.Stream(device=dev)
-    slots = [staging, tuple(torch.empty_like(t) for t in staging)]
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
     loss_host = torch.zeros(max(a.steps, 8), dtype=torch.float32).pin_memory()
@@ -403,7 +482,7 @@ def main():
             prefetch(0)
         torch.cuda.current_stream().wait_event(ready[sl])
         prefetch(i + 1)
-        loss = run_step(*slots[sl])
+        loss = wl.run_step(*slots[sl])
         consumed[sl].record()
         used[sl] = True
         loss_host[i % loss_host.numel()].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H read of the loss
@@ -411,16 +490,16 @@ def main():
     # ---- warm-up, then the timed region (device-resident inputs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     for i in range(max(a.warmup, 3)):
-        step_resident(i)
+        wl.step_resident(i)
     skip = 0
     if sampler:
         sampler.wait_ready()
         skip = sampler.mark()
     l0 = lib.launch_count()
-    ms = timed(step_resident, a.steps, "resident")
+    ms = timed(wl.step_resident, a.steps, world, dev, step_stats, "resident")
     launches = lib.launch_count() - l0
-    if graphed is not None:                                          # kernels are launched by the graph replays
-        launches = (graphed.kernels_per_replay + (1 if world > 1 else 0)) * a.steps
+    if wl.graphed is not None:                                       # kernels are launched by the graph replays
+        launches = (wl.graphed.kernels_per_replay + (1 if world > 1 else 0)) * a.steps
     clocks = sampler.stop(skip) if sampler else {}
     particles = world * b * N
     value = particles * a.steps / (ms * 1e-3)
@@ -430,10 +509,32 @@ def main():
         step_e2e(i)
     torch.cuda.synchronize()
     used[0] = used[1] = False
-    ms_e2e = timed(step_e2e, a.steps, "e2e")
+    ms_e2e = timed(step_e2e, a.steps, world, dev, step_stats, "e2e")
     assert bool(torch.isfinite(loss_host[:min(a.steps, loss_host.numel())]).all()), "e2e losses did not arrive on the host"
     e2e_value = particles * a.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # ---- BASELINE config 4: 64^3 particles, data-parallel training, run by ALL ranks (weak: 1 sample per GPU; strong:
+    # global batch 8 split over the ranks).  Same step, same timing rules; skipped with --no-extras.
+    c4 = {}
+    if not a.no_extras and a.n_side == 32 and ch == [3, 32, 16, 3]:
+        for mode, bb in (("weak", 1), ("strong", max(8 // world, 1))):
+            try:
+                w4 = Workload(nb, dev, rank, world, 64, bb, k, ch, a.kind, not a.no_graph, n_pool=2, host_copies=False)
+                for i in range(3):
+                    w4.step_resident(i)
+                st = 20
+                ms4 = timed(w4.step_resident, st, world, dev)
+                p4 = world * bb * 64 ** 3
+                c_edges = bb * 64 ** 3 * k
+                step_bytes = 1428 * c_edges + (12 + 4 * k) * bb * 64 ** 3 + 20 * c_edges + 16 * bb * 64 ** 3
+                c4[mode] = {"samples_per_gpu": bb, "global_batch": world * bb, "ms_per_step": ms4 / st, "particles_per_s": p4 * st / (ms4 * 1e-3),
+                            "step_roofline_frac": step_bytes / (ms4 / st * 1e-3) / 1e9 / measured_peak_gbs()[0], "launch": w4.graph_note}
+                del w4
+                torch.cuda.empty_cache()
+            except Exception as exc:
+                c4[mode] = {"error": repr(exc)[:300]}
+                barrier(world)
 
     if world > 1:
         torch.distributed.barrier()
@@ -445,17 +546,15 @@ def main():
     prof_steps = 3
     torch.cuda.synchronize()
     lib.prof_enable(True)
-    t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_ev0.record()
     for i in range(prof_steps):
-        train_step(*resident[i % n_pool], comm=False)
-    t_ev1.record()
+        wl.train_step(*wl.resident[i % n_pool], comm=False)
     torch.cuda.synchronize()
     report = lib.prof_report()
     lib.prof_enable(False)
     kern_ms = {n: tot / prof_steps for n, (cnt, tot) in report.items()}
     kern_cnt = {n: cnt / prof_steps for n, (cnt, tot) in report.items()}
     sum_ms = sum(kern_ms.values())
+    step_ms = ms / a.steps
     relu_by_layer = {(kk, qq): (li < len(ch) - 2) for li, (kk, qq) in enumerate(zip(ch[:-1], ch[1:]))}
     peak, peak_src = measured_peak_gbs()
     top = sorted(kern_ms.items(), key=lambda kv: -kv[1])
@@ -463,8 +562,9 @@ def main():
     for name, t in top[:40]:
         per_launch_ms = t / kern_cnt[name]
         ab = kernel_algorithmic_bytes(name, b, N, k, relu_by_layer)
+        # share: of the graph-replayed step (ms_per_step); the eager event times of all kernels sum to `eager_sum_ms`
         kernels.append({"kernel": name, "ms_per_step": round(t, 4), "launches_per_step": kern_cnt[name],
-                        "share": round(t / sum_ms, 4),
+                        "share": round(t / step_ms, 4),
                         "algorithmic_bytes": ab,
                         "achieved_gbs": (ab / (per_launch_ms * 1e-3) / 1e9) if ab else None})
     dom = kernels[0]
@@ -472,6 +572,8 @@ def main():
                 "peak_source": peak_src, "unit": "GB/s",
                 "frac": (dom["achieved_gbs"] / peak) if dom["achieved_gbs"] else None,
                 "traffic": ncu_traffic(dom["kernel"]), "share_of_step": dom["share"],
+                "share_note": "kernel time (eager, CUDA events) / ms_per_step of the graph-replayed step",
+                "eager_sum_ms": round(sum_ms, 4),
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes"],
                 "step_algorithmic_bytes": None, "kernels": kernels}
     # whole-step roofline (SURVEY §8d contract figure: 1428 B/edge + 68 B + 280 B per particle for [3,32,16,3], k=14)
@@ -479,29 +581,26 @@ def main():
         c_edges = b * N * k
         step_bytes = 1428 * c_edges + (12 + 4 * k) * b * N + 20 * c_edges + 16 * b * N
         roofline["step_algorithmic_bytes"] = step_bytes
-        roofline["step_achieved"] = step_bytes / (ms / a.steps * 1e-3) / 1e9
+        roofline["step_achieved"] = step_bytes / (step_ms * 1e-3) / 1e9
         roofline["step_frac"] = roofline["step_achieved"] / peak
 
-    # ---- secondary metric: kNN build ms at 128^3 (periodic, k=14)
     extras = {}
+    knn128 = {}
     if not a.no_extras:
-        for kind in ("uniform", "clustered"):
-            xb = torch.from_numpy(syn.make_box(kind, 1, 128 ** 3, 0)).to(dev)
-            for _ in range(2):
-                graph.get_pbc_kneighbors_csr(xb, 14, 0.05, include_self=True)
-            torch.cuda.synchronize()
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-            ev[0].record()
-            reps = 5
-            for _ in range(reps):
-                graph.get_pbc_kneighbors_csr(xb, 14, 0.05, include_self=True)
-            ev[1].record()
-            torch.cuda.synchronize()
-            t_ms = ev[0].elapsed_time(ev[1]) / reps
-            ab = 128 ** 3 * (12 + 4 * 14)
-            extras[f"knn_build_ms_128^3_{kind}"] = t_ms
-            extras[f"knn_128^3_{kind}_roofline_frac"] = ab / (t_ms * 1e-3) / 1e9 / peak
-            del xb
+        del wl
+        torch.cuda.empty_cache()
+        # ---- BASELINE config 3: kNN build sweep (includes the metric's second half: kNN build ms at 128^3)
+        try:
+            sweep = knn_sweep(nb, dev, peak, with_sklearn=not a.no_cpu_baseline)
+            extras["knn_sweep"] = sweep
+            for r in sweep:
+                if r["particles"] == "1x128^3" and r["k"] == 14:
+                    knn128[r["kind"]] = {"periodic_ms": r["periodic_ms"], "open_ms": r["open_ms"],
+                                         "periodic_roofline_frac": r["periodic_roofline_frac"]}
+        except Exception as exc:
+            extras["knn_sweep"] = {"error": repr(exc)[:300]}
+        if c4:
+            extras["config4_64^3_dp"] = c4
 
         # BASELINE config 5: 128^3-particle multi-redshift rollout INFERENCE, periodic kNN graph rebuilt every step
         # (graph.rollout_shift_inv: pbc kNN -> 9-channel edges -> [9,32,16,6] graph net -> scaled residual -> readout)
@@ -516,44 +615,41 @@ def main():
             mv5 = types.SimpleNamespace(channels=ch5, var_scope="params", get_layer_vars=st5.get_layer_vars,
                                         get_scalars=lambda: (0.01, 0.01))
             with torch.no_grad():
-                Xc = X5
-                for _ in range(2):
-                    Xc = graph.rollout_shift_inv(Xc, mv5, 14, 0.05)
-                torch.cuda.synchronize()
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                ev[0].record()
-                reps = 5
-                for _ in range(reps):
-                    Xc = graph.rollout_shift_inv(Xc, mv5, 14, 0.05)
-                ev[1].record()
-                torch.cuda.synchronize()
-            t5 = ev[0].elapsed_time(ev[1]) / reps
+                state = {"X": X5}
+
+                def roll():
+                    state["X"] = graph.rollout_shift_inv(state["X"], mv5, 14, 0.05)
+                t5 = event_ms(roll, 5)
             extras["rollout_128^3"] = {"ms_per_rollout_step": t5, "particles_per_s": n5 / (t5 * 1e-3), "channels": ch5, "k": 14,
-                                       "boundary_threshold": 0.05, "finite": bool(torch.isfinite(Xc).all()),
+                                       "boundary_threshold": 0.05, "finite": bool(torch.isfinite(state["X"]).all()),
                                        "what": "inference, periodic kNN rebuilt every step, FP64 kNN distances, tf32x3/fp32 layers"}
-            del X5, Xc
+            del X5, state
         except Exception as exc:   # the headline line must survive a failure of this extra
             extras["rollout_128^3"] = {"error": repr(exc)[:300]}
 
     # ---- the reference's CPU path on this box's host cores (bounded sample)
     cpu = None
     if not a.no_cpu_baseline and world == 1:
-        v, dt, stage = cpu_sample(a, syn, 1, 1)
-        cores = torch.get_num_threads()
+        cores = use_all_host_threads()
+        cb = a.cpu_batch or 2
+        v, dt, stage = cpu_sample(a, syn, 1, 1, cb)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": f"1 step of {a.cpu_batch} samples of the same {a.n_side}^3/k={a.k} workload "
+               "sample": f"1 step of {cb} samples of the same {a.n_side}^3/k={a.k} workload "
                          f"(kNN: sklearn KD-tree, 1 thread as shipped; layers: torch-CPU, {cores} threads)",
                "stage_s": stage}
 
+    cfg = common_config(a, world)
+    cfg.update({"math_mode": lib.get_math_mode(), "launch": graph_note, "particles_per_step": particles,
+                "edges_per_step": particles * k,
+                "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)",
+                "l2": "step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"})
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
-        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "f32 (tcgen05 TF32x3 error-compensated, FP32-class accuracy)",
                   "tf32": "tf32 (tcgen05 single pass, FP32 accumulate)"}[lib.get_math_mode()],
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "math_mode": lib.get_math_mode(), "launch": graph_note, "particles_per_step": particles, "edges_per_step": particles * k,
-                   "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)",
-                   "l2": "step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"},
+        "config": cfg,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4,
@@ -561,6 +657,8 @@ def main():
                             "back every step with a non-blocking D2H copy into pinned memory; the timed region ends with a "
                             "device-wide synchronize"},
         "gpu_launches": int(launches),
+        # second half of BASELINE's metric: periodic kNN build (k = 14, thr 0.05, self included) on one 128^3 box, ms
+        "knn_build_ms_128^3": knn128 or None,
         "step_stats": step_stats,
         "roofline": roofline,
         "cpu_baseline": cpu,

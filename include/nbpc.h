@@ -86,11 +86,28 @@ long long nbpc_prof_report(char *buf, size_t cap);
  * idx_out: int32 (B,N,k) neighbour indices LOCAL to the sample (image indices mapped back to the
  *   original particle, graph.py:888-893).  d2_out: optional float64 (B,N,k), always in
  *   distance order (NULL to skip).
+ * status: optional int32[1] device (NULL to skip): periodic=1 assumes coordinates in the unit box [0,1]
+ *   (graph.py:827-855 builds images for the unit box only); status[0] counts particles with a coordinate
+ *   outside it, for which the result is unspecified (the reference would still run its KD-tree on them).
+ *   The Python facade exposes it as KnnCSR.check().
  * Requires 1 <= k <= NBPC_KNN_MAX_K and k <= N - (include_self ? 0 : 1). */
 size_t nbpc_knn_workspace_bytes(int B, int N, int k, int periodic);
 int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N, int k,
              int periodic, double boundary_threshold, int include_self, int order,
-             int32_t *idx_out, double *d2_out, void *workspace, size_t ws_bytes, void *stream);
+             int32_t *idx_out, double *d2_out, int32_t *status, void *workspace, size_t ws_bytes, void *stream);
+
+/* The padded ("cloned") cube itself, for callers of graph.pad_cube_boundaries (graph.py:827-855; nbpc_knn never
+ * materialises it).  One sample: xyz (N,>=3) float32, row stride stride_n.
+ * nbpc_pad_cube_count: offsets int32 (N+1) = exclusive scan of the per-particle image counts (0/1/3/7,
+ *   graph.py:801-825); offsets[N] = total number of images (read it back to size the outputs).
+ * nbpc_pad_cube_emit: padded_out float64 (N + n_img, 3) = [particles; images in particle order, each particle's
+ *   images in the reference's face / edge / corner pattern order], images = (pattern*bound) + particle in float64
+ *   (NumPy's int64 + float32 promotion); idx_map_out int64 (n_img) = source particle of every image. */
+size_t nbpc_pad_cube_workspace_bytes(int N);
+int nbpc_pad_cube_count(const float *xyz, int64_t stride_n, int N, double boundary_threshold, int32_t *offsets,
+                        void *workspace, size_t ws_bytes, void *stream);
+int nbpc_pad_cube_emit(const float *xyz, int64_t stride_n, int N, double boundary_threshold, const int32_t *offsets,
+                       double *padded_out, int64_t *idx_map_out, void *stream);
 
 /* ---------------------------------------------------------------- adjacency
  * Replaces graph.to_coo_batch_ZA_diag / to_coo_batch / get_indices_from_list_CSR

@@ -33,7 +33,10 @@ SIGNATURES = {
     "nbpc_prof_enable": (_i, [_i]),
     "nbpc_prof_report": (ctypes.c_longlong, [ctypes.c_char_p, _sz]),
     "nbpc_knn_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "nbpc_knn": (_i, [_p, _i64, _i64, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _sz, _p]),
+    "nbpc_knn": (_i, [_p, _i64, _i64, _i, _i, _i, _i, _d, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_pad_cube_workspace_bytes": (_sz, [_i]),
+    "nbpc_pad_cube_count": (_i, [_p, _i64, _i, _d, _p, _p, _sz, _p]),
+    "nbpc_pad_cube_emit": (_i, [_p, _i64, _i, _d, _p, _p, _p, _p]),
     "nbpc_adjacency_workspace_bytes": (_sz, [_i, _i, _i]),
     "nbpc_adjacency": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "nbpc_segment_csr_workspace_bytes": (_sz, [_i64, _i]),

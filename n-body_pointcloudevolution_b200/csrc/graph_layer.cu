@@ -246,6 +246,13 @@ static bool gl_use_fast() {
 #endif
 }
 
+// NBPC_NO_FIRST_LAYER_FUSION=1 (read once) selects the unfused first-layer backward (cross-check)
+static bool gl_first_layer_fusion() {
+    static int cached = -1;
+    if (cached < 0) cached = getenv("NBPC_NO_FIRST_LAYER_FUSION") ? 0 : 1;
+    return cached == 1;
+}
+
 #ifndef NBPC_HOST_EMU
 static int gl_num_sms() {
     static int sms = 0;
@@ -319,7 +326,7 @@ static bool glk3_shape_ok(int k, int q) { return (k == 3 || k == 9 || k == 10) &
 #define GLK3_FOR_KQ(X) X(3, 16) X(3, 32) X(3, 64) X(9, 16) X(9, 32) X(9, 64) X(10, 16) X(10, 32) X(10, 64)
 static void glk3_launch_edge_out(int k, int q, const float *E, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
                                  int64_t c, int M, int relu, float *out, cudaStream_t stream) {
-    const uint32_t magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)M);
+    const uint32_t magic = glk3_magic(M);
 #define X(K_, Q_)                                                                                                          \
     if (k == K_ && q == Q_) {                                                                                             \
         const int epb = GLK3_THREADS / (Q_ / 4) * glk3_unroll(K_);                                                        \
@@ -366,7 +373,7 @@ static int glk3_launch_first_layer_bwd_t(const float *E, const float *dOut, cons
         }
         configured = true;
     }
-    const uint32_t magic = (uint32_t)(((uint64_t)1 << 32) / (uint32_t)M);
+    const uint32_t magic = glk3_magic(M);
     const int64_t ntiles = (edges_per_sample + GLK3_FB_TILE - 1) / GLK3_FB_TILE;
     const int64_t want = nbpc_max((int64_t)1, nbpc_min((int64_t)gl_num_sms() * 8 / B, (int64_t)max_blocks_per_sample));
     const int64_t tpb = (ntiles + want - 1) / want;
@@ -492,7 +499,7 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
                         float *dB, GlWorkspace &w, cudaStream_t stream) {
     const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
     float *dQ_col = w.Qc, *dQ_row = w.Qr;
-    if (!is_last && !dH_in && k == 3 && glk3_shape_ok(k, q) && B <= gl_max_partial_blocks() && !getenv("NBPC_NO_FIRST_LAYER_FUSION")) {
+    if (!is_last && !dH_in && k == 3 && glk3_shape_ok(k, q) && B <= gl_max_partial_blocks() && gl_first_layer_fusion()) {
         // first layer: every gradient from ONE pass over dZ (graph_layer_k3.cuh).  Blocks per sample are bounded by the
         // partial buffers: B * nb <= gl_max_partial_blocks() rows of (k,q) and nb <= ceil(N / 16) rows of the column sums
         const int nb = glk3_launch_first_layer_bwd(q, H_in, dOut, H_out, col, P_col, P_row, B, (int64_t)N * M, M, relu,

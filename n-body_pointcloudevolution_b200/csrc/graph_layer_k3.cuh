@@ -14,7 +14,9 @@
 #define GLK3_UNROLL 4
 __host__ __device__ constexpr int glk3_unroll(int K) { return K <= 4 ? 4 : 2; }   // rows in flight per thread
 
-// e / M for 0 <= e < 2^31 with magic = floor(2^32 / M): the estimate is exact or one short
+// e / M for 0 <= e < 2^31 with magic = floor(2^32 / M): the estimate is exact or one short.  M == 1 would need
+// magic = 2^32; 2^32 - 1 gives the estimate e - 1 (0 for e = 0), which the correction step turns into e.
+static inline uint32_t glk3_magic(int M) { return M == 1 ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)1 << 32) / (uint32_t)M); }
 __device__ __forceinline__ uint32_t glk3_div(uint32_t e, uint32_t M, uint32_t magic) {
     uint32_t qt = __umulhi(e, magic);
     if (e - qt * M >= M) ++qt;

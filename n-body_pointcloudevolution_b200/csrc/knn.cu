@@ -25,9 +25,6 @@
 #define KNN_FLAG_SHIFT 24
 #define KNN_THREADS 128
 #define KNN_PEND 4          // per-lane queue of accepted-but-not-yet-inserted candidates
-// Deferred insertion measured SLOWER on B200 (0.62 vs 0.57 ms at 8x32^3, k=14: lanes of a warp are rarely
-// converged inside the candidate loop, so the queue flushes per small lane group); kept for reference.
-#define KNN_DEFERRED 0
 
 struct KnnGridInfo {  // per sample, device
     float lo[3];
@@ -112,12 +109,15 @@ __global__ void knn_grid_setup(const unsigned *mm, int B, int G, int periodic, K
 // ------------------------------------------------------------------ 2. counting sort by cell
 __global__ void knn_count(const float *__restrict__ xyz, int64_t sb, int64_t sn, int B, int N, int G,
                           const KnnGridInfo *__restrict__ info, int32_t *__restrict__ cell_of_point,
-                          int32_t *__restrict__ cell_count) {
+                          int32_t *__restrict__ cell_count, int periodic, int32_t *__restrict__ status) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)B * N) return;
     const int b = (int)(t / N), i = (int)(t % N);
     const float *p = xyz + (int64_t)b * sb + (int64_t)i * sn;
     const KnnGridInfo gi = info[b];
+    // periodic mode assumes the unit box (the shell lower bounds treat edge cells as ending at 0 / 1): count offenders
+    if (periodic && status && !(p[0] >= 0.f && p[0] <= 1.f && p[1] >= 0.f && p[1] <= 1.f && p[2] >= 0.f && p[2] <= 1.f))
+        atomicAdd(&status[0], 1);
     const int cx = knn_cell_coord(p[0], gi.lo[0], gi.inv_h, G);
     const int cy = knn_cell_coord(p[1], gi.lo[1], gi.inv_h, G);
     const int cz = knn_cell_coord(p[2], gi.lo[2], gi.inv_h, G);
@@ -252,24 +252,6 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
 
     KnnTopK<K> top;
     top.init(P.k);
-#if !defined(NBPC_HOST_EMU) && KNN_DEFERRED
-    __shared__ double pend_d_s[KNN_PEND * KNN_THREADS];
-    __shared__ int pend_i_s[KNN_PEND * KNN_THREADS];
-    double *pend_d = pend_d_s + threadIdx.x;
-    int *pend_i = pend_i_s + threadIdx.x;
-    int npend = 0;
-#define KNN_FLUSH()                                                            \
-    do {                                                                       \
-        _Pragma("unroll") for (int f = 0; f < KNN_PEND; ++f) {                 \
-            if (f < npend) {                                                   \
-                const double fd = pend_d[f * KNN_THREADS];                     \
-                const int fi = pend_i[f * KNN_THREADS];                        \
-                if (top.accepts(fd, fi)) top.insert(fd, fi);                   \
-            }                                                                  \
-        }                                                                      \
-        npend = 0;                                                             \
-    } while (0)
-#endif
 
     for (int R = 0; R <= Rmax; ++R) {
         for (int dz = -R; dz <= R; ++dz) {
@@ -336,28 +318,12 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query(KnnQueryParams P) {
                             const double ty2 = __dsub_rn(py, __dadd_rn((double)c.y, oy));
                             const double tz2 = __dsub_rn(pz, __dadd_rn((double)c.z, oz));
                             const double dd = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty2, ty2)), __dmul_rn(tz2, tz2));
-#if defined(NBPC_HOST_EMU) || !KNN_DEFERRED
                             if (top.accepts(dd, cid)) top.insert(dd, cid);
-#else
-                            // Deferred insertion: a candidate that beats the (possibly stale) k-th best is parked in
-                            // a small per-lane queue; the ~K*10-instruction insert runs only when some lane of the
-                            // converged group has a full queue, and then for all lanes together.  (With immediate
-                            // insertion nearly every iteration pays the insert for the sake of one or two lanes.)
-                            if (top.accepts(dd, cid)) {
-                                pend_d[npend * KNN_THREADS] = dd;
-                                pend_i[npend * KNN_THREADS] = cid;
-                                ++npend;
-                            }
-                            if (__any_sync(__activemask(), npend == KNN_PEND)) KNN_FLUSH();
-#endif
                         }
                     }
                 }
             }
         }
-#if !defined(NBPC_HOST_EMU) && KNN_DEFERRED
-        if (__any_sync(__activemask(), npend > 0)) KNN_FLUSH();   // the termination test needs the true k-th best
-#endif
         // everything not yet visited is at least (R + margin) cells away along some axis
         const double g = ((double)R + (double)margin - 1e-3) * gi.h;
         if (g > 0.0 && top.d[K - 1] < g * g) break;
@@ -609,7 +575,7 @@ size_t nbpc_knn_workspace_bytes(int B, int N, int k, int periodic) {
 
 int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N, int k, int periodic,
              double boundary_threshold, int include_self, int order, int32_t *idx_out, double *d2_out,
-             void *workspace, size_t ws_bytes, void *stream_) {
+             int32_t *status, void *workspace, size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
     NBPC_ARG(xyz && idx_out && workspace, "null pointer");
@@ -641,8 +607,12 @@ int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N,
         nbpc_set_error("nbpc_knn: memset failed");
         return NBPC_ELAUNCH;
     }
+    if (status && nbpc_memset_async(status, 0, sizeof(int32_t), stream)) {
+        nbpc_set_error("nbpc_knn: memset failed");
+        return NBPC_ELAUNCH;
+    }
     NBPC_LAUNCH(knn_count, nbpc_cdiv(P_, 256), 256, 0, stream, xyz, stride_b, stride_n, B, N, G, w.info,
-                w.cell_of_point, w.cell_start);
+                w.cell_of_point, w.cell_start, periodic, status);
     NBPC_TRY(nbpc_exclusive_scan_i32(w.cell_start, ncell + 1, w.partials, stream));
     const float lower_f = (float)boundary_threshold, upper_f = (float)(1.0 - boundary_threshold);
     NBPC_LAUNCH(knn_scatter, nbpc_cdiv(P_, 256), 256, 0, stream, xyz, stride_b, stride_n, B, N, periodic, lower_f,

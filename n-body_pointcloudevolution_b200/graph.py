@@ -21,7 +21,8 @@ import torch
 from . import ops
 
 __all__ = [
-    "KnnCSR", "Adjacency", "get_kneighbor_list", "get_pbc_kneighbors_csr", "pad_cube_boundaries",
+    "KnnCSR", "Adjacency", "get_kneighbor_list", "get_pbc_kneighbors_csr", "pad_cube_boundaries", "get_pcube_csr",
+    "get_pcube_adjacency_list",
     "get_indices_from_list_CSR", "to_coo_batch_ZA_diag", "to_coo_batch", "confirm_CSR_to_COO_index_integrity",
     "include_node_features", "get_input_features_shift_inv_ZA", "get_input_features_shift_inv",
     "shift_inv_conv", "shift_inv_layer", "network_func_shift_inv_za", "model_func_shift_inv_za",
@@ -52,7 +53,8 @@ def _to_cuda(x, dtype=None):
 class KnnCSR:
     """One sample's kNN graph: the subset of scipy.sparse.csr_matrix the reference uses."""
 
-    def __init__(self, batch_idx, sample, n_cols=None, offset=0):
+    def __init__(self, batch_idx, sample, n_cols=None, offset=0, status=None):
+        self._status = status            # int32[1] device: out-of-unit-box particles of a periodic build
         self._batch = batch_idx          # (B, N, M) int32, shared by the whole batch (local indices)
         self._sample = sample
         self._offset = offset            # graph.py:710-711 offset_idx
@@ -85,6 +87,14 @@ class KnnCSR:
         r, c = self.nonzero()
         return SimpleNamespace(row=r, col=c, data=self.data, shape=self.shape)
 
+    def check(self):
+        """Host-synchronising validation of a periodic build: get_pbc_kneighbors_csr assumes the unit box (like the
+        reference's pad_cube_boundaries, graph.py:827-855); raises if some particle had a coordinate outside [0,1]."""
+        if self._status is not None and int(self._status.item()):
+            raise ValueError(f"periodic kNN: {int(self._status.item())} particles have coordinates outside the unit box [0,1]; "
+                             "wrap them first (nn.get_readout)")
+        return True
+
     def toarray_indices(self):
         """(N, M) view of the neighbour indices."""
         return self.indices.view(self.N, self.M)
@@ -110,7 +120,7 @@ def get_kneighbor_list(X_in, M, offset_idx=False, include_self=True):
     ASCENDING COLUMN order, int32 (what `.astype(np.float32)` does to the sklearn result)."""
     X = _to_cuda(X_in, torch.float32)
     b, N, D = X.shape
-    idx, _ = ops.knn(X, int(M), False, 0.0, bool(include_self), ops._lib.ORDER_INDEX, False)
+    idx, _, _ = ops.knn(X, int(M), False, 0.0, bool(include_self), ops._lib.ORDER_INDEX, False)
     return [KnnCSR(idx, i, N, offset=(N * i if offset_idx else 0)) for i in range(b)]
 
 
@@ -130,14 +140,50 @@ def get_pbc_kneighbors_csr(X, K, boundary_threshold, include_self=False):
     rows stay DISTANCE-sorted, image columns are mapped back to the original particle."""
     Xc = _to_cuda(X, torch.float32)
     mb_size, N, D = Xc.shape
-    idx, _ = ops.knn(Xc, int(K), True, float(boundary_threshold), bool(include_self), ops._lib.ORDER_DISTANCE, False)
-    return [KnnCSR(idx, i, _n_padded(Xc[i], float(boundary_threshold))) for i in range(mb_size)]
+    idx, _, status = ops.knn(Xc, int(K), True, float(boundary_threshold), bool(include_self), ops._lib.ORDER_DISTANCE, False)
+    return [KnnCSR(idx, i, _n_padded(Xc[i], float(boundary_threshold)), status=status) for i in range(mb_size)]
+
+
+class PaddedCube(torch.Tensor):
+    """The padded cloud returned by pad_cube_boundaries: a float64 (N + n_img, 3) device tensor that remembers the
+    threshold it was built with, so that get_pcube_csr can run the periodic kNN kernel on the original particles
+    (images are regenerated on the fly from the same rule) instead of a KD-tree over the materialised cloud."""
+
+    @staticmethod
+    def wrap(t, n_particles, threshold):
+        out = t.as_subclass(PaddedCube)
+        out.n_particles, out.boundary_threshold = int(n_particles), float(threshold)
+        return out
 
 
 def pad_cube_boundaries(x, boundary_threshold):
-    raise NotImplementedError(
-        "pad_cube_boundaries (graph.py:827-855) is folded into the periodic kNN kernel: images are generated "
-        "on the fly from the same (x >= 1-thr / x <= thr) rule; call get_pbc_kneighbors_csr")
+    """graph.py:827-855 (+ face / edge / corner_outer, 801-825).  x (N, 3) float32 in the unit box ->
+    (padded (N + n_img, 3) float64, idx_map (n_img,) int64): every particle with nb coordinates within the threshold
+    of a wall gets 2^nb - 1 images, appended in particle order and, per particle, in the reference's pattern order.
+    get_pbc_kneighbors_csr does NOT go through this (its kernel generates the same images on the fly)."""
+    X = _to_cuda(x, torch.float32)
+    if X.dim() != 2:
+        raise ValueError("pad_cube_boundaries: x must be (N, 3) - one sample, as in the reference")
+    padded, idx_map = ops.pad_cube(X, float(boundary_threshold))
+    return PaddedCube.wrap(padded, X.shape[0], boundary_threshold), idx_map
+
+
+def get_pcube_csr(x, idx_map, N, K, include_self=False):
+    """graph.py:877-894: kNN graph of the first N rows of the padded cloud with image columns mapped back through
+    idx_map; rows distance-sorted.  `x` must be the padded cloud returned by pad_cube_boundaries (it carries its
+    threshold): the neighbours are computed by the periodic kernel on the N original particles, which is the same
+    search - an image exists in the padded cloud iff the kernel generates it."""
+    if not isinstance(x, PaddedCube) or x.n_particles != int(N):
+        raise TypeError("get_pcube_csr: x must be the padded cloud returned by pad_cube_boundaries(x, thr) for the same N")
+    thr = x.boundary_threshold
+    Xc = x[:N].to(torch.float32).as_subclass(torch.Tensor).unsqueeze(0)          # exact: rows [0, N) are float32 values
+    idx, _, status = ops.knn(Xc, int(K), True, thr, bool(include_self), ops._lib.ORDER_DISTANCE, False)
+    return KnnCSR(idx, 0, int(x.shape[0]), status=status)
+
+
+def get_pcube_adjacency_list(x, idx_map, N, K):
+    """graph.py:857-874: (N, K) neighbour indices, self included (kneighbors_graph(..., include_self=True))."""
+    return get_pcube_csr(x, idx_map, N, K, include_self=True).toarray_indices()
 
 
 # =============================================================================== adjacency
@@ -213,9 +259,14 @@ def confirm_CSR_to_COO_index_integrity(A, COO_feats):
 _ADJ_CACHE = {}
 
 
-def _adjacency_of(COO_feats, b, N):
+def _adjacency_of(COO_feats, b, N, need_cube=True):
+    """need_cube: the caller pools per sample (cube pool, graph.py:447) with node // N, so the (b, N) factorisation
+    must be the one the graph was built with (COO_feats[2] == COO_feats[0] // N); gathers only need b*N."""
     adj = getattr(COO_feats, "_nbpc_adjacency", None)
     if adj is not None and adj.b * adj.N == b * N:
+        if need_cube and (adj.b, adj.N) != (b, N):
+            raise ValueError(f"adjacency was built for (b, N) = ({adj.b}, {adj.N}) but the layer was called with ({b}, {N}): "
+                             "the per-sample pool (COO_feats[2]) would differ from the reference's")
         return adj
     # plain (3,c) array/tensor: rebuild the CSR transpose (cached on identity of the storage)
     coo = _to_cuda(COO_feats, torch.int32).contiguous()
@@ -229,6 +280,8 @@ def _adjacency_of(COO_feats, b, N):
         rows_ok = bool((coo[0] == torch.arange(c, device=coo.device, dtype=torch.int32) // M).all())
         if not rows_ok:
             raise ValueError("COO_feats[0] must be the fixed-degree CSR row index e // M (kNN graph layout)")
+        if need_cube and not bool((coo[2] == coo[0] // N).all()):
+            raise ValueError("COO_feats[2] must be the sample id COO_feats[0] // N (graph.py:646)")
         ptr, edge, status = ops.segment_csr(coo[1], b * N)
         if int(status.item()):
             raise ValueError("COO_feats[1] has indices outside [0, b*N)")
@@ -244,7 +297,7 @@ def _adjacency_of(COO_feats, b, N):
 def include_node_features(X_in_edges, X_in_nodes, COO_feats, redshift=None):
     """graph.py:245-275: concat [edges, nodes[row], nodes[col], (redshift)] -> (c, 9|10)."""
     nodes = _to_cuda(X_in_nodes, torch.float32)
-    adj = _adjacency_of(COO_feats, 1, nodes.shape[0])
+    adj = _adjacency_of(COO_feats, 1, nodes.shape[0], need_cube=False)
     rs = None if redshift is None else _to_cuda(redshift, torch.float32)
     return ops.include_node_features(_to_cuda(X_in_edges, torch.float32), nodes, adj.col, rs, adj.M)
 
@@ -254,7 +307,7 @@ def get_input_features_shift_inv_ZA(init_pos, ZA_displacement, coo, diag, dims):
     b, N, M = dims
     pos = _to_cuda(init_pos, torch.float32).reshape(b * N, -1)
     za = _to_cuda(ZA_displacement, torch.float32).reshape(b * N, -1)
-    adj = _adjacency_of(coo, b, N)
+    adj = _adjacency_of(coo, b, N, need_cube=False)
     return ops.edge_features(pos, za, adj.col, _to_cuda(diag, torch.int64), M)
 
 
@@ -262,7 +315,7 @@ def get_input_features_shift_inv(X_in, coo, dims):
     """graph.py:346-364: raw (non minimum-image) relative positions (c,3) and the node features X[...,3:]."""
     b, N, M = dims
     X = _to_cuda(X_in, torch.float32).reshape(b * N, -1)
-    adj = _adjacency_of(coo, b, N)
+    adj = _adjacency_of(coo, b, N, need_cube=False)
     edges = ops.edge_features(X, None, adj.col, None, M)
     return edges, X[:, 3:]
 

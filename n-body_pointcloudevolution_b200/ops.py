@@ -48,9 +48,10 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
 # ================================================================== kNN
 @torch.library.custom_op("nbpc::knn", mutates_args=())
 def knn(xyz: torch.Tensor, k: int, periodic: bool, boundary_threshold: float, include_self: bool,
-        order: int, want_d2: bool) -> Tuple[torch.Tensor, torch.Tensor]:
-    """xyz (B,N,D>=3) float32 (any strides with unit stride on the last dim) -> idx (B,N,k) int32
-    [, d2 (B,N,k) float64 in distance order; empty if not requested]."""
+        order: int, want_d2: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """xyz (B,N,D>=3) float32 (any strides with unit stride on the last dim) -> idx (B,N,k) int32,
+    d2 (B,N,k) float64 in distance order (empty if not requested), status int32[1] (periodic: particles with a
+    coordinate outside the unit box, for which the result is unspecified)."""
     _need_cuda(xyz)
     L = _lib.load()
     if xyz.dtype != torch.float32:
@@ -62,13 +63,39 @@ def knn(xyz: torch.Tensor, k: int, periodic: bool, boundary_threshold: float, in
     B, N, _ = xyz.shape
     idx = torch.empty((B, N, k), dtype=torch.int32, device=xyz.device)
     d2 = torch.empty((B, N, k) if want_d2 else (0,), dtype=torch.float64, device=xyz.device)
+    status = torch.empty((1,), dtype=torch.int32, device=xyz.device)
     ws = _workspace(L.nbpc_knn_workspace_bytes(B, N, k, int(periodic)), xyz.device)
     with torch.cuda.device(xyz.device):
         rc = L.nbpc_knn(_ptr(xyz), xyz.stride(0), xyz.stride(1), B, N, k, int(periodic), float(boundary_threshold),
-                        int(include_self), int(order), _ptr(idx), _ptr(d2) if want_d2 else None, _ptr(ws),
+                        int(include_self), int(order), _ptr(idx), _ptr(d2) if want_d2 else None, _ptr(status), _ptr(ws),
                         ws.numel(), _stream())
     _lib.check(rc, "nbpc_knn")
-    return idx, d2
+    return idx, d2, status
+
+
+def pad_cube(xyz: torch.Tensor, boundary_threshold: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One sample xyz (N, D>=3) float32 -> padded cloud (N + n_img, 3) float64, idx_map (n_img,) int64
+    (graph.py:827-855).  Host-synchronising: the number of images is read back to size the outputs."""
+    _need_cuda(xyz)
+    L = _lib.load()
+    if xyz.dtype != torch.float32:
+        xyz = xyz.to(torch.float32)
+    if xyz.dim() != 2 or xyz.shape[-1] < 3:
+        raise RuntimeError("pad_cube: xyz must be (N, D>=3)")
+    if xyz.stride(-1) != 1:
+        xyz = xyz.contiguous()
+    N = xyz.shape[0]
+    offsets = torch.empty((N + 1,), dtype=torch.int32, device=xyz.device)
+    ws = _workspace(L.nbpc_pad_cube_workspace_bytes(N), xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(L.nbpc_pad_cube_count(_ptr(xyz), xyz.stride(0), N, float(boundary_threshold), _ptr(offsets), _ptr(ws),
+                                         ws.numel(), _stream()), "nbpc_pad_cube_count")
+        n_img = int(offsets[N].item())
+        padded = torch.empty((N + n_img, 3), dtype=torch.float64, device=xyz.device)
+        idx_map = torch.empty((max(n_img, 1),), dtype=torch.int64, device=xyz.device)
+        _lib.check(L.nbpc_pad_cube_emit(_ptr(xyz), xyz.stride(0), N, float(boundary_threshold), _ptr(offsets), _ptr(padded),
+                                        _ptr(idx_map), _stream()), "nbpc_pad_cube_emit")
+    return padded, idx_map[:n_img]
 
 
 # ================================================================== adjacency

@@ -133,3 +133,34 @@ def shard_samples(n_samples, rank, world_size):
     rem = n_samples % world_size
     start = rank * per + min(rank, rem)
     return range(start, start + per + (1 if rank < rem else 0))
+
+
+class FlatParams:
+    """Named groups of parameter tensors as views into ONE flat float32 buffer (+ matching flat gradient / Adam
+    moments), for models whose variables are not the (4 W + B per layer) layout of ParamStore - experiment.py's
+    Wf / Wg / Wh / Rset / Bset / batch-norm gamma, beta.  `spec`: {group: [array-like initial values]}."""
+
+    def __init__(self, spec, device="cuda"):
+        arrays = [(g, i, torch.as_tensor(a, dtype=torch.float32)) for g, lst in spec.items() for i, a in enumerate(lst)]
+        total = sum(a.numel() for _, _, a in arrays)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.flat_grad = torch.zeros_like(self.flat)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.step_count = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        self.groups = {g: [] for g in spec}
+        off = 0
+        for g, _, a in arrays:
+            n = a.numel()
+            p = self.flat[off:off + n].view(a.shape)
+            p.copy_(a)
+            p.requires_grad_(True)
+            p.grad = self.flat_grad[off:off + n].view(a.shape)
+            self.groups[g].append(p)
+            off += n
+
+    def __getitem__(self, group):
+        return self.groups[group]
+
+    def zero_grad(self):
+        self.flat_grad.zero_()

@@ -44,3 +44,25 @@ def load_reference():
             else:
                 sys.modules[k] = v
     return ref_graph, ref_nn
+
+
+def load_experiment_functions(names=("loss", "set_transform", "res_layer", "attn_layer", "net_fwd")):
+    """experiment.py builds its TF graph, loads a data set and opens a session at import, so it cannot be imported.
+    Its layer / model FUNCTIONS (experiment.py:37-157) are extracted with `ast` and compiled UNMODIFIED into a fresh
+    namespace whose `tf` is oracle.tf_shim; the caller fills in the module-level variables those functions read
+    (Wf, Wg, Wh, Rset, Bset, kdims, num_layers, X_in)."""
+    import ast
+
+    import numpy as np
+
+    from oracle import tf_shim
+    path = os.path.join(REFERENCE_DIR, "experiment.py")
+    if not os.path.isfile(path):
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_DIR}")
+    src = open(path).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in keep} == set(names), "experiment.py no longer defines the expected functions"
+    ns = {"tf": tf_shim, "np": np}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns

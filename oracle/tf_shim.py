@@ -152,7 +152,34 @@ def variable_scope(*_a, **_k):
 
 AUTO_REUSE = object()
 
-nn = types.SimpleNamespace(relu=torch.relu, tanh=torch.tanh)
+def transpose(x, perm=None):
+    x = _t(x)
+    return x.permute(*perm) if perm is not None else x.t()
+
+
+def _leaky_relu(x, alpha=0.2):          # tf.nn.leaky_relu default alpha
+    return torch.nn.functional.leaky_relu(_t(x), negative_slope=alpha)
+
+
+def _softmax(x, axis=-1):
+    return torch.softmax(_t(x), dim=axis)
+
+
+nn = types.SimpleNamespace(relu=torch.relu, tanh=torch.tanh, leaky_relu=_leaky_relu, softmax=_softmax)
+
+
+# tf.layers.batch_normalization(x) as experiment.py:142 calls it: training=False (the default), so the layer is the
+# affine map gamma * (x - moving_mean) / sqrt(moving_variance + 0.001) + beta with the freshly initialised moving
+# statistics (mean 0, variance 1) and TRAINABLE gamma (init 1) / beta (init 0) over the last axis.  The golden
+# generator registers the (gamma, beta) pair of every call, in call order, in `layers.bn_vars`.
+def _batch_normalization(x, **_k):
+    x = _t(x)
+    gamma, beta = layers.bn_vars[layers.bn_calls % len(layers.bn_vars)]
+    layers.bn_calls += 1
+    return gamma * (x / float(np.sqrt(np.float32(1.0) + np.float32(0.001)))) + beta
+
+
+layers = types.SimpleNamespace(batch_normalization=_batch_normalization, bn_vars=[], bn_calls=0)
 
 
 # initialisers referenced at import time by utils.py:171-174 (never called by the

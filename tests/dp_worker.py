@@ -1,0 +1,63 @@
+"""Worker of tests/test_gpu_round2.py::test_dp2_gradients_match_global_batch (launched with torchrun, one rank per GPU):
+data-parallel training of the graph model over NCCL must equal single-GPU training on the global batch."""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(out_path):
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.distributed.init_process_group("nccl", device_id=dev)
+    nb = importlib.import_module("n-body_pointcloudevolution_b200")
+    syn, graph, nn_, tu = nb.synthetic, nb.graph, nb.nn, nb.train_utils
+    ch, N, k, per = [3, 32, 16, 3], 1000, 8, 2
+    B = per * world                                                  # global batch
+    steps = 3
+    batches = []
+    for i in range(steps):
+        x = syn.make_box("clustered", B, N, 40 + i)
+        za, tgt = syn.za_features(B, N, 40 + i)
+        batches.append((x, za, tgt))
+
+    def run(sample_slice, n_ranks, comm):
+        store = tu.ParamStore(ch, device=dev)
+        store.load_numpy(syn.glorot_params(ch))
+        adam = tu.AdamTF(store, lr=0.01)
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+        grads = []
+        for x, za, tgt in batches:
+            xs, zs, ts = (torch.tensor(np.ascontiguousarray(t[sample_slice]), device=dev) for t in (x, za, tgt))
+            b = xs.shape[0]
+            coo, diag = graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(xs, k))
+            loss = nn_.loss_ZA(graph.model_func_shift_inv_za(xs, coo, zs, diag, mv, (b, N, k)), ts)
+            store.zero_grad()
+            loss.backward()
+            if comm:
+                tu.allreduce_gradients(store, n_ranks)
+            grads.append(store.flat_grad.clone() / n_ranks)           # gradient of the GLOBAL-batch mean loss
+            adam.step(grad_scale=1.0 / n_ranks)
+        return torch.stack(grads), store.flat.clone()
+
+    g_dp, p_dp = run(slice(rank * per, (rank + 1) * per), world, True)        # this rank's samples, NCCL all-reduce
+    if rank == 0:
+        g_1, p_1 = run(slice(0, B), 1, False)                                  # same global batch on one GPU
+        np.savez(out_path, g_dp=g_dp.cpu().numpy(), p_dp=p_dp.cpu().numpy(), g_1=g_1.cpu().numpy(), p_1=p_1.cpu().numpy())
+    # every rank must hold identical parameters
+    gathered = [torch.empty_like(p_dp) for _ in range(world)]
+    torch.distributed.all_gather(gathered, p_dp)
+    assert all(torch.equal(gathered[0], t) for t in gathered), "replicas diverged"
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

@@ -48,7 +48,7 @@ def knn(x, k, periodic=False, thr=0.0, include_self=True, order=0, want_d2=False
     d2 = np.zeros((B, N, k), dtype=np.float64) if want_d2 else None
     w = ws(L.nbpc_knn_workspace_bytes(B, N, k, int(periodic)))
     ok(L.nbpc_knn(P(x), N * D, D, B, N, k, int(periodic), float(thr), int(include_self), order,
-                  P(idx), P(d2), P(w), w.nbytes, None))
+                  P(idx), P(d2), None, P(w), w.nbytes, None))
     return (idx, d2) if want_d2 else idx
 
 
@@ -168,3 +168,29 @@ def loss_bwd(pred, truth, pbc=False, scale=True, dloss=1.0):
     else:
         ok(L.nbpc_loss_za_bwd(P(pred), pred.shape[-1], P(truth), truth.shape[-1], rows, P(dl), P(dp), 3, None))
     return dp
+
+
+def knn_status(x, k, thr):
+    """periodic build -> number of particles outside the unit box (nbpc_knn status word)"""
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    B, N, D = x.shape
+    idx = np.zeros((B, N, k), dtype=np.int32)
+    status = np.full((1,), -1, dtype=np.int32)
+    w = ws(L.nbpc_knn_workspace_bytes(B, N, k, 1))
+    ok(L.nbpc_knn(P(x), N * D, D, B, N, k, 1, float(thr), 1, 0, P(idx), None, P(status), P(w), w.nbytes, None))
+    return int(status[0])
+
+
+def pad_cube(x, thr):
+    L = lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    N, D = x.shape
+    offsets = np.zeros(N + 1, dtype=np.int32)
+    w = ws(L.nbpc_pad_cube_workspace_bytes(N))
+    ok(L.nbpc_pad_cube_count(P(x), D, N, float(thr), P(offsets), P(w), w.nbytes, None))
+    n_img = int(offsets[N])
+    padded = np.zeros((N + n_img, 3), dtype=np.float64)
+    idx_map = np.zeros(max(n_img, 1), dtype=np.int64)
+    ok(L.nbpc_pad_cube_emit(P(x), D, N, float(thr), P(offsets), P(padded), P(idx_map), None))
+    return padded, idx_map[:n_img]

@@ -83,7 +83,7 @@ def test_knn_32_golden_hashes(nb, syn):
 ])
 def test_knn_vs_exact_oracle(nb, N, k, periodic, thr, inc):
     x = np.random.default_rng(N + k).random((2, N, 3)).astype(np.float32)
-    idx, d2 = nb.ops.knn(torch.tensor(x, device=DEV), k, periodic, thr, inc, 0, True)
+    idx, d2, _ = nb.ops.knn(torch.tensor(x, device=DEV), k, periodic, thr, inc, 0, True)
     for s in range(2):
         cloud = ref_graph.pad_cube_boundaries(x[s], thr) if periodic else (x[s].astype(np.float64), None)
         ridx, rd2 = knn_exact(cloud[0], N, k, inc, return_d2=True)
@@ -100,7 +100,7 @@ def test_knn_arbitrary_box_strided_and_ties(nb):
     ref = ref_graph.get_kneighbor_list(X, 14, backend="exact")
     assert np.array_equal(idx_of(A), np.stack([r.indices.reshape(3000, 14) for r in ref]))
     g = load_golden("lattice_8.npz")       # tie-heavy lattice: distances are defined, order is (d2, index)
-    idx, d2 = nb.ops.knn(torch.tensor(g["x"], device=DEV), 14, False, 0.0, True, 0, True)
+    idx, d2, _ = nb.ops.knn(torch.tensor(g["x"], device=DEV), 14, False, 0.0, True, 0, True)
     assert np.array_equal(d2[0].cpu().numpy(), g["knl_sorted_d2"])
     assert np.array_equal(idx[0].cpu().numpy(), knn_exact(g["x"][0].astype(np.float64), 512, 14, True))
 
@@ -122,7 +122,7 @@ def test_knn_128_cubed_properties(nb, syn, kind):
     """BASELINE size (2 097 152 particles, k=14, periodic): properties + brute-force spot check."""
     N, k = 128 ** 3, 14
     x = torch.tensor(syn.make_box(kind, 1, N, 0), device=DEV)
-    idx, d2 = nb.ops.knn(x, k, True, 0.5, True, 0, True)
+    idx, d2, _ = nb.ops.knn(x, k, True, 0.5, True, 0, True)
     idx, d2 = idx[0], d2[0]
     assert bool((idx[:, 0] == torch.arange(N, device=DEV)).all()) and bool((d2[:, 0] == 0).all())
     assert bool((d2[:, 1:] >= d2[:, :-1]).all())

@@ -77,11 +77,11 @@ class Dataset:
     @classmethod
     def load_data(cls, path):
         data = np.load(path)                                    # (1000, 32, 32, 32, 19)
-        n = data.shape[0]
+        n, side = data.shape[0], data.shape[1]                  # the reference hard-codes side = 32 (utils.py:611)
         za = data[..., 1:4].reshape(n, -1, 3)
         fpm = data[..., 7:10].reshape(n, -1, 3) - za
-        q = np.broadcast_to(cls.grid(32), za.shape)
-        return np.concatenate([q - 64, za, fpm], axis=-1).astype(np.float32)
+        q = np.broadcast_to(cls.grid(side), za.shape)
+        return np.concatenate([q - 2.0 * side, za, fpm], axis=-1).astype(np.float32)   # q - 64 for side = 32
 
     @classmethod
     def synthetic(cls, n, side):
@@ -114,7 +114,8 @@ def build_step(args, store, dev):
             za = x[..., 3:6].contiguous()
             pos = (x[..., :3] + za).contiguous()                                        # nn.get_init_pos: q + ZA displacement
             coo, diag = graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(pos, K))
-            pred = graph.model_func_shift_inv_za(x[..., :3].contiguous(), coo, za, diag, mv, (b, N, K))
+            # ONE position set for the graph and for the edge features (graph.py:289-343: "coo ... MADE FROM init_pos")
+            pred = graph.model_func_shift_inv_za(pos, coo, za, diag, mv, (b, N, K))
         return pred, nn.loss_ZA(pred, true_error)                                       # train.py:71
     return forward
 
@@ -147,30 +148,53 @@ def main(argv=None):
             torch.save({"step": step, "params": store.flat.cpu(), "m": store.m.cpu(), "v": store.v.cpu(), "channels": args.channels},
                        os.path.join(out_dir, "Session", f"chkpt-{step}.pt"))
 
-    def train_step(x, dev_step=False):
+    def grad_step(x):
         pred, loss = forward(x)
         store.zero_grad()
         loss.backward()
+        return loss
+
+    def update(dev_step=False):
         nbpc.train_utils.allreduce_gradients(store, world)
         adam.step_dev(grad_scale=1.0 / world) if dev_step else adam.step(grad_scale=1.0 / world)
+
+    def train_step(x, dev_step=False):
+        loss = grad_step(x)
+        update(dev_step)
         return loss
 
     graphed = None
     if args.graph and args.num_iters > 0:
-        # GraphedStep's warm-up steps would train on the example batch: snapshot and restore the optimiser state
+        # GraphedStep's warm-up steps would draw from the data RNG and train on the example batch: snapshot and restore
+        # the RNG and the optimiser state.  With more than one rank the NCCL all-reduce stays OUTSIDE the capture
+        # (capturing it hung with the NCCL watchdog alive, see bench.py): the graph holds kNN + forward + backward and
+        # the all-reduce + Adam are launched eagerly behind every replay.
+        rng_state = dataset.rng.get_state()
         example = torch.from_numpy(dataset.get_minibatch(args.batch_size)).to(dev)
+        dataset.rng.set_state(rng_state)
         state = [t.clone() for t in (store.flat, store.m, store.v, store.step_dev)]
-        graphed = nbpc.train_utils.GraphedStep(lambda x: train_step(x, dev_step=True), (example,), warmup=2)
+        if world == 1:
+            graphed = nbpc.train_utils.GraphedStep(lambda x: train_step(x, dev_step=True), (example,), warmup=2)
+        else:
+            graphed = nbpc.train_utils.GraphedStep(grad_step, (example,), warmup=2)
         with torch.no_grad():
             for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
                 t.copy_(s0)
+
+    def run(batch):
+        if graphed is None:
+            return train_step(batch)
+        loss = graphed(torch.from_numpy(batch).to(dev, non_blocking=True))
+        if world > 1:
+            update()
+        return loss
 
     tstart = time.time()
     if rank == 0:
         print(f"\nTraining:\n{'=' * 78}")
     for step in range(args.num_iters):
         batch = dataset.get_minibatch(args.batch_size)
-        loss = graphed(torch.from_numpy(batch).to(dev, non_blocking=True)) if graphed is not None else train_step(batch)
+        loss = run(batch)
         if (step + 1) % args.checkpoint == 0:                                          # train.py:117-120
             save(step)
             if rank == 0:
