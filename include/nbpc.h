@@ -195,13 +195,17 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
 
 /* ---------------------------------------------------------------- set layer
  * nn.set_layer (nn.py:10-28): out = (H - mean_N H) W + B on (B,N,k) -> (B,N,q); relu optional
- * (nn.py:59, 65-66).  mu (B,k) is saved for backward. */
+ * (nn.py:59, 65-66).  mu (B,k) is saved for backward.
+ * Widths with k % 32 == 0, q % 16 == 0, both <= 256 run on tcgen05 (TF32x3 by default, nbpc_set_math_mode): the mean is
+ * subtracted from the landed tile before the product, i.e. the association is the reference's (H - mu) W.
+ * Backward: relu masks dOut by [H_out > 0]; mask_input multiplies dH_in by [H_in > 0] (the ReLU backward of the layer
+ * that produced H_in, fused - nn.network_func_set chains the layers this way so that no masked copy is written). */
 size_t nbpc_set_layer_workspace_bytes(int B, int N, int k, int q);
 int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const float *W,
                        const float *bias, int relu, float *H_out, float *mu, void *workspace,
                        size_t ws_bytes, void *stream);
 int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const float *mu,
-                       int B, int N, int k, int q, const float *W, int relu, float *dH_in,
+                       int B, int N, int k, int q, const float *W, int relu, int mask_input, float *dH_in,
                        float *dW, float *dB, void *workspace, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------- readout / losses

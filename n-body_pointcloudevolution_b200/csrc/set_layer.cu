@@ -5,6 +5,7 @@
 // Barrier-free baseline kernels (one thread per output element); all reductions fixed-order.
 #include "nbpc_common.cuh"
 #include "reduce.cuh"
+#include "set_layer_tc.h"
 
 struct SetXCentered {  // (H - mu) accessor
     const float *h, *mu;
@@ -68,10 +69,39 @@ __global__ void set_bwd_in_kernel(SetDz dz, const float *__restrict__ colsum, co
     dH[t] = a;
 }
 
+// dZ = dOut * [H_out > 0] materialised (tensor-core path of a ReLU layer whose gradient does not arrive pre-masked)
+__global__ void set_mask_kernel(const float *__restrict__ g, const float *__restrict__ hout, int64_t n4, float *__restrict__ dz) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n4) return;
+    float4 v = reinterpret_cast<const float4 *>(g)[t];
+    const float4 h = reinterpret_cast<const float4 *>(hout)[t];
+    v.x = h.x > 0.f ? v.x : 0.f; v.y = h.y > 0.f ? v.y : 0.f; v.z = h.z > 0.f ? v.z : 0.f; v.w = h.w > 0.f ? v.w : 0.f;
+    reinterpret_cast<float4 *>(dz)[t] = v;
+}
+// ReLU backward of the layer that produced H_in, applied to dH_in (CUDA-core path)
+__global__ void set_mask_input_kernel(const float *__restrict__ H, int64_t n, float *__restrict__ dH) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && !(H[t] > 0.f)) dH[t] = 0.f;
+}
+
+// same as set_bwd_in_kernel with the per-sample column MEANS of dZ precomputed
+__global__ void set_bwd_in_mean_kernel(SetDz dz, const float *__restrict__ colmean, const float *__restrict__ W,
+                                       int64_t rows, int N, int k, int q, float *__restrict__ dH) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * k) return;
+    const int64_t r = t / k;
+    const int kk = (int)(t % k);
+    const int s = (int)(r / N);
+    float a = 0.f;
+    for (int qo = 0; qo < q; ++qo) a += (dz.at(r, qo) - __ldg(&colmean[s * q + qo])) * __ldg(&W[kk * q + qo]);
+    dH[t] = a;
+}
+
 struct SetWorkspace {
     float *partial;   // (B, nblk, max(k,q))
     float *colsum;    // (B, q)
     float *xty_partial;
+    float *dz;        // (B*N, q): masked dZ of the tensor-core path (q % 4 == 0 only)
     size_t bytes;
 };
 
@@ -84,7 +114,12 @@ static SetWorkspace set_carve(void *ws, size_t ws_bytes, int B, int N, int k, in
     w.colsum = a.take<float>((size_t)B * mx);
     int rpc, nc;
     xty_plan((int64_t)B * N, k, q, &rpc, &nc);
-    w.xty_partial = a.take<float>((size_t)nc * k * q);
+    size_t nparts = (size_t)nc;
+#ifndef NBPC_HOST_EMU
+    nparts = nbpc_max(nparts, (size_t)sgt_dw_max_parts());
+#endif
+    w.xty_partial = a.take<float>(nparts * k * q);
+    w.dz = a.take<float>(q % 4 == 0 ? (size_t)B * N * q : 0);
     w.bytes = a.off;
     return w;
 }
@@ -109,6 +144,17 @@ int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const floa
     }
     const int64_t rows = (int64_t)B * N;
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+#ifndef NBPC_HOST_EMU
+    if (g_nbpc_math_mode != NBPC_MATH_FP32 && sgt_gemm_shape_ok(k, q)) {
+        // tensor-core path (set_layer_tc.cu): column means, then (H - mu) W + B on tcgen05
+        sgt_colsum(H_in, k, N, B, 1.0f / (float)N, w.partial, mu, nullptr, stream);
+        if (sgt_gemm(H_in, W, 0, mu, bias, nullptr, rows, N, k, q, relu, g_nbpc_math_mode == NBPC_MATH_TF32X3, H_out, stream)) {
+            nbpc_set_error("nbpc_set_layer_fwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_set_layer_fwd");
+    }
+#endif
     NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, N, nblk,
                 B, w.partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.partial, k, nblk, B, (float)N,
@@ -121,7 +167,7 @@ int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const floa
 }
 
 int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const float *mu, int B, int N,
-                       int k, int q, const float *W, int relu, float *dH_in, float *dW, float *dB, void *workspace,
+                       int k, int q, const float *W, int relu, int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
                        size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -137,6 +183,41 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
     SetDz dz;
     dz.g = dOut; dz.hout = H_out; dz.q = q; dz.relu = relu;
+#ifndef NBPC_HOST_EMU
+    if (g_nbpc_math_mode != NBPC_MATH_FP32 && q % 4 == 0 && q <= 1024 &&
+        ((dH_in && sgt_gemm_shape_ok(q, k)) || sgt_dw_shape_ok(k, q))) {
+        const int x3 = g_nbpc_math_mode == NBPC_MATH_TF32X3;
+        const float *dZ = dOut;
+        if (relu) {   // gradient not pre-masked by the consumer: materialise dZ = dOut * [H_out > 0]
+            NBPC_LAUNCH(set_mask_kernel, nbpc_cdiv(rows * q / 4, 256), 256, 0, stream, dOut, H_out, rows * q / 4, w.dz);
+            dZ = w.dz;
+            dz.g = dZ; dz.relu = 0;
+        }
+        // per-sample column means of dZ (the adjoint of the mean subtraction) and dB = sum of dZ
+        sgt_colsum(dZ, q, N, B, 1.0f / (float)N, w.partial, w.colsum, dB, stream);
+        int rc = 0;
+        if (sgt_dw_shape_ok(k, q)) {
+            rc = sgt_dw(H_in, dZ, mu, rows, N, k, q, x3, w.xty_partial, dW, stream);
+        } else {
+            SetXCentered X;
+            X.h = H_in; X.mu = mu; X.k = k; X.N = N;
+            xty("xty_partial_set_dW", X, dz, rows, k, q, w.xty_partial, dW, stream);
+        }
+        if (!rc && dH_in) {
+            if (sgt_gemm_shape_ok(q, k)) {
+                rc = sgt_gemm(dZ, W, 1, w.colsum, nullptr, mask_input ? H_in : nullptr, rows, N, q, k, 0, x3, dH_in, stream);
+            } else {
+                NBPC_LAUNCH(set_bwd_in_mean_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, dz, w.colsum, W, rows, N, k, q, dH_in);
+                if (mask_input) NBPC_LAUNCH(set_mask_input_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, H_in, rows * k, dH_in);
+            }
+        }
+        if (rc) {
+            nbpc_set_error("nbpc_set_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_set_layer_bwd");
+    }
+#endif
     NBPC_LAUNCH(set_dz_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dz, q, N, nblk,
                 B, w.partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.partial, q, nblk, B, 1.0f,
@@ -145,9 +226,11 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
     SetXCentered X;
     X.h = H_in; X.mu = mu; X.k = k; X.N = N;
     xty("xty_partial_set_dW", X, dz, rows, k, q, w.xty_partial, dW, stream);
-    if (dH_in)
+    if (dH_in) {
         NBPC_LAUNCH(set_bwd_in_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, dz, w.colsum, W, rows, N, k, q,
                     dH_in);
+        if (mask_input) NBPC_LAUNCH(set_mask_input_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, H_in, rows * k, dH_in);
+    }
     return nbpc_check_launch("nbpc_set_layer_bwd");
 }
 

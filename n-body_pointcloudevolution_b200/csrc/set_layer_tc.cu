@@ -1,0 +1,559 @@
+// set_layer_tc.cu - tcgen05 / TMEM / TMA kernels of the permutation-equivariant set layer (nn.py:10-28):
+//
+//   forward   out = act( (H - mu_s) W + B )                     mu_s = mean over the N particles of sample s  (nn.py:25-27)
+//   backward  dH  = ( (dZ - mean_s dZ) W^T ) [* (H > 0)]        (adjoint of the mean subtraction; optional fused ReLU
+//             dW  = (H - mu_s)^T dZ                              backward of the layer that produced H)
+//
+// At the reference's default widths (utils.py:165: 6,64,128,128,256,64,128,16,3) these are (262 144 x k)(k x q) GEMMs of
+// 4 - 42 flop/B: still HBM-bound, but far beyond what the CUDA-core issue slots can stream, so they run on the tensor pipe:
+//
+//   sgt_gemm_kernel : persistent CTAs walk 128-row tiles.  The weight tile B (all K x NT of it, TF32 hi and lo) stays
+//       resident in shared memory; A streams through a ring of [128 rows x 32 floats] stages (TMA, 128-byte swizzle);
+//       converter warps subtract the per-sample column mean IN PLACE (so the product is (H - mu) W, the reference's own
+//       association, not H W - mu W) and write the TF32 residual; one thread issues tcgen05.mma kind::tf32
+//       (lo*hi + hi*lo + hi*hi in the default tf32x3 mode), FP32 accumulators double-buffered in TMEM; 4 epilogue warps
+//       read them with tcgen05.ld, add the bias, apply ReLU / the input mask and store 128-byte row segments.
+//   sgt_dw_kernel   : dW contracts over the ROWS, so both operands are MN-major (TMA SWIZZLE_128B_ATOM_32B, 32-row stages);
+//       every CTA keeps its (k x q) partial in TMEM across all of its tiles and writes it once; partials are summed over
+//       CTAs in a fixed order (deterministic).
+//   sgt_colsum_*    : per-sample column sums (mu, mean dZ, dB) - float4 streams, fixed shared-memory tree, fixed order over
+//       blocks.
+// Shapes outside (k % 32 == 0, q % 16 == 0, both <= 256) - the 6-wide input and 3-wide output layers - use the CUDA-core
+// kernels of set_layer.cu.
+#include "graph_layer_tc.cuh"
+#ifndef NBPC_HOST_EMU
+#include "set_layer_tc.h"
+
+#define SGT_CHUNK_BYTES (GLT_TILE * 128)   // one A stage: 128 rows x 32 floats
+#define SGT_DW_ROWS 32                     // rows per stage of the dW kernel
+
+// ------------------------------------------------------------------ per-sample column sums
+// partial[s][blk][C] = sum over the block's rows of sample s; grid (nblk, B), C % 4 == 0, C <= 1024
+__global__ void __launch_bounds__(256) sgt_colsum_partial_kernel(const float *__restrict__ X, int C, int N, int rows_per_block,
+                                                                 float *__restrict__ partial) {
+    __shared__ float4 red[256];
+    const int G = C >> 2, slots = 256 / G;
+    const int g = threadIdx.x % G, slot = threadIdx.x / G, s = blockIdx.y;
+    const int r0 = blockIdx.x * rows_per_block, r1 = nbpc_min(r0 + rows_per_block, N);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    if (slot < slots) {
+        const float *p = X + ((int64_t)s * N) * C + 4 * g;
+        int r = r0 + slot;
+        for (; r + 3 * slots < r1; r += 4 * slots) {   // 4 independent loads in flight
+            const float4 v0 = __ldg(reinterpret_cast<const float4 *>(p + (int64_t)r * C));
+            const float4 v1 = __ldg(reinterpret_cast<const float4 *>(p + (int64_t)(r + slots) * C));
+            const float4 v2 = __ldg(reinterpret_cast<const float4 *>(p + (int64_t)(r + 2 * slots) * C));
+            const float4 v3 = __ldg(reinterpret_cast<const float4 *>(p + (int64_t)(r + 3 * slots) * C));
+            a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+            a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+            a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+            a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+        }
+        for (; r < r1; r += slots) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(p + (int64_t)r * C));
+            a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+        }
+    }
+    float4 a = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                           (a0.w + a1.w) + (a2.w + a3.w));
+    red[threadIdx.x] = a;
+    __syncthreads();
+    // fixed order over the slots (slot counts are not powers of two for every C: sum sequentially in thread slot 0)
+    if (slot == 0) {
+        for (int sl = 1; sl < slots; ++sl) {
+            const float4 b = red[sl * G + g];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        *reinterpret_cast<float4 *>(partial + ((int64_t)s * gridDim.x + blockIdx.x) * C + 4 * g) = a;
+    }
+}
+// out[s][c] = (sum_blk partial[s][blk][c]) * scale;  total[c] = sum_s of the unscaled sums (optional)
+__global__ void sgt_colsum_final_kernel(const float *__restrict__ partial, int C, int nblk, int B, float scale, float *__restrict__ out,
+                                        float *__restrict__ total) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float tot = 0.f;
+    for (int s = 0; s < B; ++s) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float *p = partial + (int64_t)s * nblk * C + c;
+        int b = 0;
+        for (; b + 4 <= nblk; b += 4) {
+            a0 += __ldg(p + (int64_t)b * C); a1 += __ldg(p + (int64_t)(b + 1) * C);
+            a2 += __ldg(p + (int64_t)(b + 2) * C); a3 += __ldg(p + (int64_t)(b + 3) * C);
+        }
+        for (; b < nblk; ++b) a0 += __ldg(p + (int64_t)b * C);
+        const float sum = (a0 + a1) + (a2 + a3);
+        out[s * C + c] = sum * scale;
+        tot += sum;
+    }
+    if (total) total[c] = tot;
+}
+
+// ------------------------------------------------------------------ row GEMM: out = act((A - mu_s) Bm + bias) [* (mask > 0)]
+struct SgtGemmArgs {
+    const float *Bsrc;       // weights: (K, Ntot) row-major, or (Ntot, K) when b_transposed
+    const float *mu;         // (samples, K) column means subtracted from A, or nullptr
+    const float *bias;       // (Ntot) or nullptr
+    const float *mask;       // (rows, Ntot): output multiplied by [mask > 0], or nullptr
+    float *out;              // (rows, Ntot)
+    int64_t rows;
+    int rows_per_sample, K, NT, Ntot, n_ntiles, b_transposed, relu, S, L;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const SgtGemmArgs P) {
+    extern __shared__ __align__(16) unsigned char glt_smem_raw[];
+    unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
+    const int S = P.S, L = X3 ? P.L : 0, K = P.K, NT = P.NT, KC = K >> 5;
+    const int SW = NT < 32 ? NT : 32, PITCH = SW + 4;            // epilogue slab: SW accumulator columns at a time
+    const int B_BYTES = K * NT * 4;
+    unsigned char *As = base;                                     // [S][16 KB] landed (then centred) chunks = hi operand
+    unsigned char *Al = As + S * SGT_CHUNK_BYTES;                 // [L][16 KB] residuals
+    unsigned char *Bh = Al + L * SGT_CHUNK_BYTES;
+    unsigned char *Bl = Bh + B_BYTES;
+    float *Os = reinterpret_cast<float *>(Bh + B_BYTES * (X3 ? 2 : 1));   // [4 warps][32][PITCH]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + 4 * 32 * 36 * 4);
+    const uint32_t bar0 = glt_smem_u32(bars);
+    const int LB = X3 ? P.L : 1;                                  // barrier slots are laid out for max(L, 1)
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };   // per STAGE: centred (and split) data ready for the MMA
+    auto LOFREE = [&](int l) { return bar0 + 8u * (3 * S + l); };
+    auto TFULL = [&](int a) { return bar0 + 8u * (3 * S + LB + a); };
+    auto TEMPTY = [&](int a) { return bar0 + 8u * (3 * S + LB + 2 + a); };
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + LB + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (P.rows + GLT_TILE - 1) / GLT_TILE;
+    const int n_tile = blockIdx.x % P.n_ntiles, cta_m = blockIdx.x / P.n_ntiles, Gm = gridDim.x / P.n_ntiles;
+    const int n0 = n_tile * NT;
+    int tmem_cols = 32;
+    while (tmem_cols < 2 * NT) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
+        for (int l = 0; l < LB; ++l) glt_mbar_init(LOFREE(l), 1);
+        for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
+        glt_fence_barrier_init();
+        glt_prefetch_tmap(&tmA);
+    }
+    if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), tmem_cols);
+    // B operand, K-major: row n = output column n0 + n, element kk; chunk c = 32 consecutive kk of all NT rows
+    for (int i = tid; i < K * NT; i += blockDim.x) {
+        int n, kk;
+        float x;
+        if (P.b_transposed) { n = i / K; kk = i % K; x = __ldg(&P.Bsrc[(int64_t)(n0 + n) * K + kk]); }
+        else { kk = i / NT; n = i % NT; x = __ldg(&P.Bsrc[(int64_t)kk * P.Ntot + n0 + n]); }
+        const int off = (kk >> 5) * (NT * 128) + GltTile<32>::offset(n, kk & 31);
+        *reinterpret_cast<float *>(Bh + off) = X3 ? x : glt_to_tf32(x);
+        if (X3) *reinterpret_cast<float *>(Bl + off) = glt_residual(x);
+    }
+    glt_fence_proxy_async();
+    glt_tc_fence_before();
+    __syncthreads();
+    glt_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer
+            int s = 0, ph = 0;
+            for (int64_t t = cta_m; t < ntiles; t += Gm)
+                for (int c = 0; c < KC; ++c) {
+                    glt_mbar_wait(EMPTY(s), ph ^ 1);
+                    glt_mbar_expect_tx(FULL(s), SGT_CHUNK_BYTES);
+                    glt_tma_load_2d(glt_smem_u32(As + s * SGT_CHUNK_BYTES), &tmA, FULL(s), c * 32, (int)(t * GLT_TILE));
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer
+            const uint32_t idesc = glt_idesc_tf32(GLT_TILE, NT, 0, 0);
+            int s = 0, ph = 0, a = 0, aph = 0, l = 0;
+            for (int64_t t = cta_m; t < ntiles; t += Gm) {
+                glt_mbar_wait(TEMPTY(a), aph ^ 1);
+                const uint32_t d = tmem_base + a * NT;
+                uint32_t acc = 0;
+                for (int c = 0; c < KC; ++c) {
+                    glt_mbar_wait(CONV(s), ph);
+                    glt_tc_fence_after();
+                    const uint32_t a_hi = glt_smem_u32(As + s * SGT_CHUNK_BYTES), a_lo = glt_smem_u32(Al + l * SGT_CHUNK_BYTES);
+                    const uint32_t b_hi = glt_smem_u32(Bh) + c * NT * 128, b_lo = glt_smem_u32(Bl) + c * NT * 128;
+#pragma unroll
+                    for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {   // small terms first: lo*hi, hi*lo, hi*hi
+                        const uint32_t ab = (pass == 0) ? a_lo : a_hi, bb = (pass == 1) ? b_lo : b_hi;
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8) {
+                            glt_mma_tf32(d, glt_smem_desc(ab + k8 * 32, 16, 1024, 2), glt_smem_desc(bb + k8 * 32, 16, 1024, 2), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    glt_tc_commit(EMPTY(s));
+                    if (X3) { glt_tc_commit(LOFREE(l)); if (++l == L) l = 0; }
+                    if (++s == S) { s = 0; ph ^= 1; }
+                }
+                glt_tc_commit(TFULL(a));
+                if (++a == 2) { a = 0; aph ^= 1; }
+            }
+        }
+    } else if (warp < 6) {
+        // ---------------- epilogue warps: quadrant qd owns TMEM lanes / tile rows [32 qd, 32 qd + 32)
+        const int qd = warp & 3;
+        float *Ow = Os + qd * 32 * 36;
+        const int vec_per_row = SW >> 2, iters = vec_per_row;     // 32 rows * SW/4 float4 = 32 lanes * iters
+        int a = 0, aph = 0;
+        for (int64_t t = cta_m; t < ntiles; t += Gm) {
+            const int64_t row0 = t * GLT_TILE + qd * 32;
+            glt_mbar_wait(TFULL(a), aph);
+            glt_tc_fence_after();
+            const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * NT;
+            for (int cb = 0; cb < NT; cb += SW) {
+                float z[32];
+                glt_tmem_ld16(tq + cb, z);
+                if (SW == 32) glt_tmem_ld16(tq + cb + 16, z + 16);
+                glt_tc_wait_ld();
+                if (cb + SW >= NT) {          // last accumulator columns are in registers: release the TMEM stage
+                    glt_tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) glt_mbar_arrive(TEMPTY(a));
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < SW) {
+                        float4 o = make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]);
+                        if (P.bias) {
+                            const float4 bv = glf_ldg4(P.bias + n0 + cb + j);
+                            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        }
+                        if (P.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                        *reinterpret_cast<float4 *>(Ow + lane * PITCH + j) = o;
+                    }
+                }
+                __syncwarp();
+                for (int i = 0; i < iters; ++i) {
+                    const int idx = i * 32 + lane, r = idx / vec_per_row, c4 = idx % vec_per_row;
+                    const int64_t grow = row0 + r;
+                    if (grow < P.rows) {
+                        float4 v = *reinterpret_cast<const float4 *>(Ow + r * PITCH + 4 * c4);
+                        const int64_t g = grow * P.Ntot + n0 + cb + 4 * c4;
+                        if (P.mask) {
+                            const float4 m = glf_ldg4(P.mask + g);
+                            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                        }
+                        *reinterpret_cast<float4 *>(P.out + g) = v;
+                    }
+                }
+                __syncwarp();
+            }
+            if (++a == 2) { a = 0; aph ^= 1; }
+        }
+    } else {
+        // ---------------- converter warps: centre the landed chunk in place (A - mu_s) and write the TF32 residual
+        const int wtid = tid - 192;
+        int s = 0, ph = 0, l = 0, lph = 0;
+        for (int64_t t = cta_m; t < ntiles; t += Gm)
+            for (int c = 0; c < KC; ++c) {
+                glt_mbar_wait(FULL(s), ph);
+                if (X3) glt_mbar_wait(LOFREE(l), lph ^ 1);
+                float *hi = reinterpret_cast<float *>(As + s * SGT_CHUNK_BYTES);
+                float *lo = reinterpret_cast<float *>(Al + l * SGT_CHUNK_BYTES);
+#pragma unroll 4
+                for (int g = wtid; g < SGT_CHUNK_BYTES / 16; g += 128) {       // 16-byte granules: row = g / 8
+                    float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
+                    if (P.mu) {
+                        const int r = g >> 3, lu = (g & 7) ^ (r & 7);             // logical 16-byte unit inside the row
+                        const int64_t grow = nbpc_min(t * GLT_TILE + r, P.rows - 1);
+                        const float4 m = glf_ldg4(P.mu + (grow / P.rows_per_sample) * K + c * 32 + 4 * lu);
+                        x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w;
+                        *reinterpret_cast<float4 *>(hi + 4 * g) = X3 ? x : make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
+                    } else if (!X3) {
+                        *reinterpret_cast<float4 *>(hi + 4 * g) = make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
+                    }
+                    if (X3) *reinterpret_cast<float4 *>(lo + 4 * g) = make_float4(glt_residual(x.x), glt_residual(x.y), glt_residual(x.z), glt_residual(x.w));
+                }
+                glt_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(CONV(s));
+                if (++s == S) { s = 0; ph ^= 1; }
+                if (X3 && ++l == L) { l = 0; lph ^= 1; }
+            }
+    }
+    glt_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        glt_tc_fence_after();
+        glt_tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static size_t sgt_gemm_smem(bool x3, int K, int NT, int S, int L) {
+    return 1024 + (size_t)(S + (x3 ? L : 0)) * SGT_CHUNK_BYTES + (size_t)K * NT * 4 * (x3 ? 2 : 1) + 4 * 32 * 36 * 4 + 8 * (3 * 8 + 8 + 4) + 64;
+}
+
+// K-major tensor map over A (rows, K): box = 128 rows x 32 floats, 128-byte swizzle
+static int sgt_make_tmap_a(CUtensorMap *tm, const float *ptr, int64_t rows, int K) {
+    glt_encode_fn_t enc = glt_encode_fn();
+    if (!enc) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)GLT_TILE};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
+bool sgt_gemm_shape_ok(int K, int Nout) { return K % 32 == 0 && K >= 32 && K <= 256 && Nout % 16 == 0 && Nout >= 16 && Nout <= 256; }
+
+// out (rows, Nout) = act((A - mu_s) Bm + bias) [* (mask > 0)];  0 on success
+int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *mu, const float *bias, const float *mask, int64_t rows,
+             int rows_per_sample, int K, int Nout, int relu, int x3, float *out, cudaStream_t stream) {
+    if (!sgt_gemm_shape_ok(K, Nout)) return 1;
+    // N tile: the resident weight tile (hi + lo in the split mode) must leave room for >= 2 + 2 stages
+    int NT = Nout;
+    const size_t budget = 227 * 1024;
+    while (NT > 16 && sgt_gemm_smem(x3, K, NT, 2, 2) > budget) NT >>= 1;
+    if (Nout % NT || NT % 16 || sgt_gemm_smem(x3, K, NT, 2, 2) > budget) return 1;
+    int S = 2, L = 2;
+    while (S < 6 && sgt_gemm_smem(x3, K, NT, S + 1, L) <= budget) ++S;
+    if (x3 && S >= 4 && sgt_gemm_smem(x3, K, NT, S - 1, L + 1) <= budget) { --S; ++L; }
+    const size_t smem = sgt_gemm_smem(x3, K, NT, S, L);
+    auto kern = x3 ? sgt_gemm_kernel<true> : sgt_gemm_kernel<false>;
+    static bool configured[64][2];   // per device: function attributes belong to a context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev][x3 ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (dev >= 0 && dev < 64) configured[dev][x3 ? 1 : 0] = true;
+    }
+    CUtensorMap tm;
+    if (sgt_make_tmap_a(&tm, A, rows, K)) return 1;
+    SgtGemmArgs P;
+    P.Bsrc = Bsrc; P.mu = mu; P.bias = bias; P.mask = mask; P.out = out; P.rows = rows; P.rows_per_sample = rows_per_sample;
+    P.K = K; P.NT = NT; P.Ntot = Nout; P.n_ntiles = Nout / NT; P.b_transposed = b_transposed; P.relu = relu; P.S = S; P.L = L;
+    const int64_t ntiles = (rows + GLT_TILE - 1) / GLT_TILE;
+    int64_t gm = gl_num_sms() / P.n_ntiles;
+    if (gm < 1) gm = 1;
+    if (gm > ntiles) gm = ntiles;
+    const int grid = (int)(gm * P.n_ntiles);
+    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_gemm_tf32x3" : "sgt_gemm_tf32", K, Nout).c_str(), kern, grid, 320, smem, stream, tm, P);
+    return 0;
+}
+
+// ------------------------------------------------------------------ dW = (H - mu_s)^T dZ, per-CTA partials
+struct SgtDwArgs {
+    const float *mu;          // (samples, k) or nullptr
+    float *partial;           // [grid][k][q]
+    int64_t rows;
+    int rows_per_sample, k, q, S, L;
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(320) sgt_dw_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ,
+                                                     const SgtDwArgs P) {
+    constexpr int R = SGT_DW_ROWS, RCH = R * 128;                 // bytes of one [R rows x 32 floats] chunk
+    extern __shared__ __align__(16) unsigned char glt_smem_raw[];
+    unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
+    const int S = P.S, L = X3 ? P.L : 0, k = P.k, q = P.q, HCH = k >> 5, ZCH = q >> 5;
+    const int H_BYTES = HCH * RCH, STAGE = (HCH + ZCH) * RCH;
+    unsigned char *St = base, *Sl = St + S * STAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Sl + L * STAGE);
+    const uint32_t bar0 = glt_smem_u32(bars);
+    const int LB = X3 ? P.L : 1;
+    auto FULL = [&](int s) { return bar0 + 8u * s; };
+    auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
+    auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };
+    auto LOFREE = [&](int l) { return bar0 + 8u * (3 * S + l); };
+    const uint32_t DONE = bar0 + 8u * (3 * S + LB);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * S + LB + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t ntiles = (P.rows + R - 1) / R;
+    const int G = gridDim.x;
+    const int MB = (k + 127) / 128, M2 = k < 128 ? k : 128;       // k in {64, 128, 256}
+    int tmem_cols = 32;
+    while (tmem_cols < MB * q) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
+        for (int l = 0; l < LB; ++l) glt_mbar_init(LOFREE(l), 1);
+        glt_mbar_init(DONE, 1);
+        glt_fence_barrier_init();
+        glt_prefetch_tmap(&tmH);
+        glt_prefetch_tmap(&tmZ);
+    }
+    if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), tmem_cols);
+    glt_tc_fence_before();
+    __syncthreads();
+    glt_tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {   // ---------------- TMA producer
+            int s = 0, ph = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += G) {
+                glt_mbar_wait(EMPTY(s), ph ^ 1);
+                glt_mbar_expect_tx(FULL(s), STAGE);
+                unsigned char *st = St + s * STAGE;
+                for (int ch = 0; ch < HCH; ++ch) glt_tma_load_2d(glt_smem_u32(st + ch * RCH), &tmH, FULL(s), ch * 32, (int)(t * R));
+                for (int ch = 0; ch < ZCH; ++ch) glt_tma_load_2d(glt_smem_u32(st + H_BYTES + ch * RCH), &tmZ, FULL(s), ch * 32, (int)(t * R));
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {   // ---------------- MMA issuer: D[mb] (M2 x q) += H'[mb]^T (MN-major) * dZ' (MN-major)
+            const uint32_t idesc = glt_idesc_tf32(M2, q, 1, 1);
+            int s = 0, ph = 0, l = 0;
+            uint32_t acc = 0;
+            for (int64_t t = blockIdx.x; t < ntiles; t += G) {
+                glt_mbar_wait(CONV(s), ph);
+                glt_tc_fence_after();
+                const uint32_t h_hi = glt_smem_u32(St + s * STAGE), z_hi = h_hi + H_BYTES;
+                const uint32_t h_lo = glt_smem_u32(Sl + l * STAGE), z_lo = h_lo + H_BYTES;
+                for (int mb = 0; mb < MB; ++mb) {
+                    uint32_t a2 = acc;
+#pragma unroll
+                    for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {
+                        const uint32_t hb = ((pass == 0) ? h_lo : h_hi) + mb * 4 * RCH, zb = (pass == 1) ? z_lo : z_hi;
+#pragma unroll
+                        for (int k8 = 0; k8 < R / 8; ++k8) {   // 8 rows per MMA = two 4-row swizzle atoms (SBO 512); LBO = chunk stride
+                            glt_mma_tf32(tmem_base + mb * q, glt_smem_desc(hb + k8 * 1024, RCH, 512, 1), glt_smem_desc(zb + k8 * 1024, RCH, 512, 1),
+                                         idesc, a2);
+                            a2 = 1;
+                        }
+                    }
+                }
+                acc = 1;
+                glt_tc_commit(EMPTY(s));
+                if (X3) { glt_tc_commit(LOFREE(l)); if (++l == L) l = 0; }
+                if (++s == S) { s = 0; ph ^= 1; }
+            }
+            glt_tc_commit(DONE);
+        }
+    } else if (warp < 6) {
+        // ---------------- epilogue warps: one read-out of the accumulated (k x q) partial at the end
+        const int qd = warp & 3;
+        glt_mbar_wait(DONE, 0);
+        glt_tc_fence_after();
+        const bool any_tile = blockIdx.x < ntiles;
+        for (int mb = 0; mb < MB; ++mb) {
+            // M = 128: row r in lane r;  M = 64: row r in lane (r % 16) + 32 (r / 16)
+            const int row = (M2 == 128) ? qd * 32 + lane : (lane < 16 ? qd * 16 + lane : -1);
+            const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + mb * q;
+            float *dst = P.partial + ((int64_t)blockIdx.x * k + mb * 128 + (row < 0 ? 0 : row)) * q;
+            for (int cb = 0; cb < q; cb += 16) {
+                float z[16];
+                glt_tmem_ld16(tq + cb, z);
+                glt_tc_wait_ld();
+                if (row >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        *reinterpret_cast<float4 *>(dst + cb + j) = any_tile ? make_float4(z[j], z[j + 1], z[j + 2], z[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    } else {
+        // ---------------- converter warps: centre H in place, write the TF32 residuals of H and dZ
+        const int wtid = tid - 192;
+        int s = 0, ph = 0, l = 0, lph = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += G) {
+            glt_mbar_wait(FULL(s), ph);
+            if (X3) glt_mbar_wait(LOFREE(l), lph ^ 1);
+            float *hi = reinterpret_cast<float *>(St + s * STAGE);
+            float *lo = reinterpret_cast<float *>(Sl + l * STAGE);
+            const int n_gran = STAGE / 16, h_gran = H_BYTES / 16;
+#pragma unroll 4
+            for (int g = wtid; g < n_gran; g += 128) {
+                float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
+                bool wrote = false;
+                if (g < h_gran && P.mu) {
+                    // granule -> (chunk, row, 16-byte unit); 32-byte swizzle atoms: logical atom = atom ^ (row & 3)
+                    const int ch = g / (R * 8), r = (g >> 3) % R, u = g & 7;
+                    const int col = ch * 32 + ((((u >> 1) ^ (r & 3)) << 3) | ((u & 1) << 2));
+                    const int64_t grow = nbpc_min(t * R + r, P.rows - 1);
+                    const float4 m = glf_ldg4(P.mu + (grow / P.rows_per_sample) * k + col);
+                    // rows beyond the tensor were zero-filled by TMA and must stay zero
+                    if (t * R + r < P.rows) { x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w; }
+                    wrote = true;
+                }
+                if (!X3) x = make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
+                if (wrote || !X3) *reinterpret_cast<float4 *>(hi + 4 * g) = x;
+                if (X3) *reinterpret_cast<float4 *>(lo + 4 * g) = make_float4(glt_residual(x.x), glt_residual(x.y), glt_residual(x.z), glt_residual(x.w));
+            }
+            glt_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) glt_mbar_arrive(CONV(s));
+            if (++s == S) { s = 0; ph ^= 1; }
+            if (X3 && ++l == L) { l = 0; lph ^= 1; }
+        }
+    }
+    glt_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        glt_tc_fence_after();
+        glt_tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// dW[o] = sum over the CTA partials, fixed order (4 independent partial sums, then one tree)
+__global__ void sgt_dw_final_kernel(const float *__restrict__ partial, int nparts, int kq, float *__restrict__ dW) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= kq) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = 0;
+    for (; b + 4 <= nparts; b += 4) {
+        a0 += __ldg(partial + (int64_t)b * kq + o); a1 += __ldg(partial + (int64_t)(b + 1) * kq + o);
+        a2 += __ldg(partial + (int64_t)(b + 2) * kq + o); a3 += __ldg(partial + (int64_t)(b + 3) * kq + o);
+    }
+    for (; b < nparts; ++b) a0 += __ldg(partial + (int64_t)b * kq + o);
+    dW[o] = (a0 + a1) + (a2 + a3);
+}
+
+static size_t sgt_dw_smem(bool x3, int k, int q, int S, int L) {
+    return 1024 + (size_t)(S + (x3 ? L : 0)) * (size_t)(k + q) * SGT_DW_ROWS * 4 + 8 * (3 * 8 + 8 + 2) + 64;
+}
+
+bool sgt_dw_shape_ok(int k, int q) { return (k == 64 || k == 128 || k == 256) && q % 32 == 0 && q >= 32 && q <= 256 && ((k + 127) / 128) * q <= 512; }
+int sgt_dw_max_parts() { return gl_num_sms(); }
+
+// dW (k, q) = (H - mu_s)^T dZ over `rows` rows; partial: workspace of sgt_dw_max_parts() * k * q floats.  0 on success
+int sgt_dw(const float *H, const float *dZ, const float *mu, int64_t rows, int rows_per_sample, int k, int q, int x3, float *partial,
+           float *dW, cudaStream_t stream) {
+    if (!sgt_dw_shape_ok(k, q)) return 1;
+    const size_t budget = 227 * 1024;
+    int S = 2, L = 1;
+    if (sgt_dw_smem(x3, k, q, S, L) > budget) return 1;
+    while (S < 4 && sgt_dw_smem(x3, k, q, S + 1, L) <= budget) ++S;
+    if (x3 && S >= 3 && sgt_dw_smem(x3, k, q, S - 1, L + 1) <= budget) { --S; ++L; }
+    const size_t smem = sgt_dw_smem(x3, k, q, S, L);
+    auto kern = x3 ? sgt_dw_kernel<true> : sgt_dw_kernel<false>;
+    static bool configured[64][2];   // per device: function attributes belong to a context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev][x3 ? 1 : 0]) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget) != cudaSuccess) {
+            cudaGetLastError();
+            return 1;
+        }
+        if (dev >= 0 && dev < 64) configured[dev][x3 ? 1 : 0] = true;
+    }
+    CUtensorMap tmH, tmZ;
+    if (glt_make_tmap_packed(&tmH, H, rows, k, SGT_DW_ROWS) || glt_make_tmap_packed(&tmZ, dZ, rows, q, SGT_DW_ROWS)) return 1;
+    SgtDwArgs P;
+    P.mu = mu; P.partial = partial; P.rows = rows; P.rows_per_sample = rows_per_sample; P.k = k; P.q = q; P.S = S; P.L = L;
+    const int64_t ntiles = (rows + SGT_DW_ROWS - 1) / SGT_DW_ROWS;
+    const int grid = (int)nbpc_min((int64_t)gl_num_sms(), ntiles);
+    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_dw_tf32x3" : "sgt_dw_tf32", k, q).c_str(), kern, grid, 320, smem, stream, tmH, tmZ, P);
+    NBPC_LAUNCH(sgt_dw_final_kernel, nbpc_cdiv(k * q, 256), 256, 0, stream, partial, grid, k * q, dW);
+    return 0;
+}
+
+// ------------------------------------------------------------------ per-sample column sums (C % 4 == 0, C <= 1024)
+int sgt_colsum_blocks(int N) { return nbpc_cdiv(N, 1024); }
+void sgt_colsum(const float *X, int C, int N, int B, float scale, float *partial, float *out, float *total, cudaStream_t stream) {
+    const int nblk = sgt_colsum_blocks(N);
+    NBPC_LAUNCH(sgt_colsum_partial_kernel, dim3(nblk, B), 256, 0, stream, X, C, N, 1024, partial);
+    NBPC_LAUNCH(sgt_colsum_final_kernel, nbpc_cdiv(C, 128), 128, 0, stream, partial, C, nblk, B, scale, out, total);
+}
+#endif  // !NBPC_HOST_EMU

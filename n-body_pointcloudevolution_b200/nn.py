@@ -11,10 +11,10 @@ __all__ = ["set_layer", "network_func_set", "model_func_set", "get_readout", "pe
            "pbc_loss", "loss_ZA", "mse_za", "get_init_pos"]
 
 
-def _set_layer(h_in, layer_vars, relu):
+def _set_layer(h_in, layer_vars, relu, input_relu=False, grad_premasked=False):
     W, B = layer_vars
     W = W[0]  # only one weight for set layer (nn.py:22)
-    return ops.SetLayer.apply(_to_cuda(h_in, torch.float32), W, B, relu)
+    return ops.SetLayer.apply(_to_cuda(h_in, torch.float32), W, B, relu, input_relu, grad_premasked)
 
 
 def set_layer(h_in, layer_vars):
@@ -28,12 +28,15 @@ def network_func_set(X_in, model_vars):
     activation = model_vars.activation
     get_layer_vars = model_vars.get_layer_vars
     fuse = _is_relu(activation)
-    H = _set_layer(X_in, get_layer_vars(0), fuse)
+    # inside this function every hidden tensor has exactly one consumer (the next layer): the ReLU backward of layer l is
+    # applied by layer l+1's backward kernel (input_relu) and layer l skips its own mask (grad_premasked)
+    chain = fuse and num_layers > 1
+    H = _set_layer(X_in, get_layer_vars(0), fuse, input_relu=False, grad_premasked=chain)
     if not fuse:
         H = activation(H)
     for layer_idx in range(1, num_layers):
         is_last = layer_idx >= num_layers - 1
-        H = _set_layer(H, get_layer_vars(layer_idx), fuse and not is_last)
+        H = _set_layer(H, get_layer_vars(layer_idx), fuse and not is_last, input_relu=fuse, grad_premasked=fuse and not is_last)
         if not is_last and not fuse:
             H = activation(H)
     return H

@@ -403,7 +403,7 @@ def set_layer_fwd(H_in: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, relu:
 
 @torch.library.custom_op("nbpc::set_layer_bwd", mutates_args=())
 def set_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, mu: torch.Tensor, W: torch.Tensor,
-                  relu: bool, need_dH: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                  relu: bool, need_dH: bool, mask_input: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     _need_cuda(dOut, H_in, H_out, mu, W)
     L = _lib.load()
     dOut = _f32c(dOut)
@@ -415,29 +415,32 @@ def set_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, m
     dB = torch.empty((q,), dtype=torch.float32, device=dev)
     ws = _workspace(L.nbpc_set_layer_workspace_bytes(B, N, k, q), dev)
     with torch.cuda.device(dev):
-        rc = L.nbpc_set_layer_bwd(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(mu), B, N, k, q, _ptr(W), int(relu),
+        rc = L.nbpc_set_layer_bwd(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(mu), B, N, k, q, _ptr(W), int(relu), int(mask_input),
                                   _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB), _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "nbpc_set_layer_bwd")
     return dH, dW, dB
 
 
 class SetLayer(torch.autograd.Function):
-    """set_layer (nn.py:10-28) [+ fused ReLU]."""
+    """set_layer (nn.py:10-28) [+ fused ReLU].  input_relu / grad_premasked: as in GraphLayer - inside a network whose
+    hidden tensors have exactly one consumer, the ReLU backward of layer l is applied by layer l+1's backward kernel
+    (which has H_in in hand) and layer l skips its own mask (nn.network_func_set sets both consistently)."""
 
     @staticmethod
-    def forward(ctx, H_in, W, bias, relu):
+    def forward(ctx, H_in, W, bias, relu, input_relu=False, grad_premasked=False):
         H_in = _f32c(H_in)
         out, mu = set_layer_fwd(H_in, W, bias, relu)
         ctx.save_for_backward(H_in, out, mu, W)
-        ctx.relu = relu
+        ctx.cfg = (relu and not grad_premasked, input_relu)
         return out
 
     @staticmethod
     def backward(ctx, g):
         H_in, out, mu, W = ctx.saved_tensors
+        relu, input_relu = ctx.cfg
         need_dH = ctx.needs_input_grad[0]
-        dH, dW, dB = set_layer_bwd(g, H_in, out, mu, W, ctx.relu, need_dH)
-        return (dH if need_dH else None), dW, dB, None
+        dH, dW, dB = set_layer_bwd(g, H_in, out, mu, W, relu, need_dH, input_relu)
+        return (dH if need_dH else None), dW, dB, None, None, None
 
 
 # ================================================================== losses / readout

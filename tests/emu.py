@@ -132,7 +132,7 @@ def set_layer_fwd(H, W, bias, relu):
     return out, mu
 
 
-def set_layer_bwd(dOut, H, Hout, mu, W, relu, need_dH=True):
+def set_layer_bwd(dOut, H, Hout, mu, W, relu, need_dH=True, mask_input=False):
     L = lib()
     B, N, k = H.shape
     q = W.shape[1]
@@ -140,7 +140,7 @@ def set_layer_bwd(dOut, H, Hout, mu, W, relu, need_dH=True):
     dW = np.zeros((k, q), dtype=np.float32)
     dB = np.zeros((q,), dtype=np.float32)
     w = ws(L.nbpc_set_layer_workspace_bytes(B, N, k, q))
-    ok(L.nbpc_set_layer_bwd(P(dOut), P(H), P(Hout), P(mu), B, N, k, q, P(W), int(relu), P(dH), P(dW), P(dB),
+    ok(L.nbpc_set_layer_bwd(P(dOut), P(H), P(Hout), P(mu), B, N, k, q, P(W), int(relu), int(mask_input), P(dH), P(dW), P(dB),
                             P(w), w.nbytes, None))
     return dH, dW, dB
 
