@@ -431,6 +431,46 @@ def knn_sweep(nb, dev, peak, with_sklearn):
     return rows
 
 
+def set_model_bench(nb, dev, peak, steps=10):
+    """The model the reference's train.py actually runs (train.py:66): nn.model_func_set at the default widths
+    (utils.py:165), batch 8 x 32^3, one training step = forward + loss + backward + Adam, replayed from one CUDA graph.
+    Algorithmic bytes: forward s b N (2 k + q) per layer (mean pass + GEMM pass), backward s b N (2 q + 2 k)
+    (first layer: no dH: 2 q + k)."""
+    syn, nn_, tu, lib = nb.synthetic, nb.nn, nb.train_utils, nb._lib
+    ch = [6, 64, 128, 128, 256, 64, 128, 16, 3]
+    b, N = 8, 32 ** 3
+    rng = np.random.default_rng(0)
+    X = torch.from_numpy(rng.standard_normal((b, N, 6)).astype(np.float32)).to(dev)
+    Y = torch.from_numpy((0.1 * rng.standard_normal((b, N, 3))).astype(np.float32)).to(dev)
+    store = tu.ParamStore(ch, device=dev)
+    adam = tu.AdamTF(store, lr=0.001)
+    mv = store.model_vars(torch.relu)
+
+    def step(x, y):
+        loss = nn_.loss_ZA(nn_.model_func_set(x, mv), y)
+        store.zero_grad()
+        loss.backward()
+        adam.step_dev()
+        return loss
+    gs = tu.GraphedStep(step, (X, Y))
+    ms = event_ms(lambda: gs(X, Y), steps, warm=3)
+    rows = b * N
+    fwd = sum(4 * rows * (2 * k + q) for k, q in zip(ch[:-1], ch[1:]))
+    bwd = sum(4 * rows * (2 * q + (2 * k if i else k)) for i, (k, q) in enumerate(zip(ch[:-1], ch[1:])))
+    flops = 3 * 2 * rows * sum(k * q for k, q in zip(ch[:-1], ch[1:]))          # fwd + dH + dW GEMMs
+    lib.prof_enable(True)
+    for _ in range(2):
+        step(X, Y)
+    torch.cuda.synchronize()
+    rep = lib.prof_report()
+    lib.prof_enable(False)
+    kern = sorted(((n, tot / 2) for n, (cnt, tot) in rep.items()), key=lambda kv: -kv[1])[:14]
+    return {"channels": ch, "batch": b, "particles": rows, "ms_per_step": ms, "particles_per_s": rows / (ms * 1e-3), "finite": bool(torch.isfinite(gs.loss)),
+            "algorithmic_bytes": fwd + bwd, "roofline_frac": (fwd + bwd) / (ms * 1e-3) / 1e9 / peak,
+            "gemm_tflops_fp32_equiv": flops / (ms * 1e-3) / 1e12, "math_mode": lib.get_math_mode(),
+            "kernels_ms": {n: round(t, 4) for n, t in kern}}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -601,6 +641,11 @@ def main():
             extras["knn_sweep"] = {"error": repr(exc)[:300]}
         if c4:
             extras["config4_64^3_dp"] = c4
+        try:
+            extras["set_model"] = set_model_bench(nb, dev, peak)
+        except Exception as exc:
+            extras["set_model"] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
 
         # BASELINE config 5: 128^3-particle multi-redshift rollout INFERENCE, periodic kNN graph rebuilt every step
         # (graph.rollout_shift_inv: pbc kNN -> 9-channel edges -> [9,32,16,6] graph net -> scaled residual -> readout)

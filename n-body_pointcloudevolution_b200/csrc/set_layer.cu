@@ -3,9 +3,26 @@
 // Backward:  dZ = dOut * [out > 0];  dB = sum dZ;  dW = (H - mu)^T dZ;
 //            dH = (dZ - colmean_s(dZ)) W^T   (the mean-subtraction's adjoint).
 // Barrier-free baseline kernels (one thread per output element); all reductions fixed-order.
+#include <stdlib.h>
+
 #include "nbpc_common.cuh"
 #include "reduce.cuh"
 #include "set_layer_tc.h"
+#include "set_layer_small.cuh"
+
+// NBPC_BASELINE=1 (read once) keeps the barrier-free baseline kernels on the CUDA-core paths (cross-check)
+static bool gl_set_fast() {
+#ifdef NBPC_HOST_EMU
+    return false;
+#else
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("NBPC_BASELINE");
+        cached = (e && e[0] == '1') ? 0 : 1;
+    }
+    return cached == 1;
+#endif
+}
 
 struct SetXCentered {  // (H - mu) accessor
     const float *h, *mu;
@@ -97,6 +114,35 @@ __global__ void set_bwd_in_mean_kernel(SetDz dz, const float *__restrict__ colme
     dH[t] = a;
 }
 
+#ifndef NBPC_HOST_EMU
+static int set_num_sms() {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    return sms;
+}
+// dW = (H - mu)^T dZ when one side is narrow (<= 16); false if no instance exists
+static bool set_xty_narrow(const float *H, const float *mu, const float *dZ, int B, int N, int k, int q, float *partial, float *dW,
+                           cudaStream_t stream) {
+    const int sms = set_num_sms();
+    const int rpb = sgs_rows_per_block(N, B, sms), nblk = nbpc_cdiv(N, rpb);
+    bool done = false;
+    if (q <= 16 && k % 4 == 0 && k <= 1024 && sgs_narrow_ok(q)) {
+#define X(V) if (q == V) NBPC_LAUNCH_N(NbpcKName("sgs_xty_narrow_q", k, q).c_str(), (sgs_xty_narrow_kernel<V, true>), dim3(nblk, B), SGS_THREADS, 0, stream, H, mu, dZ, N, k, q, rpb, partial);
+        SGS_NARROW_LIST(X)
+#undef X
+        done = true;
+    } else if (k <= 16 && q % 4 == 0 && q <= 1024 && sgs_narrow_ok(k)) {
+#define X(V) if (k == V) NBPC_LAUNCH_N(NbpcKName("sgs_xty_narrow_k", k, q).c_str(), (sgs_xty_narrow_kernel<V, false>), dim3(nblk, B), SGS_THREADS, 0, stream, H, mu, dZ, N, k, q, rpb, partial);
+        SGS_NARROW_LIST(X)
+#undef X
+        done = true;
+    }
+    if (done) NBPC_LAUNCH(sgs_sum_partials_kernel, nbpc_cdiv(k * q, 256), 256, 0, stream, partial, nblk * B, k * q, dW);
+    return done;
+}
+#endif
+
 struct SetWorkspace {
     float *partial;   // (B, nblk, max(k,q))
     float *colsum;    // (B, q)
@@ -110,13 +156,14 @@ static SetWorkspace set_carve(void *ws, size_t ws_bytes, int B, int N, int k, in
     SetWorkspace w;
     const int mx = k > q ? k : q;
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
-    w.partial = a.take<float>((size_t)B * nblk * mx);
+    w.partial = a.take<float>((size_t)B * (nblk + 1) * mx);   // + the per-sample sums of sgt_colsum
     w.colsum = a.take<float>((size_t)B * mx);
     int rpc, nc;
     xty_plan((int64_t)B * N, k, q, &rpc, &nc);
     size_t nparts = (size_t)nc;
 #ifndef NBPC_HOST_EMU
     nparts = nbpc_max(nparts, (size_t)sgt_dw_max_parts());
+    nparts = nbpc_max(nparts, (size_t)sgs_max_blocks(N, B, set_num_sms()));
 #endif
     w.xty_partial = a.take<float>(nparts * k * q);
     w.dz = a.take<float>(q % 4 == 0 ? (size_t)B * N * q : 0);
@@ -159,6 +206,15 @@ int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const floa
                 B, w.partial);
     NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.partial, k, nblk, B, (float)N,
                 mu);  // nn.py:25
+#ifndef NBPC_HOST_EMU
+    if (gl_set_fast() && k <= 16 && q % 4 == 0 && q <= 1024 && sgs_narrow_ok(k)) {   // narrow input layer: float4 stream over q
+        const int rpb = sgs_rows_per_block(N, B, set_num_sms()), nb = nbpc_cdiv(N, rpb);
+#define X(V) if (k == V) NBPC_LAUNCH_N(NbpcKName("sgs_fwd_smallk", k, q).c_str(), sgs_fwd_smallk_kernel<V>, dim3(nb, B), SGS_THREADS, 0, stream, H_in, mu, W, bias, N, q, rpb, relu, H_out);
+        SGS_NARROW_LIST(X)
+#undef X
+        return nbpc_check_launch("nbpc_set_layer_fwd");
+    }
+#endif
     SetXCentered X;
     X.h = H_in; X.mu = mu; X.k = k; X.N = N;
     NBPC_LAUNCH(set_fwd_kernel, nbpc_cdiv(rows * q, GL_THREADS), GL_THREADS, 0, stream, X, W, bias, rows, k, q, relu,
@@ -184,28 +240,42 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
     SetDz dz;
     dz.g = dOut; dz.hout = H_out; dz.q = q; dz.relu = relu;
 #ifndef NBPC_HOST_EMU
-    if (g_nbpc_math_mode != NBPC_MATH_FP32 && q % 4 == 0 && q <= 1024 &&
-        ((dH_in && sgt_gemm_shape_ok(q, k)) || sgt_dw_shape_ok(k, q))) {
+    if (gl_set_fast() && q <= 1024 && !(relu && q % 4 != 0)) {
+        const bool tc = g_nbpc_math_mode != NBPC_MATH_FP32;
         const int x3 = g_nbpc_math_mode == NBPC_MATH_TF32X3;
         const float *dZ = dOut;
         if (relu) {   // gradient not pre-masked by the consumer: materialise dZ = dOut * [H_out > 0]
             NBPC_LAUNCH(set_mask_kernel, nbpc_cdiv(rows * q / 4, 256), 256, 0, stream, dOut, H_out, rows * q / 4, w.dz);
             dZ = w.dz;
-            dz.g = dZ; dz.relu = 0;
         }
-        // per-sample column means of dZ (the adjoint of the mean subtraction) and dB = sum of dZ
-        sgt_colsum(dZ, q, N, B, 1.0f / (float)N, w.partial, w.colsum, dB, stream);
-        int rc = 0;
-        if (sgt_dw_shape_ok(k, q)) {
-            rc = sgt_dw(H_in, dZ, mu, rows, N, k, q, x3, w.xty_partial, dW, stream);
+        dz.g = dZ; dz.relu = 0;
+        // per-sample column means of dZ (the adjoint of the mean subtraction) -> w.colsum, and dB = sum of dZ
+        if (q % 4 == 0) {
+            sgt_colsum(dZ, q, N, B, 1.0f / (float)N, w.partial, w.colsum, dB, stream);
         } else {
+            NBPC_LAUNCH(set_dz_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dz, q, N, nblk, B, w.partial);
+            NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.partial, q, nblk, B, 1.0f, w.colsum);
+            NBPC_LAUNCH(set_bias_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.colsum, B, q, dB);
+            NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.partial, q, nblk, B, (float)N, w.colsum);
+        }
+        int rc = 0;
+        // ---- dW = (H - mu)^T dZ: tensor pipe, else the narrow-side stream, else the generic fixed-order reduction
+        if (tc && sgt_dw_shape_ok(k, q)) {
+            rc = sgt_dw(H_in, dZ, mu, rows, N, k, q, x3, w.xty_partial, dW, stream);
+        } else if (!set_xty_narrow(H_in, mu, dZ, B, N, k, q, w.xty_partial, dW, stream)) {
             SetXCentered X;
             X.h = H_in; X.mu = mu; X.k = k; X.N = N;
             xty("xty_partial_set_dW", X, dz, rows, k, q, w.xty_partial, dW, stream);
         }
+        // ---- dH = (dZ - mean_s dZ) W^T [* (H_in > 0)]
         if (!rc && dH_in) {
-            if (sgt_gemm_shape_ok(q, k)) {
+            if (tc && sgt_gemm_shape_ok(q, k)) {
                 rc = sgt_gemm(dZ, W, 1, w.colsum, nullptr, mask_input ? H_in : nullptr, rows, N, q, k, 0, x3, dH_in, stream);
+            } else if (q <= 16 && k % 4 == 0 && k <= 1024 && sgs_narrow_ok(q)) {
+                const int rpb = sgs_rows_per_block(N, B, set_num_sms()), nb = nbpc_cdiv(N, rpb);
+#define X(V) if (q == V) NBPC_LAUNCH_N(NbpcKName("sgs_bwd_in_smallq", k, q).c_str(), sgs_bwd_in_smallq_kernel<V>, dim3(nb, B), SGS_THREADS, 0, stream, dZ, w.colsum, W, mask_input ? H_in : (const float *)nullptr, N, k, rpb, dH_in);
+                SGS_NARROW_LIST(X)
+#undef X
             } else {
                 NBPC_LAUNCH(set_bwd_in_mean_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, dz, w.colsum, W, rows, N, k, q, dH_in);
                 if (mask_input) NBPC_LAUNCH(set_mask_input_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, H_in, rows * k, dH_in);

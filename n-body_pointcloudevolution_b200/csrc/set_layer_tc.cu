@@ -26,6 +26,15 @@
 
 #define SGT_CHUNK_BYTES (GLT_TILE * 128)   // one A stage: 128 rows x 32 floats
 #define SGT_DW_ROWS 32                     // rows per stage of the dW kernel
+#define SGT_COLSUM_ROWS 256                // rows per block of the column-sum pass (N = 32^3, B = 8: 1024 blocks)
+
+// x / d for 0 <= x < 2^31 with magic = floor(2^32 / d) (2^32 - 1 for d = 1): the estimate is exact or one short
+__device__ __forceinline__ uint32_t sgt_div(uint32_t x, uint32_t d, uint32_t magic) {
+    uint32_t qt = __umulhi(x, magic);
+    if (x - qt * d >= d) ++qt;
+    return qt;
+}
+static inline uint32_t sgt_magic(int d) { return d == 1 ? 0xFFFFFFFFu : (uint32_t)(((uint64_t)1 << 32) / (uint32_t)d); }
 
 // ------------------------------------------------------------------ per-sample column sums
 // partial[s][blk][C] = sum over the block's rows of sample s; grid (nblk, B), C % 4 == 0, C <= 1024
@@ -67,26 +76,36 @@ __global__ void __launch_bounds__(256) sgt_colsum_partial_kernel(const float *__
         *reinterpret_cast<float4 *>(partial + ((int64_t)s * gridDim.x + blockIdx.x) * C + 4 * g) = a;
     }
 }
-// out[s][c] = (sum_blk partial[s][blk][c]) * scale;  total[c] = sum_s of the unscaled sums (optional)
+// out[s][c] = (sum_blk partial[s][blk][c]) * scale: one WARP per (sample, column) - lane l adds blocks l, l + 32, ... and
+// the lanes are combined by a fixed butterfly (deterministic)
 __global__ void sgt_colsum_final_kernel(const float *__restrict__ partial, int C, int nblk, int B, float scale, float *__restrict__ out,
-                                        float *__restrict__ total) {
+                                        float *__restrict__ sums) {
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= B * C) return;
+    const int s = t / C, c = t % C;
+    const float *p = partial + (int64_t)s * nblk * C + c;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = lane;
+    for (; b + 96 < nblk; b += 128) {
+        a0 += __ldg(p + (int64_t)b * C); a1 += __ldg(p + (int64_t)(b + 32) * C);
+        a2 += __ldg(p + (int64_t)(b + 64) * C); a3 += __ldg(p + (int64_t)(b + 96) * C);
+    }
+    for (; b < nblk; b += 32) a0 += __ldg(p + (int64_t)b * C);
+    float sum = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) {
+        out[t] = sum * scale;
+        if (sums) sums[t] = sum;
+    }
+}
+// total[c] = sum_s sums[s][c]
+__global__ void sgt_colsum_total_kernel(const float *__restrict__ sums, int C, int B, float *__restrict__ total) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float tot = 0.f;
-    for (int s = 0; s < B; ++s) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float *p = partial + (int64_t)s * nblk * C + c;
-        int b = 0;
-        for (; b + 4 <= nblk; b += 4) {
-            a0 += __ldg(p + (int64_t)b * C); a1 += __ldg(p + (int64_t)(b + 1) * C);
-            a2 += __ldg(p + (int64_t)(b + 2) * C); a3 += __ldg(p + (int64_t)(b + 3) * C);
-        }
-        for (; b < nblk; ++b) a0 += __ldg(p + (int64_t)b * C);
-        const float sum = (a0 + a1) + (a2 + a3);
-        out[s * C + c] = sum * scale;
-        tot += sum;
-    }
-    if (total) total[c] = tot;
+    for (int s = 0; s < B; ++s) tot += __ldg(&sums[s * C + c]);
+    total[c] = tot;
 }
 
 // ------------------------------------------------------------------ row GEMM: out = act((A - mu_s) Bm + bias) [* (mask > 0)]
@@ -98,6 +117,7 @@ struct SgtGemmArgs {
     float *out;              // (rows, Ntot)
     int64_t rows;
     int rows_per_sample, K, NT, Ntot, n_ntiles, b_transposed, relu, S, L;
+    uint32_t rps_magic;      // floor(2^32 / rows_per_sample) (2^32 - 1 for 1): sample of a row without a 64-bit division
 };
 
 template <bool X3>
@@ -138,15 +158,28 @@ __global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ C
         glt_prefetch_tmap(&tmA);
     }
     if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), tmem_cols);
-    // B operand, K-major: row n = output column n0 + n, element kk; chunk c = 32 consecutive kk of all NT rows
-    for (int i = tid; i < K * NT; i += blockDim.x) {
-        int n, kk;
-        float x;
-        if (P.b_transposed) { n = i / K; kk = i % K; x = __ldg(&P.Bsrc[(int64_t)(n0 + n) * K + kk]); }
-        else { kk = i / NT; n = i % NT; x = __ldg(&P.Bsrc[(int64_t)kk * P.Ntot + n0 + n]); }
-        const int off = (kk >> 5) * (NT * 128) + GltTile<32>::offset(n, kk & 31);
-        *reinterpret_cast<float *>(Bh + off) = X3 ? x : glt_to_tf32(x);
-        if (X3) *reinterpret_cast<float *>(Bl + off) = glt_residual(x);
+    // B operand, K-major: row n = output column n0 + n, element kk; chunk c = 32 consecutive kk of all NT rows.
+    // 8 independent global loads per thread and step (a one-load-per-iteration loop cost ~30 us per launch in latency)
+    for (int i0 = tid; i0 < K * NT; i0 += 8 * blockDim.x) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < K * NT) {
+                const int n = P.b_transposed ? i / K : i % NT, kk = P.b_transposed ? i % K : i / NT;
+                x[u] = __ldg(P.b_transposed ? &P.Bsrc[(int64_t)(n0 + n) * K + kk] : &P.Bsrc[(int64_t)kk * P.Ntot + n0 + n]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < K * NT) {
+                const int n = P.b_transposed ? i / K : i % NT, kk = P.b_transposed ? i % K : i / NT;
+                const int off = (kk >> 5) * (NT * 128) + GltTile<32>::offset(n, kk & 31);
+                *reinterpret_cast<float *>(Bh + off) = X3 ? x[u] : glt_to_tf32(x[u]);
+                if (X3) *reinterpret_cast<float *>(Bl + off) = glt_residual(x[u]);
+            }
+        }
     }
     glt_fence_proxy_async();
     glt_tc_fence_before();
@@ -207,6 +240,16 @@ __global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ C
             glt_tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * NT;
             for (int cb = 0; cb < NT; cb += SW) {
+                // the input-mask rows of this slab are requested first: 8 independent loads in flight (issued one by one in
+                // front of each store they cost one HBM round trip per row segment: 5.5 us per slab)
+                float4 mk[8];
+                if (P.mask) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int idx = i * 32 + lane, r = idx / vec_per_row, c4 = idx % vec_per_row;
+                        if (i < iters && row0 + r < P.rows) mk[i] = glf_ldg4(P.mask + (row0 + r) * P.Ntot + n0 + cb + 4 * c4);
+                    }
+                }
                 float z[32];
                 glt_tmem_ld16(tq + cb, z);
                 if (SW == 32) glt_tmem_ld16(tq + cb + 16, z + 16);
@@ -229,17 +272,17 @@ __global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ C
                     }
                 }
                 __syncwarp();
-                for (int i = 0; i < iters; ++i) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
                     const int idx = i * 32 + lane, r = idx / vec_per_row, c4 = idx % vec_per_row;
                     const int64_t grow = row0 + r;
-                    if (grow < P.rows) {
+                    if (i < iters && grow < P.rows) {
                         float4 v = *reinterpret_cast<const float4 *>(Ow + r * PITCH + 4 * c4);
-                        const int64_t g = grow * P.Ntot + n0 + cb + 4 * c4;
                         if (P.mask) {
-                            const float4 m = glf_ldg4(P.mask + g);
+                            const float4 m = mk[i];
                             v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
                         }
-                        *reinterpret_cast<float4 *>(P.out + g) = v;
+                        *reinterpret_cast<float4 *>(P.out + grow * P.Ntot + n0 + cb + 4 * c4) = v;
                     }
                 }
                 __syncwarp();
@@ -256,13 +299,18 @@ __global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ C
                 if (X3) glt_mbar_wait(LOFREE(l), lph ^ 1);
                 float *hi = reinterpret_cast<float *>(As + s * SGT_CHUNK_BYTES);
                 float *lo = reinterpret_cast<float *>(Al + l * SGT_CHUNK_BYTES);
+                // sample of tile row r = s0 + (rem0 + r) / rows_per_sample: one 64-bit division per chunk, none per granule
+                const int64_t trow = t * GLT_TILE;
+                const int64_t s0 = trow / P.rows_per_sample;
+                const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample), last = (uint32_t)nbpc_min((int64_t)GLT_TILE - 1, P.rows - 1 - trow);
+                const float *mu0 = P.mu ? P.mu + s0 * K + c * 32 : nullptr;
 #pragma unroll 4
                 for (int g = wtid; g < SGT_CHUNK_BYTES / 16; g += 128) {       // 16-byte granules: row = g / 8
                     float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
                     if (P.mu) {
                         const int r = g >> 3, lu = (g & 7) ^ (r & 7);             // logical 16-byte unit inside the row
-                        const int64_t grow = nbpc_min(t * GLT_TILE + r, P.rows - 1);
-                        const float4 m = glf_ldg4(P.mu + (grow / P.rows_per_sample) * K + c * 32 + 4 * lu);
+                        const uint32_t ds = sgt_div(rem0 + nbpc_min((uint32_t)r, last), (uint32_t)P.rows_per_sample, P.rps_magic);
+                        const float4 m = glf_ldg4(mu0 + ds * K + 4 * lu);
                         x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w;
                         *reinterpret_cast<float4 *>(hi + 4 * g) = X3 ? x : make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
                     } else if (!X3) {
@@ -312,9 +360,18 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     const size_t budget = 227 * 1024;
     while (NT > 16 && sgt_gemm_smem(x3, K, NT, 2, 2) > budget) NT >>= 1;
     if (Nout % NT || NT % 16 || sgt_gemm_smem(x3, K, NT, 2, 2) > budget) return 1;
+    // tuning override NBPC_SGT="NT,S,L" (read once)
+    static int env_nt = -1, env_s = 0, env_l = 0;
+    if (env_nt < 0) {
+        const char *e = getenv("NBPC_SGT");
+        env_nt = 0;
+        if (e) sscanf(e, "%d,%d,%d", &env_nt, &env_s, &env_l);
+    }
+    if (env_nt >= 16 && env_nt < NT && Nout % env_nt == 0 && env_nt % 16 == 0) NT = env_nt;
     int S = 2, L = 2;
     while (S < 6 && sgt_gemm_smem(x3, K, NT, S + 1, L) <= budget) ++S;
     if (x3 && S >= 4 && sgt_gemm_smem(x3, K, NT, S - 1, L + 1) <= budget) { --S; ++L; }
+    if (env_s >= 1 && env_l >= 1 && env_s <= 8 && env_l <= 8 && sgt_gemm_smem(x3, K, NT, env_s, env_l) <= budget) { S = env_s; L = env_l; }
     const size_t smem = sgt_gemm_smem(x3, K, NT, S, L);
     auto kern = x3 ? sgt_gemm_kernel<true> : sgt_gemm_kernel<false>;
     static bool configured[64][2];   // per device: function attributes belong to a context
@@ -332,6 +389,7 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     SgtGemmArgs P;
     P.Bsrc = Bsrc; P.mu = mu; P.bias = bias; P.mask = mask; P.out = out; P.rows = rows; P.rows_per_sample = rows_per_sample;
     P.K = K; P.NT = NT; P.Ntot = Nout; P.n_ntiles = Nout / NT; P.b_transposed = b_transposed; P.relu = relu; P.S = S; P.L = L;
+    P.rps_magic = sgt_magic(rows_per_sample);
     const int64_t ntiles = (rows + GLT_TILE - 1) / GLT_TILE;
     int64_t gm = gl_num_sms() / P.n_ntiles;
     if (gm < 1) gm = 1;
@@ -347,12 +405,14 @@ struct SgtDwArgs {
     float *partial;           // [grid][k][q]
     int64_t rows;
     int rows_per_sample, k, q, S, L;
+    uint32_t rps_magic;
 };
 
 template <bool X3>
 __global__ void __launch_bounds__(320) sgt_dw_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ,
                                                      const SgtDwArgs P) {
     constexpr int R = SGT_DW_ROWS, RCH = R * 128;                 // bytes of one [R rows x 32 floats] chunk
+    static_assert(R == 32, "the converter's granule -> (chunk, row) mapping assumes 32-row chunks");
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
     const int S = P.S, L = X3 ? P.L : 0, k = P.k, q = P.q, HCH = k >> 5, ZCH = q >> 5;
@@ -463,18 +523,26 @@ __global__ void __launch_bounds__(320) sgt_dw_kernel(const __grid_constant__ CUt
             float *hi = reinterpret_cast<float *>(St + s * STAGE);
             float *lo = reinterpret_cast<float *>(Sl + l * STAGE);
             const int n_gran = STAGE / 16, h_gran = H_BYTES / 16;
+            const int64_t trow = t * R;
+            const int64_t s0 = trow / P.rows_per_sample;
+            const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample);
+            const int n_valid = (int)nbpc_min((int64_t)R, P.rows - trow);
+            const float *mu0 = P.mu ? P.mu + s0 * k : nullptr;
 #pragma unroll 4
             for (int g = wtid; g < n_gran; g += 128) {
                 float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
                 bool wrote = false;
                 if (g < h_gran && P.mu) {
-                    // granule -> (chunk, row, 16-byte unit); 32-byte swizzle atoms: logical atom = atom ^ (row & 3)
-                    const int ch = g / (R * 8), r = (g >> 3) % R, u = g & 7;
+                    // granule -> (chunk, row, 16-byte unit); R = 32 rows x 8 granules per chunk; 32-byte swizzle atoms:
+                    // logical atom = atom ^ (row & 3)
+                    const int ch = g >> 8, r = (g >> 3) & (R - 1), u = g & 7;
                     const int col = ch * 32 + ((((u >> 1) ^ (r & 3)) << 3) | ((u & 1) << 2));
-                    const int64_t grow = nbpc_min(t * R + r, P.rows - 1);
-                    const float4 m = glf_ldg4(P.mu + (grow / P.rows_per_sample) * k + col);
                     // rows beyond the tensor were zero-filled by TMA and must stay zero
-                    if (t * R + r < P.rows) { x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w; }
+                    if (r < n_valid) {
+                        const uint32_t ds = sgt_div(rem0 + (uint32_t)r, (uint32_t)P.rows_per_sample, P.rps_magic);
+                        const float4 m = glf_ldg4(mu0 + ds * k + col);
+                        x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w;
+                    }
                     wrote = true;
                 }
                 if (!X3) x = make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
@@ -542,6 +610,7 @@ int sgt_dw(const float *H, const float *dZ, const float *mu, int64_t rows, int r
     if (glt_make_tmap_packed(&tmH, H, rows, k, SGT_DW_ROWS) || glt_make_tmap_packed(&tmZ, dZ, rows, q, SGT_DW_ROWS)) return 1;
     SgtDwArgs P;
     P.mu = mu; P.partial = partial; P.rows = rows; P.rows_per_sample = rows_per_sample; P.k = k; P.q = q; P.S = S; P.L = L;
+    P.rps_magic = sgt_magic(rows_per_sample);
     const int64_t ntiles = (rows + SGT_DW_ROWS - 1) / SGT_DW_ROWS;
     const int grid = (int)nbpc_min((int64_t)gl_num_sms(), ntiles);
     NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_dw_tf32x3" : "sgt_dw_tf32", k, q).c_str(), kern, grid, 320, smem, stream, tmH, tmZ, P);
@@ -550,10 +619,13 @@ int sgt_dw(const float *H, const float *dZ, const float *mu, int64_t rows, int r
 }
 
 // ------------------------------------------------------------------ per-sample column sums (C % 4 == 0, C <= 1024)
-int sgt_colsum_blocks(int N) { return nbpc_cdiv(N, 1024); }
+int sgt_colsum_blocks(int N) { return nbpc_cdiv(N, SGT_COLSUM_ROWS); }
 void sgt_colsum(const float *X, int C, int N, int B, float scale, float *partial, float *out, float *total, cudaStream_t stream) {
     const int nblk = sgt_colsum_blocks(N);
-    NBPC_LAUNCH(sgt_colsum_partial_kernel, dim3(nblk, B), 256, 0, stream, X, C, N, 1024, partial);
-    NBPC_LAUNCH(sgt_colsum_final_kernel, nbpc_cdiv(C, 128), 128, 0, stream, partial, C, nblk, B, scale, out, total);
+    NBPC_LAUNCH(sgt_colsum_partial_kernel, dim3(nblk, B), 256, 0, stream, X, C, N, SGT_COLSUM_ROWS, partial);
+    // the unscaled per-sample sums go behind the partials (the caller's buffer holds B * (nblk + 1) * C floats)
+    float *sums = total ? partial + (size_t)B * nblk * C : nullptr;
+    NBPC_LAUNCH(sgt_colsum_final_kernel, nbpc_cdiv((int64_t)B * C * 32, 256), 256, 0, stream, partial, C, nblk, B, scale, out, sums);
+    if (total) NBPC_LAUNCH(sgt_colsum_total_kernel, nbpc_cdiv(C, 128), 128, 0, stream, sums, C, B, total);
 }
 #endif  // !NBPC_HOST_EMU

@@ -14,7 +14,7 @@ int sgt_dw_max_parts();
 int sgt_dw(const float *H, const float *dZ, const float *mu, int64_t rows, int rows_per_sample, int k, int q, int x3, float *partial,
            float *dW, cudaStream_t stream);
 // out[s][c] = scale * sum_n X[s][n][c] (C % 4 == 0, C <= 1024), total[c] = sum_s of the unscaled sums (optional);
-// partial: B * sgt_colsum_blocks(N) * C floats
+// partial: B * (sgt_colsum_blocks(N) + 1) * C floats
 int sgt_colsum_blocks(int N);
 void sgt_colsum(const float *X, int C, int N, int B, float scale, float *partial, float *out, float *total, cudaStream_t stream);
 #endif
