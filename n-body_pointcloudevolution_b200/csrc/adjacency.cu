@@ -61,16 +61,16 @@ __global__ void seg_sort_kernel(const int32_t *__restrict__ seg_ptr, int32_t *__
 }
 
 struct SegWorkspace {
-    int32_t *fill, *partials, *flags;
+    int32_t *fill, *partials, *flags, *rank;
     size_t bytes;
 };
-static SegWorkspace seg_carve(void *ws, size_t ws_bytes, int64_t n_items, int num_segs) {
-    (void)n_items;
+static SegWorkspace seg_carve(void *ws, size_t ws_bytes, int64_t n_items, int num_segs, bool with_rank = false) {
     NbpcArena a(ws, ws_bytes);
     SegWorkspace w;
     w.fill = a.take<int32_t>((size_t)num_segs);
     w.partials = a.take<int32_t>(nbpc_scan_partials_count((int64_t)num_segs + 1));
     w.flags = a.take<int32_t>(2);
+    w.rank = a.take<int32_t>(with_rank ? (size_t)n_items : 0);
     w.bytes = a.off;
     return w;
 }
@@ -131,6 +131,72 @@ __global__ void adj_diag_kernel(const int32_t *__restrict__ coo_col, int BN, int
     if (cnt != 1) atomicAdd(&status[0], 1);
 }
 
+// ------------------------------------------------------------------ kNN adjacency, fused pipeline
+// One pass over the neighbour lists writes the COO rows AND counts the in-degrees; the value the counting atomic returns
+// is the edge's (arbitrary but unique) rank inside its column bucket, so the fill pass is a plain scatter without atomics.
+__global__ void adj_coo_count_kernel(const int32_t *__restrict__ idx, int B, int N, int M, int32_t *__restrict__ coo,
+                                     int32_t *__restrict__ seg_ptr, int32_t *__restrict__ rank, int32_t *__restrict__ status) {
+    const int64_t c = (int64_t)B * N * M;
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= c) return;
+    const int row = (int)(e / M);
+    const int s = row / N;
+    int col = idx[e];
+    if (col < 0 || col >= N) {
+        atomicAdd(&status[1], 1);
+        col = col < 0 ? 0 : N - 1;
+    }
+    const int gcol = s * N + col;
+    coo[e] = row;              // graph.py:644
+    coo[c + e] = gcol;         // graph.py:645
+    coo[2 * c + e] = s;        // graph.py:646
+    rank[e] = atomicAdd(&seg_ptr[gcol], 1);
+}
+
+__global__ void adj_fill_kernel(const int32_t *__restrict__ gcol, const int32_t *__restrict__ rank, int64_t c,
+                                const int32_t *__restrict__ seg_ptr, int32_t *__restrict__ members) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= c) return;
+    members[__ldg(&seg_ptr[gcol[e]]) + rank[e]] = (int32_t)e;
+}
+
+#ifndef NBPC_HOST_EMU
+// ascending edge ids inside every bucket: a block stages the contiguous member range of SEGS consecutive buckets in
+// shared memory, every thread insertion-sorts its own (short) bucket there, the range goes back coalesced.  Ranges that
+// do not fit (pathological in-degrees) are sorted in global memory.
+#define ADJ_SORT_SEGS 256
+#define ADJ_SORT_CAP 8192
+__global__ void __launch_bounds__(ADJ_SORT_SEGS) adj_sort_kernel(const int32_t *__restrict__ seg_ptr, int32_t *__restrict__ members,
+                                                                 int num_segs) {
+    __shared__ int32_t buf[ADJ_SORT_CAP];
+    const int s0 = blockIdx.x * ADJ_SORT_SEGS, s1 = nbpc_min(s0 + ADJ_SORT_SEGS, num_segs);
+    const int lo = seg_ptr[s0], hi = seg_ptr[s1], n = hi - lo;
+    const int s = s0 + threadIdx.x;
+    const bool fits = n <= ADJ_SORT_CAP;
+    int32_t *base = fits ? buf - lo : members;
+    if (fits) {
+        for (int i = threadIdx.x; i < n; i += ADJ_SORT_SEGS) buf[i] = members[lo + i];
+        __syncthreads();
+    }
+    if (s < s1) {
+        const int b = seg_ptr[s], e = seg_ptr[s + 1];
+        for (int i = b + 1; i < e; ++i) {
+            const int v = base[i];
+            int j = i - 1;
+            while (j >= b && base[j] > v) {
+                base[j + 1] = base[j];
+                --j;
+            }
+            base[j + 1] = v;
+        }
+    }
+    if (fits) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += ADJ_SORT_SEGS) members[lo + i] = buf[i];
+    }
+}
+#endif
+
 extern "C" {
 
 size_t nbpc_segment_csr_workspace_bytes(int64_t n_items, int num_segs) {
@@ -156,7 +222,7 @@ int nbpc_segment_csr(const int32_t *ids, int64_t n_items, int num_segs, int32_t 
 
 size_t nbpc_adjacency_workspace_bytes(int B, int N, int M) {
     if (B < 1 || N < 1 || M < 1) return 0;
-    return seg_carve(nullptr, 0, (int64_t)B * N * M, B * N).bytes;
+    return seg_carve(nullptr, 0, (int64_t)B * N * M, B * N, true).bytes;
 }
 
 int nbpc_adjacency(const int32_t *idx, int B, int N, int M, int32_t *coo_out, int64_t *diag_out,
@@ -168,7 +234,7 @@ int nbpc_adjacency(const int32_t *idx, int B, int N, int M, int32_t *coo_out, in
     NBPC_ARG(B >= 1 && N >= 1 && M >= 1, "B, N, M must be positive");
     const int64_t c = (int64_t)B * N * M;
     NBPC_ARG(c < ((int64_t)1 << 31), "B*N*M must fit int32");
-    SegWorkspace w = seg_carve(workspace, ws_bytes, c, B * N);
+    SegWorkspace w = seg_carve(workspace, ws_bytes, c, B * N, true);
     if (w.bytes > ws_bytes) {
         nbpc_set_error("nbpc_adjacency: workspace too small");
         return NBPC_EWORKSPACE;
@@ -178,6 +244,22 @@ int nbpc_adjacency(const int32_t *idx, int B, int N, int M, int32_t *coo_out, in
         return NBPC_ELAUNCH;
     }
     const int T = 256;
+#ifndef NBPC_HOST_EMU
+    {
+        // fused pipeline: COO rows + in-degree count (+ bucket rank) -> scan -> atomic-free fill -> shared-memory bucket sort
+        const int num_segs = B * N;
+        if (nbpc_memset_async(csrT_ptr, 0, sizeof(int32_t) * ((size_t)num_segs + 1), stream)) {
+            nbpc_set_error("nbpc_adjacency: memset failed");
+            return NBPC_ELAUNCH;
+        }
+        NBPC_LAUNCH(adj_coo_count_kernel, nbpc_cdiv(c, T), T, 0, stream, idx, B, N, M, coo_out, csrT_ptr, w.rank, status);
+        NBPC_LAUNCH(adj_diag_kernel, nbpc_cdiv(num_segs, T), T, 0, stream, coo_out + c, num_segs, M, diag_out, status);
+        NBPC_TRY(nbpc_exclusive_scan_i32(csrT_ptr, (int64_t)num_segs + 1, w.partials, stream));
+        NBPC_LAUNCH(adj_fill_kernel, nbpc_cdiv(c, T), T, 0, stream, coo_out + c, w.rank, c, csrT_ptr, csrT_edge);
+        NBPC_LAUNCH(adj_sort_kernel, nbpc_cdiv(num_segs, ADJ_SORT_SEGS), ADJ_SORT_SEGS, 0, stream, csrT_ptr, csrT_edge, num_segs);
+        return nbpc_check_launch("nbpc_adjacency");
+    }
+#endif
     NBPC_LAUNCH(adj_coo_kernel, nbpc_cdiv(c, T), T, 0, stream, idx, B, N, M, coo_out, status);
     NBPC_LAUNCH(adj_diag_kernel, nbpc_cdiv(B * N, T), T, 0, stream, coo_out + c, B * N, M, diag_out, status);
     NBPC_TRY(segment_csr_impl(coo_out + c, c, B * N, csrT_ptr, csrT_edge, status, w, stream));

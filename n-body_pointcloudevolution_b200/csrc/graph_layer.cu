@@ -246,6 +246,18 @@ static bool gl_use_fast() {
 #endif
 }
 
+// Alternating traversal (NBPC_ZIGZAG=0 disables, read once): the pooling kernels and the first-layer backward read the
+// edge tensor their predecessor has just written starting from its END, where the last ~100 MB are still in the 126 MB
+// L2; the edge kernel that follows them starts at the head again, which the reversed reader touched last.
+static int gl_zigzag() {
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("NBPC_ZIGZAG");
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached;
+}
+
 // NBPC_NO_FIRST_LAYER_FUSION=1 (read once) selects the unfused first-layer backward (cross-check)
 static bool gl_first_layer_fusion() {
     static int cached = -1;
@@ -379,7 +391,7 @@ static int glk3_launch_first_layer_bwd_t(const float *E, const float *dOut, cons
     const int64_t tpb = (ntiles + want - 1) / want;
     const int nblk = (int)((ntiles + tpb - 1) / tpb);
     NBPC_LAUNCH_N(NbpcKName("glk3_first_layer_bwd_kernel", 3, Q).c_str(), kern, dim3(nblk, B), GLK3_THREADS, smem, stream, E, dOut, Hout, col,
-                  P_col, P_row, (uint32_t)edges_per_sample, (uint32_t)tpb, (uint32_t)M, magic, part1, part2, part3, colsum_partial);
+                  P_col, P_row, (uint32_t)edges_per_sample, (uint32_t)tpb, (uint32_t)M, magic, part1, part2, part3, colsum_partial, gl_zigzag());
     return nblk;
 }
 static int glk3_launch_first_layer_bwd(int q, const float *E, const float *dOut, const float *Hout, const int32_t *col,
@@ -435,7 +447,7 @@ static int gln_launch_pool(const float *H, int k, int q, int B, int N, int M, co
     if (k == K_) {                                                                                                     \
         nblk = nbpc_cdiv(N, gln_pool_nodes_per_block(K_));                                                             \
         NBPC_LAUNCH_N(NbpcKName("gln_pool_kernel", k, q).c_str(), gln_pool_kernel<K_>, dim3(nblk, B), GLN_THREADS, 0, stream, H, M, N, \
-                      csrT_ptr, csrT_edge, P_row, P_col, partial);                                                     \
+                      csrT_ptr, csrT_edge, P_row, P_col, partial, gl_zigzag());                                        \
     }
     X(16) X(32) X(64)
 #undef X
@@ -527,8 +539,8 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
 #define X(Q_)                                                                                                           \
     if (q == Q_) {                                                                                                     \
         nblk = nbpc_cdiv(N, gln_pool_nodes_per_block(Q_));                                                             \
-        if (relu) NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, true>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial); \
-        else NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, false>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial); \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, true>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial, gl_zigzag()); \
+        else NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, false>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial, gl_zigzag()); \
     }
         X(16) X(32) X(64)
 #undef X

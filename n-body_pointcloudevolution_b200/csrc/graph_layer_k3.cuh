@@ -163,15 +163,17 @@ template <int Q, bool RELU>
 __global__ void __launch_bounds__(GLK3_THREADS) glk3_first_layer_bwd_kernel(
     const float *__restrict__ E, const float *__restrict__ dOut, const float *__restrict__ Hout, const int32_t *__restrict__ col,
     const float *__restrict__ P_col, const float *__restrict__ P_row, uint32_t edges_per_sample, uint32_t tiles_per_block, uint32_t M,
-    uint32_t magic, float *__restrict__ part1, float *__restrict__ part2, float *__restrict__ part3, float *__restrict__ colsum_partial) {
+    uint32_t magic, float *__restrict__ part1, float *__restrict__ part2, float *__restrict__ part3, float *__restrict__ colsum_partial,
+    int rev) {
     using Cfg = Glk3FbCfg<Q, RELU>;
     constexpr int K = 3, G = Q / 4, SLOTS = GLK3_THREADS / G, TILE = GLK3_FB_TILE, S = GLK3_FB_STAGES;
     extern __shared__ __align__(16) float glk3_smem[];
     const int tid = threadIdx.x, g = tid % G, slot = tid / G;
-    const uint32_t s = blockIdx.y;
+    // rev: the blocks walk dZ from its end (what the producing kernel wrote last is still in L2); same partial slots
+    const uint32_t bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x, s = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
     const uint32_t e_sample = s * edges_per_sample, e_sample_end = e_sample + edges_per_sample;
     const uint32_t ntiles_sample = (edges_per_sample + TILE - 1) / TILE;
-    const uint32_t t_begin = blockIdx.x * tiles_per_block, t_end = nbpc_min(t_begin + tiles_per_block, ntiles_sample);
+    const uint32_t t_begin = bx * tiles_per_block, t_end = nbpc_min(t_begin + tiles_per_block, ntiles_sample);
 
     auto issue = [&](uint32_t t, int st) {
         float *Zs = glk3_smem + (size_t)st * Cfg::STAGE_F, *Hs = Zs + Cfg::ZF;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(GLK3_THREADS) glk3_first_layer_bwd_kernel(
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
     float4 *red = reinterpret_cast<float4 *>(glk3_smem);
-    const size_t blk = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const size_t blk = (size_t)s * gridDim.x + bx;
     // 10 rows (3 x dW1, 3 x dW2, 3 x dW3, column sum) through the same fixed tree over the slots, one at a time
 #pragma unroll 1
     for (int r = 0; r < 3 * K + 1; ++r) {

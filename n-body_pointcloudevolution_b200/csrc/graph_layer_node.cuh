@@ -44,11 +44,13 @@ template <int K>
 __global__ void __launch_bounds__(GLN_THREADS) gln_pool_kernel(const float *__restrict__ H, int M, int N,
                                                                 const int32_t *__restrict__ csrT_ptr,
                                                                 const int32_t *__restrict__ csrT_edge, float *__restrict__ P_row,
-                                                                float *__restrict__ P_col, float *__restrict__ partial) {
+                                                                float *__restrict__ P_col, float *__restrict__ partial, int rev) {
     constexpr int G = K / 4, NPB = GLN_THREADS / G;
     __shared__ float4 red[GLN_THREADS];
     const int g = threadIdx.x % G, slot = threadIdx.x / G;
-    const int local = blockIdx.x * NPB + slot, s = blockIdx.y;
+    // rev: walk the edge tensor from its END (the part the producing kernel wrote last is still in L2); results identical
+    const int bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x, s = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+    const int local = bx * NPB + slot;
     float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (local < N) {
         const int64_t node = (int64_t)s * N + local;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_pool_kernel(const float *__re
         *reinterpret_cast<float4 *>(P_col + node * K + 4 * g) = make_float4(cs.x / fc, cs.y / fc, cs.z / fc, cs.w / fc);
     }
     gln_block_colsum<G>(red, pr);
-    if (slot == 0) *reinterpret_cast<float4 *>(partial + ((int64_t)s * gridDim.x + blockIdx.x) * K + 4 * g) = red[threadIdx.x];
+    if (slot == 0) *reinterpret_cast<float4 *>(partial + ((int64_t)s * gridDim.x + bx) * K + 4 * g) = red[threadIdx.x];
 }
 
 // ------------------------------------------------------------------ forward pooling, runtime K <= 32 (the 3-channel
@@ -131,11 +133,12 @@ template <int Q, bool RELU>
 __global__ void __launch_bounds__(GLN_THREADS) gln_bwd_pool_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout, int M,
                                                                     int N, const int32_t *__restrict__ csrT_ptr,
                                                                     const int32_t *__restrict__ csrT_edge, float *__restrict__ dQ_row,
-                                                                    float *__restrict__ dQ_col, float *__restrict__ partial) {
+                                                                    float *__restrict__ dQ_col, float *__restrict__ partial, int rev) {
     constexpr int G = Q / 4, NPB = GLN_THREADS / G;
     __shared__ float4 red[GLN_THREADS];
     const int g = threadIdx.x % G, slot = threadIdx.x / G;
-    const int local = blockIdx.x * NPB + slot, s = blockIdx.y;
+    const int bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x, s = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+    const int local = bx * NPB + slot;
     auto dz = [&](int64_t e) {
         float4 v = __ldg(reinterpret_cast<const float4 *>(dOut + e * Q + 4 * g));
         if (RELU) {
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_bwd_pool_kernel(const float *
         *reinterpret_cast<float4 *>(dQ_col + node * Q + 4 * g) = cs;
     }
     gln_block_colsum<G>(red, rs);
-    if (slot == 0) *reinterpret_cast<float4 *>(partial + ((int64_t)s * gridDim.x + blockIdx.x) * Q + 4 * g) = red[threadIdx.x];
+    if (slot == 0) *reinterpret_cast<float4 *>(partial + ((int64_t)s * gridDim.x + bx) * Q + 4 * g) = red[threadIdx.x];
 }
 
 // ------------------------------------------------------------------ tiny per-sample kernels (grid = B, runtime k, q)
