@@ -328,17 +328,29 @@ class Workload:
 
         # The whole step (kNN build, adjacency, forward, backward, Adam) is captured once in a CUDA graph and replayed, so
         # the timed region is not limited by the host's launch rate; --no-graph launches eagerly.
-        self.graphed, self.graph_note = None, "eager launches (--no-graph)"
+        self.graphed, self.graph_note, self.pipelined = None, "eager launches (--no-graph)", False
         if use_graph:
             try:
                 if world == 1:
                     self.graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), self.resident[0])
                     self.graph_note = "one CUDA graph replay per step (whole step captured once)"
                 else:
-                    # the NCCL all-reduce stays outside the capture (capturing it hung with the NCCL watchdog thread alive):
-                    # graph = kNN build + forward + backward; all-reduce and Adam are launched eagerly behind it
-                    self.graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, comm=False, update=False), self.resident[0])
-                    self.graph_note = "one CUDA graph replay per step (kNN + forward + backward), NCCL all-reduce and Adam launched eagerly"
+                    # the NCCL all-reduce is INSIDE the graph, on a forked stream next to the kNN build of the same replay:
+                    # replay i all-reduces and applies the gradient of step i-1 while the graph of step i is built
+                    # (train_utils.PipelinedStep; same parameter sequence as the plain loop)
+                    def prep(x, za, tgt):
+                        return graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(x, k))
+
+                    def grad(ctx, x, za, tgt):
+                        coo, diag = ctx
+                        loss = nn_.loss_ZA(graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k)), tgt)
+                        store.zero_grad()
+                        loss.backward()
+                        return loss
+                    self.graphed = tu.PipelinedStep(prep, grad, store, adam, world, self.resident[0])
+                    self.pipelined = True
+                    self.graph_note = ("one CUDA graph replay per step, NCCL all-reduce + Adam of step i-1 captured on a forked "
+                                       "stream next to the kNN build of step i")
             except Exception as exc:
                 self.graphed, self.graph_note = None, f"eager launches (graph capture failed: {repr(exc)[:200]})"
                 torch.cuda.synchronize()
@@ -347,10 +359,18 @@ class Workload:
         if self.graphed is None:
             return self.train_step(x, za, tgt)
         loss = self.graphed(x, za, tgt)
-        if self.world > 1:
+        if self.world > 1 and not self.pipelined:
             self.nb.train_utils.allreduce_gradients(self.store, self.world)
             self.adam.step(grad_scale=1.0 / self.world)
         return loss
+
+    def close(self):
+        """Apply a pending pipelined update and drop the CUDA graph (must precede destroy_process_group)."""
+        if self.graphed is not None:
+            if self.pipelined:
+                self.graphed.flush()
+            self.graphed.close()
+            self.graphed = None
 
     def step_resident(self, i):
         return self.run_step(*self.resident[i % self.n_pool])
@@ -539,7 +559,7 @@ def main():
     ms = timed(wl.step_resident, a.steps, world, dev, step_stats, "resident")
     launches = lib.launch_count() - l0
     if wl.graphed is not None:                                       # kernels are launched by the graph replays
-        launches = (wl.graphed.kernels_per_replay + (1 if world > 1 else 0)) * a.steps
+        launches = (wl.graphed.kernels_per_replay + (1 if world > 1 else 0)) * a.steps   # + the NCCL kernel
     clocks = sampler.stop(skip) if sampler else {}
     particles = world * b * N
     value = particles * a.steps / (ms * 1e-3)
@@ -570,13 +590,16 @@ def main():
                 step_bytes = 1428 * c_edges + (12 + 4 * k) * bb * 64 ** 3 + 20 * c_edges + 16 * bb * 64 ** 3
                 c4[mode] = {"samples_per_gpu": bb, "global_batch": world * bb, "ms_per_step": ms4 / st, "particles_per_s": p4 * st / (ms4 * 1e-3),
                             "step_roofline_frac": step_bytes / (ms4 / st * 1e-3) / 1e9 / measured_peak_gbs()[0], "launch": w4.graph_note}
+                w4.close()
                 del w4
                 torch.cuda.empty_cache()
             except Exception as exc:
                 c4[mode] = {"error": repr(exc)[:300]}
                 barrier(world)
 
+    graphed_kernels = wl.graphed.kernels_per_replay if wl.graphed is not None else None
     if world > 1:
+        wl.close()                                                    # a live graph holding NCCL kernels hangs the teardown
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     if rank != 0:

@@ -237,7 +237,8 @@ int nbpc_adam_tf(float *param, const float *grad, float *m, float *v, int64_t n,
 
 /* Same step with the step count t kept in device memory (*step_counter is incremented first, then used): every launch
  * parameter is then identical from step to step, so a whole training step can be captured in a CUDA graph and
- * replayed. */
+ * replayed.  If the incremented counter is still <= 0 the call updates nothing: a pipelined loop that applies the update
+ * of step t at the start of step t+1 (overlapping the gradient all-reduce with the next graph build) starts it at -1. */
 int nbpc_adam_tf_dev(float *param, const float *grad, float *m, float *v, int64_t n, float lr,
                      float beta1, float beta2, float eps, int64_t *step_counter, float grad_scale, void *stream);
 

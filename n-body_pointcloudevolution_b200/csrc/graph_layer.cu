@@ -29,6 +29,23 @@ __global__ void edge_features_kernel(const float *__restrict__ pos, int ld, cons
     for (int d = 0; d < 3; ++d) out[e * 3 + d] = __ldg(&pos[j * ld + d]) - __ldg(&pos[r * ld + d]);
 }
 
+// same, with the ZA displacement of the row node added on its self edge (graph.py:320-341) in the same pass:
+// edge e receives za[r] iff diag[r] == e (one launch instead of the gather + the scatter-add)
+__global__ void edge_features_za_kernel(const float *__restrict__ pos, int ld, const float *__restrict__ za, int ld_za,
+                                        const int32_t *__restrict__ col, const int64_t *__restrict__ diag, int64_t c, int M,
+                                        float *__restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= c) return;
+    const int64_t r = e / M, j = col[e];
+    const bool self = __ldg(&diag[r]) == e;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float v = __ldg(&pos[j * ld + d]) - __ldg(&pos[r * ld + d]);
+        if (self) v += __ldg(&za[r * ld_za + d]);
+        out[e * 3 + d] = v;
+    }
+}
+
 __global__ void edge_add_diag_kernel(const float *__restrict__ za, int ld, const int64_t *__restrict__ diag,
                                      int64_t n_diag, int64_t c, float *__restrict__ out) {
     int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -469,9 +486,14 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
     float *Cq = w.dCq;
     NBPC_LAUNCH(gln_cube_fwd_kernel, B, GLN_TINY_THREADS, 0, stream, w.cube_partial, nblk, N, k, q, W + 3 * kq, bias, P_cube, Cq);
 #define X(K_, Q_)                                                                                                       \
-    if (k == K_ && q == Q_)                                                                                            \
-        NBPC_LAUNCH_N(NbpcKName("gln_node_project_kernel", k, q).c_str(), (gln_node_project_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, \
-                      0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);
+    if (k == K_ && q == Q_) {                                                                                          \
+        if constexpr (Q_ % 8 == 0 && K_ <= 10)                                                                         \
+            NBPC_LAUNCH_N(NbpcKName("gln_node_project8_kernel", k, q).c_str(), (gln_node_project8_kernel<K_, Q_>), gln_node_grid(BN * 8), GLN_THREADS, \
+                          0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);                                     \
+        else                                                                                                           \
+            NBPC_LAUNCH_N(NbpcKName("gln_node_project2_kernel", k, q).c_str(), (gln_node_project2_kernel<K_, Q_>), gln_node_grid(BN * 2), GLN_THREADS, \
+                          0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);                                     \
+    }
     GLN_FOR_KQ(X)
 #undef X
     if (is_last) {
@@ -550,9 +572,10 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
     // ---- G_col, G_row
     if (dH_in) {
 #define X(K_, Q_)                                                                                                       \
-    if (k == K_ && q == Q_)                                                                                            \
-        NBPC_LAUNCH_N(NbpcKName("gln_node_grad_kernel", k, q).c_str(), (gln_node_grad_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, 0,  \
-                      stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr);
+    if (k == K_ && q == Q_) {                                                                                          \
+        NBPC_LAUNCH_N(NbpcKName("gln_node_grad2_kernel", k, q).c_str(), (gln_node_grad2_kernel<K_, Q_>), gln_node_grid(BN * 2), GLN_THREADS, 0,  \
+                      stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr);            \
+    }
         GLN_FOR_KQ(X)
 #undef X
     }
@@ -607,6 +630,11 @@ int nbpc_edge_features_za(const float *pos, int ld_pos, const float *za, int ld_
     NBPC_ARG(pos && col && edges_out, "null pointer");
     NBPC_ARG(BN >= 1 && M >= 1 && ld_pos >= 3, "bad sizes");
     const int64_t c = (int64_t)BN * M;
+    if (za && n_diag == BN && diag && ld_za >= 3) {   // one diagonal entry per row node: fused gather + self-edge add
+        NBPC_LAUNCH(edge_features_za_kernel, nbpc_cdiv(c, GL_THREADS), GL_THREADS, 0, stream, pos, ld_pos, za, ld_za, col, diag, c, M,
+                    edges_out);
+        return nbpc_check_launch("nbpc_edge_features_za");
+    }
     NBPC_LAUNCH(edge_features_kernel, nbpc_cdiv(c, GL_THREADS), GL_THREADS, 0, stream, pos, ld_pos, col, c, M, edges_out);
     if (za && n_diag > 0) {
         NBPC_ARG(diag && ld_za >= 3, "diag/za");

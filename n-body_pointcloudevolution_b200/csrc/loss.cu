@@ -136,6 +136,9 @@ __global__ void adam_tf_dev_kernel(float *__restrict__ p, const float *__restric
                                    float b2, float eps, float gscale) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // a counter that is still <= 0 after the tick makes the call a no-op: a pipelined loop that issues the update of step
+    // t at the START of step t+1 (train_utils.PipelinedStep) starts the counter at -1 so that its first replay updates nothing
+    if (*step <= 0) return;
     const double t = (double)*step;
     const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
     const float gi = g[i] * gscale;

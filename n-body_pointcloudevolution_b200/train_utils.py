@@ -119,6 +119,77 @@ class GraphedStep:
         self.graph.replay()
         return self.loss
 
+    def close(self):
+        """Drop the graph (required before destroy_process_group() if it holds NCCL kernels)."""
+        self.graph = None
+        torch.cuda.synchronize()
+
+
+class PipelinedStep:
+    """Data-parallel training step captured as ONE CUDA graph, NCCL all-reduce included, with the collective hidden
+    behind work that does not need the parameters:
+
+        replay i:   side stream : all-reduce(gradient of step i-1) -> Adam update of step i-1
+                    main stream : prep_fn(*inputs)        (kNN graph build, adjacency, edge features: no parameters)
+                    join        : grad_fn(ctx, *inputs)   (forward, loss, backward -> gradient of step i)
+
+    The sequence of parameter values is exactly that of the plain loop (update i-1 lands before forward i); the update of
+    the LAST step is applied by flush().  The Adam step counter starts at -1, which makes the update of the first replay a
+    no-op (nbpc_adam_tf_dev).  prep_fn(*static_inputs) -> ctx; grad_fn(ctx, *static_inputs) -> loss, and must zero the
+    gradient buffer before its backward.  close() must be called before torch.distributed.destroy_process_group():
+    destroying a process group while a live CUDA graph holds its NCCL kernels hangs."""
+
+    def __init__(self, prep_fn, grad_fn, store, adam, world, example_inputs, warmup=2):
+        self.store, self.adam, self.world = store, adam, world
+        self.static_in = tuple(torch.empty_like(t).copy_(t) for t in example_inputs)
+        self.side = torch.cuda.Stream()
+        state = [t.clone() for t in (store.flat, store.m, store.v)]
+
+        def body():
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                allreduce_gradients(store, world)
+                adam.step_dev(grad_scale=1.0 / world)
+            ctx = prep_fn(*self.static_in)
+            main.wait_stream(self.side)
+            return grad_fn(ctx, *self.static_in)
+
+        warm = torch.cuda.Stream()
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):                      # lazy initialisations (NCCL communicator included) outside the capture
+            for _ in range(max(warmup, 1)):
+                body()
+        torch.cuda.current_stream().wait_stream(warm)
+        torch.cuda.synchronize()
+        with torch.no_grad():                              # the warm-up steps trained on the example batch: undo
+            for t, s0 in zip((store.flat, store.m, store.v), state):
+                t.copy_(s0)
+            store.flat_grad.zero_()
+            store.step_dev.fill_(-1)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.loss = body()
+        self.kernels_per_replay = _lib.launch_count() - n0
+
+    def __call__(self, *inputs):
+        for d, s in zip(self.static_in, inputs):
+            if d.data_ptr() != s.data_ptr():
+                d.copy_(s, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def flush(self):
+        """Apply the update of the last replayed step (eagerly)."""
+        allreduce_gradients(self.store, self.world)
+        self.adam.step_dev(grad_scale=1.0 / self.world)
+        self.store.flat_grad.zero_()
+
+    def close(self):
+        self.graph = None
+        torch.cuda.synchronize()
+
 
 def allreduce_gradients(store, world_size):
     """Sum the flat gradient buffer over ranks (NCCL over NVLink on GPUs; gloo in CPU tests)."""

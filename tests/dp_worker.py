@@ -48,9 +48,35 @@ def main(out_path):
         return torch.stack(grads), store.flat.clone()
 
     g_dp, p_dp = run(slice(rank * per, (rank + 1) * per), world, True)        # this rank's samples, NCCL all-reduce
+
+    # the same data-parallel run with the whole step (NCCL all-reduce included) captured in one CUDA graph
+    def run_pipelined():
+        store = tu.ParamStore(ch, device=dev)
+        store.load_numpy(syn.glorot_params(ch))
+        adam = tu.AdamTF(store, lr=0.01)
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+        sl = slice(rank * per, (rank + 1) * per)
+        dev_batches = [tuple(torch.tensor(np.ascontiguousarray(t[sl]), device=dev) for t in bt) for bt in batches]
+
+        def prep(x, za, tgt):
+            return graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(x, k))
+
+        def grad(ctx, x, za, tgt):
+            loss = nn_.loss_ZA(graph.model_func_shift_inv_za(x, ctx[0], za, ctx[1], mv, (per, N, k)), tgt)
+            store.zero_grad()
+            loss.backward()
+            return loss
+        ps = tu.PipelinedStep(prep, grad, store, adam, world, dev_batches[0])
+        for bt in dev_batches:
+            ps(*bt)
+        ps.flush()
+        ps.close()
+        return store.flat.clone()
+    p_pipe = run_pipelined()
     if rank == 0:
         g_1, p_1 = run(slice(0, B), 1, False)                                  # same global batch on one GPU
-        np.savez(out_path, g_dp=g_dp.cpu().numpy(), p_dp=p_dp.cpu().numpy(), g_1=g_1.cpu().numpy(), p_1=p_1.cpu().numpy())
+        np.savez(out_path, g_dp=g_dp.cpu().numpy(), p_dp=p_dp.cpu().numpy(), g_1=g_1.cpu().numpy(), p_1=p_1.cpu().numpy(),
+                 p_pipe=p_pipe.cpu().numpy())
     # every rank must hold identical parameters
     gathered = [torch.empty_like(p_dp) for _ in range(world)]
     torch.distributed.all_gather(gathered, p_dp)

@@ -165,29 +165,28 @@ def main(argv=None):
 
     graphed = None
     if args.graph and args.num_iters > 0:
-        # GraphedStep's warm-up steps would draw from the data RNG and train on the example batch: snapshot and restore
-        # the RNG and the optimiser state.  With more than one rank the NCCL all-reduce stays OUTSIDE the capture
-        # (capturing it hung with the NCCL watchdog alive, see bench.py): the graph holds kNN + forward + backward and
-        # the all-reduce + Adam are launched eagerly behind every replay.
+        # The warm-up steps of the capture would draw from the data RNG and train on the example batch: snapshot and restore
+        # the RNG and the optimiser state.  With more than one rank the graph also holds the NCCL all-reduce: replay i
+        # all-reduces and applies the gradient of step i-1 on a forked stream while the kNN graph of step i is built
+        # (train_utils.PipelinedStep: same parameter sequence; a checkpoint written in that mode holds the parameters
+        # BEFORE the update of the step whose loss is printed next to it).
         rng_state = dataset.rng.get_state()
         example = torch.from_numpy(dataset.get_minibatch(args.batch_size)).to(dev)
         dataset.rng.set_state(rng_state)
         state = [t.clone() for t in (store.flat, store.m, store.v, store.step_dev)]
         if world == 1:
             graphed = nbpc.train_utils.GraphedStep(lambda x: train_step(x, dev_step=True), (example,), warmup=2)
+            with torch.no_grad():
+                for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
+                    t.copy_(s0)
         else:
-            graphed = nbpc.train_utils.GraphedStep(grad_step, (example,), warmup=2)
-        with torch.no_grad():
-            for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
-                t.copy_(s0)
+            # NCCL all-reduce + Adam of step i-1 are captured on a forked stream at the start of replay i
+            graphed = nbpc.train_utils.PipelinedStep(lambda x: None, lambda ctx, x: grad_step(x), store, adam, world, (example,), warmup=2)
 
     def run(batch):
         if graphed is None:
             return train_step(batch)
-        loss = graphed(torch.from_numpy(batch).to(dev, non_blocking=True))
-        if world > 1:
-            update()
-        return loss
+        return graphed(torch.from_numpy(batch).to(dev, non_blocking=True))
 
     tstart = time.time()
     if rank == 0:
@@ -199,6 +198,10 @@ def main(argv=None):
             save(step)
             if rank == 0:
                 print(f"Checkpoint {step + 1:>6} :  {float(loss.detach()):.8f}")
+    if graphed is not None:
+        if world > 1:
+            graphed.flush()                                                            # the update of the last step
+        graphed.close()
     torch.cuda.synchronize()
     if rank == 0:
         print(f"Training finished!\n\tElapsed time: {(time.time() - tstart) / 60:.2f}m")
