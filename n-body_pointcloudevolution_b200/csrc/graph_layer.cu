@@ -491,7 +491,7 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
             NBPC_LAUNCH_N(NbpcKName("gln_node_project8_kernel", k, q).c_str(), (gln_node_project8_kernel<K_, Q_>), gln_node_grid(BN * 8), GLN_THREADS, \
                           0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);                                     \
         else                                                                                                           \
-            NBPC_LAUNCH_N(NbpcKName("gln_node_project2_kernel", k, q).c_str(), (gln_node_project2_kernel<K_, Q_>), gln_node_grid(BN * 2), GLN_THREADS, \
+            NBPC_LAUNCH_N(NbpcKName("gln_node_project_kernel", k, q).c_str(), (gln_node_project_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, \
                           0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);                                     \
     }
     GLN_FOR_KQ(X)
@@ -573,7 +573,7 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
     if (dH_in) {
 #define X(K_, Q_)                                                                                                       \
     if (k == K_ && q == Q_) {                                                                                          \
-        NBPC_LAUNCH_N(NbpcKName("gln_node_grad2_kernel", k, q).c_str(), (gln_node_grad2_kernel<K_, Q_>), gln_node_grid(BN * 2), GLN_THREADS, 0,  \
+        NBPC_LAUNCH_N(NbpcKName("gln_node_grad_kernel", k, q).c_str(), (gln_node_grad_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, 0,  \
                       stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr);            \
     }
         GLN_FOR_KQ(X)

@@ -354,9 +354,10 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_node_grad_kernel(const float 
 }
 
 // ------------------------------------------------------------------ 8 threads per node (Q % 8 == 0 / K % 8 == 0)
-// The thread-per-node projections above keep 1024 FMAs in one thread and leave the SM with too few warps (262 144 nodes =
-// 0.86 of one wave): 45 us for 100 MB.  Here a node's outputs are split over 8 adjacent lanes; every lane reads the whole
-// input row (the 8 lanes hit the same L1 lines) and its slice of the weights from shared memory.
+// For the narrow first layer (K <= 10) a node's outputs are split over 8 adjacent lanes: every lane reads the whole (short)
+// input row and its slice of the weights from shared memory (21 us instead of 31 us at k = 3, q = 32).  Measured and NOT kept
+// for K >= 16: 8 lanes per node re-read every 128-byte row 8 times through L1 (59 us vs 45 us), 2 lanes per node (lane parity
+// = col / row term) break the warp-broadcast weight loads (57 us).
 template <int K, int Q>
 __global__ void __launch_bounds__(GLN_THREADS) gln_node_project8_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
                                                                          const float *__restrict__ Cq, const float *__restrict__ W, int BN,
@@ -388,71 +389,6 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_node_project8_kernel(const fl
         for (int j = 0; j < QT; ++j) a3[j] += __ldg(&cq[j]);
         gln_store_row<QT>(Q_col + node * Q + q0, a2);
         gln_store_row<QT>(Q_row + node * Q + q0, a3);
-    }
-}
-
-// ------------------------------------------------------------------ 2 threads per node: lane parity selects the col / row term
-// (same instruction stream, different pointers: no divergence, no redundant loads, twice the warps of the thread-per-node
-// kernels; the 8-lane version above re-reads every row 8 times through L1 and only pays off for the 3-wide first layer)
-template <int K, int Q>
-__global__ void __launch_bounds__(GLN_THREADS) gln_node_project2_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
-                                                                         const float *__restrict__ Cq, const float *__restrict__ W, int BN,
-                                                                         int N, float *__restrict__ Q_col, float *__restrict__ Q_row) {
-    constexpr int QP = (Q + 3) / 4 * 4;
-    __shared__ __align__(16) float Ws[2][K * QP];
-    for (int i = threadIdx.x; i < K * QP; i += GLN_THREADS) {
-        const int kk = i / QP, qo = i % QP;
-        Ws[0][i] = qo < Q ? __ldg(&W[(int64_t)K * Q + kk * Q + qo]) : 0.f;
-        Ws[1][i] = qo < Q ? __ldg(&W[2 * (int64_t)K * Q + kk * Q + qo]) : 0.f;
-    }
-    __syncthreads();
-    const int which = threadIdx.x & 1;
-    const float *src = which ? P_row : P_col, *Wsel = Ws[which];
-    float *dst = which ? Q_row : Q_col;
-    for (int64_t node = ((int64_t)blockIdx.x * GLN_THREADS + threadIdx.x) >> 1; node < BN; node += ((int64_t)gridDim.x * GLN_THREADS) >> 1) {
-        float x[K], y[Q];
-        gln_load_row<K>(src + node * K, x);
-        gln_matvec<K, Q>(x, Wsel, y);
-        if (which) {
-            const float *cq = Cq + (node / N) * Q;
-#pragma unroll
-            for (int j = 0; j < Q; ++j) y[j] += __ldg(&cq[j]);
-        }
-        gln_store_row<Q>(dst + node * Q, y);
-    }
-}
-
-template <int K, int Q>
-__global__ void __launch_bounds__(GLN_THREADS) gln_node_grad2_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
-                                                                      const float *__restrict__ Gq, const float *__restrict__ W,
-                                                                      const int32_t *__restrict__ csrT_ptr, int BN, int N, int M,
-                                                                      int add_w1, float *__restrict__ G_col, float *__restrict__ G_row) {
-    constexpr int KP = (K + 3) / 4 * 4;
-    __shared__ __align__(16) float Wt[2][Q * KP];   // transposed: [q][k]
-    for (int i = threadIdx.x; i < Q * KP; i += GLN_THREADS) {
-        const int qo = i / KP, kk = i % KP;
-        Wt[0][i] = kk < K ? __ldg(&W[(int64_t)K * Q + kk * Q + qo]) : 0.f;
-        Wt[1][i] = kk < K ? __ldg(&W[2 * (int64_t)K * Q + kk * Q + qo]) + (add_w1 ? __ldg(&W[kk * Q + qo]) : 0.f) : 0.f;
-    }
-    __syncthreads();
-    const float rm = 1.f / (float)M;
-    const int which = threadIdx.x & 1;
-    const float *src = which ? dQ_row : dQ_col, *Wsel = Wt[which];
-    float *dst = which ? G_row : G_col;
-    for (int64_t node = ((int64_t)blockIdx.x * GLN_THREADS + threadIdx.x) >> 1; node < BN; node += ((int64_t)gridDim.x * GLN_THREADS) >> 1) {
-        float x[Q], y[K];
-        gln_load_row<Q>(src + node * Q, x);
-        gln_matvec<Q, K>(x, Wsel, y);
-        if (which) {
-            const float *gq = Gq + (node / N) * K;
-#pragma unroll
-            for (int j = 0; j < K; ++j) y[j] = fmaf(y[j], rm, __ldg(&gq[j]));
-        } else {
-            const float ri = 1.f / (float)nbpc_max(__ldg(&csrT_ptr[node + 1]) - __ldg(&csrT_ptr[node]), 1);
-#pragma unroll
-            for (int j = 0; j < K; ++j) y[j] = y[j] * ri;
-        }
-        gln_store_row<K>(dst + node * K, y);
     }
 }
 

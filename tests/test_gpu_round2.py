@@ -207,7 +207,7 @@ def test_experiment_net_golden(nb):
                       ("beta", ex.Beta)):
         for i, p in enumerate(mod):
             ref = g[f"f64_g{name}{i}"]
-            np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=2e-3, atol=1e-3 * float(np.abs(ref).max()) + 1e-12,
+            np.testing.assert_allclose(p.grad.cpu().numpy(), ref, rtol=2e-3, atol=1e-3 * float(np.abs(ref).max()) + 1e-7,   # + 1e-7: gradients that are exactly 0 in exact arithmetic (beta under a mean subtraction)
                                        err_msg=f"{name}{i}")
 
 
