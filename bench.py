@@ -491,6 +491,35 @@ def set_model_bench(nb, dev, peak, steps=10):
             "kernels_ms": {n: round(t, 4) for n, t in kern}}
 
 
+def layer15_bench(nb, dev, peak, steps=5):
+    """the 15-weight layer (graph.py:20-229) as a training step - symmetrised adjacency build + 3-layer net
+    [3,32,16,3] forward + loss + backward on 8 x 32^3 particles, k = 14 (csrc/graph15.cu: node-level pooling / projections +
+    one edge kernel per direction)."""
+    syn, graph, nn_ = nb.synthetic, nb.graph, nb.nn
+    ch, b, N, k = [3, 32, 16, 3], 8, 32 ** 3, 14
+    x = torch.from_numpy(syn.make_box("uniform", b, N, 0)).to(dev)
+    tgt = torch.from_numpy(syn.za_features(b, N, 0)[1]).to(dev)
+    rng = np.random.default_rng(3)
+    tp = [(torch.tensor((rng.standard_normal((15, kk, qq)) * np.sqrt(2.0 / (kk + qq))).astype(np.float32), device=dev, requires_grad=True),
+           torch.zeros((2, qq), device=dev, requires_grad=True)) for kk, qq in zip(ch[:-1], ch[1:])]
+    mgr = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=lambda i: tp[i])
+    t_adj = event_ms(lambda: graph.get_symmetrized_adjacency(graph.get_kneighbor_list(x, k)), 3, warm=1)
+    adj = graph.get_symmetrized_adjacency(graph.get_kneighbor_list(x, k))
+    S = int(adj["row"].numel())
+    edges = (x.reshape(b * N, 3)[adj["col"].long()] - x.reshape(b * N, 3)[adj["row"].long()]).contiguous()
+
+    def step():
+        for W, B in tp:
+            W.grad = None
+            B.grad = None
+        loss = nn_.loss_ZA(graph.model_func_15op_shift_inv_za(edges, adj, mgr, (b, N, k)), tgt)
+        loss.backward()
+        return loss
+    ms = event_ms(step, steps, warm=2)
+    return {"channels": ch, "particles": b * N, "edges_symmetrised": S, "adjacency_build_ms": t_adj, "fwd_bwd_ms": ms,
+            "particles_per_s": b * N / (ms * 1e-3), "finite": bool(torch.isfinite(step()))}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -668,6 +697,10 @@ def main():
             extras["set_model"] = set_model_bench(nb, dev, peak)
         except Exception as exc:
             extras["set_model"] = {"error": repr(exc)[:300]}
+        try:
+            extras["layer15"] = layer15_bench(nb, dev, peak)
+        except Exception as exc:
+            extras["layer15"] = {"error": repr(exc)[:300]}
         torch.cuda.empty_cache()
 
         # BASELINE config 5: 128^3-particle multi-redshift rollout INFERENCE, periodic kNN graph rebuilt every step

@@ -193,6 +193,34 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                          int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
                          size_t ws_bytes, void *stream);
 
+/* ---------------------------------------------------------------- 15-weight layer on a symmetrised adjacency
+ * graph.shift_inv_15op_layer (graph.py:20-200).  The reference ships no builder for its `adj` dict; nbpc_sym_adjacency_*
+ * builds the canonical one from a kNN graph: the union A u A^T of every sample, edges sorted row-major, with
+ *   row, col (S): node ids of every edge;  all (S): sample of every edge;  tra (S): position of the transposed edge;
+ *   dia (B*N): position of the self edge of every node;  dal (B*N): sample of every node;  row_ptr (B*N+1): edge range
+ *   of every row.  idx (B,N,M) are the kNN lists (self edge included), csrT_* the in-edge lists of nbpc_adjacency.
+ * nbpc_sym_adjacency_count fills row_ptr (row_ptr[B*N] = S, to be read back); nbpc_sym_adjacency_emit the rest;
+ * status[0] counts rows without a self edge, status[1] edges without a transposed partner (both must be 0).
+ * nbpc_graph15_layer_fwd/bwd: H (S,k) -> H_out (S,q) [+ ReLU]; W (15,k,q), Bias (2,q) as graph.py:135-192; the pooled
+ * node tensors Hr, Hc, Hd (B*N,k) and Ha, Hp (B,k) are saved for backward.  Pooled operands are projected once per node
+ * and gathered by ONE edge kernel per direction; all reductions have a fixed order. */
+size_t nbpc_sym_adjacency_workspace_bytes(int B, int N);
+int nbpc_sym_adjacency_count(const int32_t *idx, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M,
+                             int32_t *row_ptr, void *workspace, size_t ws_bytes, void *stream);
+int nbpc_sym_adjacency_emit(const int32_t *idx, const int32_t *csrT_ptr, const int32_t *csrT_edge, const int32_t *row_ptr,
+                            int B, int N, int M, int64_t S, int32_t *row, int32_t *col, int32_t *all, int32_t *tra,
+                            int32_t *dia, int32_t *dal, int32_t *status, void *stream);
+size_t nbpc_graph15_workspace_bytes(int B, int N, int64_t S, int k, int q);
+int nbpc_graph15_layer_fwd(const float *H, const int32_t *row, const int32_t *col, const int32_t *tra, const int32_t *dia,
+                           const int32_t *row_ptr, int B, int N, int64_t S, int k, int q, const float *W, const float *Bias,
+                           int relu, float *H_out, float *Hr, float *Hc, float *Hd, float *Ha, float *Hp, void *workspace,
+                           size_t ws_bytes, void *stream);
+int nbpc_graph15_layer_bwd(const float *dOut, const float *H, const float *H_out, const int32_t *row, const int32_t *col,
+                           const int32_t *tra, const int32_t *dia, const int32_t *row_ptr, int B, int N, int64_t S, int k,
+                           int q, const float *W, const float *Hr, const float *Hc, const float *Hd, const float *Ha,
+                           const float *Hp, int relu, float *dH, float *dW, float *dB, void *workspace, size_t ws_bytes,
+                           void *stream);
+
 /* ---------------------------------------------------------------- set layer
  * nn.set_layer (nn.py:10-28): out = (H - mean_N H) W + B on (B,N,k) -> (B,N,q); relu optional
  * (nn.py:59, 65-66).  mu (B,k) is saved for backward.

@@ -50,6 +50,13 @@ SIGNATURES = {
     "nbpc_graph_layer_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "nbpc_graph_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i,
                                   _p, _p, _p, _p, _sz, _p]),
+    "nbpc_sym_adjacency_workspace_bytes": (_sz, [_i, _i]),
+    "nbpc_sym_adjacency_count": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),
+    "nbpc_sym_adjacency_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "nbpc_graph15_workspace_bytes": (_sz, [_i, _i, _i64, _i, _i]),
+    "nbpc_graph15_layer_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_graph15_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p,
+                                    _p, _sz, _p]),
     "nbpc_set_layer_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "nbpc_set_layer_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
     "nbpc_set_layer_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),

@@ -1,0 +1,479 @@
+// graph15.cu - the 15-weight shift-invariant layer (/root/reference/graph.py:20-200, the permutation-equivariant basis
+// of https://openreview.net/pdf?id=Syx72jC9tm) on a SYMMETRISED adjacency, fused like the 4-weight layer: pooled operands are
+// projected once per NODE, the edge level is one kernel per direction.
+//
+// Canonical adjacency (what nbpc_sym_adjacency_* builds; the reference ships no builder): the union A u A^T of every sample's
+// kNN graph, edges sorted row-major (row, col), self edge in every row.  Then
+//   * row i owns the contiguous edge range [row_ptr[i], row_ptr[i+1]),
+//   * the in-edges of node j are tra[row_ptr[j] .. row_ptr[j+1]) - already in ascending edge order -, so the reference's
+//     pool over adj["col"] needs no second CSR, and in-degree == out-degree,
+//   * adj["all"] = row / N, adj["dal"] = node / N (samples are contiguous).
+//
+// Forward (same sums as graph.py:144-199, associated at node level; Hr / Hc follow the reference's naming: Hr pools over
+// adj["col"], Hc over adj["row"]):
+//   Hc[i] = mean_{e in row i} H[e]     Hr[i] = mean_{e in row i} H[tra[e]]     Hd[i] = H[dia[i]]
+//   Ha[s] = mean_{e in s} H[e]         Hp[s] = mean_{i in s} Hd[i]
+//   Ta[s] = Ha W9 + Hp W11 + B[1]      Tda[s] = Ha W10 + Hp W12 + B[0]
+//   Tc[i] = Hr W3 + Hc W7 + Hd W13     Tr[i] = Hr W4 + Hc W6 + Hd W14 + Ta[s]     Td[i] = Hd W2 + Hr W5 + Hc W8 + Tda[s]
+//   out[e] = act( H[e] W0 + H[tra[e]] W1 + Tc[col[e]] + Tr[row[e]] + [e == dia[row[e]]] Td[row[e]] )
+// Backward mirrors it; every reduction runs in a fixed order (no float atomics): results are bit-reproducible.
+#include "nbpc_common.cuh"
+#include "reduce.cuh"
+#include "scan.cuh"
+
+#define G15_THREADS 256
+
+// ------------------------------------------------------------------ symmetrised adjacency builder
+// merge of row i's out-neighbours (sorted copy of its kNN list) and in-neighbours (rows of its in-edges, ascending):
+// calls emit(c) for every distinct neighbour in ascending order; returns the count
+template <class F>
+__device__ __forceinline__ int g15_merge_row(const int32_t *__restrict__ idx_row, int M, const int32_t *__restrict__ csrT_edge, int tb,
+                                             int te, int node_local, int sample_base, F emit) {
+    // the kNN list in ascending order (get_kneighbor_list delivers it sorted; distance-ordered lists are sorted here)
+    int32_t out[NBPC_KNN_MAX_K];
+    for (int m = 0; m < M; ++m) {
+        const int32_t v = idx_row[m];
+        int j = m - 1;
+        while (j >= 0 && out[j] > v) {
+            out[j + 1] = out[j];
+            --j;
+        }
+        out[j + 1] = v;
+    }
+    (void)node_local;
+    int a = 0, b = tb, n = 0, last = -1;
+    while (a < M || b < te) {
+        const int va = a < M ? out[a] : 0x7FFFFFFF;
+        const int vb = b < te ? csrT_edge[b] / M - sample_base : 0x7FFFFFFF;   // local row id of the in-edge
+        const int v = va < vb ? va : vb;
+        if (va <= vb) ++a;
+        if (vb <= va) ++b;
+        if (v != last) {
+            emit(n, v);
+            ++n;
+            last = v;
+        }
+    }
+    return n;
+}
+
+__global__ void g15_adj_count_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ csrT_ptr,
+                                     const int32_t *__restrict__ csrT_edge, int BN, int N, int M, int32_t *__restrict__ deg) {
+    int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node > BN) return;
+    if (node == BN) { deg[BN] = 0; return; }
+    const int s = node / N;
+    deg[node] = g15_merge_row(idx + (int64_t)node * M, M, csrT_edge, csrT_ptr[node], csrT_ptr[node + 1], node - s * N, s * N,
+                              [](int, int) {});
+}
+
+__global__ void g15_adj_emit_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ csrT_ptr,
+                                    const int32_t *__restrict__ csrT_edge, const int32_t *__restrict__ row_ptr, int BN, int N, int M,
+                                    int32_t *__restrict__ row, int32_t *__restrict__ col, int32_t *__restrict__ all,
+                                    int32_t *__restrict__ dal) {
+    int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= BN) return;
+    const int s = node / N, base = row_ptr[node];
+    dal[node] = s;
+    g15_merge_row(idx + (int64_t)node * M, M, csrT_edge, csrT_ptr[node], csrT_ptr[node + 1], node - s * N, s * N, [&](int n, int v) {
+        row[base + n] = node;
+        col[base + n] = s * N + v;
+        all[base + n] = s;
+    });
+}
+
+// position of value v in the sorted range col[b, e), or -1
+__device__ __forceinline__ int g15_find(const int32_t *__restrict__ col, int b, int e, int v) {
+    int lo = b, hi = e - 1;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1, c = col[mid];
+        if (c == v) return mid;
+        if (c < v) lo = mid + 1; else hi = mid - 1;
+    }
+    return -1;
+}
+
+__global__ void g15_adj_tra_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, const int32_t *__restrict__ row_ptr,
+                                   int64_t S, int BN, int32_t *__restrict__ tra, int32_t *__restrict__ dia, int32_t *__restrict__ status) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < S) {
+        const int i = row[e], c = col[e];
+        const int p = g15_find(col, row_ptr[c], row_ptr[c + 1], i);   // the transposed edge (c, i)
+        if (p < 0) atomicAdd(&status[1], 1);
+        tra[e] = p < 0 ? (int32_t)e : p;
+    }
+    if (e < BN) {
+        const int node = (int)e;
+        const int p = g15_find(col, row_ptr[node], row_ptr[node + 1], node);
+        if (p < 0) atomicAdd(&status[0], 1);                          // a row without its self edge
+        dia[node] = p < 0 ? row_ptr[node] : p;
+    }
+}
+
+// ------------------------------------------------------------------ node-level pooling (forward: means; backward: sums)
+// thread per (node, channel): Xc = pool over the node's row, Xr = pool over tra[row] (= the node's in-edges), Xd = X[dia]
+__global__ void g15_pool_kernel(const float *__restrict__ X, int C, const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ tra,
+                                const int32_t *__restrict__ dia, int BN, int mean, float *__restrict__ Xc, float *__restrict__ Xr,
+                                float *__restrict__ Xd) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * C) return;
+    const int node = (int)(t / C), ch = (int)(t % C);
+    const int b = row_ptr[node], e = row_ptr[node + 1];
+    float sc = 0.f, sr = 0.f;
+    for (int p = b; p < e; ++p) {
+        sc += X[(int64_t)p * C + ch];
+        sr += X[(int64_t)tra[p] * C + ch];
+    }
+    const float d = mean ? (float)nbpc_max(e - b, 1) : 1.f;
+    Xc[t] = sc / d;
+    Xr[t] = sr / d;
+    Xd[t] = X[(int64_t)dia[node] * C + ch];
+}
+
+// per-sample reductions over the nodes (grid = B, fixed tree): out1[s] = sum_i w_i X1[i] * scale1, out2[s] = sum_i X2[i] * scale2
+// with w_i = deg_i if by_degree (sum over edges = sum over nodes of degree x row mean), else 1
+__global__ void __launch_bounds__(G15_THREADS) g15_sample_sum_kernel(const float *__restrict__ X1, const float *__restrict__ X2, int C, int N,
+                                                                     const int32_t *__restrict__ row_ptr, int by_degree, int mean,
+                                                                     float *__restrict__ out1, float *__restrict__ out2) {
+    const int s = blockIdx.x;
+    const int64_t n0 = (int64_t)s * N;
+    const float S_s = (float)(row_ptr[n0 + N] - row_ptr[n0]);
+#ifdef NBPC_HOST_EMU
+    // host emulation (test infrastructure): the launch loops over the threads sequentially, thread 0 does the sample
+    if (threadIdx.x != 0) return;
+    for (int ch = 0; ch < C; ++ch) {
+        float part1[G15_THREADS], part2[G15_THREADS];
+        for (int t = 0; t < G15_THREADS; ++t) {
+            float a1 = 0.f, a2 = 0.f;
+            for (int i = t; i < N; i += G15_THREADS) {
+                const float w = by_degree ? (float)(row_ptr[n0 + i + 1] - row_ptr[n0 + i]) : 1.f;
+                a1 += w * X1[(n0 + i) * C + ch];
+                a2 += X2[(n0 + i) * C + ch];
+            }
+            part1[t] = a1; part2[t] = a2;
+        }
+        for (int st = G15_THREADS / 2; st >= 1; st >>= 1)
+            for (int t = 0; t < st; ++t) { part1[t] += part1[t + st]; part2[t] += part2[t + st]; }
+        out1[s * C + ch] = mean ? part1[0] / S_s : part1[0];
+        out2[s * C + ch] = mean ? part2[0] / (float)N : part2[0];
+    }
+#else
+    __shared__ float r1[G15_THREADS], r2[G15_THREADS];
+    for (int ch = 0; ch < C; ++ch) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = threadIdx.x; i < N; i += G15_THREADS) {
+            const float w = by_degree ? (float)(row_ptr[n0 + i + 1] - row_ptr[n0 + i]) : 1.f;
+            a1 += w * X1[(n0 + i) * C + ch];
+            a2 += X2[(n0 + i) * C + ch];
+        }
+        r1[threadIdx.x] = a1;
+        r2[threadIdx.x] = a2;
+        __syncthreads();
+        for (int st = G15_THREADS / 2; st >= 1; st >>= 1) {
+            if ((int)threadIdx.x < st) { r1[threadIdx.x] += r1[threadIdx.x + st]; r2[threadIdx.x] += r2[threadIdx.x + st]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            out1[s * C + ch] = mean ? r1[0] / S_s : r1[0];
+            out2[s * C + ch] = mean ? r2[0] / (float)N : r2[0];
+        }
+        __syncthreads();
+    }
+#endif
+}
+
+// per-sample constants: Ta[s] = Ha W9 + Hp W11 + B[1], Tda[s] = Ha W10 + Hp W12 + B[0]
+__global__ void g15_sample_project_kernel(const float *__restrict__ Ha, const float *__restrict__ Hp, const float *__restrict__ W,
+                                          const float *__restrict__ Bias, int B, int k, int q, float *__restrict__ Ta, float *__restrict__ Tda) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * q) return;
+    const int s = t / q, qo = t % q;
+    const int64_t kq = (int64_t)k * q;
+    float a = 0.f, d = 0.f;
+    for (int kk = 0; kk < k; ++kk) {
+        const float ha = Ha[s * k + kk], hp = Hp[s * k + kk];
+        a += ha * W[9 * kq + kk * q + qo] + hp * W[11 * kq + kk * q + qo];
+        d += ha * W[10 * kq + kk * q + qo] + hp * W[12 * kq + kk * q + qo];
+    }
+    Ta[t] = a + Bias[q + qo];
+    Tda[t] = d + Bias[qo];
+}
+
+// thread per (node, output channel): the nine node-level projections
+__global__ void g15_node_project_kernel(const float *__restrict__ Hr, const float *__restrict__ Hc, const float *__restrict__ Hd,
+                                        const float *__restrict__ Ta, const float *__restrict__ Tda, const float *__restrict__ W, int BN, int N,
+                                        int k, int q, float *__restrict__ Tc, float *__restrict__ Tr, float *__restrict__ Td) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * q) return;
+    const int node = (int)(t / q), qo = (int)(t % q), s = node / N;
+    const int64_t kq = (int64_t)k * q;
+    const float *w = W + qo;
+    float tc = 0.f, tr = 0.f, td = 0.f;
+    for (int kk = 0; kk < k; ++kk) {
+        const float hr = Hr[(int64_t)node * k + kk], hc = Hc[(int64_t)node * k + kk], hd = Hd[(int64_t)node * k + kk];
+        const int64_t o = (int64_t)kk * q;
+        tc += hr * __ldg(&w[3 * kq + o]) + hc * __ldg(&w[7 * kq + o]) + hd * __ldg(&w[13 * kq + o]);
+        tr += hr * __ldg(&w[4 * kq + o]) + hc * __ldg(&w[6 * kq + o]) + hd * __ldg(&w[14 * kq + o]);
+        td += hd * __ldg(&w[2 * kq + o]) + hr * __ldg(&w[5 * kq + o]) + hc * __ldg(&w[8 * kq + o]);
+    }
+    Tc[t] = tc;
+    Tr[t] = tr + Ta[s * q + qo];
+    Td[t] = td + Tda[s * q + qo];
+}
+
+// ------------------------------------------------------------------ edge level, forward: thread per (edge, output channel)
+__global__ void g15_edge_fwd_kernel(const float *__restrict__ H, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                    const int32_t *__restrict__ tra, const int32_t *__restrict__ dia, const float *__restrict__ W,
+                                    const float *__restrict__ Tc, const float *__restrict__ Tr, const float *__restrict__ Td, int64_t S, int k,
+                                    int q, int relu, float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * q) return;
+    const int64_t e = t / q;
+    const int qo = (int)(t % q);
+    const int i = row[e], j = col[e];
+    const float *h = H + e * k, *ht = H + (int64_t)tra[e] * k, *w0 = W + qo, *w1 = W + (int64_t)k * q + qo;
+    float z = 0.f;
+    for (int kk = 0; kk < k; ++kk) z += h[kk] * __ldg(&w0[(int64_t)kk * q]) + ht[kk] * __ldg(&w1[(int64_t)kk * q]);
+    z += Tc[(int64_t)j * q + qo] + Tr[(int64_t)i * q + qo];
+    if (dia[i] == e) z += Td[(int64_t)i * q + qo];
+    out[t] = (relu && z < 0.f) ? 0.f : z;
+}
+
+// dZ = dOut * [out > 0]
+__global__ void g15_mask_kernel(const float *__restrict__ g, const float *__restrict__ out, int64_t n, float *__restrict__ dz) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dz[t] = out[t] > 0.f ? g[t] : 0.f;
+}
+
+// ------------------------------------------------------------------ backward, per-sample: Ga[s] = (dTa W9^T + dTda W10^T) / S_s,
+// Gp[s] = (dTa W11^T + dTda W12^T) / N
+__global__ void g15_sample_grad_kernel(const float *__restrict__ dTa, const float *__restrict__ dTda, const float *__restrict__ W,
+                                       const int32_t *__restrict__ row_ptr, int B, int N, int k, int q, float *__restrict__ Ga,
+                                       float *__restrict__ Gp) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * k) return;
+    const int s = t / k, kk = t % k;
+    const int64_t kq = (int64_t)k * q;
+    float a = 0.f, p = 0.f;
+    for (int qo = 0; qo < q; ++qo) {
+        const float da = dTa[s * q + qo], dd = dTda[s * q + qo];
+        a += da * W[9 * kq + kk * q + qo] + dd * W[10 * kq + kk * q + qo];
+        p += da * W[11 * kq + kk * q + qo] + dd * W[12 * kq + kk * q + qo];
+    }
+    const float S_s = (float)(row_ptr[(int64_t)(s + 1) * N] - row_ptr[(int64_t)s * N]);
+    Ga[t] = a / S_s;
+    Gp[t] = p / (float)N;
+}
+
+// thread per (node, input channel): Gr' = (dTc W3^T + dTr W4^T + dTd W5^T) / deg, Gc' = (dTc W7^T + dTr W6^T + dTd W8^T) / deg,
+// Gd = dTc W13^T + dTr W14^T + dTd W2^T + Gp[s]
+__global__ void g15_node_grad_kernel(const float *__restrict__ dTc, const float *__restrict__ dTr, const float *__restrict__ dTd,
+                                     const float *__restrict__ Gp, const float *__restrict__ W, const int32_t *__restrict__ row_ptr, int BN,
+                                     int N, int k, int q, float *__restrict__ Gr, float *__restrict__ Gc, float *__restrict__ Gd) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BN * k) return;
+    const int node = (int)(t / k), kk = (int)(t % k), s = node / N;
+    const int64_t kq = (int64_t)k * q;
+    const float *w = W + (int64_t)kk * q;
+    float gr = 0.f, gc = 0.f, gd = 0.f;
+    for (int qo = 0; qo < q; ++qo) {
+        const float c = dTc[(int64_t)node * q + qo], r = dTr[(int64_t)node * q + qo], d = dTd[(int64_t)node * q + qo];
+        gr += c * __ldg(&w[3 * kq + qo]) + r * __ldg(&w[4 * kq + qo]) + d * __ldg(&w[5 * kq + qo]);
+        gc += c * __ldg(&w[7 * kq + qo]) + r * __ldg(&w[6 * kq + qo]) + d * __ldg(&w[8 * kq + qo]);
+        gd += c * __ldg(&w[13 * kq + qo]) + r * __ldg(&w[14 * kq + qo]) + d * __ldg(&w[2 * kq + qo]);
+    }
+    const float deg = (float)nbpc_max(row_ptr[node + 1] - row_ptr[node], 1);
+    Gr[t] = gr / deg;
+    Gc[t] = gc / deg;
+    Gd[t] = gd + Gp[s * k + kk];
+}
+
+// edge level, backward: thread per (edge, input channel)
+//   dH[e] = dZ[e] W0^T + dZ[tra[e]] W1^T + Gc'[row[e]] + Gr'[col[e]] + Ga[sample] + [e == dia[row[e]]] Gd[row[e]]
+__global__ void g15_edge_bwd_kernel(const float *__restrict__ dZ, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
+                                    const int32_t *__restrict__ tra, const int32_t *__restrict__ dia, const float *__restrict__ W,
+                                    const float *__restrict__ Gr, const float *__restrict__ Gc, const float *__restrict__ Gd,
+                                    const float *__restrict__ Ga, int64_t S, int N, int k, int q, float *__restrict__ dH) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * k) return;
+    const int64_t e = t / k;
+    const int kk = (int)(t % k);
+    const int i = row[e], j = col[e];
+    const float *z = dZ + e * q, *zt = dZ + (int64_t)tra[e] * q, *w0 = W + (int64_t)kk * q, *w1 = W + (int64_t)k * q + (int64_t)kk * q;
+    float a = 0.f;
+    for (int qo = 0; qo < q; ++qo) a += z[qo] * __ldg(&w0[qo]) + zt[qo] * __ldg(&w1[qo]);
+    a += Gc[(int64_t)i * k + kk] + Gr[(int64_t)j * k + kk] + Ga[(i / N) * k + kk];
+    if (dia[i] == e) a += Gd[(int64_t)i * k + kk];
+    dH[t] = a;
+}
+
+// dB[0] = sum_s dTda[s], dB[1] = sum_s dTa[s]
+__global__ void g15_bias_grad_kernel(const float *__restrict__ dTa, const float *__restrict__ dTda, int B, int q, float *__restrict__ dB) {
+    int qo = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qo >= q) return;
+    float a = 0.f, d = 0.f;
+    for (int s = 0; s < B; ++s) { a += dTa[s * q + qo]; d += dTda[s * q + qo]; }
+    dB[qo] = d;
+    dB[q + qo] = a;
+}
+
+// row accessor gathered through an index list: X[idx[r]]
+struct G15Gather {
+    const float *p;
+    const int32_t *idx;
+    int ld;
+    __device__ __forceinline__ float at(int64_t r, int ch) const { return p[(int64_t)idx[r] * ld + ch]; }
+};
+
+// ------------------------------------------------------------------ workspace
+struct G15Workspace {
+    float *Ta, *Tda;              // (B, q)
+    float *Tc, *Tr, *Td;          // (BN, q): forward projections; backward: dTc, dTr, dTd
+    float *Gr, *Gc, *Gd;          // (BN, k)
+    float *dTa, *dTda;            // (B, q)
+    float *Ga, *Gp;               // (B, k)
+    float *dZ;                    // (S, q) masked gradient
+    float *xty_partial;
+    size_t bytes;
+};
+static G15Workspace g15_carve(void *ws, size_t ws_bytes, int B, int N, int64_t S, int k, int q) {
+    NbpcArena a(ws, ws_bytes);
+    G15Workspace w;
+    const size_t BN = (size_t)B * N;
+    w.Ta = a.take<float>((size_t)B * q); w.Tda = a.take<float>((size_t)B * q);
+    w.Tc = a.take<float>(BN * q); w.Tr = a.take<float>(BN * q); w.Td = a.take<float>(BN * q);
+    w.Gr = a.take<float>(BN * k); w.Gc = a.take<float>(BN * k); w.Gd = a.take<float>(BN * k);
+    w.dTa = a.take<float>((size_t)B * q); w.dTda = a.take<float>((size_t)B * q);
+    w.Ga = a.take<float>((size_t)B * k); w.Gp = a.take<float>((size_t)B * k);
+    w.dZ = a.take<float>((size_t)S * q);
+    int rpc, nc;
+    xty_plan(S, k, q, &rpc, &nc);
+    w.xty_partial = a.take<float>((size_t)nc * k * q);
+    w.bytes = a.off;
+    return w;
+}
+
+extern "C" {
+
+size_t nbpc_sym_adjacency_workspace_bytes(int B, int N) {
+    if (B < 1 || N < 1) return 0;
+    return nbpc_align_up(sizeof(int32_t) * nbpc_scan_partials_count((int64_t)B * N + 1));
+}
+
+int nbpc_sym_adjacency_count(const int32_t *idx, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M,
+                             int32_t *row_ptr, void *workspace, size_t ws_bytes, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(idx && csrT_ptr && csrT_edge && row_ptr && workspace, "null pointer");
+    NBPC_ARG(B >= 1 && N >= 1 && M >= 1 && M <= NBPC_KNN_MAX_K, "bad sizes");
+    if (ws_bytes < nbpc_sym_adjacency_workspace_bytes(B, N)) {
+        nbpc_set_error("nbpc_sym_adjacency_count: workspace too small");
+        return NBPC_EWORKSPACE;
+    }
+    const int BN = B * N;
+    NBPC_LAUNCH(g15_adj_count_kernel, nbpc_cdiv((int64_t)BN + 1, 128), 128, 0, stream, idx, csrT_ptr, csrT_edge, BN, N, M, row_ptr);
+    NBPC_TRY(nbpc_exclusive_scan_i32(row_ptr, (int64_t)BN + 1, (int32_t *)workspace, stream));
+    return nbpc_check_launch("nbpc_sym_adjacency_count");
+}
+
+int nbpc_sym_adjacency_emit(const int32_t *idx, const int32_t *csrT_ptr, const int32_t *csrT_edge, const int32_t *row_ptr, int B, int N,
+                            int M, int64_t S, int32_t *row, int32_t *col, int32_t *all, int32_t *tra, int32_t *dia, int32_t *dal,
+                            int32_t *status, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(idx && csrT_ptr && csrT_edge && row_ptr && row && col && all && tra && dia && dal && status, "null pointer");
+    NBPC_ARG(B >= 1 && N >= 1 && M >= 1 && M <= NBPC_KNN_MAX_K && S >= 1, "bad sizes");
+    const int BN = B * N;
+    if (nbpc_memset_async(status, 0, sizeof(int32_t) * 2, stream)) {
+        nbpc_set_error("nbpc_sym_adjacency_emit: memset failed");
+        return NBPC_ELAUNCH;
+    }
+    NBPC_LAUNCH(g15_adj_emit_kernel, nbpc_cdiv(BN, 128), 128, 0, stream, idx, csrT_ptr, csrT_edge, row_ptr, BN, N, M, row, col, all, dal);
+    NBPC_LAUNCH(g15_adj_tra_kernel, nbpc_cdiv(nbpc_max(S, (int64_t)BN), 256), 256, 0, stream, row, col, row_ptr, S, BN, tra, dia, status);
+    return nbpc_check_launch("nbpc_sym_adjacency_emit");
+}
+
+size_t nbpc_graph15_workspace_bytes(int B, int N, int64_t S, int k, int q) {
+    if (B < 1 || N < 1 || S < 1 || k < 1 || q < 1) return 0;
+    return g15_carve(nullptr, 0, B, N, S, k, q).bytes;
+}
+
+int nbpc_graph15_layer_fwd(const float *H, const int32_t *row, const int32_t *col, const int32_t *tra, const int32_t *dia,
+                           const int32_t *row_ptr, int B, int N, int64_t S, int k, int q, const float *W, const float *Bias, int relu,
+                           float *H_out, float *Hr, float *Hc, float *Hd, float *Ha, float *Hp, void *workspace, size_t ws_bytes,
+                           void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(H && row && col && tra && dia && row_ptr && W && Bias && H_out && Hr && Hc && Hd && Ha && Hp && workspace, "null pointer");
+    NBPC_ARG(B >= 1 && N >= 1 && S >= 1 && k >= 1 && q >= 1 && S < ((int64_t)1 << 31), "bad sizes");
+    G15Workspace w = g15_carve(workspace, ws_bytes, B, N, S, k, q);
+    if (w.bytes > ws_bytes) {
+        nbpc_set_error("nbpc_graph15_layer_fwd: workspace too small");
+        return NBPC_EWORKSPACE;
+    }
+    const int BN = B * N, T = G15_THREADS;
+    NBPC_LAUNCH(g15_pool_kernel, nbpc_cdiv((int64_t)BN * k, T), T, 0, stream, H, k, row_ptr, tra, dia, BN, 1, Hc, Hr, Hd);
+    NBPC_LAUNCH(g15_sample_sum_kernel, B, T, 0, stream, Hc, Hd, k, N, row_ptr, 1, 1, Ha, Hp);
+    NBPC_LAUNCH(g15_sample_project_kernel, nbpc_cdiv(B * q, 128), 128, 0, stream, Ha, Hp, W, Bias, B, k, q, w.Ta, w.Tda);
+    NBPC_LAUNCH(g15_node_project_kernel, nbpc_cdiv((int64_t)BN * q, T), T, 0, stream, Hr, Hc, Hd, w.Ta, w.Tda, W, BN, N, k, q, w.Tc, w.Tr,
+                w.Td);
+    NBPC_LAUNCH(g15_edge_fwd_kernel, nbpc_cdiv(S * q, T), T, 0, stream, H, row, col, tra, dia, W, w.Tc, w.Tr, w.Td, S, k, q, relu, H_out);
+    return nbpc_check_launch("nbpc_graph15_layer_fwd");
+}
+
+int nbpc_graph15_layer_bwd(const float *dOut, const float *H, const float *H_out, const int32_t *row, const int32_t *col,
+                           const int32_t *tra, const int32_t *dia, const int32_t *row_ptr, int B, int N, int64_t S, int k, int q,
+                           const float *W, const float *Hr, const float *Hc, const float *Hd, const float *Ha, const float *Hp, int relu,
+                           float *dH, float *dW, float *dB, void *workspace, size_t ws_bytes, void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(dOut && H && row && col && tra && dia && row_ptr && W && Hr && Hc && Hd && Ha && Hp && dW && dB && workspace, "null pointer");
+    NBPC_ARG(!relu || H_out, "H_out is required when relu is set");
+    NBPC_ARG(B >= 1 && N >= 1 && S >= 1 && k >= 1 && q >= 1 && S < ((int64_t)1 << 31), "bad sizes");
+    G15Workspace w = g15_carve(workspace, ws_bytes, B, N, S, k, q);
+    if (w.bytes > ws_bytes) {
+        nbpc_set_error("nbpc_graph15_layer_bwd: workspace too small");
+        return NBPC_EWORKSPACE;
+    }
+    const int BN = B * N, T = G15_THREADS;
+    const int64_t kq = (int64_t)k * q;
+    const float *dZ = dOut;
+    if (relu) {
+        NBPC_LAUNCH(g15_mask_kernel, nbpc_cdiv(S * q, T), T, 0, stream, dOut, H_out, S * q, w.dZ);
+        dZ = w.dZ;
+    }
+    // node level: dTr = row sums, dTc = in-edge sums, dTd = the diagonal entry; per-sample sums dTa, dTda
+    float *dTc = w.Tc, *dTr = w.Tr, *dTd = w.Td;
+    NBPC_LAUNCH(g15_pool_kernel, nbpc_cdiv((int64_t)BN * q, T), T, 0, stream, dZ, q, row_ptr, tra, dia, BN, 0, dTr, dTc, dTd);
+    NBPC_LAUNCH(g15_sample_sum_kernel, B, T, 0, stream, dTr, dTd, q, N, row_ptr, 0, 0, w.dTa, w.dTda);
+    NBPC_LAUNCH(g15_bias_grad_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.dTa, w.dTda, B, q, dB);
+    // weight gradients: fixed-order X^T Y reductions
+    GlPlain x, y;
+    x.ld = k; y.ld = q;
+    y.p = dZ;
+    x.p = H;
+    xty("g15_xty_dW0", x, y, S, k, q, w.xty_partial, dW, stream);
+    G15Gather xg;
+    xg.p = H; xg.idx = tra; xg.ld = k;
+    xty("g15_xty_dW1", xg, y, S, k, q, w.xty_partial, dW + kq, stream);
+    struct { int wi; const float *X; const float *Y; } node_terms[9] = {
+        {3, Hr, dTc}, {7, Hc, dTc}, {13, Hd, dTc}, {4, Hr, dTr}, {6, Hc, dTr}, {14, Hd, dTr}, {2, Hd, dTd}, {5, Hr, dTd}, {8, Hc, dTd}};
+    for (int i = 0; i < 9; ++i) {
+        x.p = node_terms[i].X; y.p = node_terms[i].Y;
+        xty("g15_xty_node", x, y, (int64_t)BN, k, q, w.xty_partial, dW + node_terms[i].wi * kq, stream);
+    }
+    struct { int wi; const float *X; const float *Y; } sample_terms[4] = {{9, Ha, w.dTa}, {10, Ha, w.dTda}, {11, Hp, w.dTa}, {12, Hp, w.dTda}};
+    for (int i = 0; i < 4; ++i) {
+        x.p = sample_terms[i].X; y.p = sample_terms[i].Y;
+        xty("g15_xty_sample", x, y, (int64_t)B, k, q, w.xty_partial, dW + sample_terms[i].wi * kq, stream);
+    }
+    if (dH) {
+        NBPC_LAUNCH(g15_sample_grad_kernel, nbpc_cdiv(B * k, 128), 128, 0, stream, w.dTa, w.dTda, W, row_ptr, B, N, k, q, w.Ga, w.Gp);
+        NBPC_LAUNCH(g15_node_grad_kernel, nbpc_cdiv((int64_t)BN * k, T), T, 0, stream, dTc, dTr, dTd, w.Gp, W, row_ptr, BN, N, k, q, w.Gr, w.Gc,
+                    w.Gd);
+        NBPC_LAUNCH(g15_edge_bwd_kernel, nbpc_cdiv(S * k, T), T, 0, stream, dZ, row, col, tra, dia, W, w.Gr, w.Gc, w.Gd, w.Ga, S, N, k, q, dH);
+    }
+    return nbpc_check_launch("nbpc_graph15_layer_bwd");
+}
+
+}  // extern "C"

@@ -405,6 +405,7 @@ class SymAdjacency(dict):
         super().__init__(fields)
         self.b, self.N = b, N
         self._csr = {}
+        self.row_ptr = None     # set by get_symmetrized_adjacency: row-major sorted, symmetric, self edges present
 
     def csr(self, name, num_segs):
         key = (name, num_segs)
@@ -420,25 +421,19 @@ def get_symmetrized_adjacency(A):
       row, col : node ids of every edge (shifted by i*N across the batch),  all : sample id of every edge,
       tra      : position of the transposed edge (col, row),                dia : position of the self edge of every node,
       dal      : sample id of every node.
-    The kNN lists must include the self edge (include_self=True).  Index bookkeeping uses torch's device sort/unique
-    (library calls: this is graph preprocessing, not the layer arithmetic)."""
+    The kNN lists must include the self edge (include_self=True).  Built by libnbpc kernels (csrc/graph15.cu): per node, a
+    merge of its sorted out-neighbours with the rows of its in-edges (count -> scan -> emit), then a binary search per
+    edge for the transposed position."""
     idx = _as_batch(A)
     b, N, M = idx.shape
-    BN = b * N
-    dev = idx.device
-    off = (torch.arange(b, device=dev, dtype=torch.int64) * N).view(b, 1, 1)
-    cols = (idx.to(torch.int64) + off).reshape(-1)
-    rows = torch.arange(BN, device=dev, dtype=torch.int64).repeat_interleave(M)
-    keys = torch.unique(torch.cat([rows * BN + cols, cols * BN + rows]))          # sorted: row-major edge order
-    row, col = keys // BN, keys % BN
-    tra = torch.searchsorted(keys, col * BN + row)
-    nodes = torch.arange(BN, device=dev, dtype=torch.int64)
-    dia = torch.searchsorted(keys, nodes * BN + nodes)
-    if not bool((keys[dia.clamp(max=keys.numel() - 1)] == nodes * BN + nodes).all()):
+    _, _, ptr, edge, _ = ops.adjacency(idx)
+    fields, status = ops.sym_adjacency(idx, ptr, edge)
+    no_self, no_partner = status.tolist()
+    if no_self or no_partner:
         raise ValueError("get_symmetrized_adjacency: every node needs its self edge (build the kNN graph with include_self=True)")
-    i32 = lambda t: t.to(torch.int32).contiguous()
-    return SymAdjacency({"row": i32(row), "col": i32(col), "all": i32(row // N), "tra": i32(tra), "dia": i32(dia),
-                         "dal": i32(nodes // N)}, b, N)
+    adj = SymAdjacency({k: v for k, v in fields.items() if k != "row_ptr"}, b, N)
+    adj.row_ptr = fields["row_ptr"]         # canonical layout: enables the fused layer kernels
+    return adj
 
 
 def _as_sym(adj, b, N):
@@ -447,7 +442,7 @@ def _as_sym(adj, b, N):
     return SymAdjacency({k: _to_cuda(v, torch.int32).contiguous().reshape(-1) for k, v in adj.items()}, b, N)
 
 
-def shift_inv_15op_layer(H_in, adj, bN, layer_vars, is_last=False):
+def shift_inv_15op_layer(H_in, adj, bN, layer_vars, is_last=False, _relu=False):
     """graph.py:20-200: the 15-weight permutation-equivariant basis on a symmetrised adjacency.  W (15, k, q), B (2, q);
     H_in (S, k) -> (S, q), or (b, N, q) if is_last (pooled over adj["row"]).
     Same sums as the reference, associated at node level: every pooled operand is projected once per NODE and then
@@ -464,6 +459,18 @@ def shift_inv_15op_layer(H_in, adj, bN, layer_vars, is_last=False):
     H = _to_cuda(H_in, torch.float32)
     adj = _as_sym(adj, b, N)
     S = H.shape[0]
+    if adj.row_ptr is not None and (adj.b, adj.N) == (b, N):
+        # canonical adjacency (get_symmetrized_adjacency): fused node-level + edge-level kernels
+        out = ops.Graph15Layer.apply(H, W, B, adj["row"], adj["col"], adj["tra"], adj["dia"], adj.row_ptr, b, N, bool(_relu))
+        if is_last:
+            key = ("_rows", BN)
+            if key not in adj._csr:
+                adj._csr[key] = (adj.row_ptr, torch.arange(S, dtype=torch.int32, device=H.device))
+            ptr, mem = adj._csr[key]
+            return ops.SegmentPool.apply(out, adj["row"], ptr, mem, False).reshape(b, N, -1)
+        return out
+    if _relu:
+        raise ValueError("the fused ReLU needs the canonical adjacency of get_symmetrized_adjacency")
     lin = ops.Linear.apply
 
     def pool(h, name, nseg):
@@ -497,11 +504,15 @@ def shift_inv_15op_layer(H_in, adj, bN, layer_vars, is_last=False):
 
 def network_func_15op_shift_inv_za(edges, adj, num_layers, dims, activation, sess_mgr):
     """graph.py:202-216"""
-    H = activation(shift_inv_15op_layer(edges, adj, dims, sess_mgr.get_layer_vars(0)))
+    adj = _as_sym(adj, dims[0], dims[1])
+    fuse = _is_relu(activation) and adj.row_ptr is not None      # ReLU inside the edge kernel (canonical adjacency only)
+    H = shift_inv_15op_layer(edges, adj, dims, sess_mgr.get_layer_vars(0), _relu=fuse)
+    if not fuse:
+        H = activation(H)
     for layer_idx in range(1, num_layers):
         is_last = layer_idx == num_layers - 1
-        H = shift_inv_15op_layer(H, adj, dims, sess_mgr.get_layer_vars(layer_idx), is_last=is_last)
-        if not is_last:
+        H = shift_inv_15op_layer(H, adj, dims, sess_mgr.get_layer_vars(layer_idx), is_last=is_last, _relu=fuse and not is_last)
+        if not is_last and not fuse:
             H = activation(H)
     return H
 

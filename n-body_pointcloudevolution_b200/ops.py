@@ -382,6 +382,80 @@ class GraphLayer(torch.autograd.Function):
         return (dH if need_dH else None), dW, dB, None, None, None, None, None, None, None, None, None, None
 
 
+# ================================================================== 15-weight layer (graph.py:20-200)
+def sym_adjacency(idx: torch.Tensor, csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor):
+    """kNN lists idx (B,N,M) + their in-edge lists -> the canonical symmetrised adjacency: dict of int32 device tensors
+    row, col, all, tra (S), dia, dal (B*N), row_ptr (B*N+1), and status int32[2].  Host-synchronising (S is read back)."""
+    _need_cuda(idx, csrT_ptr, csrT_edge)
+    L = _lib.load()
+    idx = _i32c(idx)
+    B, N, M = idx.shape
+    BN, dev = B * N, idx.device
+    row_ptr = torch.empty((BN + 1,), dtype=torch.int32, device=dev)
+    ws = _workspace(L.nbpc_sym_adjacency_workspace_bytes(B, N), dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.nbpc_sym_adjacency_count(_ptr(idx), _ptr(csrT_ptr), _ptr(csrT_edge), B, N, M, _ptr(row_ptr), _ptr(ws), ws.numel(),
+                                              _stream()), "nbpc_sym_adjacency_count")
+        S = int(row_ptr[BN].item())
+        out = {n: torch.empty((S,), dtype=torch.int32, device=dev) for n in ("row", "col", "all", "tra")}
+        out.update({n: torch.empty((BN,), dtype=torch.int32, device=dev) for n in ("dia", "dal")})
+        status = torch.empty((2,), dtype=torch.int32, device=dev)
+        _lib.check(L.nbpc_sym_adjacency_emit(_ptr(idx), _ptr(csrT_ptr), _ptr(csrT_edge), _ptr(row_ptr), B, N, M, S, _ptr(out["row"]),
+                                             _ptr(out["col"]), _ptr(out["all"]), _ptr(out["tra"]), _ptr(out["dia"]), _ptr(out["dal"]),
+                                             _ptr(status), _stream()), "nbpc_sym_adjacency_emit")
+    out["row_ptr"] = row_ptr
+    return out, status
+
+
+class Graph15Layer(torch.autograd.Function):
+    """shift_inv_15op_layer (graph.py:20-200) [+ fused ReLU] on the canonical symmetrised adjacency: node-level pooling and
+    projections + ONE edge kernel per direction (csrc/graph15.cu); deterministic backward."""
+
+    @staticmethod
+    def forward(ctx, H, W, Bias, row, col, tra, dia, row_ptr, B, N, relu):
+        _need_cuda(H, W, Bias, row, col, tra, dia, row_ptr)
+        L = _lib.load()
+        H, W, Bias = _f32c(H), _f32c(W), _f32c(Bias)
+        S, k = H.shape
+        q = W.shape[2]
+        if W.shape[0] != 15 or W.shape[1] != k or Bias.shape != (2, q) or row.numel() != S:
+            raise RuntimeError(f"graph15: shape mismatch H {tuple(H.shape)}, W {tuple(W.shape)}, B {tuple(Bias.shape)}, S {row.numel()}")
+        dev, BN = H.device, B * N
+        out = torch.empty((S, q), dtype=torch.float32, device=dev)
+        Hr, Hc, Hd = (torch.empty((BN, k), dtype=torch.float32, device=dev) for _ in range(3))
+        Ha, Hp = (torch.empty((B, k), dtype=torch.float32, device=dev) for _ in range(2))
+        ws = _workspace(L.nbpc_graph15_workspace_bytes(B, N, S, k, q), dev)
+        with torch.cuda.device(dev):
+            rc = L.nbpc_graph15_layer_fwd(_ptr(H), _ptr(row), _ptr(col), _ptr(tra), _ptr(dia), _ptr(row_ptr), B, N, S, k, q, _ptr(W),
+                                          _ptr(Bias), int(relu), _ptr(out), _ptr(Hr), _ptr(Hc), _ptr(Hd), _ptr(Ha), _ptr(Hp), _ptr(ws),
+                                          ws.numel(), _stream())
+        _lib.check(rc, "nbpc_graph15_layer_fwd")
+        ctx.save_for_backward(H, out, W, row, col, tra, dia, row_ptr, Hr, Hc, Hd, Ha, Hp)
+        ctx.cfg = (B, N, relu)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        H, out, W, row, col, tra, dia, row_ptr, Hr, Hc, Hd, Ha, Hp = ctx.saved_tensors
+        B, N, relu = ctx.cfg
+        L = _lib.load()
+        g = _f32c(g)
+        S, k = H.shape
+        q = W.shape[2]
+        dev = H.device
+        need_dH = ctx.needs_input_grad[0]
+        dH = torch.empty((S, k), dtype=torch.float32, device=dev) if need_dH else None
+        dW = torch.empty((15, k, q), dtype=torch.float32, device=dev)
+        dB = torch.empty((2, q), dtype=torch.float32, device=dev)
+        ws = _workspace(L.nbpc_graph15_workspace_bytes(B, N, S, k, q), dev)
+        with torch.cuda.device(dev):
+            rc = L.nbpc_graph15_layer_bwd(_ptr(g), _ptr(H), _ptr(out), _ptr(row), _ptr(col), _ptr(tra), _ptr(dia), _ptr(row_ptr), B, N, S,
+                                          k, q, _ptr(W), _ptr(Hr), _ptr(Hc), _ptr(Hd), _ptr(Ha), _ptr(Hp), int(relu), _ptr(dH), _ptr(dW),
+                                          _ptr(dB), _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "nbpc_graph15_layer_bwd")
+        return dH, dW, dB, None, None, None, None, None, None, None, None
+
+
 # ================================================================== set layer
 @torch.library.custom_op("nbpc::set_layer_fwd", mutates_args=())
 def set_layer_fwd(H_in: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, relu: bool) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -194,3 +194,52 @@ def pad_cube(x, thr):
     idx_map = np.zeros(max(n_img, 1), dtype=np.int64)
     ok(L.nbpc_pad_cube_emit(P(x), D, N, float(thr), P(offsets), P(padded), P(idx_map), None))
     return padded, idx_map[:n_img]
+
+
+def sym_adjacency(idx):
+    """canonical symmetrised adjacency of kNN lists idx (B,N,M) through the C ABI (host emulation)"""
+    L = lib()
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    B, N, M = idx.shape
+    _, _, ptr, edge, _ = adjacency(idx)
+    BN = B * N
+    row_ptr = np.zeros(BN + 1, dtype=np.int32)
+    w = ws(L.nbpc_sym_adjacency_workspace_bytes(B, N))
+    ok(L.nbpc_sym_adjacency_count(P(idx), P(ptr), P(edge), B, N, M, P(row_ptr), P(w), w.nbytes, None))
+    S = int(row_ptr[BN])
+    out = {n: np.zeros(S, dtype=np.int32) for n in ("row", "col", "all", "tra")}
+    out.update({n: np.zeros(BN, dtype=np.int32) for n in ("dia", "dal")})
+    status = np.zeros(2, dtype=np.int32)
+    ok(L.nbpc_sym_adjacency_emit(P(idx), P(ptr), P(edge), P(row_ptr), B, N, M, S, P(out["row"]), P(out["col"]), P(out["all"]),
+                                 P(out["tra"]), P(out["dia"]), P(out["dal"]), P(status), None))
+    out["row_ptr"] = row_ptr
+    return out, status
+
+
+def graph15_fwd(H, adj, B, N, W, Bias, relu=False):
+    L = lib()
+    H, W, Bias = (np.ascontiguousarray(a, dtype=np.float32) for a in (H, W, Bias))
+    S, k = H.shape
+    q = W.shape[2]
+    out = np.zeros((S, q), dtype=np.float32)
+    Hr, Hc, Hd = (np.zeros((B * N, k), dtype=np.float32) for _ in range(3))
+    Ha, Hp = (np.zeros((B, k), dtype=np.float32) for _ in range(2))
+    w = ws(L.nbpc_graph15_workspace_bytes(B, N, S, k, q))
+    ok(L.nbpc_graph15_layer_fwd(P(H), P(adj["row"]), P(adj["col"]), P(adj["tra"]), P(adj["dia"]), P(adj["row_ptr"]), B, N, S, k, q, P(W),
+                                P(Bias), int(relu), P(out), P(Hr), P(Hc), P(Hd), P(Ha), P(Hp), P(w), w.nbytes, None))
+    return out, (Hr, Hc, Hd, Ha, Hp)
+
+
+def graph15_bwd(dOut, H, Hout, adj, B, N, W, saved, relu=False, need_dH=True):
+    L = lib()
+    dOut, H, Hout, W = (np.ascontiguousarray(a, dtype=np.float32) for a in (dOut, H, Hout, W))
+    S, k = H.shape
+    q = W.shape[2]
+    Hr, Hc, Hd, Ha, Hp = saved
+    dH = np.zeros((S, k), dtype=np.float32) if need_dH else None
+    dW = np.zeros((15, k, q), dtype=np.float32)
+    dB = np.zeros((2, q), dtype=np.float32)
+    w = ws(L.nbpc_graph15_workspace_bytes(B, N, S, k, q))
+    ok(L.nbpc_graph15_layer_bwd(P(dOut), P(H), P(Hout), P(adj["row"]), P(adj["col"]), P(adj["tra"]), P(adj["dia"]), P(adj["row_ptr"]), B, N,
+                                S, k, q, P(W), P(Hr), P(Hc), P(Hd), P(Ha), P(Hp), int(relu), P(dH), P(dW), P(dB), P(w), w.nbytes, None))
+    return dH, dW, dB

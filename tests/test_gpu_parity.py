@@ -801,7 +801,8 @@ def test_15op_layer_golden(nb):
     loss = ((net - torch.tensor(g["tgt"], device=DEV)) ** 2).sum(-1).mean()
     loss.backward()
     np.testing.assert_allclose(lay0.detach().cpu().numpy(), g["f32_layer0"], rtol=2e-5, atol=2e-5)
-    assert torch.equal(lay0, lay0_d)
+    # the plain-dict path composes the layer from primitives (any adjacency); the canonical path runs the fused kernels
+    np.testing.assert_allclose(lay0_d.detach().cpu().numpy(), lay0.detach().cpu().numpy(), rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(net.detach().cpu().numpy(), g["f32_net"], rtol=2e-5, atol=2e-5)
     np.testing.assert_allclose(loss.item(), float(g["f64_loss"]), rtol=1e-5)
     np.testing.assert_allclose(H.grad.cpu().numpy(), g["f64_gH"], rtol=2e-4, atol=2e-6)
