@@ -222,6 +222,7 @@ __global__ void g15_node_project_kernel(const float *__restrict__ Hr, const floa
 }
 
 // ------------------------------------------------------------------ edge level, forward: thread per (edge, output channel)
+// (barrier-free baseline: host emulation, and widths that are not multiples of 4)
 __global__ void g15_edge_fwd_kernel(const float *__restrict__ H, const int32_t *__restrict__ row, const int32_t *__restrict__ col,
                                     const int32_t *__restrict__ tra, const int32_t *__restrict__ dia, const float *__restrict__ W,
                                     const float *__restrict__ Tc, const float *__restrict__ Tr, const float *__restrict__ Td, int64_t S, int k,
@@ -238,6 +239,184 @@ __global__ void g15_edge_fwd_kernel(const float *__restrict__ H, const int32_t *
     if (dia[i] == e) z += Td[(int64_t)i * q + qo];
     out[t] = (relu && z < 0.f) ? 0.f : z;
 }
+
+#ifndef NBPC_HOST_EMU
+// q % 4 == 0: thread per (edge, 4 output channels); W0 | W1 staged in shared memory ([2][k][q]); the two input rows are read
+// as scalars broadcast over the q/4 threads of the edge, every thread keeps 4 accumulators
+__global__ void __launch_bounds__(G15_THREADS) g15_edge_fwd4_kernel(const float *__restrict__ H, const int32_t *__restrict__ row,
+                                                                    const int32_t *__restrict__ col, const int32_t *__restrict__ tra,
+                                                                    const int32_t *__restrict__ dia, const float *__restrict__ W,
+                                                                    const float *__restrict__ Tc, const float *__restrict__ Tr,
+                                                                    const float *__restrict__ Td, int64_t S, int k, int q, int relu,
+                                                                    float *__restrict__ out) {
+    extern __shared__ __align__(16) float g15_ws[];
+    for (int i = threadIdx.x; i < 2 * k * q; i += G15_THREADS) g15_ws[i] = __ldg(&W[i]);   // W[0], W[1] are contiguous
+    __syncthreads();
+    const int G = q >> 2, epb = G15_THREADS / G;
+    const int g = threadIdx.x % G, slot = threadIdx.x / G;
+    if (slot >= epb) return;
+    const float *w0 = g15_ws + 4 * g, *w1 = g15_ws + k * q + 4 * g;
+    for (int64_t e = (int64_t)blockIdx.x * epb + slot; e < S; e += (int64_t)gridDim.x * epb) {
+        const int i = __ldg(&row[e]), j = __ldg(&col[e]);
+        const float *h = H + e * k, *ht = H + (int64_t)__ldg(&tra[e]) * k;
+        float4 z = __ldg(reinterpret_cast<const float4 *>(Tc + (int64_t)j * q + 4 * g));
+        const float4 r = __ldg(reinterpret_cast<const float4 *>(Tr + (int64_t)i * q + 4 * g));
+        z.x += r.x; z.y += r.y; z.z += r.z; z.w += r.w;
+        if (__ldg(&dia[i]) == e) {
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(Td + (int64_t)i * q + 4 * g));
+            z.x += d.x; z.y += d.y; z.z += d.z; z.w += d.w;
+        }
+        for (int kk = 0; kk < k; ++kk) {
+            const float a = __ldg(&h[kk]), b = __ldg(&ht[kk]);
+            const float4 u = *reinterpret_cast<const float4 *>(w0 + kk * q), v = *reinterpret_cast<const float4 *>(w1 + kk * q);
+            z.x = fmaf(a, u.x, z.x); z.y = fmaf(a, u.y, z.y); z.z = fmaf(a, u.z, z.z); z.w = fmaf(a, u.w, z.w);
+            z.x = fmaf(b, v.x, z.x); z.y = fmaf(b, v.y, z.y); z.z = fmaf(b, v.z, z.z); z.w = fmaf(b, v.w, z.w);
+        }
+        if (relu) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
+        *reinterpret_cast<float4 *>(out + e * q + 4 * g) = z;
+    }
+}
+
+// k % 4 == 0: thread per (edge, 4 input channels); W0^T | W1^T staged in shared memory ([2][q][k])
+__global__ void __launch_bounds__(G15_THREADS) g15_edge_bwd4_kernel(const float *__restrict__ dZ, const int32_t *__restrict__ row,
+                                                                    const int32_t *__restrict__ col, const int32_t *__restrict__ tra,
+                                                                    const int32_t *__restrict__ dia, const float *__restrict__ W,
+                                                                    const float *__restrict__ Gr, const float *__restrict__ Gc,
+                                                                    const float *__restrict__ Gd, const float *__restrict__ Ga, int64_t S,
+                                                                    int N, int k, int q, float *__restrict__ dH) {
+    extern __shared__ __align__(16) float g15_ws[];
+    for (int i = threadIdx.x; i < 2 * k * q; i += G15_THREADS) {      // transposed: [w][qo][kk]
+        const int wsel = i / (k * q), r = i % (k * q), kk = r / q, qo = r % q;
+        g15_ws[wsel * k * q + qo * k + kk] = __ldg(&W[i]);
+    }
+    __syncthreads();
+    const int G = k >> 2, epb = G15_THREADS / G;
+    const int g = threadIdx.x % G, slot = threadIdx.x / G;
+    if (slot >= epb) return;
+    const float *w0 = g15_ws + 4 * g, *w1 = g15_ws + k * q + 4 * g;
+    for (int64_t e = (int64_t)blockIdx.x * epb + slot; e < S; e += (int64_t)gridDim.x * epb) {
+        const int i = __ldg(&row[e]), j = __ldg(&col[e]);
+        const float *z = dZ + e * q, *zt = dZ + (int64_t)__ldg(&tra[e]) * q;
+        float4 a = __ldg(reinterpret_cast<const float4 *>(Gc + (int64_t)i * k + 4 * g));
+        const float4 r = __ldg(reinterpret_cast<const float4 *>(Gr + (int64_t)j * k + 4 * g));
+        const float4 s4 = __ldg(reinterpret_cast<const float4 *>(Ga + (int64_t)(i / N) * k + 4 * g));
+        a.x += r.x + s4.x; a.y += r.y + s4.y; a.z += r.z + s4.z; a.w += r.w + s4.w;
+        if (__ldg(&dia[i]) == e) {
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(Gd + (int64_t)i * k + 4 * g));
+            a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
+        }
+        for (int qo = 0; qo < q; ++qo) {
+            const float x = __ldg(&z[qo]), y = __ldg(&zt[qo]);
+            const float4 u = *reinterpret_cast<const float4 *>(w0 + qo * k), v = *reinterpret_cast<const float4 *>(w1 + qo * k);
+            a.x = fmaf(x, u.x, a.x); a.y = fmaf(x, u.y, a.y); a.z = fmaf(x, u.z, a.z); a.w = fmaf(x, u.w, a.w);
+            a.x = fmaf(y, v.x, a.x); a.y = fmaf(y, v.y, a.y); a.z = fmaf(y, v.z, a.z); a.w = fmaf(y, v.w, a.w);
+        }
+        *reinterpret_cast<float4 *>(dH + e * k + 4 * g) = a;
+    }
+}
+
+// ---- tiled deterministic X^T Y (optionally X gathered through xidx): a block accumulates a contiguous row range in
+// 64-row shared-memory tiles; thread t owns the outputs t, t + 256, ... of the (k x q) matrix; partial[blk][k][q]
+#define G15_XTY_ROWS 64
+__global__ void __launch_bounds__(G15_THREADS) g15_xty_tiled_kernel(const float *__restrict__ X, const int32_t *__restrict__ xidx,
+                                                                    const float *__restrict__ Y, int64_t n, int64_t rows_per_block, int k,
+                                                                    int q, float *__restrict__ partial) {
+    extern __shared__ __align__(16) float g15_ws[];
+    float *Xs = g15_ws, *Ys = g15_ws + G15_XTY_ROWS * k;
+    const int kq = k * q;
+    float acc[16];                                   // k * q <= 4096
+#pragma unroll
+    for (int u = 0; u < 16; ++u) acc[u] = 0.f;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = nbpc_min(r0 + rows_per_block, n);
+    for (int64_t t0 = r0; t0 < r1; t0 += G15_XTY_ROWS) {
+        const int rows = (int)nbpc_min((int64_t)G15_XTY_ROWS, r1 - t0);
+        for (int i = threadIdx.x; i < rows * k; i += G15_THREADS) {
+            const int r = i / k, c = i % k;
+            const int64_t src = xidx ? (int64_t)__ldg(&xidx[t0 + r]) : t0 + r;
+            Xs[i] = __ldg(&X[src * k + c]);
+        }
+        for (int i = threadIdx.x; i < rows * q; i += G15_THREADS) Ys[i] = __ldg(&Y[t0 * q + i]);
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int o = threadIdx.x + u * G15_THREADS;
+            if (o < kq) {
+                const int kk = o / q, qo = o % q;
+                float a = acc[u];
+                for (int r = 0; r < rows; ++r) a = fmaf(Xs[r * k + kk], Ys[r * q + qo], a);
+                acc[u] = a;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int o = threadIdx.x + u * G15_THREADS;
+        if (o < kq) partial[(int64_t)blockIdx.x * kq + o] = acc[u];
+    }
+}
+// one warp per output: lane l adds the partials l, l + 32, ..., fixed butterfly over the lanes
+__global__ void g15_xty_final_kernel(const float *__restrict__ partial, int nparts, int kq, float *__restrict__ out) {
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (o >= kq) return;
+    float a0 = 0.f, a1 = 0.f;
+    int b = lane;
+    for (; b + 32 < nparts; b += 64) {
+        a0 += __ldg(partial + (int64_t)b * kq + o);
+        a1 += __ldg(partial + (int64_t)(b + 32) * kq + o);
+    }
+    for (; b < nparts; b += 32) a0 += __ldg(partial + (int64_t)b * kq + o);
+    float sum = a0 + a1;
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
+    if (lane == 0) out[o] = sum;
+}
+#define G15_XTY_MAX_BLOCKS 1184
+static bool g15_xty_tiled_ok(int k, int q) { return k * q <= 4096 && (size_t)G15_XTY_ROWS * (k + q) * 4 <= 48 * 1024; }
+static void g15_xty_tiled(const char *name, const float *X, const int32_t *xidx, const float *Y, int64_t n, int k, int q, float *partial,
+                          float *out, cudaStream_t stream) {
+    // node-level products (<= 1 M rows) use a quarter of the blocks: their partial reduction would otherwise dominate
+    int64_t nblk = nbpc_min((int64_t)(n < (1 << 20) ? G15_XTY_MAX_BLOCKS / 4 : G15_XTY_MAX_BLOCKS), (n + G15_XTY_ROWS - 1) / G15_XTY_ROWS);
+    int64_t rpb = (n + nblk - 1) / nblk;
+    rpb = (rpb + G15_XTY_ROWS - 1) / G15_XTY_ROWS * G15_XTY_ROWS;
+    nblk = (n + rpb - 1) / rpb;
+    NBPC_LAUNCH_N(name, g15_xty_tiled_kernel, (int)nblk, G15_THREADS, sizeof(float) * G15_XTY_ROWS * (k + q), stream, X, xidx, Y, n, rpb, k, q,
+                  partial);
+    NBPC_LAUNCH(g15_xty_final_kernel, nbpc_cdiv((int64_t)k * q * 32, 256), 256, 0, stream, partial, (int)nblk, k * q, out);
+}
+
+// per-sample column sums in two levels: partial[s][blk][C] over 256-node chunks, then the fixed-order final
+__global__ void __launch_bounds__(G15_THREADS) g15_sample_partial_kernel(const float *__restrict__ X1, const float *__restrict__ X2, int C,
+                                                                         int N, const int32_t *__restrict__ row_ptr, int by_degree,
+                                                                         float *__restrict__ p1, float *__restrict__ p2) {
+    const int s = blockIdx.y, n_begin = blockIdx.x * 256, n_end = nbpc_min(n_begin + 256, N);
+    const int64_t n0 = (int64_t)s * N;
+    for (int ch = threadIdx.x; ch < C; ch += G15_THREADS) {
+        float a1 = 0.f, a2 = 0.f;
+        for (int i = n_begin; i < n_end; ++i) {
+            const float w = by_degree ? (float)(row_ptr[n0 + i + 1] - row_ptr[n0 + i]) : 1.f;
+            a1 += w * X1[(n0 + i) * C + ch];
+            a2 += X2[(n0 + i) * C + ch];
+        }
+        p1[((int64_t)s * gridDim.x + blockIdx.x) * C + ch] = a1;
+        p2[((int64_t)s * gridDim.x + blockIdx.x) * C + ch] = a2;
+    }
+}
+__global__ void g15_sample_final_kernel(const float *__restrict__ p1, const float *__restrict__ p2, int C, int nblk, int N,
+                                        const int32_t *__restrict__ row_ptr, int mean, int B, float *__restrict__ out1, float *__restrict__ out2) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * C) return;
+    const int s = t / C, ch = t % C;
+    float a1 = 0.f, a2 = 0.f;
+    for (int b = 0; b < nblk; ++b) {
+        a1 += p1[((int64_t)s * nblk + b) * C + ch];
+        a2 += p2[((int64_t)s * nblk + b) * C + ch];
+    }
+    const float S_s = (float)(row_ptr[(int64_t)(s + 1) * N] - row_ptr[(int64_t)s * N]);
+    out1[t] = mean ? a1 / S_s : a1;
+    out2[t] = mean ? a2 / (float)N : a2;
+}
+#endif  // !NBPC_HOST_EMU
 
 // dZ = dOut * [out > 0]
 __global__ void g15_mask_kernel(const float *__restrict__ g, const float *__restrict__ out, int64_t n, float *__restrict__ dz) {
@@ -334,6 +513,7 @@ struct G15Workspace {
     float *Ga, *Gp;               // (B, k)
     float *dZ;                    // (S, q) masked gradient
     float *xty_partial;
+    float *sp1, *sp2;             // per-sample column-sum partials (B, ceil(N/256), max(k,q))
     size_t bytes;
 };
 static G15Workspace g15_carve(void *ws, size_t ws_bytes, int B, int N, int64_t S, int k, int q) {
@@ -348,9 +528,51 @@ static G15Workspace g15_carve(void *ws, size_t ws_bytes, int B, int N, int64_t S
     w.dZ = a.take<float>((size_t)S * q);
     int rpc, nc;
     xty_plan(S, k, q, &rpc, &nc);
-    w.xty_partial = a.take<float>((size_t)nc * k * q);
+    size_t nparts = (size_t)nc;
+#ifndef NBPC_HOST_EMU
+    nparts = nbpc_max(nparts, (size_t)G15_XTY_MAX_BLOCKS);
+#endif
+    w.xty_partial = a.take<float>(nparts * k * q);
+    const size_t mx = (size_t)(k > q ? k : q), nb = (size_t)nbpc_cdiv(N, 256);
+    w.sp1 = a.take<float>((size_t)B * nb * mx);
+    w.sp2 = a.take<float>((size_t)B * nb * mx);
     w.bytes = a.off;
     return w;
+}
+
+// per-sample sums: two-level on the device, the single-block kernel under host emulation
+static void g15_sample_sums(const float *X1, const float *X2, int C, int B, int N, const int32_t *row_ptr, int by_degree, int mean, float *out1,
+                            float *out2, G15Workspace &w, cudaStream_t stream) {
+#ifndef NBPC_HOST_EMU
+    const int nb = nbpc_cdiv(N, 256);
+    NBPC_LAUNCH(g15_sample_partial_kernel, dim3(nb, B), G15_THREADS, 0, stream, X1, X2, C, N, row_ptr, by_degree, w.sp1, w.sp2);
+    NBPC_LAUNCH(g15_sample_final_kernel, nbpc_cdiv(B * C, 128), 128, 0, stream, w.sp1, w.sp2, C, nb, N, row_ptr, mean, B, out1, out2);
+#else
+    (void)w;
+    NBPC_LAUNCH(g15_sample_sum_kernel, B, G15_THREADS, 0, stream, X1, X2, C, N, row_ptr, by_degree, mean, out1, out2);
+#endif
+}
+
+// X^T Y (X optionally gathered through xidx): tiled kernel on the device, the generic fixed-order reduction otherwise
+static void g15_xty(const char *name, const float *X, const int32_t *xidx, const float *Y, int64_t n, int k, int q, float *partial, float *out,
+                    cudaStream_t stream) {
+#ifndef NBPC_HOST_EMU
+    if (g15_xty_tiled_ok(k, q)) {
+        g15_xty_tiled(name, X, xidx, Y, n, k, q, partial, out, stream);
+        return;
+    }
+#endif
+    GlPlain y;
+    y.p = Y; y.ld = q;
+    if (xidx) {
+        G15Gather xg;
+        xg.p = X; xg.idx = xidx; xg.ld = k;
+        xty(name, xg, y, n, k, q, partial, out, stream);
+    } else {
+        GlPlain x;
+        x.p = X; x.ld = k;
+        xty(name, x, y, n, k, q, partial, out, stream);
+    }
 }
 
 extern "C" {
@@ -413,11 +635,21 @@ int nbpc_graph15_layer_fwd(const float *H, const int32_t *row, const int32_t *co
     }
     const int BN = B * N, T = G15_THREADS;
     NBPC_LAUNCH(g15_pool_kernel, nbpc_cdiv((int64_t)BN * k, T), T, 0, stream, H, k, row_ptr, tra, dia, BN, 1, Hc, Hr, Hd);
-    NBPC_LAUNCH(g15_sample_sum_kernel, B, T, 0, stream, Hc, Hd, k, N, row_ptr, 1, 1, Ha, Hp);
+    g15_sample_sums(Hc, Hd, k, B, N, row_ptr, 1, 1, Ha, Hp, w, stream);
     NBPC_LAUNCH(g15_sample_project_kernel, nbpc_cdiv(B * q, 128), 128, 0, stream, Ha, Hp, W, Bias, B, k, q, w.Ta, w.Tda);
     NBPC_LAUNCH(g15_node_project_kernel, nbpc_cdiv((int64_t)BN * q, T), T, 0, stream, Hr, Hc, Hd, w.Ta, w.Tda, W, BN, N, k, q, w.Tc, w.Tr,
                 w.Td);
-    NBPC_LAUNCH(g15_edge_fwd_kernel, nbpc_cdiv(S * q, T), T, 0, stream, H, row, col, tra, dia, W, w.Tc, w.Tr, w.Td, S, k, q, relu, H_out);
+#ifndef NBPC_HOST_EMU
+    if (q % 4 == 0 && q <= 4 * T && (size_t)2 * k * q * sizeof(float) <= 48 * 1024) {
+        const int epb = T / (q / 4);
+        const int grid = (int)nbpc_min((int64_t)nbpc_cdiv(S, epb), (int64_t)G15_XTY_MAX_BLOCKS * 4);
+        NBPC_LAUNCH_N(NbpcKName("g15_edge_fwd4_kernel", k, q).c_str(), g15_edge_fwd4_kernel, grid, T, sizeof(float) * 2 * k * q, stream, H, row, col,
+                      tra, dia, W, w.Tc, w.Tr, w.Td, S, k, q, relu, H_out);
+        return nbpc_check_launch("nbpc_graph15_layer_fwd");
+    }
+#endif
+    NBPC_LAUNCH_N(NbpcKName("g15_edge_fwd_kernel", k, q).c_str(), g15_edge_fwd_kernel, nbpc_cdiv(S * q, T), T, 0, stream, H, row, col, tra, dia, W,
+                  w.Tc, w.Tr, w.Td, S, k, q, relu, H_out);
     return nbpc_check_launch("nbpc_graph15_layer_fwd");
 }
 
@@ -445,33 +677,34 @@ int nbpc_graph15_layer_bwd(const float *dOut, const float *H, const float *H_out
     // node level: dTr = row sums, dTc = in-edge sums, dTd = the diagonal entry; per-sample sums dTa, dTda
     float *dTc = w.Tc, *dTr = w.Tr, *dTd = w.Td;
     NBPC_LAUNCH(g15_pool_kernel, nbpc_cdiv((int64_t)BN * q, T), T, 0, stream, dZ, q, row_ptr, tra, dia, BN, 0, dTr, dTc, dTd);
-    NBPC_LAUNCH(g15_sample_sum_kernel, B, T, 0, stream, dTr, dTd, q, N, row_ptr, 0, 0, w.dTa, w.dTda);
+    g15_sample_sums(dTr, dTd, q, B, N, row_ptr, 0, 0, w.dTa, w.dTda, w, stream);
     NBPC_LAUNCH(g15_bias_grad_kernel, nbpc_cdiv(q, 64), 64, 0, stream, w.dTa, w.dTda, B, q, dB);
     // weight gradients: fixed-order X^T Y reductions
-    GlPlain x, y;
-    x.ld = k; y.ld = q;
-    y.p = dZ;
-    x.p = H;
-    xty("g15_xty_dW0", x, y, S, k, q, w.xty_partial, dW, stream);
-    G15Gather xg;
-    xg.p = H; xg.idx = tra; xg.ld = k;
-    xty("g15_xty_dW1", xg, y, S, k, q, w.xty_partial, dW + kq, stream);
+    g15_xty("g15_xty_dW0", H, nullptr, dZ, S, k, q, w.xty_partial, dW, stream);
+    g15_xty("g15_xty_dW1", H, tra, dZ, S, k, q, w.xty_partial, dW + kq, stream);
     struct { int wi; const float *X; const float *Y; } node_terms[9] = {
         {3, Hr, dTc}, {7, Hc, dTc}, {13, Hd, dTc}, {4, Hr, dTr}, {6, Hc, dTr}, {14, Hd, dTr}, {2, Hd, dTd}, {5, Hr, dTd}, {8, Hc, dTd}};
-    for (int i = 0; i < 9; ++i) {
-        x.p = node_terms[i].X; y.p = node_terms[i].Y;
-        xty("g15_xty_node", x, y, (int64_t)BN, k, q, w.xty_partial, dW + node_terms[i].wi * kq, stream);
-    }
+    for (int i = 0; i < 9; ++i)
+        g15_xty("g15_xty_node", node_terms[i].X, nullptr, node_terms[i].Y, (int64_t)BN, k, q, w.xty_partial, dW + node_terms[i].wi * kq, stream);
     struct { int wi; const float *X; const float *Y; } sample_terms[4] = {{9, Ha, w.dTa}, {10, Ha, w.dTda}, {11, Hp, w.dTa}, {12, Hp, w.dTda}};
-    for (int i = 0; i < 4; ++i) {
-        x.p = sample_terms[i].X; y.p = sample_terms[i].Y;
-        xty("g15_xty_sample", x, y, (int64_t)B, k, q, w.xty_partial, dW + sample_terms[i].wi * kq, stream);
-    }
+    for (int i = 0; i < 4; ++i)
+        g15_xty("g15_xty_sample", sample_terms[i].X, nullptr, sample_terms[i].Y, (int64_t)B, k, q, w.xty_partial, dW + sample_terms[i].wi * kq,
+                stream);
     if (dH) {
         NBPC_LAUNCH(g15_sample_grad_kernel, nbpc_cdiv(B * k, 128), 128, 0, stream, w.dTa, w.dTda, W, row_ptr, B, N, k, q, w.Ga, w.Gp);
         NBPC_LAUNCH(g15_node_grad_kernel, nbpc_cdiv((int64_t)BN * k, T), T, 0, stream, dTc, dTr, dTd, w.Gp, W, row_ptr, BN, N, k, q, w.Gr, w.Gc,
                     w.Gd);
-        NBPC_LAUNCH(g15_edge_bwd_kernel, nbpc_cdiv(S * k, T), T, 0, stream, dZ, row, col, tra, dia, W, w.Gr, w.Gc, w.Gd, w.Ga, S, N, k, q, dH);
+#ifndef NBPC_HOST_EMU
+        if (k % 4 == 0 && k <= 4 * T && (size_t)2 * k * q * sizeof(float) <= 48 * 1024) {
+            const int epb = T / (k / 4);
+            const int grid = (int)nbpc_min((int64_t)nbpc_cdiv(S, epb), (int64_t)G15_XTY_MAX_BLOCKS * 4);
+            NBPC_LAUNCH_N(NbpcKName("g15_edge_bwd4_kernel", k, q).c_str(), g15_edge_bwd4_kernel, grid, T, sizeof(float) * 2 * k * q, stream, dZ, row,
+                          col, tra, dia, W, w.Gr, w.Gc, w.Gd, w.Ga, S, N, k, q, dH);
+            return nbpc_check_launch("nbpc_graph15_layer_bwd");
+        }
+#endif
+        NBPC_LAUNCH_N(NbpcKName("g15_edge_bwd_kernel", k, q).c_str(), g15_edge_bwd_kernel, nbpc_cdiv(S * k, T), T, 0, stream, dZ, row, col, tra, dia,
+                      W, w.Gr, w.Gc, w.Gd, w.Ga, S, N, k, q, dH);
     }
     return nbpc_check_launch("nbpc_graph15_layer_bwd");
 }
