@@ -193,6 +193,33 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                          int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
                          size_t ws_bytes, void *stream);
 
+/* Virtual layer input.  Inside a network the output of the FIRST graph layer, H1[e] = relu(E[e] W1 + Q_col[col[e]] +
+ * Q_row[e / M]), is a function of the 12-byte edge feature row and two L2-resident node tables; materialising it is 44 % of
+ * the bytes a [3,32,16,3] training step moves.  With node_only = 1 nbpc_graph_layer_fwd_v stops after the node-level terms
+ * of that layer (H_out may be NULL) and leaves Q_col / Q_row (B*N, q) in the caller's buffers; the NEXT layer is then called
+ * with `vin` describing that virtual tensor instead of H_in (NULL): its pooling, forward and backward edge kernels
+ * recompute the rows with one shared expression (bit-identical to the materialised tensor).  vin->k = 3 input channels,
+ * hidden layers of width 16 / 32 / 64, split-mode arithmetic (NBPC_MATH_TF32X3); nbpc_graph_layer_vin_supported says whether
+ * the current configuration has the kernels.  The backward of a virtual-input layer needs mask_input = 1 (the virtual tensor
+ * is a ReLU output, its mask is recomputed) and relu = 0 (gradient pre-masked by the consumer). */
+typedef struct nbpc_virtual_input {
+    const float *E;       /* (c, k) edge features of the producing layer */
+    const float *W1;      /* (k, width) its first weight */
+    const float *Q_col;   /* (B*N, width) */
+    const float *Q_row;   /* (B*N, width) */
+    int k;                /* 3 */
+} nbpc_virtual_input;
+int nbpc_graph_layer_vin_supported(int k0, int k, int q, int64_t c);
+int nbpc_graph_layer_fwd_v(const float *H_in, const nbpc_virtual_input *vin, const int32_t *col, const int32_t *csrT_ptr,
+                           const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *bias,
+                           int is_last, int relu, int node_only, float *H_out, float *P_col, float *P_row, float *P_cube,
+                           float *Q_col_out, float *Q_row_out, void *workspace, size_t ws_bytes, void *stream);
+int nbpc_graph_layer_bwd_v(const float *dOut, const float *H_in, const nbpc_virtual_input *vin, const float *H_out,
+                           const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k,
+                           int q, const float *W, const float *P_col, const float *P_row, const float *P_cube, int is_last,
+                           int relu, int mask_input, float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes,
+                           void *stream);
+
 /* ---------------------------------------------------------------- 15-weight layer on a symmetrised adjacency
  * graph.shift_inv_15op_layer (graph.py:20-200).  The reference ships no builder for its `adj` dict; nbpc_sym_adjacency_*
  * builds the canonical one from a kNN graph: the union A u A^T of every sample, edges sorted row-major, with

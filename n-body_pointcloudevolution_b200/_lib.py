@@ -57,6 +57,10 @@ SIGNATURES = {
     "nbpc_graph15_layer_fwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "nbpc_graph15_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i64, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p,
                                     _p, _sz, _p]),
+    "nbpc_graph_layer_vin_supported": (_i, [_i, _i, _i, _i64]),
+    "nbpc_graph_layer_fwd_v": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_graph_layer_bwd_v": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i,
+                                    _p, _p, _p, _p, _sz, _p]),
     "nbpc_set_layer_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "nbpc_set_layer_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
     "nbpc_set_layer_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
@@ -82,6 +86,12 @@ def bind(cdll):
         fn.restype = res
         fn.argtypes = args
     return cdll
+
+
+class VirtualInput(ctypes.Structure):
+    """nbpc_virtual_input (include/nbpc.h)"""
+    _fields_ = [("E", ctypes.c_void_p), ("W1", ctypes.c_void_p), ("Q_col", ctypes.c_void_p), ("Q_row", ctypes.c_void_p),
+                ("k", ctypes.c_int)]
 
 
 _lib = None

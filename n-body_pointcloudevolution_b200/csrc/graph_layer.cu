@@ -284,7 +284,8 @@ static bool gl_first_layer_fusion() {
 
 #ifndef NBPC_HOST_EMU
 static int gl_num_sms() {
-    static int sms = 0;
+    static int sms_d[NBPC_MAX_DEVICES];
+    int &sms = sms_d[nbpc_device_slot()];
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -348,6 +349,7 @@ static GlWorkspace gl_carve(void *ws, size_t ws_bytes, int B, int N, int M, int 
 
 #include "graph_layer_tc.h"
 #include "graph_layer_k3.cuh"
+#include "graph_layer_vin.cuh"
 
 #ifndef NBPC_HOST_EMU
 // ---- first-layer (k = 3 / 9 / 10) streaming kernels
@@ -393,7 +395,8 @@ static int glk3_launch_first_layer_bwd_t(const float *E, const float *dOut, cons
                                          float *part1, float *part2, float *part3, float *colsum_partial, cudaStream_t stream) {
     auto kern = glk3_first_layer_bwd_kernel<Q, RELU>;
     const size_t smem = Glk3FbCfg<Q, RELU>::SMEM;
-    static bool configured = false;
+    static bool configured_d[NBPC_MAX_DEVICES];   // per device: function attributes belong to a context
+    bool &configured = configured_d[nbpc_device_slot()];
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared) != cudaSuccess) {
@@ -478,41 +481,79 @@ static int gln_launch_pool(const float *H, int k, int q, int B, int N, int M, co
     return nblk;
 }
 
+// pooling of a VIRTUAL input tensor (graph_layer_vin.cuh); returns the partial blocks per sample (0: no instance)
+static int gln_launch_pool_vin(const GlVin &V, int k0, int k, int q, const int32_t *col, int B, int N, int M, const int32_t *csrT_ptr,
+                               const int32_t *csrT_edge, float *P_row, float *P_col, float *partial, cudaStream_t stream) {
+    int nblk = 0;
+    if (k0 != 3) return 0;
+#define X(K_)                                                                                                           \
+    if (k == K_) {                                                                                                     \
+        nblk = nbpc_cdiv(N, GLV_THREADS / (K_ / 4));                                                                   \
+        NBPC_LAUNCH_N(NbpcKName("gln_pool_vin_kernel", k, q).c_str(), (gln_pool_vin_kernel<3, K_>), dim3(nblk, B), GLV_THREADS, 0, stream, V, \
+                      col, M, glv_magic(M), N, csrT_ptr, csrT_edge, P_row, P_col, partial);                            \
+    }
+    X(16) X(32) X(64)
+#undef X
+    return nblk;
+}
+
+// vin: the layer input is virtual (H_in is then null); node_only: stop after the node-level terms (the caller keeps
+// Q_col / Q_row in Qc_dst / Qr_dst and a LATER layer consumes this layer's output as a virtual input)
 static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M,
                         int k, int q, const float *W, const float *bias, int is_last, int relu, float *H_out, float *P_col,
-                        float *P_row, float *P_cube, GlWorkspace &w, cudaStream_t stream) {
+                        float *P_row, float *P_cube, GlWorkspace &w, cudaStream_t stream, const GlVin *vin = nullptr, int vin_k0 = 0,
+                        int node_only = 0, float *Qc_dst = nullptr, float *Qr_dst = nullptr) {
     const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
-    const int nblk = gln_launch_pool(H_in, k, q, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream);
+    float *Qc = Qc_dst ? Qc_dst : w.Qc, *Qr = Qr_dst ? Qr_dst : w.Qr;
+    int nblk;
+    if (vin) {
+        nblk = gln_launch_pool_vin(*vin, vin_k0, k, q, col, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream);
+        if (!nblk) {
+            nbpc_set_error("nbpc_graph_layer_fwd_v: no virtual-input pooling kernel for these widths");
+            return NBPC_EINVAL;
+        }
+    } else {
+        nblk = gln_launch_pool(H_in, k, q, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream);
+    }
     float *Cq = w.dCq;
     NBPC_LAUNCH(gln_cube_fwd_kernel, B, GLN_TINY_THREADS, 0, stream, w.cube_partial, nblk, N, k, q, W + 3 * kq, bias, P_cube, Cq);
 #define X(K_, Q_)                                                                                                       \
     if (k == K_ && q == Q_) {                                                                                          \
         if constexpr (Q_ % 8 == 0 && K_ <= 10)                                                                         \
             NBPC_LAUNCH_N(NbpcKName("gln_node_project8_kernel", k, q).c_str(), (gln_node_project8_kernel<K_, Q_>), gln_node_grid(BN * 8), GLN_THREADS, \
-                          0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);                                     \
+                          0, stream, P_col, P_row, Cq, W, (int)BN, N, Qc, Qr);                                     \
         else                                                                                                           \
             NBPC_LAUNCH_N(NbpcKName("gln_node_project_kernel", k, q).c_str(), (gln_node_project_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, \
-                          0, stream, P_col, P_row, Cq, W, (int)BN, N, w.Qc, w.Qr);                                     \
+                          0, stream, P_col, P_row, Cq, W, (int)BN, N, Qc, Qr);                                     \
     }
     GLN_FOR_KQ(X)
 #undef X
+    if (node_only) return nbpc_check_launch("nbpc_graph_layer_fwd");
+    if (vin) {
+        if (is_last || !glt_fwd_vin_shape_ok(vin_k0, k, q) ||
+            glt_edge_out_vin(vin_k0, k, q, vin, col, W, Qc, Qr, c, M, relu, H_out, stream)) {
+            nbpc_set_error("nbpc_graph_layer_fwd_v: could not set up the virtual-input tensor-core kernel");
+            return NBPC_ELAUNCH;
+        }
+        return nbpc_check_launch("nbpc_graph_layer_fwd");
+    }
     if (is_last) {
         NBPC_LAUNCH_N(NbpcKName("glf_last_out_kernel", k, q).c_str(), glf_last_out_kernel, nbpc_cdiv(BN * q, 256), 256, 0, stream, P_row,
-                      col, W, w.Qc, w.Qr, (int)BN, M, k, q, relu, H_out);
+                      col, W, Qc, Qr, (int)BN, M, k, q, relu, H_out);
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (g_nbpc_math_mode != NBPC_MATH_FP32 && glt_fwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3)) {
-        if (glt_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, g_nbpc_math_mode == NBPC_MATH_TF32X3, H_out, stream)) {
+        if (glt_edge_out(k, q, H_in, col, W, Qc, Qr, c, M, relu, g_nbpc_math_mode == NBPC_MATH_TF32X3, H_out, stream)) {
             nbpc_set_error("nbpc_graph_layer_fwd: could not set up the tensor-core kernel (tensor map / shared memory)");
             return NBPC_ELAUNCH;
         }
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (glk3_shape_ok(k, q)) {
-        glk3_launch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+        glk3_launch_edge_out(k, q, H_in, col, W, Qc, Qr, c, M, relu, H_out, stream);
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
-    const int rc = glf_dispatch_edge_out(k, q, H_in, col, W, w.Qc, w.Qr, c, M, relu, H_out, stream);
+    const int rc = glf_dispatch_edge_out(k, q, H_in, col, W, Qc, Qr, c, M, relu, H_out, stream);
     if (rc) {
         nbpc_set_error("nbpc_graph_layer_fwd: could not configure shared memory");
         return NBPC_ELAUNCH;
@@ -530,9 +571,13 @@ static bool gl_fused_ok(int k, int q, int is_last) {
 static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out, const int32_t *col, const int32_t *csrT_ptr,
                         const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *P_col,
                         const float *P_row, const float *P_cube, int is_last, int relu, int mask_input, float *dH_in, float *dW,
-                        float *dB, GlWorkspace &w, cudaStream_t stream) {
+                        float *dB, GlWorkspace &w, cudaStream_t stream, const GlVin *vin = nullptr, int vin_k0 = 0) {
     const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
     float *dQ_col = w.Qc, *dQ_row = w.Qr;
+    if (vin && (is_last || relu || !mask_input || !dH_in || g_nbpc_math_mode != NBPC_MATH_TF32X3 || !glt_bwd_vin_shape_ok(vin_k0, k, q, c))) {
+        nbpc_set_error("nbpc_graph_layer_bwd_v: the virtual input needs a hidden layer in split mode whose gradient arrives pre-masked");
+        return NBPC_EINVAL;
+    }
     if (!is_last && !dH_in && k == 3 && glk3_shape_ok(k, q) && B <= gl_max_partial_blocks() && gl_first_layer_fusion()) {
         // first layer: every gradient from ONE pass over dZ (graph_layer_k3.cuh).  Blocks per sample are bounded by the
         // partial buffers: B * nb <= gl_max_partial_blocks() rows of (k,q) and nb <= ceil(N / 16) rows of the column sums
@@ -596,6 +641,13 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
         if (dH_in)   // the row term (dOutM W1^T) / M is already in G_row (gln_node_grad_kernel, add_w1)
             NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256, 0,
                           stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, c, M, k, dH_in);
+    } else if (vin) {
+        const int nb = glt_edge_bwd_vin(vin_k0, k, q, dOut, vin, col, W, w.Gc, w.Gr, c, M, dH_in, w.xty_partial, stream);
+        if (nb <= 0) {
+            nbpc_set_error("nbpc_graph_layer_bwd_v: could not set up the virtual-input tensor-core kernel");
+            return NBPC_ELAUNCH;
+        }
+        fa.part[0] = w.xty_partial; fa.n[0] = nb;
     } else if (!relu && dH_in && g_nbpc_math_mode != NBPC_MATH_FP32 && glt_bwd_shape_ok(k, q, g_nbpc_math_mode == NBPC_MATH_TF32X3, c)) {
         const int nb = glt_edge_bwd(k, q, dOut, H_in, col, W, w.Gc, w.Gr, c, M, mask_input, g_nbpc_math_mode == NBPC_MATH_TF32X3, dH_in,
                                     w.xty_partial, stream);
@@ -690,14 +742,34 @@ size_t nbpc_graph_layer_workspace_bytes(int B, int N, int M, int k, int q) {
     return gl_carve(nullptr, 0, B, N, M, k, q).bytes;
 }
 
+int nbpc_graph_layer_vin_supported(int k0, int k, int q, int64_t c) {
+#ifdef NBPC_HOST_EMU
+    (void)k0; (void)k; (void)q; (void)c;
+    return 0;
+#else
+    return gl_use_fast() && g_nbpc_math_mode == NBPC_MATH_TF32X3 && k0 == 3 && gl_fused_ok(k, q, 0) && glt_fwd_vin_shape_ok(k0, k, q) &&
+                   glt_bwd_vin_shape_ok(k0, k, q, c) ? 1 : 0;
+#endif
+}
+
 int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge,
                          int B, int N, int M, int k, int q, const float *W, const float *bias, int is_last,
                          int relu, float *H_out, float *P_col, float *P_row, float *P_cube, void *workspace,
                          size_t ws_bytes, void *stream_) {
+    return nbpc_graph_layer_fwd_v(H_in, nullptr, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, 0, H_out, P_col, P_row,
+                                  P_cube, nullptr, nullptr, workspace, ws_bytes, stream_);
+}
+
+int nbpc_graph_layer_fwd_v(const float *H_in, const nbpc_virtual_input *vin, const int32_t *col, const int32_t *csrT_ptr,
+                           const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *bias, int is_last,
+                           int relu, int node_only, float *H_out, float *P_col, float *P_row, float *P_cube, float *Q_col_out,
+                           float *Q_row_out, void *workspace, size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
-    NBPC_ARG(H_in && col && csrT_ptr && csrT_edge && W && bias && H_out && P_col && P_row && P_cube && workspace,
+    NBPC_ARG((H_in || vin) && col && csrT_ptr && csrT_edge && W && bias && (H_out || node_only) && P_col && P_row && P_cube && workspace,
              "null pointer");
+    NBPC_ARG(!node_only || (Q_col_out && Q_row_out), "node_only needs Q_col_out / Q_row_out");
+    NBPC_ARG(!vin || (vin->E && vin->W1 && vin->Q_col && vin->Q_row), "virtual input: null pointer");
     NBPC_ARG(B >= 1 && N >= 1 && M >= 1 && k >= 1 && q >= 1, "bad sizes");
     const int64_t BN = (int64_t)B * N, c = BN * M;
     NBPC_ARG(c < ((int64_t)1 << 31), "B*N*M must fit int32");
@@ -710,9 +782,17 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
     const bool fast = gl_use_fast();
     (void)fast;
 #ifndef NBPC_HOST_EMU
-    if (fast && gl_fused_ok(k, q, is_last))
-        return gl_fwd_fused(H_in, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, H_out, P_col, P_row, P_cube, w, stream);
+    if (fast && gl_fused_ok(k, q, is_last)) {
+        GlVin V;
+        if (vin) { V.E = vin->E; V.W1 = vin->W1; V.Qc = vin->Q_col; V.Qr = vin->Q_row; }
+        return gl_fwd_fused(H_in, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, H_out, P_col, P_row, P_cube, w, stream,
+                            vin ? &V : nullptr, vin ? vin->k : 0, node_only, Q_col_out, Q_row_out);
+    }
 #endif
+    if (vin || node_only) {
+        nbpc_set_error("nbpc_graph_layer_fwd_v: virtual input / node-only mode needs the fused device path (see nbpc_graph_layer_vin_supported)");
+        return NBPC_EINVAL;
+    }
     // ---- pooling: P_row, P_col
     bool done = false;
 #ifndef NBPC_HOST_EMU
@@ -795,10 +875,19 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                          const float *W, const float *P_col, const float *P_row, const float *P_cube, int is_last,
                          int relu, int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
                          size_t ws_bytes, void *stream_) {
+    return nbpc_graph_layer_bwd_v(dOut, H_in, nullptr, H_out, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, P_col, P_row, P_cube, is_last, relu,
+                                  mask_input, dH_in, dW, dB, workspace, ws_bytes, stream_);
+}
+
+int nbpc_graph_layer_bwd_v(const float *dOut, const float *H_in, const nbpc_virtual_input *vin, const float *H_out, const int32_t *col,
+                           const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W,
+                           const float *P_col, const float *P_row, const float *P_cube, int is_last, int relu, int mask_input,
+                           float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
-    NBPC_ARG(dOut && H_in && col && csrT_ptr && csrT_edge && W && P_col && P_row && P_cube && dW && dB && workspace,
+    NBPC_ARG(dOut && (H_in || vin) && col && csrT_ptr && csrT_edge && W && P_col && P_row && P_cube && dW && dB && workspace,
              "null pointer");
+    NBPC_ARG(!vin || (vin->E && vin->W1 && vin->Q_col && vin->Q_row), "virtual input: null pointer");
     NBPC_ARG(!relu || H_out, "H_out is required when relu is set");
     NBPC_ARG(B >= 1 && N >= 1 && M >= 1 && k >= 1 && q >= 1, "bad sizes");
     const int64_t BN = (int64_t)B * N, c = BN * M;
@@ -816,10 +905,17 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
     const bool fast = gl_use_fast();
     (void)fast;
 #ifndef NBPC_HOST_EMU
-    if (fast && gl_fused_ok(k, q, is_last) && (!dH_in || k % 4 == 0))
+    if (fast && gl_fused_ok(k, q, is_last) && (!dH_in || k % 4 == 0)) {
+        GlVin V;
+        if (vin) { V.E = vin->E; V.W1 = vin->W1; V.Qc = vin->Q_col; V.Qr = vin->Q_row; }
         return gl_bwd_fused(dOut, H_in, H_out, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, P_col, P_row, P_cube, is_last, relu,
-                            mask_input, dH_in, dW, dB, w, stream);
+                            mask_input, dH_in, dW, dB, w, stream, vin ? &V : nullptr, vin ? vin->k : 0);
+    }
 #endif
+    if (vin) {
+        nbpc_set_error("nbpc_graph_layer_bwd_v: the virtual input needs the fused device path (see nbpc_graph_layer_vin_supported)");
+        return NBPC_EINVAL;
+    }
 
     // ---- dQ_row, dQ_col
     bool done = false;

@@ -70,7 +70,8 @@ static int glf_launch_edge_out_t(const float *H, const int32_t *col, const float
     constexpr int KS = (K == 3) ? 0 : glf_stride(K), QS = glf_stride(Q);
     const size_t smem = sizeof(float) * (size_t)(((K * Q + 3) / 4) * 4 + GLF_TE * QS + 2 * GLF_TE * KS);
     auto kern = glf_edge_out_kernel<K, Q, RELU>;
-    static int grid_cache = 0;
+    static int grid_cache_d[NBPC_MAX_DEVICES];   // per device
+    int &grid_cache = grid_cache_d[nbpc_device_slot()];
     const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;
     if (!grid_cache) grid_cache = glf_persistent_grid(kern, GLF_THREADS, smem);
     if (grid_cache < 0) return 1;
@@ -95,7 +96,8 @@ static int glf_launch_edge_bwd_t(const char *name, const float *dOut, const floa
     constexpr int TILE = GLF_TE * (KS + QS + (RELU ? QS : 0));
     const size_t smem = sizeof(float) * (size_t)(Q * KP + 2 * TILE);
     auto kern = glf_edge_bwd_kernel<K, Q, RELU, HAS_DH, MASK_IN>;
-    static int grid_cache = 0;
+    static int grid_cache_d[NBPC_MAX_DEVICES];   // per device
+    int &grid_cache = grid_cache_d[nbpc_device_slot()];
     if (!grid_cache) grid_cache = glf_persistent_grid(kern, GLF_THREADS, smem);
     if (grid_cache < 0) return -1;
     const int64_t ntiles = (c + GLF_TE - 1) / GLF_TE;

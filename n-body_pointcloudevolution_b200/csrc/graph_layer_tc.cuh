@@ -54,7 +54,8 @@ __device__ __forceinline__ void glf_store_warp_rows(const float *swarp, float *_
     }
 }
 static int gl_num_sms() {
-    static int sms = 0;
+    static int sms_d[NBPC_MAX_DEVICES];
+    int &sms = sms_d[nbpc_device_slot()];
     if (!sms) {
         int dev = 0;
         cudaGetDevice(&dev);

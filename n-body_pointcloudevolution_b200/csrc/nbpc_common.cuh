@@ -90,6 +90,20 @@ static inline int nbpc_memset_async(void *p, int v, size_t n, cudaStream_t s) {
 }
 #endif
 
+// per-device caches (occupancy / function attributes belong to a device): slot of the current device in a table of
+// NBPC_MAX_DEVICES entries (devices beyond the table share the last slot and are re-configured on every call by callers
+// that check `slot < NBPC_MAX_DEVICES - 1`)
+#define NBPC_MAX_DEVICES 64
+static inline int nbpc_device_slot() {
+#ifdef NBPC_HOST_EMU
+    return 0;
+#else
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return dev < 0 ? 0 : (dev >= NBPC_MAX_DEVICES ? NBPC_MAX_DEVICES - 1 : dev);
+#endif
+}
+
 // kernel name carrying the layer widths ("gl_edge_out_kernel[k=32,q=16]"); only built while profiling
 struct NbpcKName {
     char buf[96];

@@ -348,6 +348,11 @@ def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
     return _layer(_to_cuda(H_in, torch.float32), COO_feats, bN, layer_vars, is_last, False)
 
 
+# NBPC_VIRTUAL_FIRST_LAYER=0 keeps the first layer's output materialised (cross-check of the recomputing kernels)
+import os as _os
+_VIRTUAL_FIRST_LAYER = _os.environ.get("NBPC_VIRTUAL_FIRST_LAYER", "1") != "0"
+
+
 def _network(H0, coo, num_layers, dims, activation, model_vars):
     """Layer loop shared by the network functions.  A ReLU activation is fused into the layer kernel; any other
     callable is applied to the un-activated layer output."""
@@ -355,10 +360,25 @@ def _network(H0, coo, num_layers, dims, activation, model_vars):
     # inside this function every hidden tensor has exactly one consumer (the next layer), so the ReLU
     # backward of layer l is applied by layer l+1's edge kernel (input_relu) and layer l skips its own mask
     chain = fuse and num_layers > 1
-    H = _layer(H0, coo, dims, model_vars.get_layer_vars(0), False, fuse, input_relu=False, grad_premasked=chain)
-    if not fuse:
-        H = activation(H)
-    for layer_idx in range(1, num_layers):
+    first = 1
+    if fuse and num_layers >= 3 and not H0.requires_grad and _VIRTUAL_FIRST_LAYER:
+        # the first layer's (c, q) output is never materialised: layer 1 computes its node-level terms only and layer 2
+        # recomputes the rows it needs from the 12-byte edge features (ops.GraphLayerVirtualIn, csrc/graph_layer_vin.cuh)
+        b, N = dims
+        adj = _adjacency_of(coo, b, N)
+        (W0, B0), (W1, B1) = model_vars.get_layer_vars(0), model_vars.get_layer_vars(1)
+        W0 = W0 if isinstance(W0, torch.Tensor) and W0.dim() == 3 else torch.stack(list(W0[:4]))
+        W1 = W1 if isinstance(W1, torch.Tensor) and W1.dim() == 3 else torch.stack(list(W1[:4]))
+        k0, q0, q1 = W0.shape[1], W0.shape[2], W1.shape[2]
+        if H0.shape[1] == k0 and W1.shape[1] == q0 and ops.graph_layer_vin_supported(k0, q0, q1, H0.shape[0]):
+            Hv, Qc, Qr = ops.GraphLayerNodeOnly.apply(H0, W0, B0, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M)
+            H = ops.GraphLayerVirtualIn.apply(Hv, W1, B1, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M, True, True, H0, W0[0], Qc, Qr)
+            first = 2
+    if first == 1:
+        H = _layer(H0, coo, dims, model_vars.get_layer_vars(0), False, fuse, input_relu=False, grad_premasked=chain)
+        if not fuse:
+            H = activation(H)
+    for layer_idx in range(first, num_layers):
         is_last = layer_idx == num_layers - 1
         H = _layer(H, coo, dims, model_vars.get_layer_vars(layer_idx), is_last, fuse and not is_last,
                    input_relu=fuse, grad_premasked=fuse and not is_last)

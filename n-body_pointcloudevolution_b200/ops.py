@@ -352,6 +352,104 @@ def graph_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor,
     return dH, dW, dB
 
 
+def _vin_struct(vin):
+    E, W1, Qc, Qr = vin
+    return _lib.VirtualInput(E.data_ptr(), W1.data_ptr(), Qc.data_ptr(), Qr.data_ptr(), int(E.shape[1]))
+
+
+def graph_layer_vin_supported(k0: int, k: int, q: int, c: int) -> bool:
+    """Whether the next layer can consume a (k0 -> k) first layer's output as a VIRTUAL input (include/nbpc.h)."""
+    return bool(_lib.load().nbpc_graph_layer_vin_supported(int(k0), int(k), int(q), int(c)))
+
+
+class GraphLayerNodeOnly(torch.autograd.Function):
+    """First graph layer of a network whose output is consumed as a VIRTUAL input by the next layer: only the node-level
+    terms are computed (pooling of the edge features, Q_col, Q_row); the (c, q) edge tensor is never written.  Returns a
+    zero-stride placeholder of the output's shape (it carries the gradient dH1 back) plus Q_col, Q_row."""
+
+    @staticmethod
+    def forward(ctx, E, W, bias, col, csrT_ptr, csrT_edge, B, N, M):
+        _need_cuda(E, W, bias, col)
+        L = _lib.load()
+        E, W, bias = _f32c(E), _f32c(W), _f32c(bias)
+        k, q = W.shape[1], W.shape[2]
+        c, BN, dev = B * N * M, B * N, E.device
+        P_col = torch.empty((BN, k), dtype=torch.float32, device=dev)
+        P_row = torch.empty((BN, k), dtype=torch.float32, device=dev)
+        P_cube = torch.empty((B, k), dtype=torch.float32, device=dev)
+        Qc = torch.empty((BN, q), dtype=torch.float32, device=dev)
+        Qr = torch.empty((BN, q), dtype=torch.float32, device=dev)
+        ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+        with torch.cuda.device(dev):
+            rc = L.nbpc_graph_layer_fwd_v(_ptr(E), None, _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge), B, N, M, k, q, _ptr(W), _ptr(bias), 0, 1,
+                                          1, None, _ptr(P_col), _ptr(P_row), _ptr(P_cube), _ptr(Qc), _ptr(Qr), _ptr(ws), ws.numel(),
+                                          _stream())
+        _lib.check(rc, "nbpc_graph_layer_fwd_v")
+        ctx.save_for_backward(E, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube)
+        ctx.cfg = (B, N, M)
+        placeholder = torch.zeros(1, dtype=torch.float32, device=dev).expand(c, q)
+        ctx.mark_non_differentiable(Qc, Qr)
+        return placeholder, Qc, Qr
+
+    @staticmethod
+    def backward(ctx, g, _gqc, _gqr):
+        E, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube = ctx.saved_tensors
+        B, N, M = ctx.cfg
+        # g = dH1, already masked by the consumer (which recomputed H1): plain first-layer backward, no input gradient
+        _, dW, dB = graph_layer_bwd(g.contiguous(), E, g, col, csrT_ptr, csrT_edge, W, P_col, P_row, P_cube, B, N, M, False, False,
+                                    False, False)
+        return None, dW, dB, None, None, None, None, None, None
+
+
+class GraphLayerVirtualIn(torch.autograd.Function):
+    """Hidden graph layer whose input is the virtual tensor of GraphLayerNodeOnly: pooling, forward and backward edge
+    kernels recompute H1[e] = relu(E[e] W1 + Q_col[col[e]] + Q_row[e / M]) (csrc/graph_layer_vin.cuh)."""
+
+    @staticmethod
+    def forward(ctx, H_placeholder, W, bias, col, csrT_ptr, csrT_edge, B, N, M, relu, grad_premasked, E, W1a, Qc1, Qr1):
+        L = _lib.load()
+        W, bias = _f32c(W), _f32c(bias)
+        vin = (_f32c(E), _f32c(W1a), Qc1, Qr1)
+        k, q = W.shape[1], W.shape[2]
+        c, BN, dev = B * N * M, B * N, W.device
+        out = torch.empty((c, q), dtype=torch.float32, device=dev)
+        P_col = torch.empty((BN, k), dtype=torch.float32, device=dev)
+        P_row = torch.empty((BN, k), dtype=torch.float32, device=dev)
+        P_cube = torch.empty((B, k), dtype=torch.float32, device=dev)
+        ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+        vs = _vin_struct(vin)
+        with torch.cuda.device(dev):
+            rc = L.nbpc_graph_layer_fwd_v(None, ctypes.byref(vs), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge), B, N, M, k, q, _ptr(W),
+                                          _ptr(bias), 0, int(relu), 0, _ptr(out), _ptr(P_col), _ptr(P_row), _ptr(P_cube), None, None,
+                                          _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "nbpc_graph_layer_fwd_v")
+        ctx.save_for_backward(out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube, *vin)
+        ctx.cfg = (B, N, M, relu and not grad_premasked)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube, E, W1a, Qc1, Qr1 = ctx.saved_tensors
+        B, N, M, relu = ctx.cfg
+        if relu:
+            raise RuntimeError("virtual-input layer: the gradient must arrive pre-masked (graph._network chains the layers)")
+        L = _lib.load()
+        g = _f32c(g)
+        k, q = W.shape[1], W.shape[2]
+        c, dev = B * N * M, W.device
+        dH = torch.empty((c, k), dtype=torch.float32, device=dev)
+        dW = torch.empty((4, k, q), dtype=torch.float32, device=dev)
+        dB = torch.empty((q,), dtype=torch.float32, device=dev)
+        ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+        vs = _vin_struct((E, W1a, Qc1, Qr1))
+        with torch.cuda.device(dev):
+            rc = L.nbpc_graph_layer_bwd_v(_ptr(g), None, ctypes.byref(vs), _ptr(out), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge), B, N, M, k,
+                                          q, _ptr(W), _ptr(P_col), _ptr(P_row), _ptr(P_cube), 0, 0, 1, _ptr(dH), _ptr(dW), _ptr(dB),
+                                          _ptr(ws), ws.numel(), _stream())
+        _lib.check(rc, "nbpc_graph_layer_bwd_v")
+        return dH, dW, dB, None, None, None, None, None, None, None, None, None, None, None, None
+
+
 class GraphLayer(torch.autograd.Function):
     """shift_inv_layer (graph.py:394-456) [+ fused ReLU], backward through the CSR transpose.
 
