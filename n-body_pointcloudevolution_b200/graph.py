@@ -348,9 +348,20 @@ def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
     return _layer(_to_cuda(H_in, torch.float32), COO_feats, bN, layer_vars, is_last, False)
 
 
-# NBPC_VIRTUAL_FIRST_LAYER=0 keeps the first layer's output materialised (cross-check of the recomputing kernels)
+# Virtual first layer (csrc/graph_layer_vin.cuh): layer 1's (c, q) output is not materialised, layer 2's kernels recompute its
+# rows.  It removes 44 % of the step's HBM bytes and is bit-identical to the materialised path, but measured SLOWER on B200
+# (2.71 vs 2.00 ms per step at 8 x 32^3: four generator warps per CTA cannot keep enough L2 gathers in flight - the
+# materialising kernel does the same gathers with 2048 threads per SM), so it is opt-in: NBPC_VIRTUAL_FIRST_LAYER=1 or
+# set_virtual_first_layer(True).
 import os as _os
-_VIRTUAL_FIRST_LAYER = _os.environ.get("NBPC_VIRTUAL_FIRST_LAYER", "1") != "0"
+_VIRTUAL_FIRST_LAYER = _os.environ.get("NBPC_VIRTUAL_FIRST_LAYER", "0") == "1"
+
+
+def set_virtual_first_layer(on):
+    """Opt in / out of the recomputing (virtual first layer) kernels; returns the previous setting."""
+    global _VIRTUAL_FIRST_LAYER
+    old, _VIRTUAL_FIRST_LAYER = _VIRTUAL_FIRST_LAYER, bool(on)
+    return old
 
 
 def _network(H0, coo, num_layers, dims, activation, model_vars):

@@ -264,6 +264,35 @@ def test_train_py_forward_matches_oracle(nb):
     np.testing.assert_allclose(loss.item(), rloss.item(), rtol=2e-5)
 
 
+# =============================================================================== virtual first layer (graph_layer_vin.cuh)
+@pytest.mark.parametrize("b,N,M,ch", [(2, 4096, 14, [3, 32, 16, 3]), (3, 601, 10, [3, 16, 32, 3]), (1, 1000, 7, [3, 64, 16, 16, 3])])
+def test_virtual_first_layer_is_bit_identical(nb, syn, b, N, M, ch):
+    """The recomputing kernels (layer 1's output never materialised: virtual-input pooling, tcgen05 forward and backward with
+    generator warps) against the materialising path on the same inputs: prediction, loss and every gradient BIT-identical
+    (one shared expression produces the rows in every consumer)."""
+    x = torch.tensor(syn.make_box("clustered", b, N, 3), device=DEV)
+    za, tgt = (torch.tensor(t, device=DEV) for t in syn.za_features(b, N, 3))
+    outs = []
+    for virtual in (False, True):
+        old = nb.graph.set_virtual_first_layer(virtual)
+        try:
+            store = nb.train_utils.ParamStore(ch, device=DEV)
+            store.load_numpy(syn.glorot_params(ch))
+            mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+            coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, M))
+            n0 = nb._lib.launch_count()
+            pred = nb.graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, M))
+            loss = nb.nn.loss_ZA(pred, tgt)
+            store.zero_grad()
+            loss.backward()
+            torch.cuda.synchronize()
+            outs.append((pred.detach().clone(), float(loss.detach()), store.flat_grad.clone(), nb._lib.launch_count() - n0))
+        finally:
+            nb.graph.set_virtual_first_layer(old)
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
+    assert outs[1][3] == outs[0][3] - 1                       # one launch less: the first layer's edge kernel
+
+
 # =============================================================================== M = 1 (ADVICE: magic divisor overflow)
 @pytest.mark.parametrize("ch", [[3, 16, 3], [3, 32, 16, 3]])
 def test_graph_model_single_neighbour(nb, ch):
