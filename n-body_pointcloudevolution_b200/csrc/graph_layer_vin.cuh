@@ -64,16 +64,23 @@ __global__ void __launch_bounds__(GLV_THREADS) gln_pool_vin_kernel(const GlVin V
         float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
         const int64_t e0 = node * M;
         int m = 0;
-        for (; m + 2 <= M; m += 2) {   // two edges in flight
-            const int c0 = __ldg(&col[e0 + m]), c1 = __ldg(&col[e0 + m + 1]);
-            float x0[K0], x1[K0];
+        for (; m + 4 <= M; m += 4) {   // four edges in flight (two dependent L2 round trips each: col -> Q_col row)
+            int cc[4];
+            float x[4][K0];
+            float4 q[4];
 #pragma unroll
-            for (int kk = 0; kk < K0; ++kk) { x0[kk] = __ldg(&V.E[(e0 + m) * K0 + kk]); x1[kk] = __ldg(&V.E[(e0 + m + 1) * K0 + kk]); }
-            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(V.Qc + (int64_t)c0 * K + 4 * g));
-            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(V.Qc + (int64_t)c1 * K + 4 * g));
-            const float4 h0 = glv_row4<K0>(x0, w, q0, qr_own), h1 = glv_row4<K0>(x1, w, q1, qr_own);
-            rs.x += h0.x; rs.y += h0.y; rs.z += h0.z; rs.w += h0.w;
-            rs.x += h1.x; rs.y += h1.y; rs.z += h1.z; rs.w += h1.w;
+            for (int u = 0; u < 4; ++u) cc[u] = __ldg(&col[e0 + m + u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int kk = 0; kk < K0; ++kk) x[u][kk] = __ldg(&V.E[(e0 + m + u) * K0 + kk]);
+                q[u] = __ldg(reinterpret_cast<const float4 *>(V.Qc + (int64_t)cc[u] * K + 4 * g));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 h = glv_row4<K0>(x[u], w, q[u], qr_own);
+                rs.x += h.x; rs.y += h.y; rs.z += h.z; rs.w += h.w;
+            }
         }
         for (; m < M; ++m) {
             const int c0 = __ldg(&col[e0 + m]);
@@ -90,16 +97,23 @@ __global__ void __launch_bounds__(GLV_THREADS) gln_pool_vin_kernel(const GlVin V
         const int b = csrT_ptr[node], e = csrT_ptr[node + 1];
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         int p = b;
-        for (; p + 2 <= e; p += 2) {
-            const uint32_t ea = (uint32_t)__ldg(&csrT_edge[p]), eb = (uint32_t)__ldg(&csrT_edge[p + 1]);
-            float x0[K0], x1[K0];
+        for (; p + 4 <= e; p += 4) {
+            uint32_t ee[4];
+            float x[4][K0];
+            float4 q[4];
 #pragma unroll
-            for (int kk = 0; kk < K0; ++kk) { x0[kk] = __ldg(&V.E[(int64_t)ea * K0 + kk]); x1[kk] = __ldg(&V.E[(int64_t)eb * K0 + kk]); }
-            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(V.Qr + (int64_t)glv_div(ea, M, magic) * K + 4 * g));
-            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(V.Qr + (int64_t)glv_div(eb, M, magic) * K + 4 * g));
-            const float4 h0 = glv_row4<K0>(x0, w, qc_own, q0), h1 = glv_row4<K0>(x1, w, qc_own, q1);
-            cs.x += h0.x; cs.y += h0.y; cs.z += h0.z; cs.w += h0.w;
-            cs.x += h1.x; cs.y += h1.y; cs.z += h1.z; cs.w += h1.w;
+            for (int u = 0; u < 4; ++u) ee[u] = (uint32_t)__ldg(&csrT_edge[p + u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                for (int kk = 0; kk < K0; ++kk) x[u][kk] = __ldg(&V.E[(int64_t)ee[u] * K0 + kk]);
+                q[u] = __ldg(reinterpret_cast<const float4 *>(V.Qr + (int64_t)glv_div(ee[u], M, magic) * K + 4 * g));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 h = glv_row4<K0>(x[u], w, qc_own, q[u]);
+                cs.x += h.x; cs.y += h.y; cs.z += h.z; cs.w += h.w;
+            }
         }
         for (; p < e; ++p) {
             const uint32_t ea = (uint32_t)__ldg(&csrT_edge[p]);
