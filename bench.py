@@ -253,11 +253,13 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
         return n * (2 * 4 * q + 2 * 4 * k + 4)
     if base in ("glf_node_xty_dW2", "glf_node_xty_dW3"):       # node tensors X (n,k) and Y (n,q), once per layer
         return None
-    if base == "edge_features_kernel":
+    if base in ("edge_features_kernel", "edge_features_za_kernel"):
         return c * (4 + 12) + n * 12
     if base in ("adj_coo_kernel",):
         return c * (4 + 12)
-    if base in ("seg_count_kernel", "seg_fill_kernel"):
+    if base == "adj_coo_count_kernel":                         # idx in, COO rows + bucket rank out
+        return c * (4 + 12 + 4)
+    if base in ("seg_count_kernel", "seg_fill_kernel", "adj_fill_kernel"):
         return c * 8
     return None
 

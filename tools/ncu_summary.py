@@ -58,7 +58,10 @@ def main():
     except Exception:
         traffic = {}
     for rep in a.reports:
-        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        if rep.endswith(".csv"):     # `ncu -i x.ncu-rep --page raw --csv > x.csv` exported on the GPU box (reports > 64 MiB do not travel)
+            raw = open(rep).read()
+        else:
+            raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         head, units, body = rows[0], rows[1], rows[2:]
         col = {h: i for i, h in enumerate(head)}
