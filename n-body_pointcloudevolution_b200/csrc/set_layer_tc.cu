@@ -26,6 +26,8 @@
 
 #define SGT_CHUNK_BYTES (GLT_TILE * 128)   // one A stage: 128 rows x 32 floats
 #define SGT_DW_ROWS 32                     // rows per stage of the dW kernel
+#define SGT_CONV_WARPS 8                   // converter warps (centre + TF32 residual): 4 left the stage cycle latency-bound
+#define SGT_THREADS (192 + 32 * SGT_CONV_WARPS)
 #define SGT_COLSUM_ROWS 256                // rows per block of the column-sum pass (N = 32^3, B = 8: 1024 blocks)
 
 // x / d for 0 <= x < 2^31 with magic = floor(2^32 / d) (2^32 - 1 for d = 1): the estimate is exact or one short
@@ -121,7 +123,7 @@ struct SgtGemmArgs {
 };
 
 template <bool X3>
-__global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const SgtGemmArgs P) {
+__global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const SgtGemmArgs P) {
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
     const int S = P.S, L = X3 ? P.L : 0, K = P.K, NT = P.NT, KC = K >> 5;
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ C
     while (tmem_cols < 2 * NT) tmem_cols <<= 1;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), SGT_CONV_WARPS); }
         for (int l = 0; l < LB; ++l) glt_mbar_init(LOFREE(l), 1);
         for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
         glt_fence_barrier_init();
@@ -305,7 +307,7 @@ __global__ void __launch_bounds__(320) sgt_gemm_kernel(const __grid_constant__ C
                 const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample), last = (uint32_t)nbpc_min((int64_t)GLT_TILE - 1, P.rows - 1 - trow);
                 const float *mu0 = P.mu ? P.mu + s0 * K + c * 32 : nullptr;
 #pragma unroll 4
-                for (int g = wtid; g < SGT_CHUNK_BYTES / 16; g += 128) {       // 16-byte granules: row = g / 8
+                for (int g = wtid; g < SGT_CHUNK_BYTES / 16; g += 32 * SGT_CONV_WARPS) {       // 16-byte granules: row = g / 8
                     float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
                     if (P.mu) {
                         const int r = g >> 3, lu = (g & 7) ^ (r & 7);             // logical 16-byte unit inside the row
@@ -395,7 +397,7 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     if (gm < 1) gm = 1;
     if (gm > ntiles) gm = ntiles;
     const int grid = (int)(gm * P.n_ntiles);
-    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_gemm_tf32x3" : "sgt_gemm_tf32", K, Nout).c_str(), kern, grid, 320, smem, stream, tm, P);
+    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_gemm_tf32x3" : "sgt_gemm_tf32", K, Nout).c_str(), kern, grid, SGT_THREADS, smem, stream, tm, P);
     return 0;
 }
 
@@ -409,7 +411,7 @@ struct SgtDwArgs {
 };
 
 template <bool X3>
-__global__ void __launch_bounds__(320) sgt_dw_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ,
+__global__ void __launch_bounds__(SGT_THREADS) sgt_dw_kernel(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmZ,
                                                      const SgtDwArgs P) {
     constexpr int R = SGT_DW_ROWS, RCH = R * 128;                 // bytes of one [R rows x 32 floats] chunk
     static_assert(R == 32, "the converter's granule -> (chunk, row) mapping assumes 32-row chunks");
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(320) sgt_dw_kernel(const __grid_constant__ CUt
     while (tmem_cols < MB * q) tmem_cols <<= 1;
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), 4); }
+        for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), SGT_CONV_WARPS); }
         for (int l = 0; l < LB; ++l) glt_mbar_init(LOFREE(l), 1);
         glt_mbar_init(DONE, 1);
         glt_fence_barrier_init();
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(320) sgt_dw_kernel(const __grid_constant__ CUt
             const int n_valid = (int)nbpc_min((int64_t)R, P.rows - trow);
             const float *mu0 = P.mu ? P.mu + s0 * k : nullptr;
 #pragma unroll 4
-            for (int g = wtid; g < n_gran; g += 128) {
+            for (int g = wtid; g < n_gran; g += 32 * SGT_CONV_WARPS) {
                 float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
                 bool wrote = false;
                 if (g < h_gran && P.mu) {
@@ -613,7 +615,7 @@ int sgt_dw(const float *H, const float *dZ, const float *mu, int64_t rows, int r
     P.rps_magic = sgt_magic(rows_per_sample);
     const int64_t ntiles = (rows + SGT_DW_ROWS - 1) / SGT_DW_ROWS;
     const int grid = (int)nbpc_min((int64_t)gl_num_sms(), ntiles);
-    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_dw_tf32x3" : "sgt_dw_tf32", k, q).c_str(), kern, grid, 320, smem, stream, tmH, tmZ, P);
+    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_dw_tf32x3" : "sgt_dw_tf32", k, q).c_str(), kern, grid, SGT_THREADS, smem, stream, tmH, tmZ, P);
     NBPC_LAUNCH(sgt_dw_final_kernel, nbpc_cdiv(k * q, 256), 256, 0, stream, partial, grid, k * q, dW);
     return 0;
 }
