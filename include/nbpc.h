@@ -282,6 +282,12 @@ int nbpc_pbc_loss_bwd(const float *pred, int ld_pred, const float *truth, int ld
 int nbpc_periodic_boundary_dist(const float *pred, int ld_pred, const float *truth, int ld_truth,
                                 int64_t rows, float *dist_out, void *stream);
 int nbpc_readout(const float *h, int64_t rows, int C, float *out, void *stream);
+/* Scaled residual update of the multi-redshift model (graph.py:558-566, the reference's legacy block): X (rows, ldx >= 6) =
+ * [position, velocity], net (rows, C) with C = 3 | 6:  out[:, :3] = net[:, :3] * loc_scalar + loc + vel * vel_scalar,
+ * out[:, 3:6] = net[:, 3:6] * vel_scalar + vel.  Forward only (inference / rollout; with trainable scalars the facade
+ * composes the update from differentiable ops). */
+int nbpc_residual_update(const float *X, int ldx, const float *net, int C, int64_t rows, float loc_scalar, float vel_scalar,
+                         float *out, void *stream);
 
 /* ---------------------------------------------------------------- optimiser
  * tf.train.AdamOptimizer as used by train.py:70 (TF "epsilon-hat" form):

@@ -71,6 +71,7 @@ SIGNATURES = {
     "nbpc_pbc_loss_bwd": (_i, [_p, _i, _p, _i, _i64, _i, _p, _p, _i, _p]),
     "nbpc_periodic_boundary_dist": (_i, [_p, _i, _p, _i, _i64, _p, _p]),
     "nbpc_readout": (_i, [_p, _i64, _i, _p, _p]),
+    "nbpc_residual_update": (_i, [_p, _i, _p, _i, _i64, _f, _f, _p, _p]),
     "nbpc_linear": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p]),
     "nbpc_xty_workspace_bytes": (_sz, [_i64, _i, _i]),
     "nbpc_xty": (_i, [_p, _p, _i64, _i, _i, _p, _p, _sz, _p]),

@@ -225,6 +225,30 @@ int nbpc_periodic_boundary_dist(const float *pred, int ld_pred, const float *tru
     return nbpc_check_launch("nbpc_periodic_boundary_dist");
 }
 
+// scaled residual update of the multi-redshift model (graph.py:558-566): X (rows, >= 6) = [loc, vel], net (rows, C), C = 3 | 6
+//   out[:, :3] = net[:, :3] * loc_scalar + loc + vel * vel_scalar;   out[:, 3:6] = net[:, 3:6] * vel_scalar + vel   (C = 6)
+__global__ void residual_update_kernel(const float *__restrict__ X, int ldx, const float *__restrict__ net, int C, int64_t rows,
+                                       float loc_scalar, float vel_scalar, float *__restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * C) return;
+    const int64_t r = t / C;
+    const int ch = (int)(t % C);
+    const float n = net[t];
+    if (ch < 3) out[t] = n * loc_scalar + X[r * ldx + ch] + X[r * ldx + 3 + ch] * vel_scalar;
+    else out[t] = n * vel_scalar + X[r * ldx + ch];
+}
+
+int nbpc_residual_update(const float *X, int ldx, const float *net, int C, int64_t rows, float loc_scalar, float vel_scalar, float *out,
+                         void *stream_) {
+    NBPC_TRY(nbpc_require_sm100());
+    cudaStream_t stream = (cudaStream_t)stream_;
+    NBPC_ARG(X && net && out, "null pointer");
+    NBPC_ARG(rows >= 1 && (C == 3 || C == 6) && ldx >= 6, "bad sizes");
+    NBPC_LAUNCH(residual_update_kernel, nbpc_cdiv(rows * C, LOSS_THREADS), LOSS_THREADS, 0, stream, X, ldx, net, C, rows, loc_scalar,
+                vel_scalar, out);
+    return nbpc_check_launch("nbpc_residual_update");
+}
+
 int nbpc_readout(const float *h, int64_t rows, int C, float *out, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -120,6 +120,8 @@ struct SgtGemmArgs {
     int64_t rows;
     int rows_per_sample, K, NT, Ntot, n_ntiles, b_transposed, relu, S, L;
     uint32_t rps_magic;      // floor(2^32 / rows_per_sample) (2^32 - 1 for 1): sample of a row without a 64-bit division
+    int dbg;                 // NBPC_SGT_DEBUG (profiling experiments only, results are WRONG): 1 no output stores, 2 no epilogue
+                             // work at all, 4 converters only signal
 };
 
 template <bool X3>
@@ -234,13 +236,21 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
         // ---------------- epilogue warps: quadrant qd owns TMEM lanes / tile rows [32 qd, 32 qd + 32)
         const int qd = warp & 3;
         float *Ow = Os + qd * 32 * 36;
-        const int vec_per_row = SW >> 2, iters = vec_per_row;     // 32 rows * SW/4 float4 = 32 lanes * iters
+        const int vshift = SW == 32 ? 3 : 2, vmask = (1 << vshift) - 1, iters = 1 << vshift;   // 32 rows * SW/4 float4 = 32 lanes * iters
+        // (shifts: a runtime division by SW/4 in the two loops below cost more than the stores)
         int a = 0, aph = 0;
         for (int64_t t = cta_m; t < ntiles; t += Gm) {
             const int64_t row0 = t * GLT_TILE + qd * 32;
             glt_mbar_wait(TFULL(a), aph);
             glt_tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * NT;
+            if (P.dbg & 2) {
+                glt_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) glt_mbar_arrive(TEMPTY(a));
+                if (++a == 2) { a = 0; aph ^= 1; }
+                continue;
+            }
             for (int cb = 0; cb < NT; cb += SW) {
                 // the input-mask rows of this slab are requested first: 8 independent loads in flight (issued one by one in
                 // front of each store they cost one HBM round trip per row segment: 5.5 us per slab)
@@ -248,7 +258,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                 if (P.mask) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int idx = i * 32 + lane, r = idx / vec_per_row, c4 = idx % vec_per_row;
+                        const int idx = i * 32 + lane, r = idx >> vshift, c4 = idx & vmask;
                         if (i < iters && row0 + r < P.rows) mk[i] = glf_ldg4(P.mask + (row0 + r) * P.Ntot + n0 + cb + 4 * c4);
                     }
                 }
@@ -276,9 +286,9 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int idx = i * 32 + lane, r = idx / vec_per_row, c4 = idx % vec_per_row;
+                    const int idx = i * 32 + lane, r = idx >> vshift, c4 = idx & vmask;
                     const int64_t grow = row0 + r;
-                    if (i < iters && grow < P.rows) {
+                    if (i < iters && grow < P.rows && !(P.dbg & 1)) {
                         float4 v = *reinterpret_cast<const float4 *>(Ow + r * PITCH + 4 * c4);
                         if (P.mask) {
                             const float4 m = mk[i];
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                 const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample), last = (uint32_t)nbpc_min((int64_t)GLT_TILE - 1, P.rows - 1 - trow);
                 const float *mu0 = P.mu ? P.mu + s0 * K + c * 32 : nullptr;
 #pragma unroll 4
-                for (int g = wtid; g < SGT_CHUNK_BYTES / 16; g += 32 * SGT_CONV_WARPS) {       // 16-byte granules: row = g / 8
+                for (int g = (P.dbg & 4) ? SGT_CHUNK_BYTES : wtid; g < SGT_CHUNK_BYTES / 16; g += 32 * SGT_CONV_WARPS) {   // 16-byte granules: row = g / 8
                     float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
                     if (P.mu) {
                         const int r = g >> 3, lu = (g & 7) ^ (r & 7);             // logical 16-byte unit inside the row
@@ -392,6 +402,12 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     P.Bsrc = Bsrc; P.mu = mu; P.bias = bias; P.mask = mask; P.out = out; P.rows = rows; P.rows_per_sample = rows_per_sample;
     P.K = K; P.NT = NT; P.Ntot = Nout; P.n_ntiles = Nout / NT; P.b_transposed = b_transposed; P.relu = relu; P.S = S; P.L = L;
     P.rps_magic = sgt_magic(rows_per_sample);
+    static int dbg = -1;
+    if (dbg < 0) {
+        const char *e = getenv("NBPC_SGT_DEBUG");
+        dbg = e ? atoi(e) : 0;
+    }
+    P.dbg = dbg;
     const int64_t ntiles = (rows + GLT_TILE - 1) / GLT_TILE;
     int64_t gm = gl_num_sms() / P.n_ntiles;
     if (gm < 1) gm = 1;

@@ -419,6 +419,9 @@ def model_func_shift_inv(X_in, COO_feats, model_vars, dims, activation=torch.rel
     edges, nodes = get_input_features_shift_inv(X, COO_feats, dims)
     net_out = network_func_shift_inv(edges, nodes, COO_feats, num_layers, dims[:-1], activation, model_vars, redshift)
     loc_scalar, vel_scalar = model_vars.get_scalars()
+    if (not torch.is_grad_enabled() or not (net_out.requires_grad or isinstance(loc_scalar, torch.Tensor))) and \
+            not isinstance(loc_scalar, torch.Tensor) and not isinstance(vel_scalar, torch.Tensor) and net_out.shape[-1] in (3, 6):
+        return ops.residual_update(X, net_out, loc_scalar, vel_scalar)      # inference / rollout: one kernel
     loc, vel = X[..., :3], X[..., 3:]
     H_out = net_out[..., :3] * loc_scalar + loc + vel * vel_scalar
     if net_out.shape[-1] > 3:

@@ -699,6 +699,20 @@ def readout(h: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def residual_update(X: torch.Tensor, net: torch.Tensor, loc_scalar: float, vel_scalar: float) -> torch.Tensor:
+    """graph.py:558-566 in one kernel (forward only): X (..., >= 6) = [loc, vel], net (..., 3 | 6)."""
+    _need_cuda(X, net)
+    L = _lib.load()
+    X, net = _f32c(X), _f32c(net)
+    C, ldx = net.shape[-1], X.shape[-1]
+    rows = net.numel() // C
+    out = torch.empty_like(net)
+    with torch.cuda.device(net.device):
+        rc = L.nbpc_residual_update(_ptr(X), ldx, _ptr(net), C, rows, float(loc_scalar), float(vel_scalar), _ptr(out), _stream())
+    _lib.check(rc, "nbpc_residual_update")
+    return out
+
+
 class Readout(torch.autograd.Function):
     """get_readout (nn.py:107-119): d readout / d h = 1 almost everywhere (tf.sign has zero gradient)."""
 
