@@ -205,6 +205,12 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     } else if (warp == 1) {
         if (lane == 0) {   // ---------------- MMA issuer
             const uint32_t idesc = glt_idesc_tf32(GLT_TILE, NT, 0, 0);
+            // The issuing thread's own instruction stream bounds the chunk rate (one thread, ~5 cycles per dependent
+            // instruction): descriptors are built ONCE and advanced by adding to their 14-bit address field (units of 16 bytes:
+            // +2 per 8-float K step, +1024 per 16 KB stage, + NT * 8 per weight chunk)
+            const uint64_t a_hi0 = glt_smem_desc(glt_smem_u32(As), 16, 1024, 2), a_lo0 = glt_smem_desc(glt_smem_u32(Al), 16, 1024, 2);
+            const uint64_t b_hi0 = glt_smem_desc(glt_smem_u32(Bh), 16, 1024, 2), b_lo0 = glt_smem_desc(glt_smem_u32(Bl), 16, 1024, 2);
+            const uint32_t b_step = (uint32_t)NT * 8;
             int s = 0, ph = 0, a = 0, aph = 0, l = 0;
             for (int64_t t = cta_m; t < ntiles; t += Gm) {
                 glt_mbar_wait(TEMPTY(a), aph ^ 1);
@@ -213,14 +219,14 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                 for (int c = 0; c < KC; ++c) {
                     glt_mbar_wait(CONV(s), ph);
                     glt_tc_fence_after();
-                    const uint32_t a_hi = glt_smem_u32(As + s * SGT_CHUNK_BYTES), a_lo = glt_smem_u32(Al + l * SGT_CHUNK_BYTES);
-                    const uint32_t b_hi = glt_smem_u32(Bh) + c * NT * 128, b_lo = glt_smem_u32(Bl) + c * NT * 128;
+                    const uint64_t a_hi = a_hi0 + (uint64_t)(s * (SGT_CHUNK_BYTES >> 4)), a_lo = a_lo0 + (uint64_t)(l * (SGT_CHUNK_BYTES >> 4));
+                    const uint64_t b_hi = b_hi0 + (uint64_t)(c * b_step), b_lo = b_lo0 + (uint64_t)(c * b_step);
 #pragma unroll
                     for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {   // small terms first: lo*hi, hi*lo, hi*hi
-                        const uint32_t ab = (pass == 0) ? a_lo : a_hi, bb = (pass == 1) ? b_lo : b_hi;
+                        const uint64_t ab = (pass == 0) ? a_lo : a_hi, bb = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
                         for (int k8 = 0; k8 < 4; ++k8) {
-                            glt_mma_tf32(d, glt_smem_desc(ab + k8 * 32, 16, 1024, 2), glt_smem_desc(bb + k8 * 32, 16, 1024, 2), idesc, acc);
+                            glt_mma_tf32(d, ab + 2 * k8, bb + 2 * k8, idesc, acc);
                             acc = 1;
                         }
                     }
@@ -482,22 +488,25 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_dw_kernel(const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {   // ---------------- MMA issuer: D[mb] (M2 x q) += H'[mb]^T (MN-major) * dZ' (MN-major)
             const uint32_t idesc = glt_idesc_tf32(M2, q, 1, 1);
+            // descriptors built once, advanced through the address field (16-byte units): +64 per 8-row K step,
+            // + 4 chunks per M block, + STAGE per ring slot
+            const uint64_t h_hi0 = glt_smem_desc(glt_smem_u32(St), RCH, 512, 1), h_lo0 = glt_smem_desc(glt_smem_u32(Sl), RCH, 512, 1);
+            const uint32_t st_step = (uint32_t)STAGE >> 4, z_off = (uint32_t)H_BYTES >> 4, mb_step = (uint32_t)(4 * RCH) >> 4;
             int s = 0, ph = 0, l = 0;
             uint32_t acc = 0;
             for (int64_t t = blockIdx.x; t < ntiles; t += G) {
                 glt_mbar_wait(CONV(s), ph);
                 glt_tc_fence_after();
-                const uint32_t h_hi = glt_smem_u32(St + s * STAGE), z_hi = h_hi + H_BYTES;
-                const uint32_t h_lo = glt_smem_u32(Sl + l * STAGE), z_lo = h_lo + H_BYTES;
+                const uint64_t h_hi = h_hi0 + (uint64_t)(s * st_step), z_hi = h_hi + z_off;
+                const uint64_t h_lo = h_lo0 + (uint64_t)(l * st_step), z_lo = h_lo + z_off;
                 for (int mb = 0; mb < MB; ++mb) {
                     uint32_t a2 = acc;
 #pragma unroll
                     for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {
-                        const uint32_t hb = ((pass == 0) ? h_lo : h_hi) + mb * 4 * RCH, zb = (pass == 1) ? z_lo : z_hi;
+                        const uint64_t hb = ((pass == 0) ? h_lo : h_hi) + (uint64_t)(mb * mb_step), zb = (pass == 1) ? z_lo : z_hi;
 #pragma unroll
                         for (int k8 = 0; k8 < R / 8; ++k8) {   // 8 rows per MMA = two 4-row swizzle atoms (SBO 512); LBO = chunk stride
-                            glt_mma_tf32(tmem_base + mb * q, glt_smem_desc(hb + k8 * 1024, RCH, 512, 1), glt_smem_desc(zb + k8 * 1024, RCH, 512, 1),
-                                         idesc, a2);
+                            glt_mma_tf32(tmem_base + mb * q, hb + 64 * k8, zb + 64 * k8, idesc, a2);
                             a2 = 1;
                         }
                     }
