@@ -196,10 +196,10 @@ __device__ __forceinline__ float glt_to_tf32(float x) {
 // produced, at the same position of a second buffer.  hi * hi + hi * lo + lo * hi then carries ~2^-20 relative error per
 // product instead of 2^-11.  128 converter threads, one 16-byte granule per thread per step, 4 loads in flight.
 __device__ __forceinline__ float glt_residual(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-template <int N_FLOATS>
+template <int N_FLOATS, int NTHREADS = 128>
 __device__ __forceinline__ void glt_split_inplace(const float *hi, float *lo, int tid) {
-    constexpr int STEP = 128 * 4, NSTEP = N_FLOATS / STEP;
-    static_assert(N_FLOATS % STEP == 0, "tile size must be a multiple of 512 floats");
+    constexpr int STEP = NTHREADS * 4, NSTEP = N_FLOATS / STEP;
+    static_assert(N_FLOATS % STEP == 0, "tile size must be a multiple of 4 floats per converter thread");
     int s = 0;
 #pragma unroll 1
     for (; s + 4 <= NSTEP; s += 4) {

@@ -98,7 +98,8 @@ def test_set_model_default_widths_golden(nb, syn):
 
 
 @pytest.mark.parametrize("mode", ["tf32x3", "fp32", "tf32"])
-@pytest.mark.parametrize("b,N,ch", [(3, 1000, [6, 64, 128, 32, 3]), (2, 333, [6, 32, 256, 64, 16, 3]), (1, 4096, [6, 128, 128, 3])])
+@pytest.mark.parametrize("b,N,ch", [(3, 1000, [6, 64, 128, 32, 3]), (2, 333, [6, 32, 256, 64, 16, 3]), (1, 4096, [6, 128, 128, 3]),
+                                    (2, 50, [6, 64, 32, 3]), (5, 7, [6, 32, 32, 3])])
 def test_set_model_tensor_core_shapes_vs_oracle(nb, mode, b, N, ch):
     """The tcgen05 set-layer kernels (row GEMM with in-place mean subtraction, MN-major dW GEMM, fused input mask) on ragged
     shapes: N not a multiple of the 128-row tile (tiles straddle samples), two N tiles (k=32 -> q=256 backward), the narrow
