@@ -58,7 +58,8 @@ def parse():
 def common_config(a, world):
     """The keys both arms print identically (the driver compares the arms' configs)."""
     N = a.n_side ** 3
-    return {"workload": workload_name(a), "particles_per_step_per_gpu": a.batch * N, "edges_per_step_per_gpu": a.batch * N * a.k}
+    return {"workload": workload_name(a), "particles_per_step_per_gpu": a.batch * N, "edges_per_step_per_gpu": a.batch * N * a.k,
+            "l2": "inputs larger than L2: a step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"}
 
 
 def workload_name(a):
@@ -741,11 +742,9 @@ def main():
                          f"(kNN: sklearn KD-tree, 1 thread as shipped; layers: torch-CPU, {cores} threads)",
                "stage_s": stage}
 
-    cfg = common_config(a, world)
-    cfg.update({"math_mode": lib.get_math_mode(), "launch": graph_note, "particles_per_step": particles,
-                "edges_per_step": particles * k,
-                "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)",
-                "l2": "step streams ~5 GB of edge tensors (>> 126 MB L2) and rotates 4 distinct input batches"})
+    cfg = common_config(a, world)                                     # identical in both arms
+    arm = {"math_mode": lib.get_math_mode(), "launch": graph_note, "particles_per_step": particles, "edges_per_step": particles * k,
+           "parallelism": f"dp{world} (sample-sharded, 1 NCCL all-reduce of {store.flat.numel()} floats/step)"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -753,6 +752,7 @@ def main():
                   "tf32": "tf32 (tcgen05 single pass, FP32 accumulate)"}[lib.get_math_mode()],
         "data": "synthetic",
         "config": cfg,
+        "arm": arm,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4,
