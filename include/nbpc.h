@@ -92,6 +92,16 @@ long long nbpc_prof_report(char *buf, size_t cap);
  *   The Python facade exposes it as KnnCSR.check().
  * Requires 1 <= k <= NBPC_KNN_MAX_K and k <= N - (include_self ? 0 : 1). */
 size_t nbpc_knn_workspace_bytes(int B, int N, int k, int periodic);
+/* Query kernel of nbpc_knn (same result bit for bit, different work distribution):
+ *   NBPC_KNN_AUTO    thread-per-query for k <= 16, warp-per-query for 16 < k <= 32 (measured crossover)
+ *   NBPC_KNN_THREAD  one thread per query, register-resident sorted list, warp-uniform loops with deferred insertion
+ *   NBPC_KNN_WARP    one warp per query (k <= 32): FP32 keys sorted across the lanes, FP64 re-evaluation of the survivors
+ * The process default comes from the environment variable NBPC_KNN_V (2 = thread, 3 = warp), else NBPC_KNN_AUTO. */
+#define NBPC_KNN_AUTO 0
+#define NBPC_KNN_THREAD 2
+#define NBPC_KNN_WARP 3
+int nbpc_set_knn_kernel(int kernel);
+int nbpc_get_knn_kernel(void);
 int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N, int k,
              int periodic, double boundary_threshold, int include_self, int order,
              int32_t *idx_out, double *d2_out, int32_t *status, void *workspace, size_t ws_bytes, void *stream);

@@ -9,6 +9,7 @@ fallback: calls raise RuntimeError without an sm_100 GPU.
 """
 from . import _lib  # noqa: F401
 from . import synthetic  # noqa: F401
+from ._lib import get_knn_kernel, set_knn_kernel  # noqa: F401  (thread-per-query | warp-per-query kNN kernel)
 from ._lib import get_math_mode, set_math_mode  # noqa: F401  (fp32 | tf32x3 | tf32 edge-level arithmetic)
 
 __all__ = ["_lib", "synthetic", "ops", "graph", "nn", "train_utils"]

@@ -29,6 +29,8 @@ SIGNATURES = {
     "nbpc_device_check": (_i, []),
     "nbpc_set_math_mode": (_i, [_i]),
     "nbpc_get_math_mode": (_i, []),
+    "nbpc_set_knn_kernel": (_i, [_i]),
+    "nbpc_get_knn_kernel": (_i, []),
     "nbpc_launch_count": (ctypes.c_longlong, []),
     "nbpc_prof_enable": (_i, [_i]),
     "nbpc_prof_report": (ctypes.c_longlong, [ctypes.c_char_p, _sz]),
@@ -130,6 +132,20 @@ def set_math_mode(mode):
 def get_math_mode():
     m = int(load().nbpc_get_math_mode())
     return {v: k for k, v in MATH_MODES.items()}[m]
+
+
+KNN_KERNELS = {"auto": 0, "thread": 2, "warp": 3}
+
+
+def set_knn_kernel(kernel):
+    """Query kernel of nbpc_knn: 'auto' (by k), 'thread' (one thread per query) or 'warp' (one warp per query, k <= 32).
+    Same result bit for bit; process-global; see include/nbpc.h."""
+    check(load().nbpc_set_knn_kernel(KNN_KERNELS[kernel] if isinstance(kernel, str) else int(kernel)), "nbpc_set_knn_kernel")
+
+
+def get_knn_kernel():
+    k = int(load().nbpc_get_knn_kernel())
+    return {v: n for n, v in KNN_KERNELS.items()}.get(k, str(k))
 
 
 def launch_count():

@@ -220,6 +220,9 @@ struct KnnQueryParams {
     int32_t *idx_out;
     double *d2_out;
     int B, N, G, k, include_self, order;
+    // thread-per-query kernels only: when set, thread t answers query todo[t] for t < *todo_count (the queries the
+    // warp-cooperative kernel handed over) instead of query t
+    const int32_t *todo, *todo_count;
 };
 
 template <int K, bool PERIODIC>
@@ -359,10 +362,12 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_uniform(KnnQueryParams 
     int *pend_i = pend_i_s + threadIdx.x;
     int npend = 0;
 
-    const int64_t total = (int64_t)P.B * P.N;
+    const int64_t total = P.todo ? (int64_t)*P.todo_count : (int64_t)P.B * P.N;
+    if ((int64_t)blockIdx.x * blockDim.x >= total) return;
     const int64_t s_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = s_raw < total;
-    const int64_t s = valid ? s_raw : total - 1;       // tail lanes shadow the last query and never write
+    const int64_t s_lin = valid ? s_raw : total - 1;   // tail lanes shadow the last query and never write
+    const int64_t s = P.todo ? (int64_t)P.todo[s_lin] : s_lin;
     const int b = (int)(s / P.N);
     const int G = P.G;
     const KnnGridInfo gi = P.info[b];
@@ -501,6 +506,9 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_query_uniform(KnnQueryParams 
     for (int m = 0; m < K; ++m)
         if (m >= K - P.k) P.idx_out[out + (m - (K - P.k))] = top.id[m];
 }
+
+// ------------------------------------------------------------------ 3c. query, one warp per query (lanes = candidates)
+#include "knn_warp.cuh"
 #endif
 
 // ------------------------------------------------------------------ host side
@@ -527,6 +535,7 @@ struct KnnWorkspace {
     int32_t *cell_of_point;
     float4 *sorted;
     int32_t *partials;
+    int32_t *todo_count;  // [1] queries handed from the warp-cooperative kernel to the thread-per-query kernel
     size_t bytes;
 };
 
@@ -541,31 +550,61 @@ static KnnWorkspace knn_carve(void *ws, size_t ws_bytes, int B, int N, int G) {
     w.cell_of_point = a.take<int32_t>((size_t)B * N);
     w.sorted = a.take<float4>((size_t)B * N);
     w.partials = a.take<int32_t>(nbpc_scan_partials_count(ncell + 1));
+    w.todo_count = a.take<int32_t>(4);
     w.bytes = a.off;
     return w;
 }
 
+// NBPC_KNN_V: 1 = per-thread traversal, 2 = warp-uniform thread-per-query kernel with deferred insertion,
+// 3 = warp-per-query kernel (k <= 32) with kernel 2 answering the queries it hands over, 0 / unset = by k
+static int knn_version_from_env() {
+    const char *e = getenv("NBPC_KNN_V");
+    const int v = e ? atoi(e) : NBPC_KNN_AUTO;
+    return (v >= 0 && v <= 3) ? v : NBPC_KNN_AUTO;
+}
+static int g_knn_version = knn_version_from_env();
+
 template <int K>
-static void knn_launch_query(const KnnQueryParams &P, int periodic, cudaStream_t stream) {
-    const int grid = nbpc_cdiv((int64_t)P.B * P.N, KNN_THREADS);
+static int knn_launch_query(KnnQueryParams P, int periodic, int32_t *todo, int32_t *todo_count, cudaStream_t stream) {
+    const int64_t nq = (int64_t)P.B * P.N;
+    const int grid = nbpc_cdiv(nq, KNN_THREADS);
+    P.todo = nullptr;
+    P.todo_count = nullptr;
 #ifndef NBPC_HOST_EMU
-    // warp-uniform kernel with deferred insertion by default; NBPC_KNN_V=1 selects the per-thread traversal
-    static int version = 0;
-    if (!version) {
-        const char *e = getenv("NBPC_KNN_V");
-        version = (e && atoi(e) == 1) ? 1 : 2;
+    // measured crossover: the warp-per-query kernel wins from the 32-wide list on (k > 16), see DESIGN.md 4.1
+    const int version = g_knn_version != NBPC_KNN_AUTO ? g_knn_version : (P.k > 16 ? NBPC_KNN_WARP : NBPC_KNN_THREAD);
+    void (*kern2)(KnnQueryParams) = periodic ? knn_query_uniform<K, true> : knn_query_uniform<K, false>;
+    if (version == 3 && P.k <= 32) {
+        if (nbpc_memset_async(todo_count, 0, sizeof(int32_t), stream)) return 1;
+        void (*kern3)(KnnQueryParams, int32_t *, int32_t *) = periodic ? knn_query_warp<true> : knn_query_warp<false>;
+        NBPC_LAUNCH_N("knn_query_warp", kern3, dim3(nbpc_cdiv(P.N, KNW_WARPS), P.B), KNW_THREADS, 0, stream, P, todo, todo_count);
+        P.todo = todo;
+        P.todo_count = todo_count;
+        NBPC_LAUNCH_N("knn_query_todo", kern2, grid, KNN_THREADS, 0, stream, P);
+        return 0;
     }
-    if (version == 2) {
-        void (*kern2)(KnnQueryParams) = periodic ? knn_query_uniform<K, true> : knn_query_uniform<K, false>;
+    if (version >= 2) {
         NBPC_LAUNCH_N("knn_query", kern2, grid, KNN_THREADS, 0, stream, P);
-        return;
+        return 0;
     }
 #endif
     void (*kern)(KnnQueryParams) = periodic ? knn_query<K, true> : knn_query<K, false>;
     NBPC_LAUNCH_N("knn_query", kern, grid, KNN_THREADS, 0, stream, P);
+    return 0;
 }
 
 extern "C" {
+
+int nbpc_set_knn_kernel(int kernel) {
+    if (kernel != NBPC_KNN_AUTO && kernel != 1 && kernel != NBPC_KNN_THREAD && kernel != NBPC_KNN_WARP) {
+        nbpc_set_error("nbpc_set_knn_kernel: unknown kernel");
+        return NBPC_EINVAL;
+    }
+    g_knn_version = kernel;
+    return NBPC_OK;
+}
+
+int nbpc_get_knn_kernel(void) { return g_knn_version; }
 
 size_t nbpc_knn_workspace_bytes(int B, int N, int k, int periodic) {
     (void)k; (void)periodic;
@@ -622,12 +661,19 @@ int nbpc_knn(const float *xyz, int64_t stride_b, int64_t stride_n, int B, int N,
     P.sorted = w.sorted; P.cell_start = w.cell_start; P.info = w.info;
     P.idx_out = idx_out; P.d2_out = d2_out;
     P.B = B; P.N = N; P.G = G; P.k = k; P.include_self = include_self; P.order = order;
-    if (k <= 8) knn_launch_query<8>(P, periodic, stream);
+    P.todo = nullptr; P.todo_count = nullptr;
+    // cell_of_point is dead after the scatter: it becomes the todo list of the warp-per-query kernel
+    int rc;
+    if (k <= 8) rc = knn_launch_query<8>(P, periodic, w.cell_of_point, w.todo_count, stream);
     // the reference's default k = 14 gets its own list length (13 % faster than the padded 16-wide list at 8 x 32^3)
-    else if (k <= 14) knn_launch_query<14>(P, periodic, stream);
-    else if (k <= 16) knn_launch_query<16>(P, periodic, stream);
-    else if (k <= 32) knn_launch_query<32>(P, periodic, stream);
-    else knn_launch_query<64>(P, periodic, stream);
+    else if (k <= 14) rc = knn_launch_query<14>(P, periodic, w.cell_of_point, w.todo_count, stream);
+    else if (k <= 16) rc = knn_launch_query<16>(P, periodic, w.cell_of_point, w.todo_count, stream);
+    else if (k <= 32) rc = knn_launch_query<32>(P, periodic, w.cell_of_point, w.todo_count, stream);
+    else rc = knn_launch_query<64>(P, periodic, w.cell_of_point, w.todo_count, stream);
+    if (rc) {
+        nbpc_set_error("nbpc_knn: memset failed");
+        return NBPC_ELAUNCH;
+    }
     return nbpc_check_launch("nbpc_knn");
 }
 

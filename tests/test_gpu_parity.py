@@ -42,8 +42,16 @@ def cuda_model_vars(g, channels, n_w=4):
 
 
 # =============================================================================== kNN
+@pytest.fixture(params=["thread", "warp"])
+def knn_kernel(nb, request):
+    """Both query kernels must produce the reference's answer bit for bit (the default picks one by k)."""
+    nb.set_knn_kernel(request.param)
+    yield request.param
+    nb.set_knn_kernel("auto")
+
+
 @pytest.mark.parametrize("kind", ["uniform", "clustered"])
-def test_knn_16_golden(nb, kind):
+def test_knn_16_golden(nb, kind, knn_kernel):
     g = load_golden("knn_16.npz")
     for seed in (0, 1, 2):
         tag = f"{kind}_s{seed}"
@@ -64,7 +72,7 @@ def test_knn_16_golden(nb, kind):
             assert np.array_equal(Ao[1].indices.cpu().numpy(), g[f"knl_{tag}"][1].reshape(-1).astype(np.int64) + 4096)
 
 
-def test_knn_32_golden_hashes(nb, syn):
+def test_knn_32_golden_hashes(nb, syn, knn_kernel):
     g = load_golden("knn_32.npz")
     for kind in ("uniform", "clustered"):
         x = syn.make_box(kind, 1, 32768, 0)
@@ -81,7 +89,7 @@ def test_knn_32_golden_hashes(nb, syn):
     (5000, 1, False, 0.0, True), (5000, 64, False, 0.0, True), (777, 33, True, 0.5, True),
     (3000, 14, True, 0.05, False), (64, 63, False, 0.0, False), (9, 8, True, 0.5, False), (1, 1, False, 0.0, True),
 ])
-def test_knn_vs_exact_oracle(nb, N, k, periodic, thr, inc):
+def test_knn_vs_exact_oracle(nb, N, k, periodic, thr, inc, knn_kernel):
     x = np.random.default_rng(N + k).random((2, N, 3)).astype(np.float32)
     idx, d2, _ = nb.ops.knn(torch.tensor(x, device=DEV), k, periodic, thr, inc, 0, True)
     for s in range(2):
@@ -93,7 +101,7 @@ def test_knn_vs_exact_oracle(nb, N, k, periodic, thr, inc):
         assert np.array_equal(idx[s].cpu().numpy(), ridx)
 
 
-def test_knn_arbitrary_box_strided_and_ties(nb):
+def test_knn_arbitrary_box_strided_and_ties(nb, knn_kernel):
     rng = np.random.default_rng(4)
     X = (rng.random((2, 3000, 9)) * 128 - 5).astype(np.float32)    # reference layout (b,N,9), Mpc/h coordinates
     A = nb.graph.get_kneighbor_list(torch.tensor(X, device=DEV), 14)
@@ -103,6 +111,54 @@ def test_knn_arbitrary_box_strided_and_ties(nb):
     idx, d2, _ = nb.ops.knn(torch.tensor(g["x"], device=DEV), 14, False, 0.0, True, 0, True)
     assert np.array_equal(d2[0].cpu().numpy(), g["knl_sorted_d2"])
     assert np.array_equal(idx[0].cpu().numpy(), knn_exact(g["x"][0].astype(np.float64), 512, 14, True))
+
+
+@pytest.mark.parametrize("case", ["uniform", "clustered", "lattice", "duplicates", "far_box", "tiny", "dense_blob"])
+@pytest.mark.parametrize("k", [5, 14, 17, 32])
+def test_knn_warp_kernel_equals_thread_kernel(nb, syn, case, k):
+    """The warp-per-query kernel (FP32 keys + FP64 re-evaluation of the survivors) against the thread-per-query kernel:
+    indices AND float64 distances identical, open and periodic, both output orders.  Lattice / duplicate inputs have
+    more than 32 candidates within the FP32 margin of the k-th distance: those queries take the hand-over path;
+    dense_blob exercises the long-run (no staging) path and the keep-list compaction."""
+    rng = np.random.default_rng(11)
+    if case in ("uniform", "clustered"):
+        x = syn.make_box(case, 2, 6000, 3)
+    elif case == "lattice":
+        g = (np.arange(12, dtype=np.float32) + 0.5) / 12
+        x = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(1, -1, 3).repeat(2, 0)
+    elif case == "duplicates":
+        x = rng.random((2, 40, 3)).astype(np.float32).repeat(50, 1)          # every point 50 times
+    elif case == "far_box":
+        x = (rng.random((2, 3000, 3)) * 1000 + 5e4).astype(np.float32)       # coarse float32 grid far from the origin
+    elif case == "tiny":
+        x = rng.random((3, 40, 3)).astype(np.float32)
+    else:
+        x = rng.random((1, 8000, 3)).astype(np.float32)
+        x[0, :3000] = 0.5 + 1e-3 * rng.standard_normal((3000, 3)).astype(np.float32)
+    xt = torch.tensor(np.ascontiguousarray(x), device=DEV)
+    for periodic, thr in ((False, 0.0), (True, 0.1)):
+        if periodic and case == "far_box":
+            continue                                                          # periodic mode is defined on the unit box
+        for order in (0, 1):
+            out = {}
+            for kern in ("thread", "warp"):
+                nb.set_knn_kernel(kern)
+                try:
+                    idx, d2, _ = nb.ops.knn(xt, k, periodic, thr, order == 0, order, True)
+                finally:
+                    nb.set_knn_kernel("auto")
+                out[kern] = (idx.cpu().numpy(), d2.cpu().numpy())
+            assert np.array_equal(out["thread"][1], out["warp"][1]), (case, k, periodic, order)
+            assert np.array_equal(out["thread"][0], out["warp"][0]), (case, k, periodic, order)
+
+
+def test_knn_kernel_selection(nb):
+    assert nb.get_knn_kernel() == "auto"
+    nb.set_knn_kernel("warp")
+    assert nb.get_knn_kernel() == "warp"
+    nb.set_knn_kernel("auto")
+    with pytest.raises(RuntimeError, match="unknown kernel"):
+        nb.set_knn_kernel(7)
 
 
 def test_knn_errors(nb):
@@ -118,7 +174,7 @@ def test_knn_errors(nb):
 
 
 @pytest.mark.parametrize("kind", ["uniform", "clustered"])
-def test_knn_128_cubed_properties(nb, syn, kind):
+def test_knn_128_cubed_properties(nb, syn, kind, knn_kernel):
     """BASELINE size (2 097 152 particles, k=14, periodic): properties + brute-force spot check."""
     N, k = 128 ** 3, 14
     x = torch.tensor(syn.make_box(kind, 1, N, 0), device=DEV)
