@@ -443,6 +443,15 @@ def knn_sweep(nb, dev, peak, with_sklearn):
                        "algorithmic_bytes": ab, "open_roofline_frac": ab / (t_open * 1e-3) / 1e9 / peak,
                        "periodic_roofline_frac": ab / (t_pbc * 1e-3) / 1e9 / peak,
                        "open_particles_per_s": b * N / (t_open * 1e-3)}
+                # the query kernel nbpc_knn picks for this k, and the other one beside it (same result bit for bit)
+                row["kernel"] = "warp-per-query" if k > 16 else "thread-per-query"
+                if side < 128:
+                    other = "thread" if k > 16 else "warp"
+                    nb.set_knn_kernel(other)
+                    try:
+                        row[f"open_ms_{other}_kernel"] = round(event_ms(lambda: graph.get_kneighbor_list(x, k), 5), 4)
+                    finally:
+                        nb.set_knn_kernel("auto")
                 if with_sklearn and (side == 32 or (side == 64 and k == 14)):
                     from oracle import ref_graph                      # CPU leg (checker code timed as the baseline)
                     t0 = time.perf_counter()

@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(KNW_THREADS, 4) knn_query_warp(KnnQueryParams 
 
     for (int R = 1, Rprev = -1; !bail; Rprev = R, ++R) {
         const int W = 2 * R + 1, nrows = W * W;
-        const float inv_w = __frcp_rn((float)W);
+        const float inv_w = __fdividef(1.f, (float)W);
         const bool prune = Tcur < INFINITY;                 // warp-uniform
         for (int r0 = 0; r0 < nrows && !bail; r0 += 32) {
             const int r = r0 + lane;
