@@ -496,7 +496,7 @@ def set_model_bench(nb, dev, peak, steps=10):
     torch.cuda.synchronize()
     rep = lib.prof_report()
     lib.prof_enable(False)
-    kern = sorted(((n, tot / 2) for n, (cnt, tot) in rep.items()), key=lambda kv: -kv[1])[:14]
+    kern = sorted(((n, tot / 2) for n, (cnt, tot) in rep.items()), key=lambda kv: -kv[1])[:int(os.environ.get("NBPC_BENCH_TOPK", "14"))]
     return {"channels": ch, "batch": b, "particles": rows, "ms_per_step": ms, "particles_per_s": rows / (ms * 1e-3), "finite": bool(torch.isfinite(gs.loss)),
             "algorithmic_bytes": fwd + bwd, "roofline_frac": (fwd + bwd) / (ms * 1e-3) / 1e9 / peak,
             "gemm_tflops_fp32_equiv": flops / (ms * 1e-3) / 1e12, "math_mode": lib.get_math_mode(),

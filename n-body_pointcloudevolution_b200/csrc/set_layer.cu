@@ -138,12 +138,42 @@ static bool set_xty_narrow(const float *H, const float *mu, const float *dZ, int
 #undef X
         done = true;
     }
-    if (done) NBPC_LAUNCH(sgs_sum_partials_kernel, nbpc_cdiv(k * q, 256), 256, 0, stream, partial, nblk * B, k * q, dW);
+    if (done) NBPC_LAUNCH(sgs_sum_partials_kernel, nbpc_cdiv(k * q, 32), 256, 0, stream, partial, nblk * B, k * q, dW);
     return done;
 }
 #endif
 
+#ifndef NBPC_HOST_EMU
+// ---- 16-wide outputs on the tensor pipe by ROW PAIRING.  The tcgen05 kernels want 32-float (128-byte) rows on the
+// contracted / narrow side.  Two consecutive rows of a (rows x 16) tensor ARE one row of its (rows/2 x 32) view, and
+// two rows of the (rows x k) side one row of a (rows/2 x 2k) view; with the block-diagonal weight W2 = diag(W, W)
+//   dH' = (dZ' - [m, m]) W2^T            is the (rows/2 x 2k) view of dH = (dZ - m) W^T, and
+//   dW2 = (H' - [mu, mu])^T dZ'  (2k x 32) carries dW in its two diagonal blocks (even rows / odd rows of the sample).
+// The zero blocks contribute exact zeros, so the arithmetic of every real term is that of the unpaired kernels.
+static bool set_pair_ok(int N, int k, int q) {
+    return q == 16 && N % 2 == 0 && sgt_gemm_shape_ok(32, 2 * k) && sgt_dw_shape_ok(2 * k, 32);
+}
+__global__ void set_pair_prepare_kernel(const float *__restrict__ W, const float *__restrict__ colmean, const float *__restrict__ mu,
+                                        int B, int k, float *__restrict__ W2, float *__restrict__ cm2, float *__restrict__ mu2) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 2 * k * 32) {                       // W2 (2k x 32) = diag(W, W), W (k x 16)
+        const int a = t / 32, b = t % 32;
+        const bool lo = a < k && b < 16, hi = a >= k && b >= 16;
+        W2[t] = lo ? W[a * 16 + b] : (hi ? W[(a - k) * 16 + (b - 16)] : 0.f);
+    }
+    if (t < B * 32) cm2[t] = colmean[(t / 32) * 16 + (t % 16)];
+    if (t < B * 2 * k) mu2[t] = mu[(t / (2 * k)) * k + (t % k)];
+}
+__global__ void set_pair_fold_kernel(const float *__restrict__ dW2, int k, float *__restrict__ dW) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * 16) return;
+    const int a = t / 16, b = t % 16;
+    dW[t] = dW2[a * 32 + b] + dW2[(k + a) * 32 + 16 + b];
+}
+#endif
+
 struct SetWorkspace {
+    float *pair;      // row-pairing scratch: W2 (2k x 32) | dW2 (2k x 32) | cm2 (B x 32) | mu2 (B x 2k)
     float *partial;   // (B, nblk, max(k,q))
     float *colsum;    // (B, q)
     float *xty_partial;
@@ -161,11 +191,17 @@ static SetWorkspace set_carve(void *ws, size_t ws_bytes, int B, int N, int k, in
     int rpc, nc;
     xty_plan((int64_t)B * N, k, q, &rpc, &nc);
     size_t nparts = (size_t)nc;
+    size_t part_elems = (size_t)k * q, pair_elems = 0;
 #ifndef NBPC_HOST_EMU
     nparts = nbpc_max(nparts, (size_t)sgt_dw_max_parts());
     nparts = nbpc_max(nparts, (size_t)sgs_max_blocks(N, B, set_num_sms()));
+    if (set_pair_ok(N, k, q)) {
+        part_elems = (size_t)2 * k * 32;         // the paired dW partials are (2k x 32)
+        pair_elems = (size_t)2 * (2 * k * 32) + (size_t)B * 32 + (size_t)B * 2 * k;
+    }
 #endif
-    w.xty_partial = a.take<float>(nparts * k * q);
+    w.pair = a.take<float>(pair_elems);
+    w.xty_partial = a.take<float>(nparts * part_elems);
     w.dz = a.take<float>(q % 4 == 0 ? (size_t)B * N * q : 0);
     w.bytes = a.off;
     return w;
@@ -259,6 +295,20 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
             NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * q, GL_THREADS), GL_THREADS, 0, stream, w.partial, q, nblk, B, (float)N, w.colsum);
         }
         int rc = 0;
+        if (tc && set_pair_ok(N, k, q)) {   // 16-wide output: both products on the tensor pipe through the row-pair views
+            float *W2 = w.pair, *dW2 = W2 + 2 * k * 32, *cm2 = dW2 + 2 * k * 32, *mu2 = cm2 + B * 32;
+            const int nprep = nbpc_max(2 * k * 32, B * 2 * k);
+            NBPC_LAUNCH(set_pair_prepare_kernel, nbpc_cdiv(nprep, 256), 256, 0, stream, W, w.colsum, mu, B, k, W2, cm2, mu2);
+            rc = sgt_dw(H_in, dZ, mu2, rows / 2, N / 2, 2 * k, 32, x3, w.xty_partial, dW2, stream);
+            if (!rc) NBPC_LAUNCH(set_pair_fold_kernel, nbpc_cdiv(k * 16, 256), 256, 0, stream, dW2, k, dW);
+            if (!rc && dH_in)
+                rc = sgt_gemm(dZ, W2, 1, cm2, nullptr, mask_input ? H_in : nullptr, rows / 2, N / 2, 32, 2 * k, 0, x3, dH_in, stream);
+            if (rc) {
+                nbpc_set_error("nbpc_set_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
+                return NBPC_ELAUNCH;
+            }
+            return nbpc_check_launch("nbpc_set_layer_bwd");
+        }
         // ---- dW = (H - mu)^T dZ: tensor pipe, else the narrow-side stream, else the generic fixed-order reduction
         if (tc && sgt_dw_shape_ok(k, q)) {
             rc = sgt_dw(H_in, dZ, mu, rows, N, k, q, x3, w.xty_partial, dW, stream);

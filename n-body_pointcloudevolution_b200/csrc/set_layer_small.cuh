@@ -151,18 +151,30 @@ __global__ void __launch_bounds__(SGS_THREADS) sgs_xty_narrow_kernel(const float
     }
 }
 
-// dW[o] = sum over blocks of partial[blk][o], fixed order
-__global__ void sgs_sum_partials_kernel(const float *__restrict__ partial, int nparts, int kq, float *__restrict__ dW) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= kq) return;
+// dW[o] = sum over blocks of partial[blk][o], fixed order: a block owns 32 outputs, its 8 slices take the partials
+// b = slice, slice + 8, ... (4 loads in flight each) and are combined in ascending slice order
+__global__ void __launch_bounds__(256) sgs_sum_partials_kernel(const float *__restrict__ partial, int nparts, int kq,
+                                                                float *__restrict__ dW) {
+    __shared__ float red[8][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + lane;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nparts; b += 4) {
-        a0 += __ldg(partial + (int64_t)b * kq + o); a1 += __ldg(partial + (int64_t)(b + 1) * kq + o);
-        a2 += __ldg(partial + (int64_t)(b + 2) * kq + o); a3 += __ldg(partial + (int64_t)(b + 3) * kq + o);
+    if (o < kq) {
+        int b = slice;
+        for (; b + 24 < nparts; b += 32) {
+            a0 += __ldg(partial + (int64_t)b * kq + o); a1 += __ldg(partial + (int64_t)(b + 8) * kq + o);
+            a2 += __ldg(partial + (int64_t)(b + 16) * kq + o); a3 += __ldg(partial + (int64_t)(b + 24) * kq + o);
+        }
+        for (; b < nparts; b += 8) a0 += __ldg(partial + (int64_t)b * kq + o);
     }
-    for (; b < nparts; ++b) a0 += __ldg(partial + (int64_t)b * kq + o);
-    dW[o] = (a0 + a1) + (a2 + a3);
+    red[slice][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (slice == 0 && o < kq) {
+        float a = red[0][lane];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) a += red[j][lane];
+        dW[o] = a;
+    }
 }
 
 // rows per block so that B * blocks-per-sample is about 8 blocks per SM (and the partial buffers stay small)
