@@ -272,6 +272,21 @@ int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const floa
 int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const float *mu,
                        int B, int N, int k, int q, const float *W, int relu, int mask_input, float *dH_in,
                        float *dW, float *dB, void *workspace, size_t ws_bytes, void *stream);
+/* Chained variants for stacks of set layers (nn.network_func_set), where every hidden tensor has exactly one consumer:
+ * the kernel that WRITES a tensor also leaves its per-sample column sums, so that the consumer does not re-read the
+ * tensor for its mean pass (the sums come out of the tcgen05 epilogue when N % 128 == 0, otherwise from a separate pass -
+ * the outputs are filled either way).
+ *   fwd: mu_given != 0: mu (B,k) is an INPUT (column means of H_in: the previous layer's mean_out); else it is computed.
+ *        mean_out (B,q), optional OUTPUT: per-sample column means of H_out (after the activation).
+ *   bwd: dz_sums (B,q), optional INPUT: per-sample column SUMS of dOut; ignored when relu != 0 (the sums of the unmasked
+ *        gradient are useless), so pass a pre-masked gradient.  dh_sums (B,k), optional OUTPUT: per-sample column sums of
+ *        dH_in (after the input mask) - the dz_sums of the layer below. */
+int nbpc_set_layer_fwd_chained(const float *H_in, int B, int N, int k, int q, const float *W, const float *bias, int relu,
+                               float *H_out, float *mu, int mu_given, float *mean_out, void *workspace, size_t ws_bytes,
+                               void *stream);
+int nbpc_set_layer_bwd_chained(const float *dOut, const float *H_in, const float *H_out, const float *mu, int B, int N,
+                               int k, int q, const float *W, int relu, int mask_input, float *dH_in, float *dW, float *dB,
+                               const float *dz_sums, float *dh_sums, void *workspace, size_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------- readout / losses
  * nn.loss_ZA (nn.py:151-166): loss = mean_rows(sum_3 (pred - truth)^2); rows = B*N.

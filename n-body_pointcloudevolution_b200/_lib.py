@@ -66,6 +66,8 @@ SIGNATURES = {
     "nbpc_set_layer_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "nbpc_set_layer_fwd": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _p, _sz, _p]),
     "nbpc_set_layer_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "nbpc_set_layer_fwd_chained": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _p, _p, _i, _p, _p, _sz, _p]),
+    "nbpc_set_layer_bwd_chained": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "nbpc_loss_workspace_bytes": (_sz, [_i64]),
     "nbpc_loss_za_fwd": (_i, [_p, _i, _p, _i, _i64, _p, _p, _sz, _p]),
     "nbpc_loss_za_bwd": (_i, [_p, _i, _p, _i, _i64, _p, _p, _i, _p]),

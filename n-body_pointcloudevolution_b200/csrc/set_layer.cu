@@ -173,6 +173,7 @@ __global__ void set_pair_fold_kernel(const float *__restrict__ dW2, int k, float
 #endif
 
 struct SetWorkspace {
+    float *csum_parts; // fused column-sum partials of the tcgen05 row GEMM (sgt_gemm_csum_floats(B, max(k,q)))
     float *pair;      // row-pairing scratch: W2 (2k x 32) | dW2 (2k x 32) | cm2 (B x 32) | mu2 (B x 2k)
     float *partial;   // (B, nblk, max(k,q))
     float *colsum;    // (B, q)
@@ -201,10 +202,40 @@ static SetWorkspace set_carve(void *ws, size_t ws_bytes, int B, int N, int k, in
     }
 #endif
     w.pair = a.take<float>(pair_elems);
+    size_t csum_elems = 0;
+#ifndef NBPC_HOST_EMU
+    if (sgt_gemm_csum_ok(N)) csum_elems = sgt_gemm_csum_floats(B, mx);
+#endif
+    w.csum_parts = a.take<float>(csum_elems);
     w.xty_partial = a.take<float>(nparts * part_elems);
     w.dz = a.take<float>(q % 4 == 0 ? (size_t)B * N * q : 0);
     w.bytes = a.off;
     return w;
+}
+
+// colmean[s][c] = sums[s][c] / N, dB[c] = sum_s sums[s][c] (per-sample column sums handed over by the producer of dOut)
+__global__ void set_from_sums_kernel(const float *__restrict__ sums, int B, int q, float inv_n, float *__restrict__ colmean,
+                                     float *__restrict__ dB) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B * q) colmean[t] = sums[t] * inv_n;
+    if (t < q) {
+        float a = 0.f;
+        for (int s = 0; s < B; ++s) a += sums[s * q + t];
+        dB[t] = a;
+    }
+}
+
+// out[s][c] = per-sample column mean (mean != 0) or sum of X (B, N, C)
+static void set_colstat(const float *X, int C, int N, int B, int mean, float *partial, float *out, cudaStream_t stream) {
+#ifndef NBPC_HOST_EMU
+    if (C % 4 == 0 && C <= 1024) {
+        sgt_colsum(X, C, N, B, mean ? 1.0f / (float)N : 1.0f, partial, out, nullptr, stream);
+        return;
+    }
+#endif
+    const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
+    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * C, GL_THREADS), GL_THREADS, 0, stream, X, C, N, nblk, B, partial);
+    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * C, GL_THREADS), GL_THREADS, 0, stream, partial, C, nblk, B, mean ? (float)N : 1.0f, out);
 }
 
 extern "C" {
@@ -216,6 +247,12 @@ size_t nbpc_set_layer_workspace_bytes(int B, int N, int k, int q) {
 
 int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const float *W, const float *bias, int relu,
                        float *H_out, float *mu, void *workspace, size_t ws_bytes, void *stream_) {
+    return nbpc_set_layer_fwd_chained(H_in, B, N, k, q, W, bias, relu, H_out, mu, 0, nullptr, workspace, ws_bytes, stream_);
+}
+
+int nbpc_set_layer_fwd_chained(const float *H_in, int B, int N, int k, int q, const float *W, const float *bias, int relu,
+                               float *H_out, float *mu, int mu_given, float *mean_out, void *workspace, size_t ws_bytes,
+                               void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
     NBPC_ARG(H_in && W && bias && H_out && mu && workspace, "null pointer");
@@ -229,25 +266,33 @@ int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const floa
     const int nblk = nbpc_cdiv(N, GL_CUBE_CHUNK);
 #ifndef NBPC_HOST_EMU
     if (g_nbpc_math_mode != NBPC_MATH_FP32 && sgt_gemm_shape_ok(k, q)) {
-        // tensor-core path (set_layer_tc.cu): column means, then (H - mu) W + B on tcgen05
-        sgt_colsum(H_in, k, N, B, 1.0f / (float)N, w.partial, mu, nullptr, stream);
-        if (sgt_gemm(H_in, W, 0, mu, bias, nullptr, rows, N, k, q, relu, g_nbpc_math_mode == NBPC_MATH_TF32X3, H_out, stream)) {
+        // tensor-core path (set_layer_tc.cu): column means (unless the producer of H_in handed them over), then
+        // (H - mu) W + B on tcgen05; the epilogue leaves the column sums of H_out for the next layer when asked
+        if (!mu_given) sgt_colsum(H_in, k, N, B, 1.0f / (float)N, w.partial, mu, nullptr, stream);
+        float *parts = (mean_out && sgt_gemm_csum_ok(N)) ? w.csum_parts : nullptr;
+        int nsets = 0;
+        if (sgt_gemm(H_in, W, 0, mu, bias, nullptr, rows, N, k, q, relu, g_nbpc_math_mode == NBPC_MATH_TF32X3, H_out, parts, &nsets, stream)) {
             nbpc_set_error("nbpc_set_layer_fwd: could not set up the tensor-core kernel (tensor map / shared memory)");
             return NBPC_ELAUNCH;
         }
+        if (parts) sgt_colsum_from_parts(parts, nsets, B, q, 1.0f / (float)N, mean_out, nullptr, stream);
+        else if (mean_out) set_colstat(H_out, q, N, B, 1, w.partial, mean_out, stream);
         return nbpc_check_launch("nbpc_set_layer_fwd");
     }
 #endif
-    NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, N, nblk,
-                B, w.partial);
-    NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.partial, k, nblk, B, (float)N,
-                mu);  // nn.py:25
+    if (!mu_given) {
+        NBPC_LAUNCH(cube_partial_kernel, nbpc_cdiv((int64_t)B * nblk * k, GL_THREADS), GL_THREADS, 0, stream, H_in, k, N, nblk,
+                    B, w.partial);
+        NBPC_LAUNCH(cube_final_kernel, nbpc_cdiv(B * k, GL_THREADS), GL_THREADS, 0, stream, w.partial, k, nblk, B, (float)N,
+                    mu);  // nn.py:25
+    }
 #ifndef NBPC_HOST_EMU
     if (gl_set_fast() && k <= 16 && q % 4 == 0 && q <= 1024 && sgs_narrow_ok(k)) {   // narrow input layer: float4 stream over q
         const int rpb = sgs_rows_per_block(N, B, set_num_sms()), nb = nbpc_cdiv(N, rpb);
 #define X(V) if (k == V) NBPC_LAUNCH_N(NbpcKName("sgs_fwd_smallk", k, q).c_str(), sgs_fwd_smallk_kernel<V>, dim3(nb, B), SGS_THREADS, 0, stream, H_in, mu, W, bias, N, q, rpb, relu, H_out);
         SGS_NARROW_LIST(X)
 #undef X
+        if (mean_out) set_colstat(H_out, q, N, B, 1, w.partial, mean_out, stream);
         return nbpc_check_launch("nbpc_set_layer_fwd");
     }
 #endif
@@ -255,13 +300,23 @@ int nbpc_set_layer_fwd(const float *H_in, int B, int N, int k, int q, const floa
     X.h = H_in; X.mu = mu; X.k = k; X.N = N;
     NBPC_LAUNCH(set_fwd_kernel, nbpc_cdiv(rows * q, GL_THREADS), GL_THREADS, 0, stream, X, W, bias, rows, k, q, relu,
                 H_out);  // nn.py:26-27
+    if (mean_out) set_colstat(H_out, q, N, B, 1, w.partial, mean_out, stream);
     return nbpc_check_launch("nbpc_set_layer_fwd");
 }
 
 int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out, const float *mu, int B, int N,
                        int k, int q, const float *W, int relu, int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
                        size_t ws_bytes, void *stream_) {
+    return nbpc_set_layer_bwd_chained(dOut, H_in, H_out, mu, B, N, k, q, W, relu, mask_input, dH_in, dW, dB, nullptr, nullptr,
+                                      workspace, ws_bytes, stream_);
+}
+
+int nbpc_set_layer_bwd_chained(const float *dOut, const float *H_in, const float *H_out, const float *mu, int B, int N,
+                               int k, int q, const float *W, int relu, int mask_input, float *dH_in, float *dW, float *dB,
+                               const float *dz_sums, float *dh_sums, void *workspace, size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
+    NBPC_ARG(!dh_sums || dH_in, "dh_sums needs dH_in");
+    if (relu) dz_sums = nullptr;   // sums of the UNMASKED gradient are of no use
     cudaStream_t stream = (cudaStream_t)stream_;
     NBPC_ARG(dOut && H_in && mu && W && dW && dB && workspace, "null pointer");
     NBPC_ARG(!relu || H_out, "H_out is required when relu is set");
@@ -286,7 +341,9 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
         }
         dz.g = dZ; dz.relu = 0;
         // per-sample column means of dZ (the adjoint of the mean subtraction) -> w.colsum, and dB = sum of dZ
-        if (q % 4 == 0) {
+        if (dz_sums) {   // handed over by the producer of dOut
+            NBPC_LAUNCH(set_from_sums_kernel, nbpc_cdiv(B * q, 256), 256, 0, stream, dz_sums, B, q, 1.0f / (float)N, w.colsum, dB);
+        } else if (q % 4 == 0) {
             sgt_colsum(dZ, q, N, B, 1.0f / (float)N, w.partial, w.colsum, dB, stream);
         } else {
             NBPC_LAUNCH(set_dz_partial_kernel, nbpc_cdiv((int64_t)B * nblk * q, GL_THREADS), GL_THREADS, 0, stream, dz, q, N, nblk, B, w.partial);
@@ -302,11 +359,12 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
             rc = sgt_dw(H_in, dZ, mu2, rows / 2, N / 2, 2 * k, 32, x3, w.xty_partial, dW2, stream);
             if (!rc) NBPC_LAUNCH(set_pair_fold_kernel, nbpc_cdiv(k * 16, 256), 256, 0, stream, dW2, k, dW);
             if (!rc && dH_in)
-                rc = sgt_gemm(dZ, W2, 1, cm2, nullptr, mask_input ? H_in : nullptr, rows / 2, N / 2, 32, 2 * k, 0, x3, dH_in, stream);
+                rc = sgt_gemm(dZ, W2, 1, cm2, nullptr, mask_input ? H_in : nullptr, rows / 2, N / 2, 32, 2 * k, 0, x3, dH_in, nullptr, nullptr, stream);
             if (rc) {
                 nbpc_set_error("nbpc_set_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
                 return NBPC_ELAUNCH;
             }
+            if (dh_sums) set_colstat(dH_in, k, N, B, 0, w.partial, dh_sums, stream);
             return nbpc_check_launch("nbpc_set_layer_bwd");
         }
         // ---- dW = (H - mu)^T dZ: tensor pipe, else the narrow-side stream, else the generic fixed-order reduction
@@ -319,8 +377,15 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
         }
         // ---- dH = (dZ - mean_s dZ) W^T [* (H_in > 0)]
         if (!rc && dH_in) {
+            bool sums_done = false;
             if (tc && sgt_gemm_shape_ok(q, k)) {
-                rc = sgt_gemm(dZ, W, 1, w.colsum, nullptr, mask_input ? H_in : nullptr, rows, N, q, k, 0, x3, dH_in, stream);
+                float *parts = (dh_sums && sgt_gemm_csum_ok(N)) ? w.csum_parts : nullptr;
+                int nsets = 0;
+                rc = sgt_gemm(dZ, W, 1, w.colsum, nullptr, mask_input ? H_in : nullptr, rows, N, q, k, 0, x3, dH_in, parts, &nsets, stream);
+                if (!rc && parts) {
+                    sgt_colsum_from_parts(parts, nsets, B, k, 1.0f, nullptr, dh_sums, stream);
+                    sums_done = true;
+                }
             } else if (q <= 16 && k % 4 == 0 && k <= 1024 && sgs_narrow_ok(q)) {
                 const int rpb = sgs_rows_per_block(N, B, set_num_sms()), nb = nbpc_cdiv(N, rpb);
 #define X(V) if (q == V) NBPC_LAUNCH_N(NbpcKName("sgs_bwd_in_smallq", k, q).c_str(), sgs_bwd_in_smallq_kernel<V>, dim3(nb, B), SGS_THREADS, 0, stream, dZ, w.colsum, W, mask_input ? H_in : (const float *)nullptr, N, k, rpb, dH_in);
@@ -330,6 +395,7 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
                 NBPC_LAUNCH(set_bwd_in_mean_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, dz, w.colsum, W, rows, N, k, q, dH_in);
                 if (mask_input) NBPC_LAUNCH(set_mask_input_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, H_in, rows * k, dH_in);
             }
+            if (!rc && dh_sums && !sums_done) set_colstat(dH_in, k, N, B, 0, w.partial, dh_sums, stream);
         }
         if (rc) {
             nbpc_set_error("nbpc_set_layer_bwd: could not set up the tensor-core kernel (tensor map / shared memory)");
@@ -350,6 +416,7 @@ int nbpc_set_layer_bwd(const float *dOut, const float *H_in, const float *H_out,
         NBPC_LAUNCH(set_bwd_in_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, dz, w.colsum, W, rows, N, k, q,
                     dH_in);
         if (mask_input) NBPC_LAUNCH(set_mask_input_kernel, nbpc_cdiv(rows * k, GL_THREADS), GL_THREADS, 0, stream, H_in, rows * k, dH_in);
+        if (dh_sums) set_colstat(dH_in, k, N, B, 0, w.partial, dh_sums, stream);
     }
     return nbpc_check_launch("nbpc_set_layer_bwd");
 }

@@ -110,6 +110,37 @@ __global__ void sgt_colsum_total_kernel(const float *__restrict__ sums, int C, i
     total[c] = tot;
 }
 
+// out[o] = scale * sum over sets of parts[set][o] (o = sample * C + c), sums[o] = the unscaled sum (optional); fixed order:
+// a block owns 32 outputs, its 32 slices take the sets slice, slice + 32, ... (4 loads in flight) and are combined in
+// ascending slice order
+__global__ void __launch_bounds__(1024) sgt_colsum_from_parts_kernel(const float *__restrict__ parts, int nsets, int BC, float scale,
+                                                                      float *__restrict__ out, float *__restrict__ sums) {
+    __shared__ float red[32][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (o < BC) {
+        int b = slice;
+        for (; b + 96 < nsets; b += 128) {
+            a0 += __ldg(parts + (int64_t)b * BC + o); a1 += __ldg(parts + (int64_t)(b + 32) * BC + o);
+            a2 += __ldg(parts + (int64_t)(b + 64) * BC + o); a3 += __ldg(parts + (int64_t)(b + 96) * BC + o);
+        }
+        for (; b < nsets; b += 32) a0 += __ldg(parts + (int64_t)b * BC + o);
+    }
+    red[slice][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (slice == 0 && o < BC) {
+        float a = red[0][lane];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) a += red[j][lane];
+        if (out) out[o] = a * scale;
+        if (sums) sums[o] = a;
+    }
+}
+void sgt_colsum_from_parts(const float *parts, int nsets, int B, int C, float scale, float *out, float *sums, cudaStream_t stream) {
+    NBPC_LAUNCH(sgt_colsum_from_parts_kernel, nbpc_cdiv(B * C, 32), 1024, 0, stream, parts, nsets, B * C, scale, out, sums);
+}
+
 // ------------------------------------------------------------------ row GEMM: out = act((A - mu_s) Bm + bias) [* (mask > 0)]
 struct SgtGemmArgs {
     const float *Bsrc;       // weights: (K, Ntot) row-major, or (Ntot, K) when b_transposed
@@ -122,6 +153,9 @@ struct SgtGemmArgs {
     uint32_t rps_magic;      // floor(2^32 / rows_per_sample) (2^32 - 1 for 1): sample of a row without a 64-bit division
     int dbg;                 // NBPC_SGT_DEBUG (profiling experiments only, results are WRONG): 1 no output stores, 2 no epilogue
                              // work at all, 4 converters only signal
+    float *csum;             // optional: per-sample column sums of `out`, [gridDim.x / n_ntiles][samples][Ntot] partials
+                             // (one set per CTA row; requires rows_per_sample % 128 == 0)
+    int samples, tiles_per_sample;
 };
 
 template <bool X3>
@@ -136,7 +170,8 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     unsigned char *Bh = Al + L * SGT_CHUNK_BYTES;
     unsigned char *Bl = Bh + B_BYTES;
     float *Os = reinterpret_cast<float *>(Bh + B_BYTES * (X3 ? 2 : 1));   // [4 warps][32][PITCH]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Os) + 4 * 32 * 36 * 4);
+    float *Cs = Os + 4 * 32 * 36;                                 // [4 warps][256] running column sums of the current sample
+    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Cs) + 4 * 256 * 4);
     const uint32_t bar0 = glt_smem_u32(bars);
     const int LB = X3 ? P.L : 1;                                  // barrier slots are laid out for max(L, 1)
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -245,8 +280,28 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
         const int vshift = SW == 32 ? 3 : 2, vmask = (1 << vshift) - 1, iters = 1 << vshift;   // 32 rows * SW/4 float4 = 32 lanes * iters
         // (shifts: a runtime division by SW/4 in the two loops below cost more than the stores)
         int a = 0, aph = 0;
+        // fused column sums of the output (the next layer's mean / the previous layer's bias gradient): per warp, per sample
+        float *Cw = Cs + qd * 256;
+        int cur_sample = -1;
+        // (the four epilogue warps walk the same tiles, so they flush at the same points: named barrier 1, 128 threads;
+        // their sums are combined in warp order 0..3, one partial set per CTA row)
+        auto csum_flush = [&]() {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (cur_sample >= 0) {
+                float *dst = P.csum + ((int64_t)cta_m * P.samples + cur_sample) * P.Ntot + n0;
+                for (int i = qd * 32 + lane; i < NT; i += 128) dst[i] = ((Cs[i] + Cs[256 + i]) + Cs[512 + i]) + Cs[768 + i];
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = lane; i < NT; i += 32) Cw[i] = 0.f;
+            __syncwarp();
+        };
+        if (P.csum) csum_flush();
         for (int64_t t = cta_m; t < ntiles; t += Gm) {
             const int64_t row0 = t * GLT_TILE + qd * 32;
+            if (P.csum) {
+                const int st = (int)t / P.tiles_per_sample;
+                if (st != cur_sample) { csum_flush(); cur_sample = st; }
+            }
             glt_mbar_wait(TFULL(a), aph);
             glt_tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * NT;
@@ -290,6 +345,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                     }
                 }
                 __syncwarp();
+                float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);       // this lane's rows of column group (lane & vmask)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int idx = i * 32 + lane, r = idx >> vshift, c4 = idx & vmask;
@@ -301,12 +357,26 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                             v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
                         }
                         *reinterpret_cast<float4 *>(P.out + grow * P.Ntot + n0 + cb + 4 * c4) = v;
+                        if (P.csum) { cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w; }
+                    }
+                }
+                if (P.csum) {   // lanes with the same column group hold different rows: butterfly, then lanes 0..vmask accumulate
+                    for (int m = vmask + 1; m < 32; m <<= 1) {
+                        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, m); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, m);
+                        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, m); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, m);
+                    }
+                    if (lane <= vmask) {
+                        float4 *acc = reinterpret_cast<float4 *>(Cw + cb + 4 * lane);
+                        float4 o = *acc;
+                        o.x += cs.x; o.y += cs.y; o.z += cs.z; o.w += cs.w;
+                        *acc = o;
                     }
                 }
                 __syncwarp();
             }
             if (++a == 2) { a = 0; aph ^= 1; }
         }
+        if (P.csum) csum_flush();
     } else {
         // ---------------- converter warps: centre the landed chunk in place (A - mu_s) and write the TF32 residual
         const int wtid = tid - 192;
@@ -352,7 +422,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
 }
 
 static size_t sgt_gemm_smem(bool x3, int K, int NT, int S, int L) {
-    return 1024 + (size_t)(S + (x3 ? L : 0)) * SGT_CHUNK_BYTES + (size_t)K * NT * 4 * (x3 ? 2 : 1) + 4 * 32 * 36 * 4 + 8 * (3 * 8 + 8 + 4) + 64;
+    return 1024 + (size_t)(S + (x3 ? L : 0)) * SGT_CHUNK_BYTES + (size_t)K * NT * 4 * (x3 ? 2 : 1) + 4 * 32 * 36 * 4 + 4 * 256 * 4 + 8 * (3 * 8 + 8 + 4) + 64;
 }
 
 // K-major tensor map over A (rows, K): box = 128 rows x 32 floats, 128-byte swizzle
@@ -370,9 +440,15 @@ static int sgt_make_tmap_a(CUtensorMap *tm, const float *ptr, int64_t rows, int 
 bool sgt_gemm_shape_ok(int K, int Nout) { return K % 32 == 0 && K >= 32 && K <= 256 && Nout % 16 == 0 && Nout >= 16 && Nout <= 256; }
 
 // out (rows, Nout) = act((A - mu_s) Bm + bias) [* (mask > 0)];  0 on success
+// csum_parts (optional, sgt_gemm_csum_ok): the kernel also leaves per-sample column sums of `out` as *n_sets partial sets
+// [set][sample][Nout] (sgt_colsum_from_parts adds them up in a fixed order); sgt_gemm_csum_floats(samples, Nout) floats
+bool sgt_gemm_csum_ok(int rows_per_sample) { return rows_per_sample % GLT_TILE == 0; }
+size_t sgt_gemm_csum_floats(int samples, int Nout) { return (size_t)gl_num_sms() * samples * Nout; }
+
 int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *mu, const float *bias, const float *mask, int64_t rows,
-             int rows_per_sample, int K, int Nout, int relu, int x3, float *out, cudaStream_t stream) {
+             int rows_per_sample, int K, int Nout, int relu, int x3, float *out, float *csum_parts, int *n_sets, cudaStream_t stream) {
     if (!sgt_gemm_shape_ok(K, Nout)) return 1;
+    if (csum_parts && !sgt_gemm_csum_ok(rows_per_sample)) return 1;
     // N tile: the resident weight tile (hi + lo in the split mode) must leave room for >= 2 + 2 stages
     int NT = Nout;
     const size_t budget = 227 * 1024;
@@ -418,6 +494,12 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     int64_t gm = gl_num_sms() / P.n_ntiles;
     if (gm < 1) gm = 1;
     if (gm > ntiles) gm = ntiles;
+    P.csum = csum_parts; P.samples = (int)(rows / rows_per_sample); P.tiles_per_sample = nbpc_max(rows_per_sample / GLT_TILE, 1);
+    if (csum_parts) {
+        *n_sets = (int)gm;
+        // a CTA row only writes the samples its tiles visit: with fewer tiles per sample than CTA rows some sets stay unwritten
+        if (P.tiles_per_sample < gm && cudaMemsetAsync(csum_parts, 0, sizeof(float) * (size_t)gm * P.samples * Nout, stream) != cudaSuccess) return 1;
+    }
     const int grid = (int)(gm * P.n_ntiles);
     NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_gemm_tf32x3" : "sgt_gemm_tf32", K, Nout).c_str(), kern, grid, SGT_THREADS, smem, stream, tm, P);
     return 0;

@@ -6,8 +6,14 @@
 // row GEMM out (rows, Nout) = act((A - mu_s) Bm + bias) [* (mask > 0)], A (rows, K); Bm = Bsrc (K, Nout) or, with b_transposed,
 // Bsrc^T for Bsrc (Nout, K); mu (samples, K) / bias (Nout) / mask (rows, Nout) may be null.  K % 32 == 0, Nout % 16 == 0, <= 256
 bool sgt_gemm_shape_ok(int K, int Nout);
+// csum_parts (optional; requires sgt_gemm_csum_ok, sgt_gemm_csum_floats(samples, Nout) floats): per-sample column sums of `out` as
+// *n_sets partial sets [set][sample][Nout], to be added up by sgt_colsum_from_parts
+bool sgt_gemm_csum_ok(int rows_per_sample);
+size_t sgt_gemm_csum_floats(int samples, int Nout);
 int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *mu, const float *bias, const float *mask, int64_t rows,
-             int rows_per_sample, int K, int Nout, int relu, int x3, float *out, cudaStream_t stream);
+             int rows_per_sample, int K, int Nout, int relu, int x3, float *out, float *csum_parts, int *n_sets, cudaStream_t stream);
+// out[s][c] = scale * sum over sets, sums[s][c] = the unscaled sum (either may be null)
+void sgt_colsum_from_parts(const float *parts, int nsets, int B, int C, float scale, float *out, float *sums, cudaStream_t stream);
 // dW (k, q) = (H - mu_s)^T dZ; k in {64, 128, 256}, q % 32 == 0, q <= 256; partial: sgt_dw_max_parts() * k * q floats
 bool sgt_dw_shape_ok(int k, int q);
 int sgt_dw_max_parts();

@@ -11,10 +11,10 @@ __all__ = ["set_layer", "network_func_set", "model_func_set", "get_readout", "pe
            "pbc_loss", "loss_ZA", "mse_za", "get_init_pos"]
 
 
-def _set_layer(h_in, layer_vars, relu, input_relu=False, grad_premasked=False):
+def _set_layer(h_in, layer_vars, relu, input_relu=False, grad_premasked=False, chain=None, idx=0, last=True):
     W, B = layer_vars
     W = W[0]  # only one weight for set layer (nn.py:22)
-    return ops.SetLayer.apply(_to_cuda(h_in, torch.float32), W, B, relu, input_relu, grad_premasked)
+    return ops.SetLayer.apply(_to_cuda(h_in, torch.float32), W, B, relu, input_relu, grad_premasked, chain, idx, last)
 
 
 def set_layer(h_in, layer_vars):
@@ -29,14 +29,17 @@ def network_func_set(X_in, model_vars):
     get_layer_vars = model_vars.get_layer_vars
     fuse = _is_relu(activation)
     # inside this function every hidden tensor has exactly one consumer (the next layer): the ReLU backward of layer l is
-    # applied by layer l+1's backward kernel (input_relu) and layer l skips its own mask (grad_premasked)
+    # applied by layer l+1's backward kernel (input_relu) and layer l skips its own mask (grad_premasked); the kernel that
+    # writes a hidden tensor (or its gradient) also hands its per-sample column sums to that consumer (ops.SetChain)
     chain = fuse and num_layers > 1
-    H = _set_layer(X_in, get_layer_vars(0), fuse, input_relu=False, grad_premasked=chain)
+    sc = ops.SetChain() if chain else None
+    H = _set_layer(X_in, get_layer_vars(0), fuse, input_relu=False, grad_premasked=chain, chain=sc, idx=0, last=num_layers == 1)
     if not fuse:
         H = activation(H)
     for layer_idx in range(1, num_layers):
         is_last = layer_idx >= num_layers - 1
-        H = _set_layer(H, get_layer_vars(layer_idx), fuse and not is_last, input_relu=fuse, grad_premasked=fuse and not is_last)
+        H = _set_layer(H, get_layer_vars(layer_idx), fuse and not is_last, input_relu=fuse, grad_premasked=fuse and not is_last,
+                       chain=sc, idx=layer_idx, last=is_last)
         if not is_last and not fuse:
             H = activation(H)
     return H

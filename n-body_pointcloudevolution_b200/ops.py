@@ -6,6 +6,7 @@ op launches hand-written sm_100a kernels through ctypes; none has a CPU or eager
 fallback (a CPU tensor raises).
 """
 import ctypes
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -556,7 +557,10 @@ class Graph15Layer(torch.autograd.Function):
 
 # ================================================================== set layer
 @torch.library.custom_op("nbpc::set_layer_fwd", mutates_args=())
-def set_layer_fwd(H_in: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, relu: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+def set_layer_fwd(H_in: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, relu: bool, mu_in: Optional[torch.Tensor] = None,
+                  want_mean_out: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (H_out, mu, mean_out).  mu_in: column means of H_in handed over by the layer that wrote H_in (skips the mean
+    pass); want_mean_out: also return the per-sample column means of H_out (else an empty tensor)."""
     _need_cuda(H_in, W, bias)
     L = _lib.load()
     H_in, W, bias = _f32c(H_in), _f32c(W), _f32c(bias)
@@ -564,55 +568,87 @@ def set_layer_fwd(H_in: torch.Tensor, W: torch.Tensor, bias: torch.Tensor, relu:
     q = W.shape[1]
     dev = H_in.device
     out = torch.empty((B, N, q), dtype=torch.float32, device=dev)
-    mu = torch.empty((B, k), dtype=torch.float32, device=dev)
+    mu = _f32c(mu_in).reshape(B, k) if mu_in is not None else torch.empty((B, k), dtype=torch.float32, device=dev)
+    mean_out = torch.empty((B, q) if want_mean_out else (0,), dtype=torch.float32, device=dev)
     ws = _workspace(L.nbpc_set_layer_workspace_bytes(B, N, k, q), dev)
     with torch.cuda.device(dev):
-        rc = L.nbpc_set_layer_fwd(_ptr(H_in), B, N, k, q, _ptr(W), _ptr(bias), int(relu), _ptr(out), _ptr(mu),
-                                  _ptr(ws), ws.numel(), _stream())
+        rc = L.nbpc_set_layer_fwd_chained(_ptr(H_in), B, N, k, q, _ptr(W), _ptr(bias), int(relu), _ptr(out), _ptr(mu),
+                                          int(mu_in is not None), _ptr(mean_out) if want_mean_out else None,
+                                          _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "nbpc_set_layer_fwd")
-    return out, mu
+    return out, (mu.clone() if mu_in is not None else mu), mean_out
 
 
 @torch.library.custom_op("nbpc::set_layer_bwd", mutates_args=())
 def set_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, mu: torch.Tensor, W: torch.Tensor,
-                  relu: bool, need_dH: bool, mask_input: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+                  relu: bool, need_dH: bool, mask_input: bool = False, dz_sums: Optional[torch.Tensor] = None,
+                  want_dh_sums: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (dH, dW, dB, dh_sums).  dz_sums: per-sample column sums of dOut handed over by the layer that wrote dOut;
+    want_dh_sums: also return the per-sample column sums of dH (else an empty tensor)."""
     _need_cuda(dOut, H_in, H_out, mu, W)
     L = _lib.load()
     dOut = _f32c(dOut)
     B, N, k = H_in.shape
     q = W.shape[1]
     dev = H_in.device
+    want_dh_sums = want_dh_sums and need_dH
     dH = torch.empty((B, N, k) if need_dH else (0,), dtype=torch.float32, device=dev)
     dW = torch.empty((k, q), dtype=torch.float32, device=dev)
     dB = torch.empty((q,), dtype=torch.float32, device=dev)
+    dh_sums = torch.empty((B, k) if want_dh_sums else (0,), dtype=torch.float32, device=dev)
     ws = _workspace(L.nbpc_set_layer_workspace_bytes(B, N, k, q), dev)
     with torch.cuda.device(dev):
-        rc = L.nbpc_set_layer_bwd(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(mu), B, N, k, q, _ptr(W), int(relu), int(mask_input),
-                                  _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB), _ptr(ws), ws.numel(), _stream())
+        rc = L.nbpc_set_layer_bwd_chained(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(mu), B, N, k, q, _ptr(W), int(relu), int(mask_input),
+                                          _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB),
+                                          _ptr(_f32c(dz_sums)) if dz_sums is not None else None,
+                                          _ptr(dh_sums) if want_dh_sums else None, _ptr(ws), ws.numel(), _stream())
     _lib.check(rc, "nbpc_set_layer_bwd")
-    return dH, dW, dB
+    return dH, dW, dB, dh_sums
+
+
+class SetChain:
+    """Side channel between the set layers of one nn.network_func_set stack (every hidden tensor has exactly one consumer,
+    the next layer): layer l's forward leaves the column means of its output for layer l+1's forward, layer l+1's
+    backward leaves the column sums of its dH for layer l's backward - the kernels that WRITE those tensors produce the
+    sums, so nobody re-reads a (B,N,C) tensor for a mean pass.  Entries are popped by their single consumer; a missing
+    entry just means the consumer computes the statistic itself."""
+
+    def __init__(self):
+        self.mean = {}     # layer index -> (B,k) column means of that layer's input
+        self.dsum = {}     # layer index -> (B,q) column sums of that layer's output gradient
 
 
 class SetLayer(torch.autograd.Function):
     """set_layer (nn.py:10-28) [+ fused ReLU].  input_relu / grad_premasked: as in GraphLayer - inside a network whose
     hidden tensors have exactly one consumer, the ReLU backward of layer l is applied by layer l+1's backward kernel
-    (which has H_in in hand) and layer l skips its own mask (nn.network_func_set sets both consistently)."""
+    (which has H_in in hand) and layer l skips its own mask (nn.network_func_set sets both consistently).
+    chain / idx / last: SetChain of the stack, this layer's index and whether it is the last one."""
 
     @staticmethod
-    def forward(ctx, H_in, W, bias, relu, input_relu=False, grad_premasked=False):
+    def forward(ctx, H_in, W, bias, relu, input_relu=False, grad_premasked=False, chain=None, idx=0, last=True):
         H_in = _f32c(H_in)
-        out, mu = set_layer_fwd(H_in, W, bias, relu)
+        mu_in = chain.mean.pop(idx, None) if chain is not None else None
+        fwd_fuse = chain is not None and not last
+        out, mu, mean_out = set_layer_fwd(H_in, W, bias, relu, mu_in, fwd_fuse)
+        if fwd_fuse:
+            chain.mean[idx + 1] = mean_out
         ctx.save_for_backward(H_in, out, mu, W)
         ctx.cfg = (relu and not grad_premasked, input_relu)
+        ctx.chain = (chain, idx)
         return out
 
     @staticmethod
     def backward(ctx, g):
         H_in, out, mu, W = ctx.saved_tensors
         relu, input_relu = ctx.cfg
+        chain, idx = ctx.chain
         need_dH = ctx.needs_input_grad[0]
-        dH, dW, dB = set_layer_bwd(g, H_in, out, mu, W, relu, need_dH, input_relu)
-        return (dH if need_dH else None), dW, dB, None, None, None
+        dz_sums = chain.dsum.pop(idx, None) if (chain is not None and not relu) else None
+        want = chain is not None and idx > 0 and need_dH
+        dH, dW, dB, dh_sums = set_layer_bwd(g, H_in, out, mu, W, relu, need_dH, input_relu, dz_sums, want)
+        if want:
+            chain.dsum[idx - 1] = dh_sums
+        return (dH if need_dH else None), dW, dB, None, None, None, None, None, None
 
 
 # ================================================================== losses / readout

@@ -145,6 +145,33 @@ def set_layer_bwd(dOut, H, Hout, mu, W, relu, need_dH=True, mask_input=False):
     return dH, dW, dB
 
 
+def set_layer_fwd_chained(H, W, bias, relu, mu_in=None, want_mean_out=True):
+    L = lib()
+    B, N, k = H.shape
+    q = W.shape[1]
+    out = np.zeros((B, N, q), dtype=np.float32)
+    mu = np.ascontiguousarray(mu_in, dtype=np.float32).copy() if mu_in is not None else np.zeros((B, k), dtype=np.float32)
+    mean_out = np.zeros((B, q), dtype=np.float32) if want_mean_out else None
+    w = ws(L.nbpc_set_layer_workspace_bytes(B, N, k, q))
+    ok(L.nbpc_set_layer_fwd_chained(P(H), B, N, k, q, P(W), P(bias), int(relu), P(out), P(mu), int(mu_in is not None), P(mean_out),
+                                    P(w), w.nbytes, None))
+    return out, mu, mean_out
+
+
+def set_layer_bwd_chained(dOut, H, Hout, mu, W, relu, mask_input=False, dz_sums=None, want_dh_sums=True):
+    L = lib()
+    B, N, k = H.shape
+    q = W.shape[1]
+    dH = np.zeros((B, N, k), dtype=np.float32)
+    dW = np.zeros((k, q), dtype=np.float32)
+    dB = np.zeros((q,), dtype=np.float32)
+    dh_sums = np.zeros((B, k), dtype=np.float32) if want_dh_sums else None
+    w = ws(L.nbpc_set_layer_workspace_bytes(B, N, k, q))
+    ok(L.nbpc_set_layer_bwd_chained(P(dOut), P(H), P(Hout), P(mu), B, N, k, q, P(W), int(relu), int(mask_input), P(dH), P(dW), P(dB),
+                                    P(dz_sums), P(dh_sums), P(w), w.nbytes, None))
+    return dH, dW, dB, dh_sums
+
+
 def loss(pred, truth, pbc=False, scale=True):
     L = lib()
     rows = pred.shape[0] * pred.shape[1]
