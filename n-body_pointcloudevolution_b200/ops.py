@@ -6,7 +6,6 @@ op launches hand-written sm_100a kernels through ctypes; none has a CPU or eager
 fallback (a CPU tensor raises).
 """
 import ctypes
-import os
 from typing import List, Optional, Tuple
 
 import torch
