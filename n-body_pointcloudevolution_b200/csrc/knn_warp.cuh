@@ -10,16 +10,17 @@
 //     so far; T = the k-th entry of that list is the pruning / termination bound;
 //   * candidates whose key is within the FP32 error margin of T (knw_thr) are remembered; when the search ends, those
 //     still within the margin of the final T (k of them unless there are near-ties) are re-evaluated in FP64 with the
-//     reference's operation order, and the exact (d2, index) order decides.  More than 32 such candidates (massive
-//     ties, e.g. k > 18 on an exact lattice shell) or a keep-list overflow send the query to the thread-per-query
-//     kernel through a todo list - the result never depends on which kernel produced it.
+//     reference's operation order (one per lane, two per lane when there are 33..64), and the exact (d2, index) order
+//     decides.  More than 64 such candidates (massive ties: exact lattice shells, duplicated points) or a keep-list
+//     overflow send the query to the thread-per-query kernel through a todo list - the result never depends on which
+//     kernel produced it.
 //
 // Error margin.  u = 2^-24.  Open box: t_f = fl(p - c) has relative error u, key = fma chain of three non-negative
 // terms: |key - d2| <= 6u d2.  The k smallest keys are <= T, so the exact k-th distance d2* <= T / (1 - 6u), and any
-// candidate with d2 <= d2* has key <= T (1 + 6u) / (1 - 6u) < T (1 + 1e-5).  Periodic images: t_f = fl(fl(p - c) - s),
-// |error| <= u (1 + 2|t|) per axis for ANY coordinates, i.e. sqrt(key) is within sqrt(T) (1 + 14u) + 3.7u; the margin
-// used is (sqrt(T) (1 + 1e-5) + 2e-6)^2.  Both margins are far wider than needed: the price is an occasional extra
-// FP64 evaluation.
+// candidate with d2 <= d2* has key <= T (1 + 6u) / (1 - 6u) = T (1 + 7.2e-7); the margin used is T (1 + 2e-6).  Periodic
+// images: t_f = fl(fl(p - c) - s), |error| <= u (1 + 2|t|) per axis for ANY coordinates, i.e. sqrt(key) is within
+// sqrt(T) (1 + 14u) + 3.7u = sqrt(T) (1 + 8.3e-7) + 2.2e-7; the margin used is (sqrt(T) (1 + 2e-6) + 5e-7)^2.  A wider
+// margin only costs extra FP64 evaluations (and, for k = 32, more queries with more than 32 survivors).
 #pragma once
 
 #define KNW_WARPS 8
@@ -32,10 +33,10 @@
 template <bool PERIODIC>
 __device__ __forceinline__ float knw_thr(float T) {
     if (PERIODIC) {
-        const float a = sqrtf(T) * 1.00001f + 2e-6f;
+        const float a = sqrtf(T) * 1.000002f + 5e-7f;
         return a * a * 1.000001f;
     }
-    return T * 1.00001f + 1e-37f;
+    return T * 1.000002f + 1e-37f;
 }
 
 // one compare-exchange of the bitonic networks below: the lane whose bit `bit` is clear keeps the smaller value
@@ -95,6 +96,11 @@ __device__ __forceinline__ float knw_sqrt_approx(float x) {
 // -1 (flag 2, x >= upper): the code IS the required flag pattern.
 __device__ __forceinline__ int knw_axis_code(int s) { return s > 0 ? 1 : (s < 0 ? 2 : 0); }
 __device__ __forceinline__ float knw_axis_shift(int c2) { return (float)(c2 & 1) - (float)(c2 >> 1); }
+
+__device__ __forceinline__ void knw_merge32_pair(double &d, int &id, int lane) {
+#pragma unroll
+    for (int stride = 16; stride > 0; stride >>= 1) knw_cx_pair(d, id, stride, stride, lane);
+}
 
 template <bool PERIODIC>
 __global__ void __launch_bounds__(KNW_THREADS, 4) knn_query_warp(KnnQueryParams P, int32_t *__restrict__ todo,
@@ -355,33 +361,51 @@ __global__ void __launch_bounds__(KNW_THREADS, 4) knn_query_warp(KnnQueryParams 
 
     if (!bail) {
         compact_keep();                     // the candidates within the margin of the final bound
-        if (n_keep > 32 || n_keep < k) bail = true;
+        if (n_keep > 64 || n_keep < k) bail = true;
     }
     if (bail) {                             // hand the query to the thread-per-query kernel
         if (lane == 0) todo[atomicAdd(todo_count, 1)] = (int32_t)s;
         return;
     }
 
-    // exact re-evaluation (the reference's float64 operation order) of the survivors, one per lane
-    double dd = INFINITY;
-    int cid = 0x7FFFFFFF;
-    if (lane < n_keep) {
-        const int e = kj[lane];
-        const float4 c = __ldg(&recs[e & KNN_IDX_MASK]);
-        cid = __float_as_int(c.w) & KNN_IDX_MASK;
-        double ox = 0.0, oy = 0.0, oz = 0.0;
-        if (PERIODIC) {
-            const int code = e >> KNN_FLAG_SHIFT;
-            ox = (double)knw_axis_shift(code & 3); oy = (double)knw_axis_shift((code >> 2) & 3); oz = (double)knw_axis_shift((code >> 4) & 3);
+    // exact re-evaluation (the reference's float64 operation order) of the survivors: one per lane, two when there are
+    // more than 32 (near-ties around the k-th distance, only possible for k close to 32)
+    auto exact = [&](int i, double &dd, int &cid) {
+        dd = INFINITY;
+        cid = 0x7FFFFFFF;
+        if (i < n_keep) {
+            const int e = kj[i];
+            const float4 c = __ldg(&recs[e & KNN_IDX_MASK]);
+            cid = __float_as_int(c.w) & KNN_IDX_MASK;
+            double ox = 0.0, oy = 0.0, oz = 0.0;
+            if (PERIODIC) {
+                const int code = e >> KNN_FLAG_SHIFT;
+                ox = (double)knw_axis_shift(code & 3); oy = (double)knw_axis_shift((code >> 2) & 3); oz = (double)knw_axis_shift((code >> 4) & 3);
+            }
+            const double tx = __dsub_rn((double)me.x, __dadd_rn((double)c.x, ox));
+            const double ty = __dsub_rn((double)me.y, __dadd_rn((double)c.y, oy));
+            const double tz = __dsub_rn((double)me.z, __dadd_rn((double)c.z, oz));
+            dd = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
         }
-        const double tx = __dsub_rn((double)me.x, __dadd_rn((double)c.x, ox));
-        const double ty = __dsub_rn((double)me.y, __dadd_rn((double)c.y, oy));
-        const double tz = __dsub_rn((double)me.z, __dadd_rn((double)c.z, oz));
-        dd = __dadd_rn(__dadd_rn(__dmul_rn(tx, tx), __dmul_rn(ty, ty)), __dmul_rn(tz, tz));
-    }
+    };
+    double dd;
+    int cid;
+    exact(lane, dd, cid);
     const int64_t out = ((int64_t)b * P.N + my_id) * k;
     const bool by_distance = P.order != NBPC_ORDER_INDEX;
-    if (n_keep > k || by_distance || P.d2_out) knw_sort32_pair(dd, cid, lane);   // exact (d2, index) order
+    if (n_keep > 32) {                      // the 32 smallest of two sorted runs: min(A[i], B[31 - i]) is bitonic
+        double d2;
+        int c2;
+        exact(32 + lane, d2, c2);
+        knw_sort32_pair(dd, cid, lane);
+        knw_sort32_pair(d2, c2, lane);
+        const double rd = __shfl_xor_sync(KNW_FULL, d2, 31);
+        const int rc = __shfl_xor_sync(KNW_FULL, c2, 31);
+        if ((rd < dd) | ((rd == dd) & (rc < cid))) { dd = rd; cid = rc; }
+        knw_merge32_pair(dd, cid, lane);
+    } else if (n_keep > k || by_distance || P.d2_out) {
+        knw_sort32_pair(dd, cid, lane);     // exact (d2, index) order
+    }
     if (P.d2_out && lane < k) P.d2_out[out + lane] = dd;
     if (by_distance) {
         if (lane < k) P.idx_out[out + lane] = cid;
