@@ -100,6 +100,14 @@ __device__ __forceinline__ void glt_tma_load_2d(uint32_t dst, const CUtensorMap 
                  : "r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
                  : "memory");
 }
+// smem -> global tile store (bulk async group of the issuing thread); OOB parts of the box are clipped
+__device__ __forceinline__ void glt_tma_store_2d(const CUtensorMap *tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void glt_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void glt_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ void glt_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void glt_prefetch_tmap(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }

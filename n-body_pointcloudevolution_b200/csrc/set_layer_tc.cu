@@ -156,10 +156,12 @@ struct SgtGemmArgs {
     float *csum;             // optional: per-sample column sums of `out`, [gridDim.x / n_ntiles][samples][Ntot] partials
                              // (one set per CTA row; requires rows_per_sample % 128 == 0)
     int samples, tiles_per_sample;
+    int obuf;                // staging tiles per epilogue warp (1 or 2)
 };
 
 template <bool X3>
-__global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const SgtGemmArgs P) {
+__global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmO,
+                                                               const SgtGemmArgs P) {
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
     const int S = P.S, L = X3 ? P.L : 0, K = P.K, NT = P.NT, KC = K >> 5;
@@ -169,9 +171,11 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     unsigned char *Al = As + S * SGT_CHUNK_BYTES;                 // [L][16 KB] residuals
     unsigned char *Bh = Al + L * SGT_CHUNK_BYTES;
     unsigned char *Bl = Bh + B_BYTES;
-    float *Os = reinterpret_cast<float *>(Bh + B_BYTES * (X3 ? 2 : 1));   // [4 warps][32][PITCH]
-    float *Cs = Os + 4 * 32 * 36;                                 // [4 warps][256] running column sums of the current sample
-    uint64_t *bars = reinterpret_cast<uint64_t *>(reinterpret_cast<unsigned char *>(Cs) + 4 * 256 * 4);
+    unsigned char *Ob = Bh + B_BYTES * (X3 ? 2 : 1);              // [4 warps][obuf][32 rows x 128 B] output staging (TMA store, 128-B swizzle)
+    float *Os = reinterpret_cast<float *>(Ob);                    // NT = 16 only: [4 warps][32][PITCH = 20] (aliases Ob)
+    float *Cs = reinterpret_cast<float *>(Ob + 4 * P.obuf * 4096); // [4 warps][256] running column sums of the current sample
+    float *Bs = Cs + 4 * 256;                                     // [256] bias of this CTA's columns
+    uint64_t *bars = reinterpret_cast<uint64_t *>(Bs + 256);
     const uint32_t bar0 = glt_smem_u32(bars);
     const int LB = X3 ? P.L : 1;                                  // barrier slots are laid out for max(L, 1)
     auto FULL = [&](int s) { return bar0 + 8u * s; };
@@ -195,6 +199,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
         for (int a = 0; a < 2; ++a) { glt_mbar_init(TFULL(a), 1); glt_mbar_init(TEMPTY(a), 4); }
         glt_fence_barrier_init();
         glt_prefetch_tmap(&tmA);
+        glt_prefetch_tmap(&tmO);
     }
     if (warp == 1) glt_tmem_alloc(glt_smem_u32(tmem_slot), tmem_cols);
     // B operand, K-major: row n = output column n0 + n, element kk; chunk c = 32 consecutive kk of all NT rows.
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
             }
         }
     }
+    for (int i = tid; i < NT; i += blockDim.x) Bs[i] = P.bias ? __ldg(&P.bias[n0 + i]) : 0.f;
     glt_fence_proxy_async();
     glt_tc_fence_before();
     __syncthreads();
@@ -276,7 +282,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     } else if (warp < 6) {
         // ---------------- epilogue warps: quadrant qd owns TMEM lanes / tile rows [32 qd, 32 qd + 32)
         const int qd = warp & 3;
-        float *Ow = Os + qd * 32 * 36;
+        float *Ow = Os + qd * 32 * 20;               // (16-column path: PITCH = 20)
         const int vshift = SW == 32 ? 3 : 2, vmask = (1 << vshift) - 1, iters = 1 << vshift;   // 32 rows * SW/4 float4 = 32 lanes * iters
         // (shifts: a runtime division by SW/4 in the two loops below cost more than the stores)
         int a = 0, aph = 0;
@@ -296,6 +302,96 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
             __syncwarp();
         };
         if (P.csum) csum_flush();
+        if (SW == 32) {
+            // ---- 32-column slabs: lane = tile row.  The lane adds the bias (shared memory), applies ReLU / the input mask
+            // (its own 128-byte row segment, requested one slab ahead) and writes its row into a 128-byte-swizzled staging
+            // tile; one elected lane hands the tile to the TMA store engine (coalescing, address generation and the
+            // clipping of the last tile's rows are the engine's job).  Two staging tiles per warp: the store of slab i
+            // reads its tile while slab i + 1 is assembled.  Column sums are taken from the staged tile (lane = column).
+            unsigned char *ob = Ob + qd * P.obuf * 4096;
+            const uint32_t bmask = (uint32_t)P.obuf - 1;
+            const uint32_t ob_u32 = glt_smem_u32(ob);
+            const int cq = lane >> 2, cw = (lane & 3) * 4;
+            uint32_t nslab = 0;
+            float4 mk[8];
+            auto mask_issue = [&](int64_t grow, int col0) {
+                if (grow < P.rows) {
+                    const float *mp = P.mask + grow * P.Ntot + col0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) mk[j] = glf_ldg4(mp + 4 * j);
+                }
+            };
+            if (P.mask && cta_m < ntiles) mask_issue((int64_t)cta_m * GLT_TILE + qd * 32 + lane, n0);
+            for (int64_t t = cta_m; t < ntiles; t += Gm) {
+                const int64_t row0 = t * GLT_TILE + qd * 32;
+                if (P.csum) {
+                    const int st = (int)t / P.tiles_per_sample;
+                    if (st != cur_sample) { csum_flush(); cur_sample = st; }
+                }
+                glt_mbar_wait(TFULL(a), aph);
+                glt_tc_fence_after();
+                const uint32_t tq = tmem_base + ((uint32_t)(qd * 32) << 16) + a * NT;
+                for (int cb = 0; cb < NT; cb += 32) {
+                    float z[32];
+                    glt_tmem_ld16(tq + cb, z);
+                    glt_tmem_ld16(tq + cb + 16, z + 16);
+                    glt_tc_wait_ld();
+                    if (cb + 32 >= NT) {          // last accumulator columns are in registers: release the TMEM stage
+                        glt_tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) glt_mbar_arrive(TEMPTY(a));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 bv = *reinterpret_cast<const float4 *>(Bs + cb + 4 * j);
+                        z[4 * j] += bv.x; z[4 * j + 1] += bv.y; z[4 * j + 2] += bv.z; z[4 * j + 3] += bv.w;
+                    }
+                    if (P.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) z[j] = fmaxf(z[j], 0.f);
+                    }
+                    if (P.mask) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            z[4 * j] = mk[j].x > 0.f ? z[4 * j] : 0.f; z[4 * j + 1] = mk[j].y > 0.f ? z[4 * j + 1] : 0.f;
+                            z[4 * j + 2] = mk[j].z > 0.f ? z[4 * j + 2] : 0.f; z[4 * j + 3] = mk[j].w > 0.f ? z[4 * j + 3] : 0.f;
+                        }
+                        // the mask registers are free: request the next slab's (or the next tile's first) row segment now
+                        if (cb + 32 < NT) mask_issue(row0 + lane, n0 + cb + 32);
+                        else if (t + Gm < ntiles) mask_issue((t + Gm) * GLT_TILE + qd * 32 + lane, n0);
+                    }
+                    // the staging tile of this slab was last used two slabs ago: its store must have finished reading
+                    if (lane == 0) { if (bmask) glt_bulk_wait_read<1>(); else glt_bulk_wait_read<0>(); }
+                    __syncwarp();
+                    unsigned char *buf = ob + (nslab & bmask) * 4096;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(z[4 * j], z[4 * j + 1], z[4 * j + 2], z[4 * j + 3]);
+                    glt_fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !(P.dbg & 1)) {
+                        glt_tma_store_2d(&tmO, ob_u32 + (nslab & bmask) * 4096, n0 + cb, (int)row0);
+                        glt_bulk_commit();
+                    }
+                    if (P.csum) {                 // column (cb + lane) of the staged tile, valid rows only
+                        const int nv = (int)nbpc_min((int64_t)32, P.rows - row0);
+                        const unsigned char *colp = buf + cw;
+                        float sum = 0.f;
+                        if (nv == 32) {
+#pragma unroll
+                            for (int r = 0; r < 32; ++r) sum += *reinterpret_cast<const float *>(colp + r * 128 + ((cq ^ (r & 7)) << 4));
+                        } else {
+                            for (int r = 0; r < nv; ++r) sum += *reinterpret_cast<const float *>(colp + r * 128 + ((cq ^ (r & 7)) << 4));
+                        }
+                        Cw[cb + lane] += sum;
+                    }
+                    ++nslab;
+                }
+                if (++a == 2) { a = 0; aph ^= 1; }
+            }
+            if (lane == 0) glt_bulk_wait_all();
+            __syncwarp();
+        } else
         for (int64_t t = cta_m; t < ntiles; t += Gm) {
             const int64_t row0 = t * GLT_TILE + qd * 32;
             if (P.csum) {
@@ -421,8 +517,8 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     }
 }
 
-static size_t sgt_gemm_smem(bool x3, int K, int NT, int S, int L) {
-    return 1024 + (size_t)(S + (x3 ? L : 0)) * SGT_CHUNK_BYTES + (size_t)K * NT * 4 * (x3 ? 2 : 1) + 4 * 32 * 36 * 4 + 4 * 256 * 4 + 8 * (3 * 8 + 8 + 4) + 64;
+static size_t sgt_gemm_smem(bool x3, int K, int NT, int S, int L, int obuf = 1) {
+    return 1024 + (size_t)(S + (x3 ? L : 0)) * SGT_CHUNK_BYTES + (size_t)K * NT * 4 * (x3 ? 2 : 1) + (size_t)4 * obuf * 4096 + 4 * 256 * 4 + 256 * 4 + 8 * (3 * 8 + 8 + 4) + 64;
 }
 
 // K-major tensor map over A (rows, K): box = 128 rows x 32 floats, 128-byte swizzle
@@ -432,6 +528,18 @@ static int sgt_make_tmap_a(CUtensorMap *tm, const float *ptr, int64_t rows, int 
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 4};
     cuuint32_t box[2] = {32u, (cuuint32_t)GLT_TILE};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
+}
+
+// tensor map over out (rows, Nout) for the epilogue's tile stores: box = 32 rows x 32 floats, 128-byte swizzle
+static int sgt_make_tmap_out(CUtensorMap *tm, const float *ptr, int64_t rows, int Nout) {
+    glt_encode_fn_t enc = glt_encode_fn();
+    if (!enc) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)Nout, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Nout * 4};
+    cuuint32_t box[2] = {32u, 32u};
     cuuint32_t estr[2] = {1, 1};
     return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : 1;
@@ -466,7 +574,9 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     while (S < 6 && sgt_gemm_smem(x3, K, NT, S + 1, L) <= budget) ++S;
     if (x3 && S >= 4 && sgt_gemm_smem(x3, K, NT, S - 1, L + 1) <= budget) { --S; ++L; }
     if (env_s >= 1 && env_l >= 1 && env_s <= 8 && env_l <= 8 && sgt_gemm_smem(x3, K, NT, env_s, env_l) <= budget) { S = env_s; L = env_l; }
-    const size_t smem = sgt_gemm_smem(x3, K, NT, S, L);
+    // a second staging tile per epilogue warp (the store of slab i overlaps the assembly of slab i + 1) if it costs no stage
+    const int obuf = sgt_gemm_smem(x3, K, NT, S, L, 2) <= budget ? 2 : 1;
+    const size_t smem = sgt_gemm_smem(x3, K, NT, S, L, obuf);
     auto kern = x3 ? sgt_gemm_kernel<true> : sgt_gemm_kernel<false>;
     static bool configured[64][2];   // per device: function attributes belong to a context
     int dev = 0;
@@ -478,12 +588,18 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
         }
         if (dev >= 0 && dev < 64) configured[dev][x3 ? 1 : 0] = true;
     }
-    CUtensorMap tm;
+    CUtensorMap tm, tmo;
     if (sgt_make_tmap_a(&tm, A, rows, K)) return 1;
+    if (NT >= 32) {
+        if (sgt_make_tmap_out(&tmo, out, rows, Nout)) return 1;
+    } else {
+        tmo = tm;   // unused by the 16-column epilogue
+    }
     SgtGemmArgs P;
     P.Bsrc = Bsrc; P.mu = mu; P.bias = bias; P.mask = mask; P.out = out; P.rows = rows; P.rows_per_sample = rows_per_sample;
     P.K = K; P.NT = NT; P.Ntot = Nout; P.n_ntiles = Nout / NT; P.b_transposed = b_transposed; P.relu = relu; P.S = S; P.L = L;
     P.rps_magic = sgt_magic(rows_per_sample);
+    P.obuf = obuf;
     static int dbg = -1;
     if (dbg < 0) {
         const char *e = getenv("NBPC_SGT_DEBUG");
@@ -501,7 +617,7 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
         if (P.tiles_per_sample < gm && cudaMemsetAsync(csum_parts, 0, sizeof(float) * (size_t)gm * P.samples * Nout, stream) != cudaSuccess) return 1;
     }
     const int grid = (int)(gm * P.n_ntiles);
-    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_gemm_tf32x3" : "sgt_gemm_tf32", K, Nout).c_str(), kern, grid, SGT_THREADS, smem, stream, tm, P);
+    NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_gemm_tf32x3" : "sgt_gemm_tf32", K, Nout).c_str(), kern, grid, SGT_THREADS, smem, stream, tm, tmo, P);
     return 0;
 }
 
