@@ -477,24 +477,32 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
         // ---------------- converter warps: centre the landed chunk in place (A - mu_s) and write the TF32 residual
         const int wtid = tid - 192;
         int s = 0, ph = 0, l = 0, lph = 0;
-        for (int64_t t = cta_m; t < ntiles; t += Gm)
+        // a thread's granules g = wtid + 256 i all lie in the same logical 16-byte unit of their rows (rows advance by 32)
+        const int lu_t = (wtid & 7) ^ ((wtid >> 3) & 7);
+        for (int64_t t = cta_m; t < ntiles; t += Gm) {
+            // sample of tile row r = s0 + (rem0 + r) / rows_per_sample: one 64-bit division per tile, none per granule
+            const int64_t trow = t * GLT_TILE;
+            const int64_t s0 = trow / P.rows_per_sample;
+            const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample), last = (uint32_t)nbpc_min((int64_t)GLT_TILE - 1, P.rows - 1 - trow);
+            const bool one_sample = rem0 + last < (uint32_t)P.rows_per_sample;   // the usual case: one mean row for the whole tile
             for (int c = 0; c < KC; ++c) {
+                const float *mu0 = P.mu ? P.mu + s0 * K + c * 32 : nullptr;
+                float4 mt = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.mu && one_sample) mt = glf_ldg4(mu0 + 4 * lu_t);           // requested before the wait for the data
                 glt_mbar_wait(FULL(s), ph);
                 if (X3) glt_mbar_wait(LOFREE(l), lph ^ 1);
                 float *hi = reinterpret_cast<float *>(As + s * SGT_CHUNK_BYTES);
                 float *lo = reinterpret_cast<float *>(Al + l * SGT_CHUNK_BYTES);
-                // sample of tile row r = s0 + (rem0 + r) / rows_per_sample: one 64-bit division per chunk, none per granule
-                const int64_t trow = t * GLT_TILE;
-                const int64_t s0 = trow / P.rows_per_sample;
-                const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample), last = (uint32_t)nbpc_min((int64_t)GLT_TILE - 1, P.rows - 1 - trow);
-                const float *mu0 = P.mu ? P.mu + s0 * K + c * 32 : nullptr;
 #pragma unroll 4
                 for (int g = (P.dbg & 4) ? SGT_CHUNK_BYTES : wtid; g < SGT_CHUNK_BYTES / 16; g += 32 * SGT_CONV_WARPS) {   // 16-byte granules: row = g / 8
                     float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
                     if (P.mu) {
-                        const int r = g >> 3, lu = (g & 7) ^ (r & 7);             // logical 16-byte unit inside the row
-                        const uint32_t ds = sgt_div(rem0 + nbpc_min((uint32_t)r, last), (uint32_t)P.rows_per_sample, P.rps_magic);
-                        const float4 m = glf_ldg4(mu0 + ds * K + 4 * lu);
+                        float4 m = mt;
+                        if (!one_sample) {
+                            const int r = g >> 3;
+                            const uint32_t ds = sgt_div(rem0 + nbpc_min((uint32_t)r, last), (uint32_t)P.rows_per_sample, P.rps_magic);
+                            m = glf_ldg4(mu0 + ds * K + 4 * lu_t);
+                        }
                         x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w;
                         *reinterpret_cast<float4 *>(hi + 4 * g) = X3 ? x : make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
                     } else if (!X3) {
@@ -508,6 +516,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                 if (++s == S) { s = 0; ph ^= 1; }
                 if (X3 && ++l == L) { l = 0; lph ^= 1; }
             }
+        }
     }
     glt_tc_fence_before();
     __syncthreads();
