@@ -157,6 +157,7 @@ struct SgtGemmArgs {
                              // (one set per CTA row; requires rows_per_sample % 128 == 0)
     int samples, tiles_per_sample;
     int obuf;                // staging tiles per epilogue warp (1 or 2)
+    int lo_tmem;             // TF32x3: number of A-residual slots kept in TENSOR memory (0: the residual ring is in shared memory)
 };
 
 template <bool X3>
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                                                                const SgtGemmArgs P) {
     extern __shared__ __align__(16) unsigned char glt_smem_raw[];
     unsigned char *base = glt_smem_raw + ((1024 - (glt_smem_u32(glt_smem_raw) & 1023)) & 1023);
-    const int S = P.S, L = X3 ? P.L : 0, K = P.K, NT = P.NT, KC = K >> 5;
+    const int S = P.S, L = (X3 && !P.lo_tmem) ? P.L : 0, K = P.K, NT = P.NT, KC = K >> 5;
+    const int LT = X3 ? P.lo_tmem : 0;                            // residual slots in tensor memory (32 columns each, after the accumulators)
     const int SW = NT < 32 ? NT : 32, PITCH = SW + 4;            // epilogue slab: SW accumulator columns at a time
     const int B_BYTES = K * NT * 4;
     unsigned char *As = base;                                     // [S][16 KB] landed (then centred) chunks = hi operand
@@ -177,7 +179,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     float *Bs = Cs + 4 * 256;                                     // [256] bias of this CTA's columns
     uint64_t *bars = reinterpret_cast<uint64_t *>(Bs + 256);
     const uint32_t bar0 = glt_smem_u32(bars);
-    const int LB = X3 ? P.L : 1;                                  // barrier slots are laid out for max(L, 1)
+    const int LB = X3 ? (P.lo_tmem ? P.lo_tmem : P.L) : 1;        // barrier slots are laid out for max(residual slots, 1)
     auto FULL = [&](int s) { return bar0 + 8u * s; };
     auto EMPTY = [&](int s) { return bar0 + 8u * (S + s); };
     auto CONV = [&](int s) { return bar0 + 8u * (2 * S + s); };   // per STAGE: centred (and split) data ready for the MMA
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
     const int n_tile = blockIdx.x % P.n_ntiles, cta_m = blockIdx.x / P.n_ntiles, Gm = gridDim.x / P.n_ntiles;
     const int n0 = n_tile * NT;
     int tmem_cols = 32;
-    while (tmem_cols < 2 * NT) tmem_cols <<= 1;
+    while (tmem_cols < 2 * NT + 32 * LT) tmem_cols <<= 1;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { glt_mbar_init(FULL(s), 1); glt_mbar_init(EMPTY(s), 1); glt_mbar_init(CONV(s), SGT_CONV_WARPS); }
@@ -262,8 +264,17 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                     glt_tc_fence_after();
                     const uint64_t a_hi = a_hi0 + (uint64_t)(s * (SGT_CHUNK_BYTES >> 4)), a_lo = a_lo0 + (uint64_t)(l * (SGT_CHUNK_BYTES >> 4));
                     const uint64_t b_hi = b_hi0 + (uint64_t)(c * b_step), b_lo = b_lo0 + (uint64_t)(c * b_step);
+                    if (X3 && LT) {                                   // lo*hi with the residual read from tensor memory
+                        const uint32_t a_t = tmem_base + 2 * NT + l * 32;
+#pragma unroll
+                        for (int k8 = 0; k8 < 4; ++k8) {
+                            glt_mma_tf32_ts(d, a_t + 8 * k8, b_hi + 2 * k8, idesc, acc);
+                            acc = 1;
+                        }
+                    }
 #pragma unroll
                     for (int pass = X3 ? 0 : 2; pass < 3; ++pass) {   // small terms first: lo*hi, hi*lo, hi*hi
+                        if (pass == 0 && LT) continue;
                         const uint64_t ab = (pass == 0) ? a_lo : a_hi, bb = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
                         for (int k8 = 0; k8 < 4; ++k8) {
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                         }
                     }
                     glt_tc_commit(EMPTY(s));
-                    if (X3) { glt_tc_commit(LOFREE(l)); if (++l == L) l = 0; }
+                    if (X3) { glt_tc_commit(LOFREE(l)); if (++l == (LT ? LT : L)) l = 0; }
                     if (++s == S) { s = 0; ph ^= 1; }
                 }
                 glt_tc_commit(TFULL(a));
@@ -477,6 +488,49 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
         // ---------------- converter warps: centre the landed chunk in place (A - mu_s) and write the TF32 residual
         const int wtid = tid - 192;
         int s = 0, ph = 0, l = 0, lph = 0;
+        if (X3 && LT) {
+            // ---- residuals to TENSOR memory: a warp may touch the 32 TMEM lanes of its quadrant (warp id % 4), so here a thread
+            // owns tile row 32 (warp % 4) + lane and half of the chunk's 32 columns (warps 6..9: columns 0..15, 10..13: 16..31).
+            // It centres its 4 granules in place (shared memory keeps the hi operand) and stores the 16 residuals into its
+            // lane of the slot's 32 columns; the MMA warp reads them as the A operand of the lo*hi products.
+            static_assert(SGT_CONV_WARPS == 8, "two converter warps per TMEM quadrant");
+            const int qd = warp & 3, half = (warp - 6) >> 2, r = qd * 32 + lane;
+            const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16) + 2 * NT + 16 * half;
+            for (int64_t t = cta_m; t < ntiles; t += Gm) {
+                const int64_t trow = t * GLT_TILE;
+                const int64_t grow = nbpc_min(trow + r, P.rows - 1);                  // rows past the end: any valid mean row
+                const float *mur = P.mu ? P.mu + (grow / P.rows_per_sample) * K + 16 * half : nullptr;
+                for (int c = 0; c < KC; ++c) {
+                    float4 m[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) m[j] = P.mu ? glf_ldg4(mur + c * 32 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    glt_mbar_wait(FULL(s), ph);
+                    glt_mbar_wait(LOFREE(l), lph ^ 1);
+                    glt_tc_fence_after();
+                    unsigned char *hi = As + s * SGT_CHUNK_BYTES + r * 128;
+                    float res[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 *px = reinterpret_cast<float4 *>(hi + (((4 * half + j) ^ (r & 7)) << 4));
+                        float4 x = *px;
+                        if (P.mu) {
+                            x.x -= m[j].x; x.y -= m[j].y; x.z -= m[j].z; x.w -= m[j].w;
+                            *px = x;
+                        }
+                        res[4 * j] = glt_residual(x.x); res[4 * j + 1] = glt_residual(x.y);
+                        res[4 * j + 2] = glt_residual(x.z); res[4 * j + 3] = glt_residual(x.w);
+                    }
+                    glt_tmem_st16(t_lane + l * 32, res);
+                    glt_tc_wait_st();
+                    glt_tc_fence_before();
+                    glt_fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) glt_mbar_arrive(CONV(s));
+                    if (++s == S) { s = 0; ph ^= 1; }
+                    if (++l == LT) { l = 0; lph ^= 1; }
+                }
+            }
+        } else {
         // a thread's granules g = wtid + 256 i all lie in the same logical 16-byte unit of their rows (rows advance by 32)
         const int lu_t = (wtid & 7) ^ ((wtid >> 3) & 7);
         for (int64_t t = cta_m; t < ntiles; t += Gm) {
@@ -516,6 +570,7 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_gemm_kernel(const __grid_cons
                 if (++s == S) { s = 0; ph ^= 1; }
                 if (X3 && ++l == L) { l = 0; lph ^= 1; }
             }
+        }
         }
     }
     glt_tc_fence_before();
@@ -583,6 +638,23 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     while (S < 6 && sgt_gemm_smem(x3, K, NT, S + 1, L) <= budget) ++S;
     if (x3 && S >= 4 && sgt_gemm_smem(x3, K, NT, S - 1, L + 1) <= budget) { --S; ++L; }
     if (env_s >= 1 && env_l >= 1 && env_s <= 8 && env_l <= 8 && sgt_gemm_smem(x3, K, NT, env_s, env_l) <= budget) { S = env_s; L = env_l; }
+    // TF32x3: the A residuals can live in tensor memory (next to the 2 NT accumulator columns) instead of a shared-memory
+    // ring, which leaves all of the ring's shared memory to landing stages (NBPC_SGT_LOTMEM=0 keeps the shared-memory ring)
+    int lo_tmem = 0;
+    static int env_lt = -1;
+    if (env_lt < 0) {
+        const char *e = getenv("NBPC_SGT_LOTMEM");
+        env_lt = e ? atoi(e) : 4;
+    }
+    if (x3 && env_lt > 0 && 2 * NT + 32 * env_lt <= 512 && rows_per_sample >= 1) {
+        lo_tmem = env_lt;
+        const int s_old = S + L;
+        L = 0;
+        S = 2;
+        while (S < 8 && sgt_gemm_smem(x3, K, NT, S + 1, 0) <= budget) ++S;
+        if (env_s >= 1 && env_s <= 8 && sgt_gemm_smem(x3, K, NT, env_s, 0) <= budget) S = env_s;
+        (void)s_old;
+    }
     // a second staging tile per epilogue warp (the store of slab i overlaps the assembly of slab i + 1) if it costs no stage
     const int obuf = sgt_gemm_smem(x3, K, NT, S, L, 2) <= budget ? 2 : 1;
     const size_t smem = sgt_gemm_smem(x3, K, NT, S, L, obuf);
@@ -609,6 +681,7 @@ int sgt_gemm(const float *A, const float *Bsrc, int b_transposed, const float *m
     P.K = K; P.NT = NT; P.Ntot = Nout; P.n_ntiles = Nout / NT; P.b_transposed = b_transposed; P.relu = relu; P.S = S; P.L = L;
     P.rps_magic = sgt_magic(rows_per_sample);
     P.obuf = obuf;
+    P.lo_tmem = lo_tmem;
     static int dbg = -1;
     if (dbg < 0) {
         const char *e = getenv("NBPC_SGT_DEBUG");
