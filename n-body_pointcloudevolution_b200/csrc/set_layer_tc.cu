@@ -837,37 +837,49 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_dw_kernel(const __grid_consta
         // ---------------- converter warps: centre H in place, write the TF32 residuals of H and dZ
         const int wtid = tid - 192;
         int s = 0, ph = 0, l = 0, lph = 0;
+        static_assert(32 * SGT_CONV_WARPS == 256, "one H granule per chunk and thread");
+        // granule g = wtid + 256 i -> (chunk i, row r_t, 16-byte unit u_t): row and unit are per-thread constants; 32-byte swizzle
+        // atoms: logical atom = atom ^ (row & 3)
+        const int r_t = (wtid >> 3) & (R - 1), u_t = wtid & 7;
+        const int col_t = (((u_t >> 1) ^ (r_t & 3)) << 3) | ((u_t & 1) << 2);
         for (int64_t t = blockIdx.x; t < ntiles; t += G) {
+            const int n_gran = STAGE / 16;
+            const int64_t trow = t * R;
+            const int n_valid = (int)nbpc_min((int64_t)R, P.rows - trow);
+            // this thread's row of the tile and its mean row, requested before the wait for the data (rows beyond the tensor
+            // were zero-filled by TMA and must stay zero)
+            const bool centre = P.mu && r_t < n_valid;
+            float4 m[8];
+            if (centre) {
+                const float *mur = P.mu + ((trow + r_t) / P.rows_per_sample) * k + col_t;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < HCH) m[i] = glf_ldg4(mur + 32 * i);
+            }
             glt_mbar_wait(FULL(s), ph);
             if (X3) glt_mbar_wait(LOFREE(l), lph ^ 1);
             float *hi = reinterpret_cast<float *>(St + s * STAGE);
             float *lo = reinterpret_cast<float *>(Sl + l * STAGE);
-            const int n_gran = STAGE / 16, h_gran = H_BYTES / 16;
-            const int64_t trow = t * R;
-            const int64_t s0 = trow / P.rows_per_sample;
-            const uint32_t rem0 = (uint32_t)(trow - s0 * P.rows_per_sample);
-            const int n_valid = (int)nbpc_min((int64_t)R, P.rows - trow);
-            const float *mu0 = P.mu ? P.mu + s0 * k : nullptr;
-#pragma unroll 4
-            for (int g = wtid; g < n_gran; g += 32 * SGT_CONV_WARPS) {
-                float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
-                bool wrote = false;
-                if (g < h_gran && P.mu) {
-                    // granule -> (chunk, row, 16-byte unit); R = 32 rows x 8 granules per chunk; 32-byte swizzle atoms:
-                    // logical atom = atom ^ (row & 3)
-                    const int ch = g >> 8, r = (g >> 3) & (R - 1), u = g & 7;
-                    const int col = ch * 32 + ((((u >> 1) ^ (r & 3)) << 3) | ((u & 1) << 2));
-                    // rows beyond the tensor were zero-filled by TMA and must stay zero
-                    if (r < n_valid) {
-                        const uint32_t ds = sgt_div(rem0 + (uint32_t)r, (uint32_t)P.rows_per_sample, P.rps_magic);
-                        const float4 m = glf_ldg4(mu0 + ds * k + col);
-                        x.x -= m.x; x.y -= m.y; x.z -= m.z; x.w -= m.w;
-                    }
-                    wrote = true;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {                   // the H chunks
+                if (i < HCH) {
+                    const int g = wtid + 256 * i;
+                    float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
+                    if (centre) { x.x -= m[i].x; x.y -= m[i].y; x.z -= m[i].z; x.w -= m[i].w; }
+                    if (!X3) x = make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
+                    if (P.mu || !X3) *reinterpret_cast<float4 *>(hi + 4 * g) = x;
+                    if (X3) *reinterpret_cast<float4 *>(lo + 4 * g) = make_float4(glt_residual(x.x), glt_residual(x.y), glt_residual(x.z), glt_residual(x.w));
                 }
-                if (!X3) x = make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
-                if (wrote || !X3) *reinterpret_cast<float4 *>(hi + 4 * g) = x;
-                if (X3) *reinterpret_cast<float4 *>(lo + 4 * g) = make_float4(glt_residual(x.x), glt_residual(x.y), glt_residual(x.z), glt_residual(x.w));
+            }
+#pragma unroll 4
+            for (int g = HCH * 256 + wtid; g < n_gran; g += 256) {   // the dZ chunks
+                float4 x = *reinterpret_cast<const float4 *>(hi + 4 * g);
+                if (!X3) {
+                    x = make_float4(glt_to_tf32(x.x), glt_to_tf32(x.y), glt_to_tf32(x.z), glt_to_tf32(x.w));
+                    *reinterpret_cast<float4 *>(hi + 4 * g) = x;
+                } else {
+                    *reinterpret_cast<float4 *>(lo + 4 * g) = make_float4(glt_residual(x.x), glt_residual(x.y), glt_residual(x.z), glt_residual(x.w));
+                }
             }
             glt_fence_proxy_async();
             __syncwarp();
@@ -882,20 +894,6 @@ __global__ void __launch_bounds__(SGT_THREADS) sgt_dw_kernel(const __grid_consta
         glt_tc_fence_after();
         glt_tmem_dealloc(tmem_base, tmem_cols);
     }
-}
-
-// dW[o] = sum over the CTA partials, fixed order (4 independent partial sums, then one tree)
-__global__ void sgt_dw_final_kernel(const float *__restrict__ partial, int nparts, int kq, float *__restrict__ dW) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= kq) return;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = 0;
-    for (; b + 4 <= nparts; b += 4) {
-        a0 += __ldg(partial + (int64_t)b * kq + o); a1 += __ldg(partial + (int64_t)(b + 1) * kq + o);
-        a2 += __ldg(partial + (int64_t)(b + 2) * kq + o); a3 += __ldg(partial + (int64_t)(b + 3) * kq + o);
-    }
-    for (; b < nparts; ++b) a0 += __ldg(partial + (int64_t)b * kq + o);
-    dW[o] = (a0 + a1) + (a2 + a3);
 }
 
 static size_t sgt_dw_smem(bool x3, int k, int q, int S, int L) {
@@ -934,7 +932,8 @@ int sgt_dw(const float *H, const float *dZ, const float *mu, int64_t rows, int r
     const int64_t ntiles = (rows + SGT_DW_ROWS - 1) / SGT_DW_ROWS;
     const int grid = (int)nbpc_min((int64_t)gl_num_sms(), ntiles);
     NBPC_LAUNCH_N(NbpcKName(x3 ? "sgt_dw_tf32x3" : "sgt_dw_tf32", k, q).c_str(), kern, grid, SGT_THREADS, smem, stream, tmH, tmZ, P);
-    NBPC_LAUNCH(sgt_dw_final_kernel, nbpc_cdiv(k * q, 256), 256, 0, stream, partial, grid, k * q, dW);
+    // fixed-order sum of the per-CTA partials (32 outputs x 32 slices per block)
+    NBPC_LAUNCH_N("sgt_dw_final_kernel", sgt_colsum_from_parts_kernel, nbpc_cdiv(k * q, 32), 1024, 0, stream, (const float *)partial, grid, k * q, 1.0f, dW, (float *)nullptr);
     return 0;
 }
 
