@@ -149,6 +149,67 @@ __global__ void adam_tf_dev_kernel(float *__restrict__ p, const float *__restric
     p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
 }
 
+#ifndef NBPC_HOST_EMU
+// The three reduction levels above in ONE launch, same summation order (bit-identical result): a block computes its 256 chunk
+// partials and the 4 second-level sums they form; the block that takes the last ticket adds the second-level sums in index
+// order.  The ticket is an integer atomic (no float atomics anywhere); it is zeroed by the launcher and left at zero.
+template <int PBC>
+__global__ void __launch_bounds__(LOSS_THREADS) loss_fused_kernel(const float *__restrict__ pred, int ldp, const float *__restrict__ truth,
+                                                                  int ldt, int64_t rows, int nchunks, int n2, float scale,
+                                                                  float *__restrict__ partial2, unsigned int *__restrict__ ticket,
+                                                                  float *__restrict__ out) {
+    static_assert(LOSS_THREADS % LOSS_FAN == 0, "a block's chunks form whole second-level groups");
+    __shared__ float sp[LOSS_THREADS];
+    __shared__ bool last;
+    const int ch = blockIdx.x * LOSS_THREADS + threadIdx.x;
+    float acc = 0.f;
+    if (ch < nchunks) {
+        const int64_t r0 = (int64_t)ch * LOSS_CHUNK, r1 = nbpc_min(r0 + LOSS_CHUNK, rows);
+        for (int64_t r = r0; r < r1; ++r) {
+            float rs = 0.f;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const float p = pred[r * ldp + d], t = truth[r * ldt + d];
+                rs = __fadd_rn(rs, PBC ? pbd_axis(p, t, nullptr) : sq_rn(__fadd_rn(p, -t)));
+            }
+            acc = __fadd_rn(acc, rs);
+        }
+    }
+    sp[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < LOSS_THREADS / LOSS_FAN) {
+        const int j = blockIdx.x * (LOSS_THREADS / LOSS_FAN) + threadIdx.x;
+        if (j < n2) {
+            const int i0 = (int)threadIdx.x * LOSS_FAN, i1 = nbpc_min(i0 + LOSS_FAN, nchunks - (int)blockIdx.x * LOSS_THREADS);
+            float a2 = 0.f;
+            for (int i = i0; i < i1; ++i) a2 = __fadd_rn(a2, sp[i]);
+            partial2[j] = a2;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    float tot = 0.f;
+    for (int j0 = 0; j0 < n2; j0 += LOSS_THREADS) {         // staged through shared memory, added in index order by one thread
+        const int j = j0 + threadIdx.x;
+        __syncthreads();
+        sp[threadIdx.x] = j < n2 ? __ldcg(&partial2[j]) : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int n = nbpc_min(LOSS_THREADS, n2 - j0);
+            for (int i = 0; i < n; ++i) tot = __fadd_rn(tot, sp[i]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        out[0] = __fmul_rn(tot / (float)rows, scale);
+        *ticket = 0u;
+    }
+}
+#endif
+
 template <int PBC>
 static int loss_fwd_impl(const float *pred, int ldp, const float *truth, int ldt, int64_t rows, float scale,
                          float *loss_out, void *workspace, size_t ws_bytes, cudaStream_t stream, const char *name) {
@@ -163,6 +224,19 @@ static int loss_fwd_impl(const float *pred, int ldp, const float *truth, int ldt
     }
     float *partial = (float *)workspace;
     float *partial2 = partial + nchunks;
+#ifndef NBPC_HOST_EMU
+    {   // one launch; `partial` (unused by it) lends its first word to the ticket
+        unsigned int *ticket = (unsigned int *)partial;
+        if (nbpc_memset_async(ticket, 0, sizeof(unsigned int), stream)) {
+            nbpc_set_error(std::string(name) + ": memset failed");
+            return NBPC_ELAUNCH;
+        }
+        void (*fused)(const float *, int, const float *, int, int64_t, int, int, float, float *, unsigned int *, float *) = loss_fused_kernel<PBC>;
+        NBPC_LAUNCH_N("loss_fused_kernel", fused, nbpc_cdiv(nchunks, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows,
+                      nchunks, n2, scale, partial2, ticket, loss_out);
+        return nbpc_check_launch(name);
+    }
+#endif
     void (*kern)(const float *, int, const float *, int, int64_t, int, float *) = loss_partial_kernel<PBC>;
     NBPC_LAUNCH_N("loss_partial_kernel", kern, nbpc_cdiv(nchunks, LOSS_THREADS), LOSS_THREADS, 0, stream, pred, ldp, truth, ldt, rows, nchunks, partial);
     NBPC_LAUNCH(loss_mid_kernel, nbpc_cdiv(n2, LOSS_THREADS), LOSS_THREADS, 0, stream, partial, nchunks, n2, partial2);

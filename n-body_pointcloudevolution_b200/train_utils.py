@@ -26,16 +26,17 @@ class ParamStore:
         for k, q in zip(channels[:-1], channels[1:]):
             sizes.append(n_w * k * q + q)
         self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
-        self.flat_grad = torch.zeros_like(self.flat)
+        self._flat_grad = torch.zeros_like(self.flat)
+        self._loose = False                                   # True: the .grad tensors are autograd's own (see zero_grad)
         gen = torch.Generator(device="cpu").manual_seed(int(seed))
-        self._W, self._B = [], []
+        self._W, self._B, self._grad_views = [], [], []
         off = 0
         for (k, q), _ in zip(zip(channels[:-1], channels[1:]), sizes):
             W = self.flat[off:off + n_w * k * q].view(n_w, k, q)
-            Wg = self.flat_grad[off:off + n_w * k * q].view(n_w, k, q)
+            Wg = self._flat_grad[off:off + n_w * k * q].view(n_w, k, q)
             off += n_w * k * q
             Bv = self.flat[off:off + q]
-            Bg = self.flat_grad[off:off + q]
+            Bg = self._flat_grad[off:off + q]
             off += q
             sigma = math.sqrt(2.0 / (k + q))   # glorot normal (utils.py:178, 357)
             init = torch.empty(n_w, k, q).normal_(0.0, sigma, generator=gen)
@@ -43,9 +44,10 @@ class ParamStore:
             Bv.fill_(1e-8)                     # utils.py:334
             W.requires_grad_(True)
             Bv.requires_grad_(True)
-            W.grad, Bv.grad = Wg, Bg           # autograd accumulates straight into the flat buffer
+            W.grad, Bv.grad = Wg, Bg           # views of the flat gradient buffer
             self._W.append(W)
             self._B.append(Bv)
+            self._grad_views.append((Wg, Bg))
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.step_count = 0                                  # AdamTF.step(): count kept on the host
@@ -67,7 +69,37 @@ class ParamStore:
                 self._B[i].copy_(torch.as_tensor(B).reshape(-1))
 
     def zero_grad(self):
-        self.flat_grad.zero_()
+        """Forget the gradients.  No kernel runs: the .grad tensors are dropped, so the next backward makes autograd ADOPT the
+        tensors the layer kernels wrote (an existing .grad would cost one accumulate kernel per parameter plus the zero fill);
+        `pack_grads` - called by every reader of `flat_grad` - gathers them into the flat buffer with one concatenation."""
+        for p in self._W + self._B:
+            p.grad = None
+        self._loose = True
+
+    def pack_grads(self):
+        if not self._loose:
+            return
+        self._loose = False
+        parts, views = [], []
+        for W, B, (Wg, Bg) in zip(self._W, self._B, self._grad_views):
+            for p, v in ((W, Wg), (B, Bg)):
+                parts.append((p.grad if p.grad is not None else torch.zeros_like(v)).reshape(-1))
+                views.append((p, v))
+        with torch.no_grad():
+            torch.cat(parts, out=self._flat_grad)
+        for p, v in views:
+            p.grad = v
+
+    @property
+    def flat_grad(self):
+        self.pack_grads()
+        return self._flat_grad
+
+    @flat_grad.setter
+    def flat_grad(self, value):                 # `store.flat_grad += x` assigns the same tensor back
+        if value is not self._flat_grad:
+            self.pack_grads()
+            self._flat_grad.copy_(value)
 
     def parameters(self):
         return self._W + self._B
@@ -153,7 +185,9 @@ class PipelinedStep:
                 adam.step_dev(grad_scale=1.0 / world)
             ctx = prep_fn(*self.static_in)
             main.wait_stream(self.side)
-            return grad_fn(ctx, *self.static_in)
+            out = grad_fn(ctx, *self.static_in)
+            store.pack_grads()                             # the next body's all-reduce reads the flat buffer of THIS capture
+            return out
 
         warm = torch.cuda.Stream()
         warm.wait_stream(torch.cuda.current_stream())
