@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying one CUDA graph per step")
     ap.add_argument("--no-extras", action="store_true", help="skip the 128^3 kNN build timing")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="one graph per step (kNN build, forward, backward in sequence) instead of building the graph of batch i+1 "
+                         "on a second stream next to the forward / backward of batch i (train_utils.OverlappedStep)")
     return ap.parse_args()
 
 
@@ -291,7 +294,7 @@ class Workload:
     """One training workload on this rank: a pool of distinct batches resident in HBM (and their pinned host copies), the
     parameter store, and the step function - eager or replayed from one CUDA graph."""
 
-    def __init__(self, nb, dev, rank, world, n_side, b, k, ch, kind, use_graph, n_pool=4, host_copies=True):
+    def __init__(self, nb, dev, rank, world, n_side, b, k, ch, kind, use_graph, n_pool=4, host_copies=True, overlap=True):
         syn, graph, nn_, tu = nb.synthetic, nb.graph, nb.nn, nb.train_utils
         self.nb, self.dev, self.world, self.b, self.N, self.k, self.ch = nb, dev, world, b, n_side ** 3, k, ch
         N = self.N
@@ -332,9 +335,27 @@ class Workload:
         # The whole step (kNN build, adjacency, forward, backward, Adam) is captured once in a CUDA graph and replayed, so
         # the timed region is not limited by the host's launch rate; --no-graph launches eagerly.
         self.graphed, self.graph_note, self.pipelined = None, "eager launches (--no-graph)", False
+        self.overlapped = False
         if use_graph:
             try:
-                if world == 1:
+                if overlap:
+                    # the graph of batch i+1 (kNN, adjacency, CSR transpose: issue-bound, no parameters) is built on a second,
+                    # low-priority stream while forward / backward / all-reduce / Adam of batch i (HBM-bound) run on the first:
+                    # every call still does one graph build and one parameter update (train_utils.OverlappedStep)
+                    def prep(x, za, tgt):
+                        return graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(x, k))
+
+                    def grad(ctx, x, za, tgt):
+                        coo, diag = ctx
+                        loss = nn_.loss_ZA(graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k)), tgt)
+                        store.zero_grad()
+                        loss.backward()
+                        return loss
+                    self.graphed = tu.OverlappedStep(prep, grad, store, adam, world, self.resident[0])
+                    self.overlapped = True
+                    self.graph_note = ("CUDA graphs on two streams: the kNN graph build of batch i+1 runs next to forward / backward / "
+                                       "all-reduce / Adam of batch i; one build and one update per step")
+                elif world == 1:
                     self.graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), self.resident[0])
                     self.graph_note = "one CUDA graph replay per step (whole step captured once)"
                 else:
@@ -362,6 +383,8 @@ class Workload:
         if self.graphed is None:
             return self.train_step(x, za, tgt)
         loss = self.graphed(x, za, tgt)
+        if self.overlapped:
+            return loss                                              # loss of the previous batch (None on the very first call)
         if self.world > 1 and not self.pipelined:
             self.nb.train_utils.allreduce_gradients(self.store, self.world)
             self.adam.step(grad_scale=1.0 / self.world)
@@ -370,10 +393,15 @@ class Workload:
     def close(self):
         """Apply a pending pipelined update and drop the CUDA graph (must precede destroy_process_group)."""
         if self.graphed is not None:
-            if self.pipelined:
+            if self.pipelined or self.overlapped:
                 self.graphed.flush()
             self.graphed.close()
             self.graphed = None
+
+    def join_streams(self):
+        """The build stream of the overlapped loop joins the current stream (a timed region then holds exactly K builds)."""
+        if self.overlapped:
+            torch.cuda.current_stream().wait_stream(self.graphed.side)
 
     def step_resident(self, i):
         return self.run_step(*self.resident[i % self.n_pool])
@@ -385,8 +413,9 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
-def timed(fn, steps, world, dev, stats=None, tag=None):
-    """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides; CUDA-event time, max over ranks (ms)."""
+def timed(fn, steps, world, dev, stats=None, tag=None, join=None):
+    """EXACTLY `steps` calls bracketed by barrier + synchronize on both sides; CUDA-event time, max over ranks (ms).
+    `join`: makes the timing stream wait for any other stream the step uses before the last event is recorded."""
     barrier(world)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     host = []
@@ -394,6 +423,8 @@ def timed(fn, steps, world, dev, stats=None, tag=None):
     t0 = time.perf_counter()
     for i in range(steps):
         fn(i)
+        if join is not None and i == steps - 1:
+            join()
         ev[i + 1].record()
         host.append(time.perf_counter() - t0)
     barrier(world)
@@ -553,7 +584,7 @@ def main():
     nb.ops.device_check()
 
     N, b, k, ch = a.n_side ** 3, a.batch, a.k, a.channels
-    wl = Workload(nb, dev, rank, world, a.n_side, b, k, ch, a.kind, not a.no_graph)
+    wl = Workload(nb, dev, rank, world, a.n_side, b, k, ch, a.kind, not a.no_graph, overlap=not a.no_overlap)
     store, host, n_pool, graph_note = wl.store, wl.host, wl.n_pool, wl.graph_note
     step_stats = {}
 
@@ -586,7 +617,8 @@ def main():
         loss = wl.run_step(*slots[sl])
         consumed[sl].record()
         used[sl] = True
-        loss_host[i % loss_host.numel()].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H read of the loss
+        if loss is not None:                                         # (overlapped loop: the loss of the previous batch)
+            loss_host[i % loss_host.numel()].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H read of the loss
 
     # ---- warm-up, then the timed region (device-resident inputs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -597,7 +629,7 @@ def main():
         sampler.wait_ready()
         skip = sampler.mark()
     l0 = lib.launch_count()
-    ms = timed(wl.step_resident, a.steps, world, dev, step_stats, "resident")
+    ms = timed(wl.step_resident, a.steps, world, dev, step_stats, "resident", join=wl.join_streams)
     launches = lib.launch_count() - l0
     if wl.graphed is not None:                                       # kernels are launched by the graph replays
         launches = (wl.graphed.kernels_per_replay + (1 if world > 1 else 0)) * a.steps   # + the NCCL kernel
@@ -610,7 +642,7 @@ def main():
         step_e2e(i)
     torch.cuda.synchronize()
     used[0] = used[1] = False
-    ms_e2e = timed(step_e2e, a.steps, world, dev, step_stats, "e2e")
+    ms_e2e = timed(step_e2e, a.steps, world, dev, step_stats, "e2e", join=wl.join_streams)
     assert bool(torch.isfinite(loss_host[:min(a.steps, loss_host.numel())]).all()), "e2e losses did not arrive on the host"
     e2e_value = particles * a.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
@@ -621,11 +653,11 @@ def main():
     if not a.no_extras and a.n_side == 32 and ch == [3, 32, 16, 3]:
         for mode, bb in (("weak", 1), ("strong", max(8 // world, 1))):
             try:
-                w4 = Workload(nb, dev, rank, world, 64, bb, k, ch, a.kind, not a.no_graph, n_pool=2, host_copies=False)
+                w4 = Workload(nb, dev, rank, world, 64, bb, k, ch, a.kind, not a.no_graph, n_pool=2, host_copies=False, overlap=not a.no_overlap)
                 for i in range(3):
                     w4.step_resident(i)
                 st = 20
-                ms4 = timed(w4.step_resident, st, world, dev)
+                ms4 = timed(w4.step_resident, st, world, dev, join=w4.join_streams)
                 p4 = world * bb * 64 ** 3
                 c_edges = bb * 64 ** 3 * k
                 step_bytes = 1428 * c_edges + (12 + 4 * k) * bb * 64 ** 3 + 20 * c_edges + 16 * bb * 64 ** 3

@@ -225,6 +225,96 @@ class PipelinedStep:
         torch.cuda.synchronize()
 
 
+class OverlappedStep:
+    """Training loop software-pipelined ACROSS steps: the neighbour graph of batch i (kNN build, adjacency, CSR transpose - no
+    parameters involved, issue-bound) is built on a second stream while the forward / backward / all-reduce / Adam of batch
+    i-1 (HBM-bound) runs on the first, so the two share the SMs instead of taking turns:
+
+        call i:   main stream (high priority): inputs_i -> slot i%2;  T[(i-1)%2]: grad_fn(ctx, batch i-1) -> all-reduce -> Adam
+                  side stream (low priority) : P[i%2]: prep_fn(batch i) -> ctx[i%2]
+
+    Four CUDA graphs (P and T for each of the two slots), ordered by events: T waits for the P of its slot (previous call),
+    P waits until the T that last read its slot has been enqueued-and-finished (stream order on main + the `staged` event).
+    Every call does one full step's work - one graph build and one parameter update - and the sequence of parameter values
+    is exactly that of the plain loop; the call returns the loss of batch i-1 (None on the first call) and flush() trains on
+    the last batch.  prep_fn(*static_inputs) -> ctx; grad_fn(ctx, *static_inputs) -> loss (zeroes the gradients before its
+    backward).  close() must precede destroy_process_group() (the T graphs hold the NCCL kernels)."""
+
+    def __init__(self, prep_fn, grad_fn, store, adam, world, example_inputs, warmup=2):
+        self.store, self.adam, self.world = store, adam, world
+        self.static_in = [tuple(torch.empty_like(t).copy_(t) for t in example_inputs) for _ in range(2)]
+        self.side = torch.cuda.Stream(priority=0)
+        cap_hi, cap_lo = torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=0)
+        state = [t.clone() for t in (store.flat, store.m, store.v, store.step_dev)]
+
+        def train(ctx, ins):
+            out = grad_fn(ctx, *ins)
+            allreduce_gradients(store, world)
+            adam.step_dev(grad_scale=1.0 / world)
+            return out
+
+        cap_hi.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap_hi):                    # lazy initialisations (NCCL communicator included) outside the captures,
+            for _ in range(max(warmup, 1)):                # on the stream the training graphs are captured on
+                train(prep_fn(*self.static_in[0]), self.static_in[0])
+        torch.cuda.current_stream().wait_stream(cap_hi)
+        torch.cuda.synchronize()
+        with torch.no_grad():                              # the warm-up steps trained on the example batch: undo
+            for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
+                t.copy_(s0)
+        self.P, self.T, self.ctx, self.loss = [None, None], [None, None], [None, None], [None, None]
+        n0 = _lib.launch_count()
+        for s in range(2):
+            self.P[s] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.P[s], stream=cap_lo):
+                self.ctx[s] = prep_fn(*self.static_in[s])
+        for s in range(2):
+            self.T[s] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.T[s], stream=cap_hi, pool=(self.T[0].pool() if s else None)):
+                self.loss[s] = train(self.ctx[s], self.static_in[s])
+        self.kernels_per_replay = (_lib.launch_count() - n0) // 2
+        with torch.no_grad():                              # (a capture runs nothing, but keep the contract explicit)
+            for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
+                t.copy_(s0)
+        self.staged = [torch.cuda.Event(), torch.cuda.Event()]
+        self.prepped = [torch.cuda.Event(), torch.cuda.Event()]
+        self.i = 0
+        torch.cuda.synchronize()
+
+    def _train(self, s):
+        main = torch.cuda.current_stream()
+        main.wait_event(self.prepped[s])
+        self.T[s].replay()
+        return self.loss[s]
+
+    def __call__(self, *inputs):
+        s = self.i & 1
+        main = torch.cuda.current_stream()
+        for d, src in zip(self.static_in[s], inputs):      # T[s] of the previous call precedes this copy in stream order
+            if d.data_ptr() != src.data_ptr():
+                d.copy_(src, non_blocking=True)
+        self.staged[s].record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.staged[s])
+            self.P[s].replay()
+            self.prepped[s].record(self.side)
+        out = self._train(1 - s) if self.i > 0 else None
+        self.i += 1
+        return out
+
+    def flush(self):
+        """Train on the batch whose graph the last call built (the pipeline's drain)."""
+        if self.i == 0:
+            return None
+        out = self._train((self.i - 1) & 1)
+        self.i = 0
+        return out
+
+    def close(self):
+        self.P = self.T = None
+        torch.cuda.synchronize()
+
+
 def allreduce_gradients(store, world_size):
     """Sum the flat gradient buffer over ranks (NCCL over NVLink on GPUs; gloo in CPU tests)."""
     if world_size > 1:

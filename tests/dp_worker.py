@@ -50,7 +50,7 @@ def main(out_path):
     g_dp, p_dp = run(slice(rank * per, (rank + 1) * per), world, True)        # this rank's samples, NCCL all-reduce
 
     # the same data-parallel run with the whole step (NCCL all-reduce included) captured in one CUDA graph
-    def run_pipelined():
+    def run_pipelined(overlapped=False):
         store = tu.ParamStore(ch, device=dev)
         store.load_numpy(syn.glorot_params(ch))
         adam = tu.AdamTF(store, lr=0.01)
@@ -66,17 +66,18 @@ def main(out_path):
             store.zero_grad()
             loss.backward()
             return loss
-        ps = tu.PipelinedStep(prep, grad, store, adam, world, dev_batches[0])
+        ps = (tu.OverlappedStep if overlapped else tu.PipelinedStep)(prep, grad, store, adam, world, dev_batches[0])
         for bt in dev_batches:
             ps(*bt)
         ps.flush()
         ps.close()
         return store.flat.clone()
     p_pipe = run_pipelined()
+    p_over = run_pipelined(overlapped=True)       # graph build of batch i+1 next to forward / backward / all-reduce / Adam of batch i
     if rank == 0:
         g_1, p_1 = run(slice(0, B), 1, False)                                  # same global batch on one GPU
         np.savez(out_path, g_dp=g_dp.cpu().numpy(), p_dp=p_dp.cpu().numpy(), g_1=g_1.cpu().numpy(), p_1=p_1.cpu().numpy(),
-                 p_pipe=p_pipe.cpu().numpy())
+                 p_pipe=p_pipe.cpu().numpy(), p_over=p_over.cpu().numpy())
     # every rank must hold identical parameters
     gathered = [torch.empty_like(p_dp) for _ in range(world)]
     torch.distributed.all_gather(gathered, p_dp)

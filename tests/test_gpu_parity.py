@@ -808,6 +808,52 @@ def test_pipelined_step_matches_eager(nb, syn):
     assert torch.equal(store_p.flat, store_e.flat) and int(store_p.step_dev.item()) == 6 == int(store_e.step_dev.item())
 
 
+def test_overlapped_step_matches_eager(nb, syn):
+    """train_utils.OverlappedStep (the graph of batch i+1 built on a second stream next to forward / backward / Adam of batch i,
+    four CUDA graphs ordered by events) reproduces the eager loop bit for bit: losses (one call late), parameters, step count."""
+    tu, graph, nn_ = nb.train_utils, nb.graph, nb.nn
+    ch, b, N, k = [3, 32, 16, 3], 2, 1000, 8
+    batches = []
+    for i in range(3):
+        x = torch.tensor(syn.make_box("uniform", b, N, 40 + i), device=DEV)
+        za, tgt = (torch.tensor(t, device=DEV) for t in syn.za_features(b, N, 40 + i))
+        batches.append((x, za, tgt))
+
+    def make():
+        store = tu.ParamStore(ch, device=DEV)
+        store.load_numpy(syn.glorot_params(ch))
+        adam = tu.AdamTF(store, lr=0.01)
+        mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+
+        def prep(x, za, tgt):
+            return graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(x, k))
+
+        def grad(ctx, x, za, tgt):
+            loss = nn_.loss_ZA(graph.model_func_shift_inv_za(x, ctx[0], za, ctx[1], mv, (b, N, k)), tgt)
+            store.zero_grad()
+            loss.backward()
+            return loss
+        return store, adam, prep, grad
+
+    store_e, adam_e, prep, grad = make()
+    eager = []
+    for i in range(7):
+        eager.append(float(grad(prep(*batches[i % 3]), *batches[i % 3]).detach()))
+        adam_e.step_dev()
+    store_o, adam_o, prep, grad = make()
+    ov = tu.OverlappedStep(prep, grad, store_o, adam_o, 1, batches[0])
+    got = []
+    for i in range(7):
+        out = ov(*batches[i % 3])
+        assert (out is None) == (i == 0)
+        if out is not None:
+            got.append(float(out.detach()))                 # (synchronises: the static loss tensor is overwritten two calls later)
+    got.append(float(ov.flush().detach()))
+    ov.close()
+    assert got == eager
+    assert torch.equal(store_o.flat, store_e.flat) and int(store_o.step_dev.item()) == 7 == int(store_e.step_dev.item())
+
+
 def test_train_step_128_cubed_finite_and_deterministic(nb, syn):
     """BASELINE's largest box as a TRAINING step (29.4 M edges, 3.8 GB edge tensors: byte offsets beyond 2^32): loss and
     every gradient finite, two runs bit-identical, and sample-independence: the same box inside a batch of one and as

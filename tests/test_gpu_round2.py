@@ -352,3 +352,4 @@ def test_dp2_gradients_match_global_batch(tmp_path):
     np.testing.assert_allclose(r["p_dp"], r["p_1"], rtol=1e-5, atol=1e-4)
     # eager DP loop (adam.step, host-side step count) vs the CUDA-graph form with the all-reduce captured (device-side count)
     np.testing.assert_allclose(r["p_pipe"], r["p_dp"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(r["p_over"], r["p_pipe"])       # two-stream form (train_utils.OverlappedStep): same updates
