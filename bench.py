@@ -228,15 +228,16 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
     relu = 2 if (k, q) in relu_by_layer and relu_by_layer[(k, q)] else 1   # masked dZ also reads H_out
     if base == "knn_query":
         return n * (12 + 4 * M)                      # xyz in, int32 idx out
-    if base in ("gl_pool_kernel", "glf_pool_kernel", "gln_pool_kernel", "gln_pool_generic_kernel"):
+    if base in ("gl_pool_kernel", "glf_pool_kernel", "gln_pool_kernel", "gln_pool_generic_kernel", "gln_pool_colonly_kernel"):
         return c * (4 * k + 4) + n * (4 + 2 * 4 * k)           # contract: the pool pass reads H ONCE
-    if base in ("gl_edge_out_kernel", "glf_edge_out_kernel", "glk3_edge_out_kernel", "glt_edge_out_tf32", "glt_edge_out_tf32x3"):
+    if base in ("gl_edge_out_kernel", "glf_edge_out_kernel", "glk3_edge_out_kernel", "glk3_edge_out_rowpool_kernel", "glt_edge_out_tf32",
+                "glt_edge_out_tf32x3"):
         return c * (4 * k + 4 + 4 * q) + n * 2 * 4 * q         # H in, col in, H_out out (+ node tables)
     if base == "gl_last_out_kernel":
         return c * (4 * k + 4) + n * 3 * 4 * q
     if base == "glf_last_out_kernel":
         return c * 4 + n * (4 * k + 3 * 4 * q)
-    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel", "gln_bwd_pool_kernel"):   # contract: dZ read ONCE by the pool pass;
+    if base in ("glb_pool_kernel", "glf_bwd_pool_kernel", "gln_bwd_pool_kernel", "gln_bwd_pool_colonly_kernel"):   # contract: dZ read ONCE by the pool pass;
         return c * (4 * q + 4) + n * (4 + 2 * 4 * q)           # the network path delivers dZ pre-masked (no H_out read)
     if base == "xty_partial_dW1":
         return c * (4 * k + 4 * q * relu)
@@ -249,7 +250,7 @@ def kernel_algorithmic_bytes(name, b, N, M, relu_by_layer):
         return c * (12 + 4 * q)
     if base == "glk3_first_layer_bwd_kernel":                  # first layer, all gradients: E, col and dZ in (once)
         return c * (12 + 4 + 4 * q) + n * 2 * 12
-    if base == "glf_last_edge_in_kernel":                      # col in, H (mask) in, dH out
+    if base in ("glf_last_edge_in_kernel", "glf_last_edge_in_rowsum_kernel"):   # col in, H (mask) in, dH out
         return c * (4 + 2 * 4 * k) + n * 2 * 4 * k
     if base == "gln_node_project_kernel":                      # P_col, P_row in; Q_col, Q_row out
         return n * (2 * 4 * k + 2 * 4 * q)

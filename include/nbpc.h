@@ -203,6 +203,32 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                          int mask_input, float *dH_in, float *dW, float *dB, void *workspace,
                          size_t ws_bytes, void *stream);
 
+/* Row-pool hand-over between consecutive layers of a network (graph.py:463-515 calls shift_inv_layer in a loop; every layer
+ * starts by pooling its input over the row, graph.py:428-449, and its backward starts by summing dZ over the row).  The kernel
+ * that WRITES an edge tensor can emit those row reductions on the way, so that the consumer reads the tensor once (in-edge gather)
+ * instead of twice.  Same summation order as the pooling kernels: results are bit-identical to the plain entry points.
+ *   forward : layer l   (direction NBPC_ROWPOOL_FWD_EMIT) writes P_row_next (B*N, q) = row means of its H_out;
+ *             layer l+1 (NBPC_ROWPOOL_FWD_TAKE) is called with p_row_given = 1 and that tensor as P_row (it is then an INPUT);
+ *   backward: layer l+1 (NBPC_ROWPOOL_BWD_EMIT) writes dQ_row_prev (B*N, k) = row sums of its dH_in;
+ *             layer l   (NBPC_ROWPOOL_BWD_TAKE, relu = 0: dOut arrives masked) is called with dQ_row_given = that tensor.
+ * nbpc_graph_layer_rowpool_supported(k, q, is_last, direction) says which layers can do which (today: the 3-channel first layer
+ * emits forward, the last layer emits backward, layers with 16 / 32 / 64 channels on the pooled side take); NULL / 0 arguments
+ * make the _rp entry points identical to nbpc_graph_layer_fwd / _bwd. */
+#define NBPC_ROWPOOL_FWD_EMIT 0
+#define NBPC_ROWPOOL_FWD_TAKE 1
+#define NBPC_ROWPOOL_BWD_EMIT 2
+#define NBPC_ROWPOOL_BWD_TAKE 3
+int nbpc_graph_layer_rowpool_supported(int k, int q, int is_last, int direction);
+int nbpc_graph_layer_fwd_rp(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N,
+                            int M, int k, int q, const float *W, const float *bias, int is_last, int relu, float *H_out,
+                            float *P_col, float *P_row, float *P_cube, int p_row_given, float *P_row_next, void *workspace,
+                            size_t ws_bytes, void *stream);
+int nbpc_graph_layer_bwd_rp(const float *dOut, const float *H_in, const float *H_out, const int32_t *col, const int32_t *csrT_ptr,
+                            const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *P_col,
+                            const float *P_row, const float *P_cube, int is_last, int relu, int mask_input, float *dH_in,
+                            float *dW, float *dB, const float *dQ_row_given, float *dQ_row_prev, void *workspace,
+                            size_t ws_bytes, void *stream);
+
 /* Virtual layer input.  Inside a network the output of the FIRST graph layer, H1[e] = relu(E[e] W1 + Q_col[col[e]] +
  * Q_row[e / M]), is a function of the 12-byte edge feature row and two L2-resident node tables; materialising it is 44 % of
  * the bytes a [3,32,16,3] training step moves.  With node_only = 1 nbpc_graph_layer_fwd_v stops after the node-level terms

@@ -52,6 +52,10 @@ SIGNATURES = {
     "nbpc_graph_layer_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "nbpc_graph_layer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i,
                                   _p, _p, _p, _p, _sz, _p]),
+    "nbpc_graph_layer_rowpool_supported": (_i, [_i, _i, _i, _i]),
+    "nbpc_graph_layer_fwd_rp": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _sz, _p]),
+    "nbpc_graph_layer_bwd_rp": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _i,
+                                     _p, _p, _p, _p, _p, _p, _sz, _p]),
     "nbpc_sym_adjacency_workspace_bytes": (_sz, [_i, _i]),
     "nbpc_sym_adjacency_count": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "nbpc_sym_adjacency_emit": (_i, [_p, _p, _p, _p, _i, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -368,6 +368,18 @@ static void glk3_launch_edge_out(int k, int q, const float *E, const int32_t *co
     GLK3_FOR_KQ(X)
 #undef X
 }
+// edge kernel that also hands the next layer its row pool (glk3_edge_out_rowpool_kernel)
+static void glk3_launch_edge_out_rowpool(int k, int q, const float *E, const int32_t *col, const float *W1, const float *Qc, const float *Qr,
+                                         int64_t BN, int M, int relu, float *out, float *P_row_next, cudaStream_t stream) {
+#define X(K_, Q_)                                                                                                          \
+    if (k == K_ && q == Q_) {                                                                                             \
+        const int grid = nbpc_cdiv(BN, GLK3_THREADS / (Q_ / 4));                                                          \
+        if (relu) NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_rowpool_kernel", k, q).c_str(), (glk3_edge_out_rowpool_kernel<K_, Q_, true>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)BN, (uint32_t)M, out, P_row_next); \
+        else NBPC_LAUNCH_N(NbpcKName("glk3_edge_out_rowpool_kernel", k, q).c_str(), (glk3_edge_out_rowpool_kernel<K_, Q_, false>), grid, GLK3_THREADS, 0, stream, E, col, W1, Qc, Qr, (uint32_t)BN, (uint32_t)M, out, P_row_next); \
+    }
+    X(3, 16) X(3, 32) X(3, 64)
+#undef X
+}
 // dW1 = E^T dZ; returns the number of per-block partials
 static int glk3_launch_edge_dw(int k, int q, const float *E, const float *dOut, const float *Hout, int64_t c, int relu, float *partial,
                                cudaStream_t stream) {
@@ -461,16 +473,19 @@ static int gln_node_grid(int64_t BN) { return (int)nbpc_min((int64_t)nbpc_cdiv(B
 
 // pooling + per-block column sums of P_row; returns the number of partial blocks per sample
 static int gln_launch_pool(const float *H, int k, int q, int B, int N, int M, const int32_t *csrT_ptr, const int32_t *csrT_edge,
-                           float *P_row, float *P_col, float *partial, cudaStream_t stream) {
+                           float *P_row, float *P_col, float *partial, cudaStream_t stream, int row_given = 0) {
     int nblk = 0;
 #define X(K_)                                                                                                           \
     if (k == K_) {                                                                                                     \
         nblk = nbpc_cdiv(N, gln_pool_nodes_per_block(K_));                                                             \
-        NBPC_LAUNCH_N(NbpcKName("gln_pool_kernel", k, q).c_str(), gln_pool_kernel<K_>, dim3(nblk, B), GLN_THREADS, 0, stream, H, M, N, \
+        if (row_given) NBPC_LAUNCH_N(NbpcKName("gln_pool_colonly_kernel", k, q).c_str(), (gln_pool_kernel<K_, true>), dim3(nblk, B), GLN_THREADS, 0, stream, H, M, N, \
+                      csrT_ptr, csrT_edge, P_row, P_col, partial, gl_zigzag());                                        \
+        else NBPC_LAUNCH_N(NbpcKName("gln_pool_kernel", k, q).c_str(), (gln_pool_kernel<K_, false>), dim3(nblk, B), GLN_THREADS, 0, stream, H, M, N, \
                       csrT_ptr, csrT_edge, P_row, P_col, partial, gl_zigzag());                                        \
     }
     X(16) X(32) X(64)
 #undef X
+    if (!nblk && row_given) return 0;                  // (callers check nbpc_graph_layer_rowpool_supported first)
     if (!nblk) {
         int KP = 1;
         while (KP < k) KP <<= 1;
@@ -497,15 +512,25 @@ static int gln_launch_pool_vin(const GlVin &V, int k0, int k, int q, const int32
     return nblk;
 }
 
+// row-pool hand-over between consecutive layers: which layers can EMIT the row pool of their output (forward: the k = 3
+// streaming edge kernel; backward: the last layer's edge-gradient kernel) and which can CONSUME one (the float4 pooling kernels)
+static bool gl_rowpool_out_ok(int k, int q, int is_last) { return !is_last && k == 3 && glk3_shape_ok(k, q); }
+static bool gl_rowpool_in_ok(int k) { return k == 16 || k == 32 || k == 64; }
+
 // vin: the layer input is virtual (H_in is then null); node_only: stop after the node-level terms (the caller keeps
 // Q_col / Q_row in Qc_dst / Qr_dst and a LATER layer consumes this layer's output as a virtual input)
 static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M,
                         int k, int q, const float *W, const float *bias, int is_last, int relu, float *H_out, float *P_col,
                         float *P_row, float *P_cube, GlWorkspace &w, cudaStream_t stream, const GlVin *vin = nullptr, int vin_k0 = 0,
-                        int node_only = 0, float *Qc_dst = nullptr, float *Qr_dst = nullptr) {
+                        int node_only = 0, float *Qc_dst = nullptr, float *Qr_dst = nullptr, int p_row_given = 0,
+                        float *P_row_next = nullptr) {
     const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
     float *Qc = Qc_dst ? Qc_dst : w.Qc, *Qr = Qr_dst ? Qr_dst : w.Qr;
     int nblk;
+    if ((p_row_given && (vin || !gl_rowpool_in_ok(k))) || (P_row_next && (vin || node_only || !gl_rowpool_out_ok(k, q, is_last)))) {
+        nbpc_set_error("nbpc_graph_layer_fwd_rp: no row-pool hand-over for these widths (see nbpc_graph_layer_rowpool_supported)");
+        return NBPC_EINVAL;
+    }
     if (vin) {
         nblk = gln_launch_pool_vin(*vin, vin_k0, k, q, col, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream);
         if (!nblk) {
@@ -513,7 +538,7 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
             return NBPC_EINVAL;
         }
     } else {
-        nblk = gln_launch_pool(H_in, k, q, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream);
+        nblk = gln_launch_pool(H_in, k, q, B, N, M, csrT_ptr, csrT_edge, P_row, P_col, w.cube_partial, stream, p_row_given);
     }
     float *Cq = w.dCq;
     NBPC_LAUNCH(gln_cube_fwd_kernel, B, GLN_TINY_THREADS, 0, stream, w.cube_partial, nblk, N, k, q, W + 3 * kq, bias, P_cube, Cq);
@@ -550,7 +575,8 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     if (glk3_shape_ok(k, q)) {
-        glk3_launch_edge_out(k, q, H_in, col, W, Qc, Qr, c, M, relu, H_out, stream);
+        if (P_row_next) glk3_launch_edge_out_rowpool(k, q, H_in, col, W, Qc, Qr, BN, M, relu, H_out, P_row_next, stream);
+        else glk3_launch_edge_out(k, q, H_in, col, W, Qc, Qr, c, M, relu, H_out, stream);
         return nbpc_check_launch("nbpc_graph_layer_fwd");
     }
     const int rc = glf_dispatch_edge_out(k, q, H_in, col, W, Qc, Qr, c, M, relu, H_out, stream);
@@ -571,9 +597,15 @@ static bool gl_fused_ok(int k, int q, int is_last) {
 static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out, const int32_t *col, const int32_t *csrT_ptr,
                         const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *P_col,
                         const float *P_row, const float *P_cube, int is_last, int relu, int mask_input, float *dH_in, float *dW,
-                        float *dB, GlWorkspace &w, cudaStream_t stream, const GlVin *vin = nullptr, int vin_k0 = 0) {
+                        float *dB, GlWorkspace &w, cudaStream_t stream, const GlVin *vin = nullptr, int vin_k0 = 0,
+                        const float *dQ_row_given = nullptr, float *dQ_row_prev = nullptr) {
     const int64_t BN = (int64_t)B * N, c = BN * M, kq = (int64_t)k * q;
-    float *dQ_col = w.Qc, *dQ_row = w.Qr;
+    float *dQ_col = w.Qc, *dQ_row = dQ_row_given ? const_cast<float *>(dQ_row_given) : w.Qr;
+    if ((dQ_row_given && (is_last || relu || vin || !gl_rowpool_in_ok(q) || (!dH_in && k == 3))) ||
+        (dQ_row_prev && !(is_last && dH_in && k % 4 == 0))) {
+        nbpc_set_error("nbpc_graph_layer_bwd_rp: no row-sum hand-over for this layer (see nbpc_graph_layer_rowpool_supported)");
+        return NBPC_EINVAL;
+    }
     if (vin && (is_last || relu || !mask_input || !dH_in || g_nbpc_math_mode != NBPC_MATH_TF32X3 || !glt_bwd_vin_shape_ok(vin_k0, k, q, c))) {
         nbpc_set_error("nbpc_graph_layer_bwd_v: the virtual input needs a hidden layer in split mode whose gradient arrives pre-masked");
         return NBPC_EINVAL;
@@ -606,7 +638,8 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
 #define X(Q_)                                                                                                           \
     if (q == Q_) {                                                                                                     \
         nblk = nbpc_cdiv(N, gln_pool_nodes_per_block(Q_));                                                             \
-        if (relu) NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, true>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial, gl_zigzag()); \
+        if (dQ_row_given) NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_colonly_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, false, true>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial, gl_zigzag()); \
+        else if (relu) NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, true>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial, gl_zigzag()); \
         else NBPC_LAUNCH_N(NbpcKName("gln_bwd_pool_kernel", k, q).c_str(), (gln_bwd_pool_kernel<Q_, false>), dim3(nblk, B), GLN_THREADS, 0, stream, dOut, H_out, M, N, csrT_ptr, csrT_edge, dQ_row, dQ_col, w.cube_partial, gl_zigzag()); \
     }
         X(16) X(32) X(64)
@@ -638,7 +671,10 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
     if (is_last) {
         // row-mean output: dZ[e] = dOutM[e/M]/M  =>  dW1 = P_row^T dOutM (= dW3), dH[e] = R[e/M] + G_col[col[e]]
         fa.part[0] = fa.part[2]; fa.n[0] = fa.n[2]; fa.tr[0] = fa.tr[2];
-        if (dH_in)   // the row term (dOutM W1^T) / M is already in G_row (gln_node_grad_kernel, add_w1)
+        if (dH_in && dQ_row_prev)   // + the row sums of dH_in for the previous layer's backward
+            NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_rowsum_kernel", k, q).c_str(), glf_last_edge_in_rowsum_kernel, nbpc_cdiv(BN * (k / 4), 256),
+                          256, 0, stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, BN, M, k, dH_in, dQ_row_prev);
+        else if (dH_in)   // the row term (dOutM W1^T) / M is already in G_row (gln_node_grad_kernel, add_w1)
             NBPC_LAUNCH_N(NbpcKName("glf_last_edge_in_kernel", k, q).c_str(), glf_last_edge_in_kernel, nbpc_cdiv(c * (k / 4), 256), 256, 0,
                           stream, col, w.Gr, w.Gc, mask_input ? H_in : (const float *)nullptr, c, M, k, dH_in);
     } else if (vin) {
@@ -760,10 +796,47 @@ int nbpc_graph_layer_fwd(const float *H_in, const int32_t *col, const int32_t *c
                                   P_cube, nullptr, nullptr, workspace, ws_bytes, stream_);
 }
 
+int nbpc_graph_layer_rowpool_supported(int k, int q, int is_last, int direction) {
+#ifdef NBPC_HOST_EMU
+    (void)k; (void)q; (void)is_last; (void)direction;
+    return 0;
+#else
+    if (!gl_use_fast() || !gl_fused_ok(k, q, is_last)) return 0;
+    switch (direction) {
+    case NBPC_ROWPOOL_FWD_EMIT: return gl_rowpool_out_ok(k, q, is_last) ? 1 : 0;
+    case NBPC_ROWPOOL_FWD_TAKE: return gl_rowpool_in_ok(k) ? 1 : 0;
+    case NBPC_ROWPOOL_BWD_EMIT: return (is_last && k % 4 == 0) ? 1 : 0;
+    case NBPC_ROWPOOL_BWD_TAKE: return (!is_last && k != 3 && gl_rowpool_in_ok(q)) ? 1 : 0;
+    }
+    return 0;
+#endif
+}
+
+static int gl_layer_fwd_entry(const float *H_in, const nbpc_virtual_input *vin, const int32_t *col, const int32_t *csrT_ptr,
+                              const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *bias, int is_last,
+                              int relu, int node_only, float *H_out, float *P_col, float *P_row, float *P_cube, float *Q_col_out,
+                              float *Q_row_out, int p_row_given, float *P_row_next, void *workspace, size_t ws_bytes, void *stream_);
+
 int nbpc_graph_layer_fwd_v(const float *H_in, const nbpc_virtual_input *vin, const int32_t *col, const int32_t *csrT_ptr,
                            const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *bias, int is_last,
                            int relu, int node_only, float *H_out, float *P_col, float *P_row, float *P_cube, float *Q_col_out,
                            float *Q_row_out, void *workspace, size_t ws_bytes, void *stream_) {
+    return gl_layer_fwd_entry(H_in, vin, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, node_only, H_out, P_col, P_row,
+                              P_cube, Q_col_out, Q_row_out, 0, nullptr, workspace, ws_bytes, stream_);
+}
+
+int nbpc_graph_layer_fwd_rp(const float *H_in, const int32_t *col, const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M,
+                            int k, int q, const float *W, const float *bias, int is_last, int relu, float *H_out, float *P_col,
+                            float *P_row, float *P_cube, int p_row_given, float *P_row_next, void *workspace, size_t ws_bytes,
+                            void *stream_) {
+    return gl_layer_fwd_entry(H_in, nullptr, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, 0, H_out, P_col, P_row, P_cube,
+                              nullptr, nullptr, p_row_given, P_row_next, workspace, ws_bytes, stream_);
+}
+
+static int gl_layer_fwd_entry(const float *H_in, const nbpc_virtual_input *vin, const int32_t *col, const int32_t *csrT_ptr,
+                              const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *bias, int is_last,
+                              int relu, int node_only, float *H_out, float *P_col, float *P_row, float *P_cube, float *Q_col_out,
+                              float *Q_row_out, int p_row_given, float *P_row_next, void *workspace, size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
     NBPC_ARG((H_in || vin) && col && csrT_ptr && csrT_edge && W && bias && (H_out || node_only) && P_col && P_row && P_cube && workspace,
@@ -786,9 +859,13 @@ int nbpc_graph_layer_fwd_v(const float *H_in, const nbpc_virtual_input *vin, con
         GlVin V;
         if (vin) { V.E = vin->E; V.W1 = vin->W1; V.Qc = vin->Q_col; V.Qr = vin->Q_row; }
         return gl_fwd_fused(H_in, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, bias, is_last, relu, H_out, P_col, P_row, P_cube, w, stream,
-                            vin ? &V : nullptr, vin ? vin->k : 0, node_only, Q_col_out, Q_row_out);
+                            vin ? &V : nullptr, vin ? vin->k : 0, node_only, Q_col_out, Q_row_out, p_row_given, P_row_next);
     }
 #endif
+    if (p_row_given || P_row_next) {
+        nbpc_set_error("nbpc_graph_layer_fwd_rp: the row-pool hand-over needs the fused device path (see nbpc_graph_layer_rowpool_supported)");
+        return NBPC_EINVAL;
+    }
     if (vin || node_only) {
         nbpc_set_error("nbpc_graph_layer_fwd_v: virtual input / node-only mode needs the fused device path (see nbpc_graph_layer_vin_supported)");
         return NBPC_EINVAL;
@@ -879,10 +956,33 @@ int nbpc_graph_layer_bwd(const float *dOut, const float *H_in, const float *H_ou
                                   mask_input, dH_in, dW, dB, workspace, ws_bytes, stream_);
 }
 
+static int gl_layer_bwd_entry(const float *dOut, const float *H_in, const nbpc_virtual_input *vin, const float *H_out, const int32_t *col,
+                              const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W,
+                              const float *P_col, const float *P_row, const float *P_cube, int is_last, int relu, int mask_input,
+                              float *dH_in, float *dW, float *dB, const float *dQ_row_given, float *dQ_row_prev, void *workspace,
+                              size_t ws_bytes, void *stream_);
+
 int nbpc_graph_layer_bwd_v(const float *dOut, const float *H_in, const nbpc_virtual_input *vin, const float *H_out, const int32_t *col,
                            const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W,
                            const float *P_col, const float *P_row, const float *P_cube, int is_last, int relu, int mask_input,
                            float *dH_in, float *dW, float *dB, void *workspace, size_t ws_bytes, void *stream_) {
+    return gl_layer_bwd_entry(dOut, H_in, vin, H_out, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, P_col, P_row, P_cube, is_last, relu,
+                              mask_input, dH_in, dW, dB, nullptr, nullptr, workspace, ws_bytes, stream_);
+}
+
+int nbpc_graph_layer_bwd_rp(const float *dOut, const float *H_in, const float *H_out, const int32_t *col, const int32_t *csrT_ptr,
+                            const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W, const float *P_col,
+                            const float *P_row, const float *P_cube, int is_last, int relu, int mask_input, float *dH_in, float *dW,
+                            float *dB, const float *dQ_row_given, float *dQ_row_prev, void *workspace, size_t ws_bytes, void *stream_) {
+    return gl_layer_bwd_entry(dOut, H_in, nullptr, H_out, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, P_col, P_row, P_cube, is_last, relu,
+                              mask_input, dH_in, dW, dB, dQ_row_given, dQ_row_prev, workspace, ws_bytes, stream_);
+}
+
+static int gl_layer_bwd_entry(const float *dOut, const float *H_in, const nbpc_virtual_input *vin, const float *H_out, const int32_t *col,
+                              const int32_t *csrT_ptr, const int32_t *csrT_edge, int B, int N, int M, int k, int q, const float *W,
+                              const float *P_col, const float *P_row, const float *P_cube, int is_last, int relu, int mask_input,
+                              float *dH_in, float *dW, float *dB, const float *dQ_row_given, float *dQ_row_prev, void *workspace,
+                              size_t ws_bytes, void *stream_) {
     NBPC_TRY(nbpc_require_sm100());
     cudaStream_t stream = (cudaStream_t)stream_;
     NBPC_ARG(dOut && (H_in || vin) && col && csrT_ptr && csrT_edge && W && P_col && P_row && P_cube && dW && dB && workspace,
@@ -909,9 +1009,13 @@ int nbpc_graph_layer_bwd_v(const float *dOut, const float *H_in, const nbpc_virt
         GlVin V;
         if (vin) { V.E = vin->E; V.W1 = vin->W1; V.Qc = vin->Q_col; V.Qr = vin->Q_row; }
         return gl_bwd_fused(dOut, H_in, H_out, col, csrT_ptr, csrT_edge, B, N, M, k, q, W, P_col, P_row, P_cube, is_last, relu,
-                            mask_input, dH_in, dW, dB, w, stream, vin ? &V : nullptr, vin ? vin->k : 0);
+                            mask_input, dH_in, dW, dB, w, stream, vin ? &V : nullptr, vin ? vin->k : 0, dQ_row_given, dQ_row_prev);
     }
 #endif
+    if (dQ_row_given || dQ_row_prev) {
+        nbpc_set_error("nbpc_graph_layer_bwd_rp: the row-sum hand-over needs the fused device path (see nbpc_graph_layer_rowpool_supported)");
+        return NBPC_EINVAL;
+    }
     if (vin) {
         nbpc_set_error("nbpc_graph_layer_bwd_v: the virtual input needs the fused device path (see nbpc_graph_layer_vin_supported)");
         return NBPC_EINVAL;

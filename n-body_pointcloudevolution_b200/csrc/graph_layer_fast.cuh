@@ -749,4 +749,42 @@ static __global__ void __launch_bounds__(256) glf_last_edge_in_kernel(const int3
     *reinterpret_cast<float4 *>(dH + e * k + 4 * g) = o;
 }
 
+// Same dH, plus the row sums the PREVIOUS layer's backward pools first: dQ_row_prev[i] = sum_m dH[i M + m] (ascending m, the
+// order of gln_bwd_pool_kernel: bit-identical hand-over).  Thread per (row node, 4-channel group), two edges in flight;
+// R[i] is loaded once per thread.
+static __global__ void __launch_bounds__(256) glf_last_edge_in_rowsum_kernel(const int32_t *__restrict__ col, const float *__restrict__ R,
+                                                                       const float *__restrict__ G_col,
+                                                                       const float *__restrict__ Hmask, int64_t n_rows, int M, int k,
+                                                                       float *__restrict__ dH, float *__restrict__ dQ_row_prev) {
+    const int G = k / 4;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_rows * G) return;
+    const int64_t row = t / G;
+    const int g = (int)(t % G);
+    const float4 r = glf_ldg4(R + row * k + 4 * g);
+    const int64_t e0 = row * M;
+    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto emit = [&](int64_t e, const float4 &gc, const float4 &h) {
+        float4 o = make_float4(r.x + gc.x, r.y + gc.y, r.z + gc.z, r.w + gc.w);
+        if (Hmask) { o.x = h.x > 0.f ? o.x : 0.f; o.y = h.y > 0.f ? o.y : 0.f; o.z = h.z > 0.f ? o.z : 0.f; o.w = h.w > 0.f ? o.w : 0.f; }
+        *reinterpret_cast<float4 *>(dH + e * k + 4 * g) = o;
+        rs.x += o.x; rs.y += o.y; rs.z += o.z; rs.w += o.w;
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    int m = 0;
+    for (; m + 2 <= M; m += 2) {
+        const int64_t ea = e0 + m, eb = ea + 1;
+        const int ca = __ldg(&col[ea]), cb = __ldg(&col[eb]);
+        const float4 ga = glf_ldg4(G_col + (int64_t)ca * k + 4 * g), gb = glf_ldg4(G_col + (int64_t)cb * k + 4 * g);
+        const float4 ha = Hmask ? glf_ldg4(Hmask + ea * k + 4 * g) : zero, hb = Hmask ? glf_ldg4(Hmask + eb * k + 4 * g) : zero;
+        emit(ea, ga, ha);
+        emit(eb, gb, hb);
+    }
+    for (; m < M; ++m) {
+        const int64_t e = e0 + m;
+        emit(e, glf_ldg4(G_col + (int64_t)__ldg(&col[e]) * k + 4 * g), Hmask ? glf_ldg4(Hmask + e * k + 4 * g) : zero);
+    }
+    *reinterpret_cast<float4 *>(dQ_row_prev + row * k + 4 * g) = rs;
+}
+
 #endif  // !NBPC_HOST_EMU

@@ -67,6 +67,65 @@ __global__ void __launch_bounds__(GLK3_THREADS) glk3_edge_out_kernel(const float
     }
 }
 
+// Same output, plus the row pool of the NEXT layer: P_row_next[i] = (1/M) sum_m out[i M + m] (graph.py:428-449 applied to
+// this layer's output).  One thread owns a 4-channel group of one ROW node and walks its M contiguous edges in ascending
+// order - the summation order of gln_pool_kernel, so the hand-over is bit-identical to pooling the stored tensor - with
+// U edges in flight; Q_row[i] is loaded once per thread instead of once per edge.  A warp instruction stores Q/4-lane
+// groups of full 16 Q-byte rows (whole 128-byte lines for Q = 32) M rows apart.
+template <int K, int Q, bool RELU>
+__global__ void __launch_bounds__(GLK3_THREADS) glk3_edge_out_rowpool_kernel(const float *__restrict__ E, const int32_t *__restrict__ col,
+                                                                              const float *__restrict__ W1, const float *__restrict__ Q_col,
+                                                                              const float *__restrict__ Q_row, uint32_t n_rows, uint32_t M,
+                                                                              float *__restrict__ out, float *__restrict__ P_row_next) {
+    constexpr int G = Q / 4, RPB = GLK3_THREADS / G, U = 2;
+    const int g = threadIdx.x % G, slot = threadIdx.x / G;
+    const uint32_t row = blockIdx.x * (uint32_t)RPB + slot;
+    if (row >= n_rows) return;
+    float4 w[K];
+#pragma unroll
+    for (int kk = 0; kk < K; ++kk) w[kk] = __ldg(reinterpret_cast<const float4 *>(W1 + kk * Q + 4 * g));
+    const float4 qr = __ldg(reinterpret_cast<const float4 *>(Q_row + (size_t)row * Q + 4 * g));
+    const uint32_t e0 = row * M;
+    float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto emit = [&](uint32_t e, const float *x, const float4 &qc) {
+        // (((x0 w0 + x1 w1) + x2 w2) + ...) + (Q_col + Q_row): the expression of glk3_edge_out_kernel
+        float4 o = make_float4(x[0] * w[0].x, x[0] * w[0].y, x[0] * w[0].z, x[0] * w[0].w);
+#pragma unroll
+        for (int kk = 1; kk < K; ++kk) {
+            o.x = fmaf(x[kk], w[kk].x, o.x); o.y = fmaf(x[kk], w[kk].y, o.y);
+            o.z = fmaf(x[kk], w[kk].z, o.z); o.w = fmaf(x[kk], w[kk].w, o.w);
+        }
+        o.x += qc.x + qr.x; o.y += qc.y + qr.y; o.z += qc.z + qr.z; o.w += qc.w + qr.w;
+        if (RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4 *>(out + (size_t)e * Q + 4 * g) = o;
+        rs.x += o.x; rs.y += o.y; rs.z += o.z; rs.w += o.w;
+    };
+    uint32_t m = 0;
+    for (; m + U <= M; m += U) {
+        float x[U][K];
+        float4 qc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t e = e0 + m + u;
+            const int cidx = __ldg(&col[e]);
+#pragma unroll
+            for (int kk = 0; kk < K; ++kk) x[u][kk] = __ldg(&E[K * (size_t)e + kk]);
+            qc[u] = __ldg(reinterpret_cast<const float4 *>(Q_col + (size_t)cidx * Q + 4 * g));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) emit(e0 + m + u, x[u], qc[u]);
+    }
+    for (; m < M; ++m) {
+        const uint32_t e = e0 + m;
+        float x[K];
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk) x[kk] = __ldg(&E[K * (size_t)e + kk]);
+        emit(e, x, __ldg(reinterpret_cast<const float4 *>(Q_col + (size_t)__ldg(&col[e]) * Q + 4 * g)));
+    }
+    const float fm = (float)M;
+    *reinterpret_cast<float4 *>(P_row_next + (size_t)row * Q + 4 * g) = make_float4(rs.x / fm, rs.y / fm, rs.z / fm, rs.w / fm);
+}
+
 //   dW1 = E^T dZ  (K x Q), dZ = dOut [* (H_out > 0)]: per-block partials, reduced over blocks in a fixed order afterwards.
 // A thread accumulates its channel group over the edges  slot + i * EPB  of the block's contiguous range (fixed order),
 // the EPB slots are then summed by a fixed shared-memory tree => bit-reproducible.

@@ -40,7 +40,9 @@ __device__ __forceinline__ void gln_block_colsum(float4 *red, float4 v) {
 // ------------------------------------------------------------------ forward pooling, K % 4 == 0
 // thread per (node, 4-channel group); grid (blocks per sample, B).  P_row = mean of the node's M contiguous edge rows,
 // P_col = mean over in-edges (CSR transpose, ascending edge id); partial[s][blk][K] = column sums of P_row over the block
-template <int K>
+// ROWGIVEN: P_row already holds the row means (handed over by the kernel that wrote H, glk3_edge_out_rowpool_kernel): H is
+// read once, by the in-edge gather
+template <int K, bool ROWGIVEN = false>
 __global__ void __launch_bounds__(GLN_THREADS) gln_pool_kernel(const float *__restrict__ H, int M, int N,
                                                                 const int32_t *__restrict__ csrT_ptr,
                                                                 const int32_t *__restrict__ csrT_edge, float *__restrict__ P_row,
@@ -54,15 +56,19 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_pool_kernel(const float *__re
     float4 pr = make_float4(0.f, 0.f, 0.f, 0.f);
     if (local < N) {
         const int64_t node = (int64_t)s * N + local;
-        const float *hr = H + (node * M) * K + 4 * g;
-        float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int m = 0; m < M; ++m) {
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(hr + (int64_t)m * K));
-            rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+        if constexpr (ROWGIVEN) {
+            pr = *reinterpret_cast<const float4 *>(P_row + node * K + 4 * g);
+        } else {
+            const float *hr = H + (node * M) * K + 4 * g;
+            float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int m = 0; m < M; ++m) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(hr + (int64_t)m * K));
+                rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+            }
+            const float fm = (float)M;
+            pr = make_float4(rs.x / fm, rs.y / fm, rs.z / fm, rs.w / fm);
+            *reinterpret_cast<float4 *>(P_row + node * K + 4 * g) = pr;
         }
-        const float fm = (float)M;
-        pr = make_float4(rs.x / fm, rs.y / fm, rs.z / fm, rs.w / fm);
-        *reinterpret_cast<float4 *>(P_row + node * K + 4 * g) = pr;
         const int b = csrT_ptr[node], e = csrT_ptr[node + 1];
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         int p = b;
@@ -129,7 +135,8 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_pool_generic_kernel(const flo
 
 // ------------------------------------------------------------------ backward pooling on dZ (c,Q), Q % 4 == 0:
 // dQ_row = row sums, dQ_col = in-edge sums, partial[s][blk][Q] = column sums of dQ_row over the block
-template <int Q, bool RELU>
+// ROWGIVEN: dQ_row already holds the row sums (handed over by the kernel that wrote dOut, glf_last_edge_in_rowsum_kernel)
+template <int Q, bool RELU, bool ROWGIVEN = false>
 __global__ void __launch_bounds__(GLN_THREADS) gln_bwd_pool_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout, int M,
                                                                     int N, const int32_t *__restrict__ csrT_ptr,
                                                                     const int32_t *__restrict__ csrT_edge, float *__restrict__ dQ_row,
@@ -151,11 +158,15 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_bwd_pool_kernel(const float *
     float4 rs = make_float4(0.f, 0.f, 0.f, 0.f);
     if (local < N) {
         const int64_t node = (int64_t)s * N + local;
-        for (int m = 0; m < M; ++m) {
-            const float4 v = dz(node * M + m);
-            rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+        if constexpr (ROWGIVEN) {
+            rs = *reinterpret_cast<const float4 *>(dQ_row + node * Q + 4 * g);
+        } else {
+            for (int m = 0; m < M; ++m) {
+                const float4 v = dz(node * M + m);
+                rs.x += v.x; rs.y += v.y; rs.z += v.z; rs.w += v.w;
+            }
+            *reinterpret_cast<float4 *>(dQ_row + node * Q + 4 * g) = rs;
         }
-        *reinterpret_cast<float4 *>(dQ_row + node * Q + 4 * g) = rs;
         const int b = csrT_ptr[node], e = csrT_ptr[node + 1];
         float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
         int p = b;

@@ -334,13 +334,40 @@ def _is_relu(fn):
     return fn in (torch.relu, torch.nn.functional.relu) or getattr(fn, "__name__", "") == "relu"
 
 
-def _layer(H_in, COO_feats, bN, layer_vars, is_last, relu, input_relu=False, grad_premasked=False):
+def _layer(H_in, COO_feats, bN, layer_vars, is_last, relu, input_relu=False, grad_premasked=False, chain=None, idx=0):
     b, N = bN
     weights, B = layer_vars
     adj = _adjacency_of(COO_feats, b, N)
     W = weights if isinstance(weights, torch.Tensor) and weights.dim() == 3 else torch.stack(list(weights[:4]))
     return ops.GraphLayer.apply(H_in, W, B, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M, bool(is_last), relu,
-                                input_relu, grad_premasked)
+                                input_relu, grad_premasked, chain, idx)
+
+
+# Row-pool hand-over (csrc: glk3_edge_out_rowpool_kernel, glf_last_edge_in_rowsum_kernel): inside a fused-ReLU network the
+# kernel that writes a hidden edge tensor also emits the row reduction the next layer (forward) / previous layer (backward)
+# starts with, so that layer reads the tensor once.  Bit-identical to the plain path; NBPC_ROWPOOL_CHAIN=0 disables.
+_ROWPOOL_CHAIN = __import__("os").environ.get("NBPC_ROWPOOL_CHAIN", "1") != "0"
+
+
+def set_rowpool_chain(on):
+    global _ROWPOOL_CHAIN
+    old, _ROWPOOL_CHAIN = _ROWPOOL_CHAIN, bool(on)
+    return old
+
+
+def _rowpool_chain(widths, first, num_layers):
+    """RowPoolChain for layers first..num_layers-1 of a fused-ReLU network with channel widths `widths` (None: nothing to hand over)."""
+    chain = ops.RowPoolChain()
+    for l in range(first, num_layers - 1):
+        (k, q), (k2, q2) = widths[l], widths[l + 1]
+        last2 = l + 1 == num_layers - 1
+        if ops.graph_layer_rowpool_supported(k, q, False, ops.ROWPOOL_FWD_EMIT) and \
+                ops.graph_layer_rowpool_supported(k2, q2, last2, ops.ROWPOOL_FWD_TAKE):
+            chain.fwd_emit.add(l)
+        if l >= 1 and ops.graph_layer_rowpool_supported(k2, q2, last2, ops.ROWPOOL_BWD_EMIT) and \
+                ops.graph_layer_rowpool_supported(k, q, False, ops.ROWPOOL_BWD_TAKE):
+            chain.bwd_emit.add(l + 1)
+    return chain if (chain.fwd_emit or chain.bwd_emit) else None
 
 
 def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
@@ -385,14 +412,23 @@ def _network(H0, coo, num_layers, dims, activation, model_vars):
             Hv, Qc, Qr = ops.GraphLayerNodeOnly.apply(H0, W0, B0, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M)
             H = ops.GraphLayerVirtualIn.apply(Hv, W1, B1, adj.col, adj.csrT_ptr, adj.csrT_edge, b, N, adj.M, True, True, H0, W0[0], Qc, Qr)
             first = 2
+    rp = None
+    if chain and _ROWPOOL_CHAIN and first == 1:
+        widths = []
+        for l in range(num_layers):
+            Wl = model_vars.get_layer_vars(l)[0]
+            Wl = Wl if isinstance(Wl, torch.Tensor) else Wl[0]
+            widths.append((int(Wl.shape[-2]), int(Wl.shape[-1])))
+        if H0.shape[1] == widths[0][0] and all(widths[l][1] == widths[l + 1][0] for l in range(num_layers - 1)):
+            rp = _rowpool_chain(widths, 0, num_layers)
     if first == 1:
-        H = _layer(H0, coo, dims, model_vars.get_layer_vars(0), False, fuse, input_relu=False, grad_premasked=chain)
+        H = _layer(H0, coo, dims, model_vars.get_layer_vars(0), False, fuse, input_relu=False, grad_premasked=chain, chain=rp, idx=0)
         if not fuse:
             H = activation(H)
     for layer_idx in range(first, num_layers):
         is_last = layer_idx == num_layers - 1
         H = _layer(H, coo, dims, model_vars.get_layer_vars(layer_idx), is_last, fuse and not is_last,
-                   input_relu=fuse, grad_premasked=fuse and not is_last)
+                   input_relu=fuse, grad_premasked=fuse and not is_last, chain=rp, idx=layer_idx)
         if not is_last and not fuse:
             H = activation(H)
     return H

@@ -352,6 +352,86 @@ def graph_layer_bwd(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor,
     return dH, dW, dB
 
 
+# ---- row-pool hand-over between consecutive layers (include/nbpc.h: nbpc_graph_layer_fwd_rp / _bwd_rp)
+ROWPOOL_FWD_EMIT, ROWPOOL_FWD_TAKE, ROWPOOL_BWD_EMIT, ROWPOOL_BWD_TAKE = 0, 1, 2, 3
+
+
+def graph_layer_rowpool_supported(k: int, q: int, is_last: bool, direction: int) -> bool:
+    return bool(_lib.load().nbpc_graph_layer_rowpool_supported(int(k), int(q), int(is_last), int(direction)))
+
+
+class RowPoolChain:
+    """Which layers of a network hand their row reductions to the neighbouring layer (graph._network fills `fwd_emit` /
+    `bwd_emit` with layer indices), and the tensors in flight: p_row[l] = row means of layer l's INPUT written by layer
+    l-1's edge kernel, dq_row[l] = row sums of layer l's dOut written by layer l+1's backward edge kernel."""
+
+    def __init__(self):
+        self.fwd_emit, self.bwd_emit = set(), set()
+        self.p_row, self.dq_row = {}, {}
+
+
+@torch.library.custom_op("nbpc::graph_layer_fwd_rp", mutates_args=())
+def graph_layer_fwd_rp(H_in: torch.Tensor, col: torch.Tensor, csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor,
+                       W: torch.Tensor, bias: torch.Tensor, B: int, N: int, M: int, is_last: bool, relu: bool,
+                       P_row_given: Optional[torch.Tensor], emit_next: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor,
+                                                                                     torch.Tensor, torch.Tensor]:
+    """graph_layer_fwd with the hand-over: -> H_out, P_col, P_row (empty if P_row_given), P_cube, P_row_next (B*N,q) (empty
+    unless emit_next)."""
+    _need_cuda(H_in, col, csrT_ptr, csrT_edge, W, bias)
+    L = _lib.load()
+    H_in, W, bias = _f32c(H_in), _f32c(W), _f32c(bias)
+    k, q = W.shape[1], W.shape[2]
+    c = B * N * M
+    if H_in.shape != (c, k) or W.shape[0] != 4 or bias.shape != (q,):
+        raise RuntimeError(f"graph_layer_fwd_rp: shape mismatch H_in {tuple(H_in.shape)} vs (c={c}, k={k}); W {tuple(W.shape)}")
+    if P_row_given is not None and (P_row_given.shape != (B * N, k) or P_row_given.dtype != torch.float32 or not P_row_given.is_contiguous()):
+        raise RuntimeError("graph_layer_fwd_rp: P_row_given must be a contiguous float32 (B*N, k) tensor")
+    dev = H_in.device
+    out = torch.empty(((B * N) if is_last else c, q), dtype=torch.float32, device=dev)
+    P_col = torch.empty((B * N, k), dtype=torch.float32, device=dev)
+    P_row = torch.empty((B * N, k) if P_row_given is None else (0,), dtype=torch.float32, device=dev)
+    P_cube = torch.empty((B, k), dtype=torch.float32, device=dev)
+    P_next = torch.empty((B * N, q) if emit_next else (0,), dtype=torch.float32, device=dev)
+    ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_graph_layer_fwd_rp(_ptr(H_in), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge), B, N, M, k, q, _ptr(W),
+                                       _ptr(bias), int(is_last), int(relu), _ptr(out), _ptr(P_col),
+                                       _ptr(P_row if P_row_given is None else P_row_given), _ptr(P_cube),
+                                       int(P_row_given is not None), _ptr(P_next) if emit_next else None, _ptr(ws), ws.numel(),
+                                       _stream())
+    _lib.check(rc, "nbpc_graph_layer_fwd_rp")
+    return out, P_col, P_row, P_cube, P_next
+
+
+@torch.library.custom_op("nbpc::graph_layer_bwd_rp", mutates_args=())
+def graph_layer_bwd_rp(dOut: torch.Tensor, H_in: torch.Tensor, H_out: torch.Tensor, col: torch.Tensor,
+                       csrT_ptr: torch.Tensor, csrT_edge: torch.Tensor, W: torch.Tensor, P_col: torch.Tensor,
+                       P_row: torch.Tensor, P_cube: torch.Tensor, B: int, N: int, M: int, is_last: bool, relu: bool,
+                       mask_input: bool, need_dH: bool, dQ_row_given: Optional[torch.Tensor],
+                       emit_prev: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    """graph_layer_bwd with the hand-over: -> dH_in, dW, dB, dQ_row_prev (B*N,k) = row sums of dH_in (empty unless emit_prev)."""
+    _need_cuda(dOut, H_in, H_out, W)
+    L = _lib.load()
+    dOut = _f32c(dOut)
+    k, q = W.shape[1], W.shape[2]
+    c = B * N * M
+    dev = H_in.device
+    if dQ_row_given is not None and (dQ_row_given.shape != (B * N, q) or dQ_row_given.dtype != torch.float32 or not dQ_row_given.is_contiguous()):
+        raise RuntimeError("graph_layer_bwd_rp: dQ_row_given must be a contiguous float32 (B*N, q) tensor")
+    dH = torch.empty((c, k) if need_dH else (0,), dtype=torch.float32, device=dev)
+    dW = torch.empty((4, k, q), dtype=torch.float32, device=dev)
+    dB = torch.empty((q,), dtype=torch.float32, device=dev)
+    dQp = torch.empty((B * N, k) if emit_prev else (0,), dtype=torch.float32, device=dev)
+    ws = _workspace(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q), dev)
+    with torch.cuda.device(dev):
+        rc = L.nbpc_graph_layer_bwd_rp(_ptr(dOut), _ptr(H_in), _ptr(H_out), _ptr(col), _ptr(csrT_ptr), _ptr(csrT_edge),
+                                       B, N, M, k, q, _ptr(W), _ptr(P_col), _ptr(P_row), _ptr(P_cube), int(is_last),
+                                       int(relu), int(mask_input), _ptr(dH) if need_dH else None, _ptr(dW), _ptr(dB),
+                                       _ptr(dQ_row_given), _ptr(dQp) if emit_prev else None, _ptr(ws), ws.numel(), _stream())
+    _lib.check(rc, "nbpc_graph_layer_bwd_rp")
+    return dH, dW, dB, dQp
+
+
 def _vin_struct(vin):
     E, W1, Qc, Qr = vin
     return _lib.VirtualInput(E.data_ptr(), W1.data_ptr(), Qc.data_ptr(), Qr.data_ptr(), int(E.shape[1]))
@@ -460,11 +540,23 @@ class GraphLayer(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, H_in, W, bias, col, csrT_ptr, csrT_edge, B, N, M, is_last, relu, input_relu=False,
-                grad_premasked=False):
+                grad_premasked=False, chain=None, idx=0):
+        """chain / idx: row-pool hand-over inside a network (RowPoolChain; this layer is layer `idx`)."""
         H_in = _f32c(H_in)
-        out, P_col, P_row, P_cube = graph_layer_fwd(H_in, col, csrT_ptr, csrT_edge, W, bias, B, N, M, is_last, relu)
+        p_given = chain.p_row.pop(idx, None) if chain is not None else None
+        emit = chain is not None and idx in chain.fwd_emit
+        if p_given is not None or emit:
+            out, P_col, P_row, P_cube, P_next = graph_layer_fwd_rp(H_in, col, csrT_ptr, csrT_edge, W, bias, B, N, M, is_last, relu,
+                                                                   p_given, emit)
+            if p_given is not None:
+                P_row = p_given
+            if emit:
+                chain.p_row[idx + 1] = P_next
+        else:
+            out, P_col, P_row, P_cube = graph_layer_fwd(H_in, col, csrT_ptr, csrT_edge, W, bias, B, N, M, is_last, relu)
         ctx.save_for_backward(H_in, out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube)
         ctx.cfg = (B, N, M, is_last, relu and not grad_premasked, input_relu)
+        ctx.chain = (chain, idx)
         if is_last:
             out = out.view(B, N, -1)
         return out
@@ -473,11 +565,20 @@ class GraphLayer(torch.autograd.Function):
     def backward(ctx, g):
         H_in, out, W, col, csrT_ptr, csrT_edge, P_col, P_row, P_cube = ctx.saved_tensors
         B, N, M, is_last, relu, input_relu = ctx.cfg
+        chain, idx = ctx.chain
         need_dH = ctx.needs_input_grad[0]
         g = g.reshape(out.shape)
-        dH, dW, dB = graph_layer_bwd(g, H_in, out, col, csrT_ptr, csrT_edge, W, P_col, P_row, P_cube, B, N, M,
-                                     is_last, relu, input_relu, need_dH)
-        return (dH if need_dH else None), dW, dB, None, None, None, None, None, None, None, None, None, None
+        dq_given = chain.dq_row.pop(idx, None) if chain is not None else None
+        emit = chain is not None and need_dH and idx in chain.bwd_emit
+        if dq_given is not None or emit:
+            dH, dW, dB, dQp = graph_layer_bwd_rp(g, H_in, out, col, csrT_ptr, csrT_edge, W, P_col, P_row, P_cube, B, N, M,
+                                                 is_last, relu, input_relu, need_dH, dq_given, emit)
+            if emit:
+                chain.dq_row[idx - 1] = dQp
+        else:
+            dH, dW, dB = graph_layer_bwd(g, H_in, out, col, csrT_ptr, csrT_edge, W, P_col, P_row, P_cube, B, N, M,
+                                         is_last, relu, input_relu, need_dH)
+        return (dH if need_dH else None), dW, dB, None, None, None, None, None, None, None, None, None, None, None, None
 
 
 # ================================================================== 15-weight layer (graph.py:20-200)

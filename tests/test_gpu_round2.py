@@ -294,6 +294,44 @@ def test_virtual_first_layer_is_bit_identical(nb, syn, b, N, M, ch):
     assert outs[1][3] == outs[0][3] - 1                       # one launch less: the first layer's edge kernel
 
 
+# =============================================================================== row-pool hand-over between layers
+@pytest.mark.parametrize("b,N,M,ch", [(2, 4096, 14, [3, 32, 16, 3]), (3, 601, 9, [3, 16, 32, 3]), (1, 1000, 1, [3, 64, 16, 16, 3]),
+                                      (2, 777, 5, [3, 32, 3]), (1, 500, 14, [3, 16, 3])])
+def test_rowpool_chain_is_bit_identical(nb, syn, b, N, M, ch):
+    """nbpc_graph_layer_fwd_rp / _bwd_rp: the first layer's edge kernel emits the row means the second layer pools first, the last
+    layer's backward edge kernel emits the row sums the previous layer's backward pools first (same summation order) -
+    prediction, loss and every gradient BIT-identical to the plain entry points, which read the edge tensors twice."""
+    x = torch.tensor(syn.make_box("clustered", b, N, 5), device=DEV)
+    za, tgt = (torch.tensor(t, device=DEV) for t in syn.za_features(b, N, 5))
+    outs = []
+    for chained in (False, True):
+        old = nb.graph.set_rowpool_chain(chained)
+        try:
+            store = nb.train_utils.ParamStore(ch, device=DEV)
+            store.load_numpy(syn.glorot_params(ch))
+            mv = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store.get_layer_vars)
+            coo, diag = nb.graph.to_coo_batch_ZA_diag(nb.graph.get_kneighbor_list(x, M))
+            nb._lib.prof_enable(True)
+            pred = nb.graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, M))
+            loss = nb.nn.loss_ZA(pred, tgt)
+            store.zero_grad()
+            loss.backward()
+            torch.cuda.synchronize()
+            names = set(nb._lib.prof_report())
+            nb._lib.prof_enable(False)
+            outs.append((pred.detach().clone(), float(loss.detach()), store.flat_grad.clone(), names))
+        finally:
+            nb._lib.prof_enable(False)
+            nb.graph.set_rowpool_chain(old)
+    assert torch.equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])
+    assert not any("rowpool" in n or "rowsum" in n or "colonly" in n for n in outs[0][3])
+    if len(ch) > 3:                                       # a hidden layer exists: both hand-overs must have run
+        assert any(n.startswith("glk3_edge_out_rowpool_kernel") for n in outs[1][3]), sorted(outs[1][3])
+        assert any(n.startswith("gln_pool_colonly_kernel") for n in outs[1][3])
+        assert any(n.startswith("glf_last_edge_in_rowsum_kernel") for n in outs[1][3])
+        assert any(n.startswith("gln_bwd_pool_colonly_kernel") for n in outs[1][3])
+
+
 # =============================================================================== M = 1 (ADVICE: magic divisor overflow)
 @pytest.mark.parametrize("ch", [[3, 16, 3], [3, 32, 16, 3]])
 def test_graph_model_single_neighbour(nb, ch):
