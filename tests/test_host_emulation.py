@@ -131,6 +131,42 @@ def test_emu_layer_odd_widths():
         np.testing.assert_allclose(dB, g[f"odd_{t}_gB"], rtol=1e-4, atol=2e-4)
 
 
+def test_emu_rowpool_entry_points_degrade_to_the_plain_layer():
+    """nbpc_graph_layer_fwd_rp / _bwd_rp (row-pool hand-over between layers, include/nbpc.h): with no hand-over requested they
+    ARE the plain entry points; the host build has none of the emitting kernels, says so (`_rowpool_supported` == 0) and rejects
+    a hand-over with NBPC_EINVAL instead of ignoring it."""
+    g = load_golden("layers_small.npz")
+    B, N = g["x"].shape[:2]; M = int(g["k"])
+    coo, diag, ptr, edge, _ = emu.adjacency(emu.knn(g["x"], M, order=1))
+    col = np.ascontiguousarray(coo[1])
+    H = g["odd_H_in"]; W = np.stack([g[f"odd_W{i}"] for i in range(4)]); Bv = g["odd_B"]
+    L, P = emu.lib(), emu.P
+    k, q = W.shape[1], W.shape[2]
+    c = B * N * M
+    for direction in range(4):
+        assert L.nbpc_graph_layer_rowpool_supported(3, 32, 0, direction) == 0
+    out, (Pc, Pr, Pq) = emu.graph_layer_fwd(H, col, ptr, edge, B, N, M, W, Bv, False, False)
+    out2, Pc2, Pr2, Pq2 = np.zeros_like(out), np.zeros_like(Pc), np.zeros_like(Pr), np.zeros_like(Pq)
+    w = emu.ws(L.nbpc_graph_layer_workspace_bytes(B, N, M, k, q))
+    emu.ok(L.nbpc_graph_layer_fwd_rp(P(H), P(col), P(ptr), P(edge), B, N, M, k, q, P(W), P(Bv), 0, 0, P(out2), P(Pc2), P(Pr2), P(Pq2),
+                                     0, None, P(w), w.nbytes, None))
+    assert np.array_equal(out, out2) and np.array_equal(Pc, Pc2) and np.array_equal(Pr, Pr2) and np.array_equal(Pq, Pq2)
+    nxt = np.zeros((B * N, q), dtype=np.float32)
+    assert L.nbpc_graph_layer_fwd_rp(P(H), P(col), P(ptr), P(edge), B, N, M, k, q, P(W), P(Bv), 0, 0, P(out2), P(Pc2), P(Pr2), P(Pq2),
+                                     0, P(nxt), P(w), w.nbytes, None) != 0
+    assert L.nbpc_graph_layer_fwd_rp(P(H), P(col), P(ptr), P(edge), B, N, M, k, q, P(W), P(Bv), 0, 0, P(out2), P(Pc2), P(Pr2), P(Pq2),
+                                     1, None, P(w), w.nbytes, None) != 0
+    gout = np.ascontiguousarray(g["odd_mid_gout"].reshape(out.shape))
+    dH, dW, dB = emu.graph_layer_bwd(gout, H, out, col, ptr, edge, B, N, M, W, (Pc, Pr, Pq), False, False)
+    dH2, dW2, dB2 = np.zeros_like(dH), np.zeros_like(dW), np.zeros_like(dB)
+    emu.ok(L.nbpc_graph_layer_bwd_rp(P(gout), P(H), P(out), P(col), P(ptr), P(edge), B, N, M, k, q, P(W), P(Pc), P(Pr), P(Pq), 0, 0, 0,
+                                     P(dH2), P(dW2), P(dB2), None, None, P(w), w.nbytes, None))
+    assert np.array_equal(dH, dH2) and np.array_equal(dW, dW2) and np.array_equal(dB, dB2)
+    dq = np.zeros((B * N, q), dtype=np.float32)
+    assert L.nbpc_graph_layer_bwd_rp(P(gout), P(H), P(out), P(col), P(ptr), P(edge), B, N, M, k, q, P(W), P(Pc), P(Pr), P(Pq), 0, 0, 0,
+                                     P(dH2), P(dW2), P(dB2), P(dq), None, P(w), w.nbytes, None) != 0
+
+
 def test_emu_set_layers_and_losses():
     g = load_golden("set_small.npz")
     ch = list(g["channels"]); L = len(ch) - 1
