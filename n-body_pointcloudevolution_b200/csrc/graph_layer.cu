@@ -662,8 +662,12 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
     for (int i = 0; i < 3; ++i) { fa.part[i] = nullptr; fa.n[i] = 0; fa.tr[i] = 0; }
     fa.part[1] = w.xty_partial2;
     fa.part[2] = w.xty_partial3;
-    if (glf_node_xty("glf_node_xty_dW2", P_col, dQ_col, BN, k, q, w.xty_partial2, nullptr, stream, &fa.n[1], &fa.tr[1]) ||
-        glf_node_xty("glf_node_xty_dW3", P_row, dQ_row, BN, k, q, w.xty_partial3, nullptr, stream, &fa.n[2], &fa.tr[2])) {
+    int nb_pair = 0, tr_pair = 0;
+    if (!glf_node_xty_pair(P_col, dQ_col, w.xty_partial2, P_row, dQ_row, w.xty_partial3, BN, k, q, stream, &nb_pair, &tr_pair)) {
+        fa.n[1] = fa.n[2] = nb_pair;            // both problems in one launch (same partials as two launches)
+        fa.tr[1] = fa.tr[2] = tr_pair;
+    } else if (glf_node_xty("glf_node_xty_dW2", P_col, dQ_col, BN, k, q, w.xty_partial2, nullptr, stream, &fa.n[1], &fa.tr[1]) ||
+               glf_node_xty("glf_node_xty_dW3", P_row, dQ_row, BN, k, q, w.xty_partial3, nullptr, stream, &fa.n[2], &fa.tr[2])) {
         nbpc_set_error("nbpc_graph_layer_bwd: could not configure the X^T Y kernel");
         return NBPC_ELAUNCH;
     }

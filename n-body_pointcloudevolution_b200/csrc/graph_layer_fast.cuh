@@ -309,13 +309,11 @@ struct GlfXty {
 // With HAS_DH = false and RELU = false this is a plain deterministic X^T Y (X = H, Y = dOut) and is
 // reused for the node-level dW2 / dW3.
 template <int K, int Q, bool RELU, bool HAS_DH, bool MASK_IN>
-__global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout,
-                                                                    const float *__restrict__ H, const int32_t *__restrict__ col,
-                                                                    const float *__restrict__ W1,
-                                                                    const float *__restrict__ G_col,
-                                                                    const float *__restrict__ G_row, int64_t c, int M,
-                                                                    int tiles_per_block, float *__restrict__ dH,
-                                                                    float *__restrict__ dW_partial) {
+__device__ __forceinline__ void glf_edge_bwd_body(const float *__restrict__ dOut, const float *__restrict__ Hout,
+                                                  const float *__restrict__ H, const int32_t *__restrict__ col,
+                                                  const float *__restrict__ W1, const float *__restrict__ G_col,
+                                                  const float *__restrict__ G_row, int64_t c, int M, int tiles_per_block,
+                                                  float *__restrict__ dH, float *__restrict__ dW_partial) {
     constexpr int KP = (K == 3) ? 4 : K;           // 3-wide rows are zero-padded to 4 for the micro-tiles
     constexpr int KS = glf_stride(KP), QS = glf_stride(Q);
     constexpr int TILE = GLF_TE * (KS + QS + (RELU ? QS : 0));   // floats per pipeline stage: Hs | Zs | (Ms)
@@ -413,6 +411,29 @@ __global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *
     glf_cp_async_wait0();
     static_assert(2 * TILE >= GlfXty<KP, Q>::NSETS * KP * Q, "reduction scratch too small");
     xty.finish(stage0, K, dW_partial + (int64_t)blockIdx.x * K * Q);
+}
+template <int K, int Q, bool RELU, bool HAS_DH, bool MASK_IN>
+__global__ void __launch_bounds__(GLF_THREADS) glf_edge_bwd_kernel(const float *__restrict__ dOut, const float *__restrict__ Hout,
+                                                                    const float *__restrict__ H, const int32_t *__restrict__ col,
+                                                                    const float *__restrict__ W1,
+                                                                    const float *__restrict__ G_col,
+                                                                    const float *__restrict__ G_row, int64_t c, int M,
+                                                                    int tiles_per_block, float *__restrict__ dH,
+                                                                    float *__restrict__ dW_partial) {
+    glf_edge_bwd_body<K, Q, RELU, HAS_DH, MASK_IN>(dOut, Hout, H, col, W1, G_col, G_row, c, M, tiles_per_block, dH, dW_partial);
+}
+// TWO independent X^T Y problems of the same shape in one launch (blockIdx.y selects): the node-level dW2 = P_col^T dQ_col and
+// dW3 = P_row^T dQ_row of a layer's backward.  Each problem's blocks, partials and summation order are those of two separate
+// launches of glf_edge_bwd_kernel<K, Q, false, false, false> (bit-identical); the kernels are latency-bound at low occupancy, so
+// the pair takes about the time of one.
+template <int K, int Q>
+__global__ void __launch_bounds__(GLF_THREADS) glf_xty_pair_kernel(const float *__restrict__ Ya, const float *__restrict__ Xa,
+                                                                    float *__restrict__ partial_a, const float *__restrict__ Yb,
+                                                                    const float *__restrict__ Xb, float *__restrict__ partial_b,
+                                                                    int64_t n, int tiles_per_block) {
+    const bool second = blockIdx.y != 0;
+    glf_edge_bwd_body<K, Q, false, false, false>(second ? Yb : Ya, nullptr, second ? Xb : Xa, nullptr, nullptr, nullptr, nullptr, n, 1,
+                                                 tiles_per_block, nullptr, second ? partial_b : partial_a);
 }
 
 // out = sum over blocks of partial[b] (rows x cols), fixed order; transpose: out is (cols x rows).

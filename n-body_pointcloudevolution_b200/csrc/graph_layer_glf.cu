@@ -172,6 +172,49 @@ int glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, in
     return 0;
 }
 
+// dW2 / dW3 partials of one layer in ONE launch (glf_xty_pair_kernel): Xa^T Ya -> partial_a, Xb^T Yb -> partial_b, same partial
+// count and layout as two glf_node_xty calls with out == nullptr; returns 1 when no micro-tile instance fits (the caller then
+// launches the two problems separately)
+template <int K, int Q>
+static int glf_launch_xty_pair_t(const float *Ya, const float *Xa, float *pa, const float *Yb, const float *Xb, float *pb, int64_t n,
+                                 cudaStream_t stream) {
+    constexpr int KP = (K == 3) ? 4 : K;
+    constexpr int KS = glf_stride(KP), QS = glf_stride(Q);
+    constexpr int TILE = GLF_TE * (KS + QS);
+    const size_t smem = sizeof(float) * (size_t)(Q * KP + 2 * TILE);
+    auto kern = glf_xty_pair_kernel<K, Q>;
+    static int grid_cache_d[NBPC_MAX_DEVICES];   // per device
+    int &grid_cache = grid_cache_d[nbpc_device_slot()];
+    // the grid of the single-problem kernel (same shared memory, same threads): the pair must produce the same partials
+    if (!grid_cache) {
+        grid_cache = glf_persistent_grid(glf_edge_bwd_kernel<K, Q, false, false, false>, GLF_THREADS, smem);
+        if (grid_cache > 0 && glf_persistent_grid(kern, GLF_THREADS, smem) < 0) grid_cache = -1;
+    }
+    if (grid_cache < 0) return -1;
+    const int64_t ntiles = (n + GLF_TE - 1) / GLF_TE;
+    int grid = (int)(ntiles < grid_cache ? ntiles : grid_cache);
+    const int tpb = (int)((ntiles + grid - 1) / grid);
+    grid = (int)((ntiles + tpb - 1) / tpb);
+    NBPC_LAUNCH_N(NbpcKName("glf_xty_pair_kernel", K, Q).c_str(), kern, dim3(grid, 2), GLF_THREADS, smem, stream, Ya, Xa, pa, Yb, Xb, pb, n, tpb);
+    return grid;
+}
+int glf_node_xty_pair(const float *Xa, const float *Ya, float *partial_a, const float *Xb, const float *Yb, float *partial_b, int64_t n,
+                      int k, int q, cudaStream_t stream, int *nb_out, int *transposed) {
+    int nb = 0;
+    *transposed = 0;
+#define XN(K_, Q_)                                                                                                    \
+    if (!nb && k == K_ && q == Q_) nb = glf_launch_xty_pair_t<K_, Q_>(Ya, Xa, partial_a, Yb, Xb, partial_b, n, stream);      \
+    if (!nb && k == Q_ && q == K_ && K_ != Q_) {                                                                     \
+        nb = glf_launch_xty_pair_t<K_, Q_>(Xa, Ya, partial_a, Xb, Yb, partial_b, n, stream);                                \
+        if (nb > 0) *transposed = 1;                                                                                 \
+    }
+    GLF_FOR_KQ(XN)
+#undef XN
+    if (nb <= 0) return 1;
+    *nb_out = nb;
+    return 0;
+}
+
 int glf_dispatch_edge_out(int k, int q, const float *H, const int32_t *col, const float *W1, const float *Qc, const float *Qr, int64_t c,
                           int M, int relu, float *out, cudaStream_t stream) {
     int rc = 1;

@@ -18,4 +18,8 @@ void glf_reduce_partials(const float *partial, int nblocks, int rows, int cols, 
 // instead of (k,q) -> *transposed) for the caller
 int glf_node_xty(const char *name, const float *X, const float *Y, int64_t n, int k, int q, float *partial, float *out,
                  cudaStream_t stream, int *nb_out = nullptr, int *transposed = nullptr);
+// the dW2 / dW3 pair of a layer (Xa^T Ya, Xb^T Yb; same shapes) in one launch; partials as from two glf_node_xty(out = nullptr)
+// calls.  Returns 1 if no micro-tile instance fits (launch them separately then)
+int glf_node_xty_pair(const float *Xa, const float *Ya, float *partial_a, const float *Xb, const float *Yb, float *partial_b, int64_t n,
+                      int k, int q, cudaStream_t stream, int *nb_out, int *transposed);
 #endif
