@@ -346,13 +346,20 @@ class Workload:
                     def prep(x, za, tgt):
                         return graph.to_coo_batch_ZA_diag(graph.get_kneighbor_list(x, k))
 
-                    def grad(ctx, x, za, tgt):
+                    def head(ctx, x, za, tgt):                       # parameter-free start of the step: edge input features
                         coo, diag = ctx
-                        loss = nn_.loss_ZA(graph.model_func_shift_inv_za(x, coo, za, diag, mv, (b, N, k)), tgt)
+                        return graph.get_input_features_shift_inv_ZA(x, za, coo, diag, (b, N, k))
+
+                    def grad(ctx, edges, x, za, tgt):
+                        coo, diag = ctx
+                        pred = graph.network_func_shift_inv_za(edges, coo, len(ch) - 1, (b, N), torch.relu, mv)
+                        loss = nn_.loss_ZA(pred, tgt)
                         store.zero_grad()
                         loss.backward()
                         return loss
-                    self.graphed = tu.OverlappedStep(prep, grad, store, adam, world, self.resident[0])
+                    # (the two calls above are the body of graph.model_func_shift_inv_za, graph.py:479-515, split at the point
+                    # where the first parameter is read, so that the previous step's all-reduce + Adam run next to `head`)
+                    self.graphed = tu.OverlappedStep(prep, grad, store, adam, world, self.resident[0], head_fn=head)
                     self.overlapped = True
                     self.graph_note = ("CUDA graphs on two streams: the kNN graph build of batch i+1 runs next to forward / backward / "
                                        "all-reduce / Adam of batch i; one build and one update per step")

@@ -238,20 +238,48 @@ class OverlappedStep:
     Every call does one full step's work - one graph build and one parameter update - and the sequence of parameter values
     is exactly that of the plain loop; the call returns the loss of batch i-1 (None on the first call) and flush() trains on
     the last batch.  prep_fn(*static_inputs) -> ctx; grad_fn(ctx, *static_inputs) -> loss (zeroes the gradients before its
-    backward).  close() must precede destroy_process_group() (the T graphs hold the NCCL kernels)."""
+    backward).  close() must precede destroy_process_group() (the T graphs hold the NCCL kernels).
 
-    def __init__(self, prep_fn, grad_fn, store, adam, world, example_inputs, warmup=2):
+    head_fn (optional): head_fn(ctx, *static_inputs) -> head is the parameter-FREE start of a training step (the edge input
+    features); grad_fn is then called as grad_fn(ctx, head, *static_inputs), and the all-reduce + Adam update of batch i-2 are
+    captured at the START of T[(i-1)%2] on a forked stream next to head_fn instead of at the end of the previous T, where
+    every rank would sit in the collective with nothing to run (same parameter sequence: the update still lands before the
+    first kernel that reads a parameter; the device-side step counter starts at -1 so that the first update is a no-op, and
+    flush() applies the last one)."""
+
+    def __init__(self, prep_fn, grad_fn, store, adam, world, example_inputs, warmup=2, head_fn=None):
         self.store, self.adam, self.world = store, adam, world
+        self.deferred = head_fn is not None
+        self.upd = torch.cuda.Stream(priority=-1)
         self.static_in = [tuple(torch.empty_like(t).copy_(t) for t in example_inputs) for _ in range(2)]
         self.side = torch.cuda.Stream(priority=0)
         cap_hi, cap_lo = torch.cuda.Stream(priority=-1), torch.cuda.Stream(priority=0)
         state = [t.clone() for t in (store.flat, store.m, store.v, store.step_dev)]
 
         def train(ctx, ins):
-            out = grad_fn(ctx, *ins)
-            allreduce_gradients(store, world)
-            adam.step_dev(grad_scale=1.0 / world)
+            if head_fn is None:
+                out = grad_fn(ctx, *ins)
+                allreduce_gradients(store, world)
+                adam.step_dev(grad_scale=1.0 / world)
+                return out
+            main = torch.cuda.current_stream()
+            self.upd.wait_stream(main)
+            with torch.cuda.stream(self.upd):              # update of the PREVIOUS training graph's gradient
+                allreduce_gradients(store, world)
+                adam.step_dev(grad_scale=1.0 / world)
+            head = head_fn(ctx, *ins)
+            main.wait_stream(self.upd)
+            out = grad_fn(ctx, head, *ins)
+            store.pack_grads()                             # the next training graph's all-reduce reads the flat buffer
             return out
+
+        def reset():
+            with torch.no_grad():
+                for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
+                    t.copy_(s0)
+                if self.deferred:
+                    store.flat_grad.zero_()
+                    store.step_dev.fill_(-1)
 
         cap_hi.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cap_hi):                    # lazy initialisations (NCCL communicator included) outside the captures,
@@ -259,9 +287,7 @@ class OverlappedStep:
                 train(prep_fn(*self.static_in[0]), self.static_in[0])
         torch.cuda.current_stream().wait_stream(cap_hi)
         torch.cuda.synchronize()
-        with torch.no_grad():                              # the warm-up steps trained on the example batch: undo
-            for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
-                t.copy_(s0)
+        reset()                                            # the warm-up steps trained on the example batch: undo
         self.P, self.T, self.ctx, self.loss = [None, None], [None, None], [None, None], [None, None]
         n0 = _lib.launch_count()
         for s in range(2):
@@ -273,9 +299,7 @@ class OverlappedStep:
             with torch.cuda.graph(self.T[s], stream=cap_hi, pool=(self.T[0].pool() if s else None)):
                 self.loss[s] = train(self.ctx[s], self.static_in[s])
         self.kernels_per_replay = (_lib.launch_count() - n0) // 2
-        with torch.no_grad():                              # (a capture runs nothing, but keep the contract explicit)
-            for t, s0 in zip((store.flat, store.m, store.v, store.step_dev), state):
-                t.copy_(s0)
+        reset()                                            # (a capture runs nothing, but keep the contract explicit)
         self.staged = [torch.cuda.Event(), torch.cuda.Event()]
         self.prepped = [torch.cuda.Event(), torch.cuda.Event()]
         self.i = 0
@@ -308,6 +332,10 @@ class OverlappedStep:
             return None
         out = self._train((self.i - 1) & 1)
         self.i = 0
+        if self.deferred:                                  # the update of the batch just trained on
+            allreduce_gradients(self.store, self.world)
+            self.adam.step_dev(grad_scale=1.0 / self.world)
+            self.store.flat_grad.zero_()
         return out
 
     def close(self):

@@ -66,7 +66,18 @@ def main(out_path):
             store.zero_grad()
             loss.backward()
             return loss
-        ps = (tu.OverlappedStep if overlapped else tu.PipelinedStep)(prep, grad, store, adam, world, dev_batches[0])
+        if overlapped:   # deferred-update form: all-reduce + Adam of a step at the start of the next training graph
+            def head(ctx, x, za, tgt):
+                return graph.get_input_features_shift_inv_ZA(x, za, ctx[0], ctx[1], (per, N, k))
+
+            def grad_h(ctx, edges, x, za, tgt):
+                loss = nn_.loss_ZA(graph.network_func_shift_inv_za(edges, ctx[0], len(ch) - 1, (per, N), torch.relu, mv), tgt)
+                store.zero_grad()
+                loss.backward()
+                return loss
+            ps = tu.OverlappedStep(prep, grad_h, store, adam, world, dev_batches[0], head_fn=head)
+        else:
+            ps = tu.PipelinedStep(prep, grad, store, adam, world, dev_batches[0])
         for bt in dev_batches:
             ps(*bt)
         ps.flush()

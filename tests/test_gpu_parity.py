@@ -808,9 +808,12 @@ def test_pipelined_step_matches_eager(nb, syn):
     assert torch.equal(store_p.flat, store_e.flat) and int(store_p.step_dev.item()) == 6 == int(store_e.step_dev.item())
 
 
-def test_overlapped_step_matches_eager(nb, syn):
+@pytest.mark.parametrize("deferred", [False, True])
+def test_overlapped_step_matches_eager(nb, syn, deferred):
     """train_utils.OverlappedStep (the graph of batch i+1 built on a second stream next to forward / backward / Adam of batch i,
-    four CUDA graphs ordered by events) reproduces the eager loop bit for bit: losses (one call late), parameters, step count."""
+    four CUDA graphs ordered by events) reproduces the eager loop bit for bit: losses (one call late), parameters, step count.
+    deferred: with a head_fn the update of a step is captured at the start of the NEXT training graph, next to the
+    parameter-free edge features."""
     tu, graph, nn_ = nb.train_utils, nb.graph, nb.nn
     ch, b, N, k = [3, 32, 16, 3], 2, 1000, 8
     batches = []
@@ -841,7 +844,20 @@ def test_overlapped_step_matches_eager(nb, syn):
         eager.append(float(grad(prep(*batches[i % 3]), *batches[i % 3]).detach()))
         adam_e.step_dev()
     store_o, adam_o, prep, grad = make()
-    ov = tu.OverlappedStep(prep, grad, store_o, adam_o, 1, batches[0])
+    if deferred:
+        mv_o = types.SimpleNamespace(channels=ch, var_scope="params", get_layer_vars=store_o.get_layer_vars)
+
+        def head(ctx, x, za, tgt):
+            return graph.get_input_features_shift_inv_ZA(x, za, ctx[0], ctx[1], (b, N, k))
+
+        def grad_h(ctx, edges, x, za, tgt):
+            loss = nn_.loss_ZA(graph.network_func_shift_inv_za(edges, ctx[0], len(ch) - 1, (b, N), torch.relu, mv_o), tgt)
+            store_o.zero_grad()
+            loss.backward()
+            return loss
+        ov = tu.OverlappedStep(prep, grad_h, store_o, adam_o, 1, batches[0], head_fn=head)
+    else:
+        ov = tu.OverlappedStep(prep, grad, store_o, adam_o, 1, batches[0])
     got = []
     for i in range(7):
         out = ov(*batches[i % 3])
