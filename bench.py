@@ -361,8 +361,9 @@ class Workload:
                     # where the first parameter is read, so that the previous step's all-reduce + Adam run next to `head`)
                     self.graphed = tu.OverlappedStep(prep, grad, store, adam, world, self.resident[0], head_fn=head)
                     self.overlapped = True
-                    self.graph_note = ("CUDA graphs on two streams: the kNN graph build of batch i+1 runs next to forward / backward / "
-                                       "all-reduce / Adam of batch i; one build and one update per step")
+                    self.graph_note = ("CUDA graphs on two streams: the kNN graph build of batch i+1 runs next to forward / backward of "
+                                       "batch i; the all-reduce + Adam of a step are captured at the start of the next training graph "
+                                       "next to its parameter-free edge features; one build and one update per step")
                 elif world == 1:
                     self.graphed = tu.GraphedStep(lambda x, za, tgt: train_step(x, za, tgt, dev_step=True), self.resident[0])
                     self.graph_note = "one CUDA graph replay per step (whole step captured once)"
@@ -601,6 +602,8 @@ def main():
     # computes (two device staging slots, event-ordered), and the loss is read back with a non-blocking D2H copy; all
     # copies complete inside the timed region (it ends with a device-wide synchronize).
     copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
+    loss_done = torch.cuda.Event()
     slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
@@ -623,10 +626,20 @@ def main():
         torch.cuda.current_stream().wait_event(ready[sl])
         prefetch(i + 1)
         loss = wl.run_step(*slots[sl])
-        consumed[sl].record()
-        used[sl] = True
+        if wl.overlapped:                                            # the build stream stages the inputs: its event says when
+            consumed[sl] = wl.graphed.inputs_read                    # the slot may be refilled (one event, re-recorded per call:
+            copy_stream.wait_event(consumed[sl])                     # make the copy stream wait for THIS recording now)
+            used[sl] = False
+        else:
+            consumed[sl].record()
+            used[sl] = True
         if loss is not None:                                         # (overlapped loop: the loss of the previous batch)
-            loss_host[i % loss_host.numel()].copy_(loss.detach().reshape(()), non_blocking=True)   # D2H read of the loss
+            # D2H read of the loss on its own stream, behind the training graph that wrote it: the 4-byte DMA does not sit
+            # between two training graphs on the compute stream
+            loss_done.record()
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(loss_done)
+                loss_host[i % loss_host.numel()].copy_(loss.detach().reshape(()), non_blocking=True)
 
     # ---- warm-up, then the timed region (device-resident inputs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -650,7 +663,11 @@ def main():
         step_e2e(i)
     torch.cuda.synchronize()
     used[0] = used[1] = False
-    ms_e2e = timed(step_e2e, a.steps, world, dev, step_stats, "e2e", join=wl.join_streams)
+    def join_e2e():                                                   # the last event covers the build, copy and read-back streams
+        wl.join_streams()
+        torch.cuda.current_stream().wait_stream(d2h_stream)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+    ms_e2e = timed(step_e2e, a.steps, world, dev, step_stats, "e2e", join=join_e2e)
     assert bool(torch.isfinite(loss_host[:min(a.steps, loss_host.numel())]).all()), "e2e losses did not arrive on the host"
     e2e_value = particles * a.steps / (ms_e2e * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in host[0])

@@ -302,6 +302,7 @@ class OverlappedStep:
         reset()                                            # (a capture runs nothing, but keep the contract explicit)
         self.staged = [torch.cuda.Event(), torch.cuda.Event()]
         self.prepped = [torch.cuda.Event(), torch.cuda.Event()]
+        self.inputs_read = torch.cuda.Event()
         self.i = 0
         torch.cuda.synchronize()
 
@@ -314,12 +315,13 @@ class OverlappedStep:
     def __call__(self, *inputs):
         s = self.i & 1
         main = torch.cuda.current_stream()
-        for d, src in zip(self.static_in[s], inputs):      # T[s] of the previous call precedes this copy in stream order
-            if d.data_ptr() != src.data_ptr():
-                d.copy_(src, non_blocking=True)
-        self.staged[s].record(main)
-        with torch.cuda.stream(self.side):
+        self.staged[s].record(main)                        # T[s] of the previous call (the last reader of slot s) precedes this
+        with torch.cuda.stream(self.side):                 # point, and so does whatever produced `inputs` on the caller's stream
             self.side.wait_event(self.staged[s])
+            for d, src in zip(self.static_in[s], inputs):  # staged on the build stream: nothing is added to the training stream
+                if d.data_ptr() != src.data_ptr():
+                    d.copy_(src, non_blocking=True)
+            self.inputs_read.record(self.side)             # `inputs` may be overwritten once this event has completed
             self.P[s].replay()
             self.prepped[s].record(self.side)
         out = self._train(1 - s) if self.i > 0 else None
