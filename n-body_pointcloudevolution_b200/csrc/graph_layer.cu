@@ -469,16 +469,6 @@ static bool gln_shape_ok(int k, int q) {
 #undef X
     return false;
 }
-// tensor-core node projections (gln_node_*_mma_kernel): default on outside NBPC_MATH_FP32; NBPC_NODE_MMA=0 keeps the
-// thread-per-node kernels (A/B measurements)
-static bool gln_use_mma() {
-    static int cached = -1;
-    if (cached < 0) {
-        const char *e = getenv("NBPC_NODE_MMA");
-        cached = (e && e[0] == '0') ? 0 : 1;
-    }
-    return cached && g_nbpc_math_mode != NBPC_MATH_FP32;
-}
 static int gln_node_grid(int64_t BN) { return (int)nbpc_min((int64_t)nbpc_cdiv(BN, GLN_THREADS), (int64_t)gl_num_sms() * 8); }
 
 // pooling + per-block column sums of P_row; returns the number of partial blocks per sample
@@ -557,11 +547,7 @@ static int gl_fwd_fused(const float *H_in, const int32_t *col, const int32_t *cs
         if constexpr (Q_ % 8 == 0 && K_ <= 10)                                                                         \
             NBPC_LAUNCH_N(NbpcKName("gln_node_project8_kernel", k, q).c_str(), (gln_node_project8_kernel<K_, Q_>), gln_node_grid(BN * 8), GLN_THREADS, \
                           0, stream, P_col, P_row, Cq, W, (int)BN, N, Qc, Qr);                                     \
-        else if (gln_mma_shape(K_, Q_) && gln_use_mma()) {                                        \
-            if constexpr (gln_mma_shape(K_, Q_))                                                                       \
-                NBPC_LAUNCH_N(NbpcKName("gln_node_project_mma_kernel", k, q).c_str(), (gln_node_project_mma_kernel<K_, Q_>), gln_node_grid(BN), \
-                              GLN_THREADS, 0, stream, P_col, P_row, Cq, W, (int)BN, N, Qc, Qr);                    \
-        } else                                                                                                         \
+        else                                                                                                           \
             NBPC_LAUNCH_N(NbpcKName("gln_node_project_kernel", k, q).c_str(), (gln_node_project_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, \
                           0, stream, P_col, P_row, Cq, W, (int)BN, N, Qc, Qr);                                     \
     }
@@ -665,13 +651,8 @@ static int gl_bwd_fused(const float *dOut, const float *H_in, const float *H_out
     if (dH_in) {
 #define X(K_, Q_)                                                                                                       \
     if (k == K_ && q == Q_) {                                                                                          \
-        if (gln_mma_shape(K_, Q_) && gln_use_mma()) {                                             \
-            if constexpr (gln_mma_shape(K_, Q_))                                                                       \
-                NBPC_LAUNCH_N(NbpcKName("gln_node_grad_mma_kernel", k, q).c_str(), (gln_node_grad_mma_kernel<K_, Q_>), gln_node_grid(BN), \
-                              GLN_THREADS, 0, stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr); \
-        } else                                                                                                         \
-            NBPC_LAUNCH_N(NbpcKName("gln_node_grad_kernel", k, q).c_str(), (gln_node_grad_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, 0,  \
-                          stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr);        \
+        NBPC_LAUNCH_N(NbpcKName("gln_node_grad_kernel", k, q).c_str(), (gln_node_grad_kernel<K_, Q_>), gln_node_grid(BN), GLN_THREADS, 0,  \
+                      stream, dQ_col, dQ_row, Gq, W, csrT_ptr, (int)BN, N, M, is_last ? 1 : 0, w.Gc, w.Gr);            \
     }
         GLN_FOR_KQ(X)
 #undef X

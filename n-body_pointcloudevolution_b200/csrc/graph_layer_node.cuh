@@ -364,166 +364,6 @@ __global__ void __launch_bounds__(GLN_THREADS) gln_node_grad_kernel(const float 
     }
 }
 
-// ------------------------------------------------------------------ warp-level tensor-core projections (K, Q in {16, 32})
-// ncu on the thread-per-node kernels above (K = 32, Q = 16, 262 144 nodes: 43 / 46 us for 100 MB): two pipes bind at once -
-// the 256 warp-broadcast LDS.128 of a thread's weights (4 cycles of the SM's shared-memory pipe each: 29 us) and the row
-// accesses (a lane reading ITS row makes every warp load touch 32 different 128-byte lines: 768 L1 wavefronts per warp).
-// Register-blocking two nodes per thread, or transposing the rows through shared memory, each moved the time by < 3 us
-// because the other bound stayed.  Here a warp owns 32 consecutive nodes: their rows are read as contiguous 512-byte segments
-// into a per-warp scratch, the (32 x K)(K x Q) product runs on the tensor cores (mma.sync m16n8k8 TF32, operands split
-// x = hi + lo with cvt.rna, three MMAs lo*hi + hi*lo + hi*hi: FP32-class accuracy like NBPC_MATH_TF32X3) with the weights
-// held in registers as B fragments, and the result leaves through the scratch as contiguous stores.  (A 32-row warp tile of
-// a 100 MB node tensor is too small for a TMA / tcgen05 / TMEM pipeline to pay; the edge-level GEMMs have one.)
-__device__ __forceinline__ void gln_split_tf32(float x, uint32_t &hi, uint32_t &lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-__device__ __forceinline__ void gln_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-// rows [node0, node0 + 32) of a (BN, C) tensor <-> the warp's scratch (row stride C + 4 floats), contiguous 16-byte accesses
-template <int C>
-__device__ __forceinline__ void gln_warp_stage_rows(const float *__restrict__ g, int node0, int BN, float *sw) {
-    constexpr int CS = C + 4, CH = C / 4;
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        const int idx = i * 32 + lane, r = idx / CH, c4 = idx % CH;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (node0 + r < BN) v = __ldg(reinterpret_cast<const float4 *>(g + (int64_t)(node0 + r) * C + 4 * c4));
-        *reinterpret_cast<float4 *>(sw + r * CS + 4 * c4) = v;
-    }
-    __syncwarp();
-}
-template <int C>
-__device__ __forceinline__ void gln_warp_flush_rows(float *__restrict__ g, int node0, int BN, const float *sw) {
-    constexpr int CS = C + 4, CH = C / 4;
-    const int lane = threadIdx.x & 31;
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        const int idx = i * 32 + lane, r = idx / CH, c4 = idx % CH;
-        if (node0 + r < BN)
-            *reinterpret_cast<float4 *>(g + (int64_t)(node0 + r) * C + 4 * c4) = *reinterpret_cast<const float4 *>(sw + r * CS + 4 * c4);
-    }
-}
-// acc (C fragments of the 32 x QO result: [m tile][n tile][4]) = X (32 x KI rows in the scratch) * B, B(k, n) = bsrc(k, n)
-template <int KI, int QO, class F>
-__device__ __forceinline__ void gln_warp_gemm(const float *sw, F bsrc, float (&acc)[2][QO / 8][4]) {
-    constexpr int KS = KI / 8, NT = QO / 8, CS = KI + 4;
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    uint32_t bh[KS][NT][2], bl[KS][NT][2];
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            gln_split_tf32(bsrc(8 * ks + t, 8 * nt + g), bh[ks][nt][0], bl[ks][nt][0]);
-            gln_split_tf32(bsrc(8 * ks + t + 4, 8 * nt + g), bh[ks][nt][1], bl[ks][nt][1]);
-        }
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[mt][nt][j] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            const float *a = sw + (16 * mt + g) * CS + 8 * ks + t;
-            uint32_t ah[4], al[4];
-            gln_split_tf32(a[0], ah[0], al[0]);
-            gln_split_tf32(a[8 * CS], ah[1], al[1]);
-            gln_split_tf32(a[4], ah[2], al[2]);
-            gln_split_tf32(a[8 * CS + 4], ah[3], al[3]);
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) {
-                gln_mma_tf32(acc[mt][nt], al, bh[ks][nt]);
-                gln_mma_tf32(acc[mt][nt], ah, bl[ks][nt]);
-                gln_mma_tf32(acc[mt][nt], ah, bh[ks][nt]);
-            }
-        }
-    }
-}
-// C fragments -> scratch (row stride QO + 4) through post(slot, col, value); slot j = this lane's fragment row g + 8 j
-template <int QO, class F>
-__device__ __forceinline__ void gln_warp_put(float *sw, const float (&acc)[2][QO / 8][4], F post) {
-    constexpr int NT = QO / 8, QS = QO + 4;
-    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    __syncwarp();                                 // every lane has read its A fragments
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int r0 = 16 * mt + g, r1 = r0 + 8, c = 8 * nt + 2 * t;
-            *reinterpret_cast<float2 *>(sw + r0 * QS + c) = make_float2(post(2 * mt, c, acc[mt][nt][0]), post(2 * mt, c + 1, acc[mt][nt][1]));
-            *reinterpret_cast<float2 *>(sw + r1 * QS + c) = make_float2(post(2 * mt + 1, c, acc[mt][nt][2]), post(2 * mt + 1, c + 1, acc[mt][nt][3]));
-        }
-}
-__host__ __device__ constexpr bool gln_mma_shape(int K, int Q) { return (K == 16 || K == 32) && (Q == 16 || Q == 32); }
-#define GLN_MMA_FOR_KQ(X) X(16, 16) X(16, 32) X(32, 16) X(32, 32)
-
-// Q_col = P_col W2;  Q_row = P_row W3 + Cq[sample]
-template <int K, int Q>
-__global__ void __launch_bounds__(GLN_THREADS) gln_node_project_mma_kernel(const float *__restrict__ P_col, const float *__restrict__ P_row,
-                                                                            const float *__restrict__ Cq, const float *__restrict__ W, int BN,
-                                                                            int N, float *__restrict__ Q_col, float *__restrict__ Q_row) {
-    constexpr int SF = 32 * ((K > Q ? K : Q) + 4);
-    __shared__ __align__(16) float scratch[(GLN_THREADS / 32) * SF];
-    float *sw = scratch + (threadIdx.x >> 5) * SF;
-    const int g = (threadIdx.x & 31) >> 2;
-    for (int node0 = (blockIdx.x * (GLN_THREADS / 32) + (threadIdx.x >> 5)) * 32; node0 < BN; node0 += gridDim.x * GLN_THREADS) {
-        float acc[2][Q / 8][4];
-        const float *W2 = W + (int64_t)K * Q, *W3 = W + 2 * (int64_t)K * Q;
-        const float *cq[4];                        // Cq row of the sample of this lane's fragment rows g, g + 8, g + 16, g + 24
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cq[j] = Cq + (nbpc_min(node0 + g + 8 * j, BN - 1) / N) * Q;
-        gln_warp_stage_rows<K>(P_col, node0, BN, sw);
-        gln_warp_gemm<K, Q>(sw, [&](int k, int n) { return __ldg(&W2[k * Q + n]); }, acc);
-        gln_warp_put<Q>(sw, acc, [&](int, int, float v) { return v; });
-        gln_warp_flush_rows<Q>(Q_col, node0, BN, sw);
-        gln_warp_stage_rows<K>(P_row, node0, BN, sw);
-        gln_warp_gemm<K, Q>(sw, [&](int k, int n) { return __ldg(&W3[k * Q + n]); }, acc);
-        gln_warp_put<Q>(sw, acc, [&](int j, int c, float v) { return v + __ldg(&cq[j][c]); });
-        gln_warp_flush_rows<Q>(Q_row, node0, BN, sw);
-    }
-}
-
-// G_col = (dQ_col W2^T) / max(indeg, 1);  G_row = (dQ_row (W3 [+ W1])^T) / M + Gq[sample]      (see gln_node_grad_kernel)
-template <int K, int Q>
-__global__ void __launch_bounds__(GLN_THREADS) gln_node_grad_mma_kernel(const float *__restrict__ dQ_col, const float *__restrict__ dQ_row,
-                                                                         const float *__restrict__ Gq, const float *__restrict__ W,
-                                                                         const int32_t *__restrict__ csrT_ptr, int BN, int N, int M,
-                                                                         int add_w1, float *__restrict__ G_col, float *__restrict__ G_row) {
-    constexpr int SF = 32 * ((K > Q ? K : Q) + 4);
-    __shared__ __align__(16) float scratch[(GLN_THREADS / 32) * SF];
-    float *sw = scratch + (threadIdx.x >> 5) * SF;
-    const int g = (threadIdx.x & 31) >> 2;
-    const float rm = 1.f / (float)M;
-    for (int node0 = (blockIdx.x * (GLN_THREADS / 32) + (threadIdx.x >> 5)) * 32; node0 < BN; node0 += gridDim.x * GLN_THREADS) {
-        float acc[2][K / 8][4];
-        const float *W1 = W, *W2 = W + (int64_t)K * Q, *W3 = W + 2 * (int64_t)K * Q;
-        float ri[4];                               // 1 / in-degree of this lane's four fragment rows g, g + 8, g + 16, g + 24
-        const float *gq[4];                        // and the Gq row of their sample
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int node = nbpc_min(node0 + g + 8 * j, BN - 1);
-            ri[j] = 1.f / (float)nbpc_max(__ldg(&csrT_ptr[node + 1]) - __ldg(&csrT_ptr[node]), 1);
-            gq[j] = Gq + (node / N) * K;
-        }
-        gln_warp_stage_rows<Q>(dQ_col, node0, BN, sw);
-        gln_warp_gemm<Q, K>(sw, [&](int q, int kk) { return __ldg(&W2[kk * Q + q]); }, acc);
-        gln_warp_put<K>(sw, acc, [&](int j, int, float v) { return v * ri[j]; });
-        gln_warp_flush_rows<K>(G_col, node0, BN, sw);
-        gln_warp_stage_rows<Q>(dQ_row, node0, BN, sw);
-        gln_warp_gemm<Q, K>(sw, [&](int q, int kk) { return __ldg(&W3[kk * Q + q]) + (add_w1 ? __ldg(&W1[kk * Q + q]) : 0.f); }, acc);
-        gln_warp_put<K>(sw, acc, [&](int j, int c, float v) { return fmaf(v, rm, __ldg(&gq[j][c])); });
-        gln_warp_flush_rows<K>(G_row, node0, BN, sw);
-    }
-}
-
 // ------------------------------------------------------------------ 8 threads per node (Q % 8 == 0 / K % 8 == 0)
 // For the narrow first layer (K <= 10) a node's outputs are split over 8 adjacent lanes: every lane reads the whole (short)
 // input row and its slice of the weights from shared memory (21 us instead of 31 us at k = 3, q = 32).  Measured and NOT kept
