@@ -593,6 +593,10 @@ def main():
     nb = importlib.import_module("n-body_pointcloudevolution_b200")
     syn, graph, tu, lib = nb.synthetic, nb.graph, nb.train_utils, nb._lib
     nb.ops.device_check()
+    try:   # the graphs are captured on their own streams and the per-kernel profile below runs eagerly on the default stream
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    except AttributeError:
+        pass
 
     N, b, k, ch = a.n_side ** 3, a.batch, a.k, a.channels
     wl = Workload(nb, dev, rank, world, a.n_side, b, k, ch, a.kind, not a.no_graph, overlap=not a.no_overlap)
@@ -698,6 +702,7 @@ def main():
                 barrier(world)
 
     graphed_kernels = wl.graphed.kernels_per_replay if wl.graphed is not None else None
+    overlapped_note = wl.overlapped
     if world > 1:
         wl.close()                                                    # a live graph holding NCCL kernels hangs the teardown
         torch.distributed.barrier()
@@ -825,8 +830,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / a.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4,
                 "pipeline": "inputs in pinned host memory, H2D one step ahead on a copy stream (2 device slots), loss read "
-                            "back every step with a non-blocking D2H copy into pinned memory; the timed region ends with a "
-                            "device-wide synchronize"},
+                            "back every step with a non-blocking D2H copy into pinned memory on its own stream; the last timed "
+                            "event waits for the build, copy and read-back streams and the region ends with a device-wide "
+                            "synchronize" + ("; overlapped loop: the loss read in step i is that of batch i-1 (each batch's "
+                                             "loss is read exactly once)" if overlapped_note else "")},
         "gpu_launches": int(launches),
         # second half of BASELINE's metric: periodic kNN build (k = 14, thr 0.05, self included) on one 128^3 box, ms
         "knn_build_ms_128^3": knn128 or None,
