@@ -13,6 +13,7 @@ Differences a caller can observe (all documented in DESIGN.md):
 """
 from types import SimpleNamespace
 
+import os as _os
 import weakref
 
 import numpy as np
@@ -346,10 +347,11 @@ def _layer(H_in, COO_feats, bN, layer_vars, is_last, relu, input_relu=False, gra
 # Row-pool hand-over (csrc: glk3_edge_out_rowpool_kernel, glf_last_edge_in_rowsum_kernel): inside a fused-ReLU network the
 # kernel that writes a hidden edge tensor also emits the row reduction the next layer (forward) / previous layer (backward)
 # starts with, so that layer reads the tensor once.  Bit-identical to the plain path; NBPC_ROWPOOL_CHAIN=0 disables.
-_ROWPOOL_CHAIN = __import__("os").environ.get("NBPC_ROWPOOL_CHAIN", "1") != "0"
+_ROWPOOL_CHAIN = _os.environ.get("NBPC_ROWPOOL_CHAIN", "1") != "0"
 
 
 def set_rowpool_chain(on):
+    """Opt out of / back into the row-pool hand-over between layers; returns the previous setting."""
     global _ROWPOOL_CHAIN
     old, _ROWPOOL_CHAIN = _ROWPOOL_CHAIN, bool(on)
     return old
@@ -380,7 +382,6 @@ def shift_inv_layer(H_in, COO_feats, bN, layer_vars, is_last=False):
 # (2.71 vs 2.00 ms per step at 8 x 32^3: four generator warps per CTA cannot keep enough L2 gathers in flight - the
 # materialising kernel does the same gathers with 2048 threads per SM), so it is opt-in: NBPC_VIRTUAL_FIRST_LAYER=1 or
 # set_virtual_first_layer(True).
-import os as _os
 _VIRTUAL_FIRST_LAYER = _os.environ.get("NBPC_VIRTUAL_FIRST_LAYER", "0") == "1"
 
 
